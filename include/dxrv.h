@@ -1,0 +1,193 @@
+/* dxrv.h -- C ABI of the B200-native solid voxelizer (libdxrv.so).
+ *
+ * This is the drop-in boundary for the voxelization path of StarsX/DXRVoxelizer.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree,
+ * DXRVoxelizer/...).  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns DXRV_OK (0) or a negative dxrv_status; the message for the last
+ *     failure on a context is available from dxrv_last_error().  Nothing throws or aborts
+ *     across the ABI (reference: bool + XUSG_N_RETURN, XUSG/Core/XUSG.h:12-15).
+ *   - a context is bound to one CUDA device and one stream; it is NOT thread-safe.  Distinct
+ *     contexts are independent (one per GPU / per stream for batches).
+ *   - host arrays are borrowed for the duration of the call only.  The context owns all
+ *     device memory.  Calls are stream-ordered/asynchronous; dxrv_fetch_grid and
+ *     dxrv_synchronize block.
+ *   - there is NO CPU fallback: without a usable CUDA device dxrv_create fails.
+ *
+ * Grid layout (the reference's UAV is RWTexture3D grid[z][y][x], Voxelizer.cpp:62-67 and
+ * DXRVoxelizer.hlsl:64-67,83-84; occupancy is its alpha channel, PSRayCast.hlsl:108):
+ *   DXRV_FORMAT_BITS : uint32 word[((z - slabBegin) * N + y) * P + (x >> 5)], bit (x & 31),
+ *                      P = (N + 31) / 32 words per x-row.  For N % 32 == 0 this is the
+ *                      linear bit index ((z*N + y)*N + x).  x, y, z are the reference's
+ *                      launch indices, so +y of the grid is -y of the scene (hlsl:49).
+ *   DXRV_FORMAT_U8   : uint8 occ[((z - slabBegin) * N + y) * N + x] in {0,1}.
+ *   DXRV_FORMAT_R10G10B10A2 : uint32 texel per voxel exactly as the reference's UAV holds it
+ *                      (Normal.xyz, 1) -> UNORM 10/10/10/2, untouched texels 0.  Only after
+ *                      a DXRV_MODE_SHADER | DXRV_EMIT_TEXELS voxelize.
+ */
+#ifndef DXRV_H
+#define DXRV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DXRV_API __attribute__((visibility("default")))
+#else
+#define DXRV_API
+#endif
+
+typedef struct dxrv_ctx dxrv_ctx;
+typedef struct dxrv_mesh dxrv_mesh;
+
+enum dxrv_status
+{
+    DXRV_OK = 0,
+    DXRV_ERR_INVALID_ARG = -1,
+    DXRV_ERR_CUDA = -2,
+    DXRV_ERR_NO_BVH = -3,   /* dxrv_voxelize before dxrv_build_bvh */
+    DXRV_ERR_NO_GRID = -4,  /* dxrv_fetch_grid before dxrv_voxelize */
+    DXRV_ERR_IO = -5,
+    DXRV_ERR_OOM = -6,
+    DXRV_ERR_UNSUPPORTED = -7
+};
+
+/* mode argument of dxrv_voxelize (low byte = algorithm, high bits = flags) */
+enum dxrv_mode
+{
+    /* Exact restatement of Content/Shaders/DXRVoxelizer.hlsl: one radial ray per voxel,
+     * closest hit, inside iff dot(normalize(interpolated normal), dir) > 0.12. */
+    DXRV_MODE_SHADER = 0,
+    /* One +x axis ray per (y,z) voxel column, watertight crossings, parity fill.  */
+    DXRV_MODE_PARITY = 1,
+    DXRV_MODE_MASK = 0xff,
+    /* MODE_SHADER only: also produce the R10G10B10A2 texel grid (4 B / voxel). */
+    DXRV_EMIT_TEXELS = 0x100
+};
+
+enum dxrv_format
+{
+    DXRV_FORMAT_BITS = 0,
+    DXRV_FORMAT_U8 = 1,
+    DXRV_FORMAT_R10G10B10A2 = 2
+};
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Replaces device/command-list acquisition (DXRVoxelizer.cpp:64-169,175-185). */
+DXRV_API int dxrv_create(dxrv_ctx** out, int cuda_device);
+DXRV_API void dxrv_destroy(dxrv_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed dxrv_create / dxrv_obj_load. */
+DXRV_API const char* dxrv_last_error(const dxrv_ctx* ctx);
+/* Run all work of this context on an existing cudaStream_t (NULL = the context's own). */
+DXRV_API int dxrv_set_stream(dxrv_ctx* ctx, void* cuda_stream);
+/* Replaces WaitForGpu (DXRVoxelizer.cpp:485-493). */
+DXRV_API int dxrv_synchronize(dxrv_ctx* ctx);
+
+/* ---- acceleration structure ------------------------------------------------------------
+ * Replaces Voxelizer::createVB/createIB (Content/Voxelizer.cpp:115-138) and
+ * Voxelizer::buildAccelerationStructures (Content/Voxelizer.cpp:264-326): one triangle
+ * geometry, float3 positions at `strideBytes` (normals at byte offset 12 when
+ * strideBytes >= 24, as ObjLoader lays them out), uint32 indices; the instance transform
+ * inverse(Scale(w) * Translate(c)) (Voxelizer.cpp:304-310) is applied as p' = (p - c) / w.
+ * bound = {cx, cy, cz, w}; NULL => computed on the device exactly as Voxelizer.cpp:52-57
+ * does from ObjLoader::computeAABB (min/max over ALL vertices).
+ * The build is an LBVH: bounds -> 30-bit Morton keys -> onesweep radix sort -> Karras
+ * hierarchy -> atomic bottom-up refit.  The host variant copies the arrays to the device. */
+DXRV_API int dxrv_build_bvh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts,
+                            uint32_t strideBytes, const uint32_t* indices, uint32_t numIndices,
+                            const float bound[4]);
+/* Same, with vertices/indices already resident in device memory of this context's GPU
+ * (they are read in place and must stay valid until the next build). */
+DXRV_API int dxrv_build_bvh_device(dxrv_ctx* ctx, const void* d_vertices, uint32_t numVerts,
+                                   uint32_t strideBytes, const uint32_t* d_indices,
+                                   uint32_t numIndices, const float bound[4]);
+/* {cx, cy, cz, w} used by the last build (synchronises). */
+DXRV_API int dxrv_get_bound(dxrv_ctx* ctx, float bound[4]);
+
+/* ---- voxelization ----------------------------------------------------------------------
+ * Replaces Voxelizer::voxelize (Content/Voxelizer.cpp:351-369): DispatchRays(N, N*N, 1) of
+ * raygenMain/closestHitMain/missMain.  N replaces the GRID_SIZE macro (Voxelizer.cpp:8).
+ * Computes grid layers z in [slabBegin, slabEnd) (0 <= slabBegin < slabEnd <= N).  Every
+ * word of the slab is written exactly once; no clear is needed. */
+DXRV_API int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin,
+                           uint32_t slabEnd);
+/* Copy the slab computed by the last dxrv_voxelize to host memory (synchronises).
+ * bytes must equal the slab size in `format`.  The reference has no read-back of the grid
+ * (only of the back buffer, DXRVoxelizer.cpp:436,476); this is the headless replacement. */
+DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format);
+/* Device pointer / byte size of the slab's DXRV_FORMAT_BITS grid (valid until the next
+ * voxelize with a different size, or destroy). */
+DXRV_API int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);
+/* Make subsequent dxrv_voxelize calls write the BITS grid into caller-owned device memory
+ * (may be peer-mapped memory of another GPU: the fill kernel's 128-bit stores then go over
+ * NVLink, fusing the slab gather into the write).  NULL restores the internal grid. */
+DXRV_API int dxrv_set_grid_target(dxrv_ctx* ctx, void* d_ptr, size_t bytes);
+/* Number of set voxels in the slab of the last voxelize (device popcount; synchronises). */
+DXRV_API int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count);
+
+/* ---- introspection ----------------------------------------------------------------------- */
+enum dxrv_info
+{
+    DXRV_INFO_NUM_TRIANGLES = 0,
+    DXRV_INFO_NUM_NODES = 1,
+    DXRV_INFO_KERNEL_LAUNCHES = 2, /* kernels launched by this context so far */
+    DXRV_INFO_CROSSINGS = 3,       /* MODE_PARITY: surface crossings found by the last voxelize */
+    DXRV_INFO_SM_COUNT = 4
+};
+DXRV_API int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value);
+
+/* Read back an internal device buffer for tests (synchronises).  `what`: */
+enum dxrv_debug_buffer
+{
+    DXRV_DBG_MORTON_SORTED = 0, /* uint32[T]   sorted Morton keys                          */
+    DXRV_DBG_PRIM_SORTED = 1,   /* uint32[T]   original triangle index per sorted slot      */
+    DXRV_DBG_NODES = 2,         /* 64 B * (T-1) internal nodes, see csrc/bvh.cuh            */
+    DXRV_DBG_TRIS = 3,          /* 48 B * T    normalised triangles in sorted order         */
+    DXRV_DBG_PARENTS = 4,       /* uint32[2T-1] parent of every node                        */
+    DXRV_DBG_ROOT_BOX = 5       /* float[6]    lo.xyz hi.xyz of the root                    */
+};
+DXRV_API int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes);
+/* Standalone key/value radix sort on the device (the LBVH's onesweep), for tests/bench:
+ * sorts n (key, value) pairs given as host arrays, in place. */
+DXRV_API int dxrv_debug_sort_pairs(dxrv_ctx* ctx, uint32_t* keys, uint32_t* values, uint32_t n);
+
+/* ---- mesh input ---------------------------------------------------------------------------
+ * Replaces XUSG::ObjLoader::Import(fileName, true, true) as called from Voxelizer::Init
+ * (Content/Voxelizer.cpp:46-47; XUSG/Optional/XUSGObjLoader.cpp:18-40): byte-identical
+ * interleaved {float3 pos; float3 nrm} vertices, uint32 indices (z flipped, index array
+ * reversed), AABB.  Pure host code. */
+DXRV_API int dxrv_obj_load(const char* path, dxrv_mesh** out);
+DXRV_API void dxrv_obj_free(dxrv_mesh* mesh);
+DXRV_API uint32_t dxrv_obj_num_vertices(const dxrv_mesh* mesh);
+DXRV_API uint32_t dxrv_obj_num_indices(const dxrv_mesh* mesh);
+DXRV_API uint32_t dxrv_obj_vertex_stride(const dxrv_mesh* mesh);
+DXRV_API const void* dxrv_obj_vertices(const dxrv_mesh* mesh);
+DXRV_API const uint32_t* dxrv_obj_indices(const dxrv_mesh* mesh);
+/* out = {min.x, min.y, min.z, max.x, max.y, max.z} (ObjLoader::GetAABB) */
+DXRV_API void dxrv_obj_aabb(const dxrv_mesh* mesh, float out[6]);
+/* out = {cx, cy, cz, w} as Voxelizer::Init derives it (Content/Voxelizer.cpp:52-57) */
+DXRV_API void dxrv_obj_bound(const dxrv_mesh* mesh, float out[4]);
+
+/* ---- pinned host staging (optional; lets dxrv_build_bvh / dxrv_fetch_grid run at full
+ * PCIe speed; replaces the upload heaps of Voxelizer.cpp:121,134) ------------------------- */
+DXRV_API void* dxrv_host_alloc(size_t bytes);
+DXRV_API void dxrv_host_free(void* p);
+
+/* ---- CUDA IPC for the fused slab gather (one process per GPU) ----------------------------- */
+/* Export a handle (64 bytes) for the internal full-size grid of `fullBytes` bytes, allocating
+ * it if needed; another process opens it with dxrv_ipc_open and passes the pointer (plus its
+ * slab offset) to dxrv_set_grid_target. */
+DXRV_API int dxrv_ipc_export_grid(dxrv_ctx* ctx, size_t fullBytes, void* handle64, void** d_ptr);
+DXRV_API int dxrv_ipc_open(dxrv_ctx* ctx, const void* handle64, void** d_ptr);
+DXRV_API int dxrv_ipc_close(dxrv_ctx* ctx, void* d_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXRV_H */
