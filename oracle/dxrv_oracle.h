@@ -1,0 +1,99 @@
+/* dxrv_oracle.h -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this.  The product (libdxrv.so) never links, loads or calls anything under oracle/.
+ *
+ * PARITY STATUS: "parity unpinned" for the voxel grid.  The reference ships no tests, no golden
+ * grids and cannot run here (Windows + D3D12/DXR + binary-only XUSG DLLs), and the arithmetic of
+ * TraceRay (BVH + ray/triangle test) lives in the D3D12 driver, which is not in the tree and has
+ * no version pin.  What IS pinned: the mesh-input stage, against the reference's own
+ * XUSGObjLoader.cpp compiled from /root/reference (oracle/Makefile -> oracle/_ref).  This file
+ * therefore restates the reference's shader logic line by line and fixes the driver-defined
+ * arithmetic with the normative contract below ("Spec H"), which the CUDA kernels implement
+ * independently and must match bit for bit.
+ *
+ * Reference logic restated (paths relative to /root/reference/DXRVoxelizer):
+ *   bound   c=(max+min)/2, w=max(ext)/2                      Content/Voxelizer.cpp:52-57
+ *   scene   p' = (p - c) / w  (instance transform)           Content/Voxelizer.cpp:304-310
+ *   launch  x = i.x, z = i.y / N, y = i.y % N                Content/Shaders/DXRVoxelizer.hlsl:64-67
+ *   ray     pos=(idx+0.5)/N*2-1; pos.y=-pos.y; O=pos;
+ *           D=normalize(pos); TMin=0; TMax=10000             DXRVoxelizer.hlsl:44-53,76-77
+ *   trace   closest hit, no culling, both faces              DXRVoxelizer.hlsl:80
+ *   chit    Nrm=n0+b.x*(n1-n0)+b.y*(n2-n0);
+ *           inside = dot(normalize(Nrm), D) > 0.12           DXRVoxelizer.hlsl:5,90-119,132-140
+ *   miss    inside = false                                   DXRVoxelizer.hlsl:79,145-148
+ *   store   if inside: grid[x,y,z] = (Normal,1) as
+ *           R10G10B10A2_UNORM, else untouched (zero)         DXRVoxelizer.hlsl:83-84; Voxelizer.cpp:65
+ *
+ * Spec H (all arithmetic IEEE-754 binary32 round-to-nearest-even, one rounding per operation,
+ * NO fused multiply-add, unless "double" is written):
+ *   min(a,b) := (a < b) ? a : b        max(a,b) := (a > b) ? a : b
+ *   normalize(v) := v / sqrt((v.x*v.x + v.y*v.y) + v.z*v.z)
+ *   dot(a,b)     := (a.x*b.x + a.y*b.y) + a.z*b.z
+ *   centre(i)    := ((float)i + 0.5f) / (float)N * 2.0f - 1.0f
+ *   edge(P,Q)    := P.p*Q.q - P.q*Q.p  (two products, one subtraction)
+ *
+ *  MODE_SHADER, ray (O, D), invD = 1.0f / D per component, triangle k = (a, b, c) in scene space:
+ *   1. box: lo/hi = componentwise min/max of a,b,c.  tin = 0, tout = 10000; per axis i in x,y,z:
+ *        t0 = (lo_i - O_i) * invD_i; t1 = (hi_i - O_i) * invD_i;
+ *        tin = max(min(t0,t1), tin);  tout = min(max(t0,t1), tout)
+ *      miss unless tin <= tout.
+ *   2. watertight test (Woop, Benthin, Wald 2013): kz = axis of largest |D| (first wins ties),
+ *      kx = kz+1, ky = kx+1 (mod 3), swapped when D[kz] < 0; Sx = D[kx]/D[kz], Sy = D[ky]/D[kz],
+ *      Sz = 1/D[kz]; A = a - O, ...; Ax = A[kx] - Sx*A[kz], Ay = A[ky] - Sy*A[kz], ...;
+ *      U = edge(C,B), V = edge(A,C), W = edge(B,A) on (x,y) = (p,q); if any of U,V,W == 0 all three
+ *      are recomputed in double from the float operands and rounded to float.
+ *      miss if (U<0||V<0||W<0) && (U>0||V>0||W>0);  det = (U+V)+W; miss if det == 0.
+ *      t = ((U*(Sz*A[kz]) + V*(Sz*B[kz])) + W*(Sz*C[kz])) / det.
+ *   3. tc = min(max(t, tin), tout); hit iff tc > 0 && tc < 10000 (NaN compares false => miss).
+ *      (Clamping t into the triangle's own slab interval makes the ordering of hits consistent
+ *      with ANY bounding hierarchy built from exact min/max boxes: a node may be skipped when its
+ *      tin exceeds the best tc so far.)
+ *   4. closest hit = lexicographic minimum of (tc, k).  b.x = V/det, b.y = W/det.
+ *   5. Nrm per component = (n0 + b.x*(n1 - n0)) + b.y*(n2 - n0); inside iff
+ *      dot(normalize(Nrm), D) > 0.12f.   Texel = UNORM10 of saturate(Normal.xyz), alpha 3.
+ *
+ *  MODE_PARITY, column (y,z): the ray is the full line {(s, Y, Z)}, Y = -centre(y), Z = centre(z).
+ *   1. (p,q) = (y - Y, z - Z) per vertex.  sU = sign of edge(C,B) evaluated EXACTLY (double
+ *      products of floats are exact); when that is 0 the sign of (C.q - B.q), and when that is 0
+ *      too the sign of (B.p - C.p) (symbolic perturbation of the ray by (+e, +e^2): a ray through
+ *      an edge or vertex is owned by exactly one side).  sV, sW alike for (A,C), (B,A).
+ *      crossing iff sU = sV = sW != 0.
+ *   2. U,V,W values as in MODE_SHADER step 2 (float, double fallback when any is 0);
+ *      det = (U+V)+W; no crossing if det == 0;  d = ((U*a.x + V*b.x) + W*c.x) / det.
+ *   3. the crossing toggles every voxel x with centre(x) > d (strict).  ix = min such x.
+ *   voxel (x,y,z) is inside iff an odd number of crossings of its column have ix <= x.
+ */
+#ifndef DXRV_ORACLE_H
+#define DXRV_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORACLE_MODE_SHADER 0u
+#define ORACLE_MODE_PARITY 1u
+#define ORACLE_TIER_BRUTE 0 /* every ray against every triangle: the oracle's own ground truth */
+#define ORACLE_TIER_ACCEL 1 /* same per-pair arithmetic, conservative culling (BVH / yz bins)    */
+
+/* {cx,cy,cz,w} from all vertices: XUSGObjLoader.cpp:386-416 + Content/Voxelizer.cpp:52-57 */
+void oracle_bound(const void* vertices, uint32_t numVerts, uint32_t strideBytes, float out[4]);
+
+/* Voxelize layers z in [z0, z1).  outBits: ((z1-z0)*N*((N+31)/32)) uint32 words, layout of
+ * DXRV_FORMAT_BITS (include/dxrv.h).  outTexels (nullable, MODE_SHADER): (z1-z0)*N*N uint32.
+ * crossings (nullable, MODE_PARITY): total surface crossings; oddColumns (nullable): number of
+ * columns with an odd crossing count (0 for a watertight mesh).
+ * threads <= 0: all OpenMP threads.  Returns 0, or -1 on invalid arguments / out of memory. */
+int oracle_voxelize(const void* vertices, uint32_t numVerts, uint32_t strideBytes,
+                    const uint32_t* indices, uint32_t numIndices, const float bound[4], uint32_t N,
+                    uint32_t mode, uint32_t z0, uint32_t z1, int tier, int threads, uint32_t* outBits,
+                    uint32_t* outTexels, uint64_t* crossings, uint64_t* oddColumns);
+
+int oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
