@@ -1,0 +1,539 @@
+// api.cu -- the C ABI of libdxrv.so (include/dxrv.h): context, device memory, launch sequencing.
+//
+// Host-side sequencing only; every byte of the hot path is produced by the kernels in lbvh.cu,
+// onesweep.cu, trace_parity.cu and trace_shader.cu.  There is deliberately no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/dxrv.h"
+#include "kernels.h"
+
+namespace dxrv
+{
+std::string& globalError();  // obj_capi.cpp
+}
+
+using namespace dxrv;
+
+struct dxrv_ctx
+{
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // mesh (either borrowed device pointers or owned staging copies)
+    uint8_t* vertsOwned = nullptr; size_t vertsCap = 0;
+    uint32_t* idxOwned = nullptr;  size_t idxCap = 0;
+    MeshView mesh{};
+    bool haveBvh = false;
+
+    // LBVH
+    uint32_t *keysA = nullptr, *keysB = nullptr, *valsA = nullptr, *valsB = nullptr;
+    BvhNode* nodes = nullptr;
+    Tri48* tris = nullptr;
+    uint32_t *nodeParent = nullptr, *leafParent = nullptr, *flags = nullptr;
+    void* sortTemp = nullptr; size_t sortTempCap = 0;
+    size_t capTris = 0;
+
+    // small device scalars: [0..3] bound, [4..9] root box, then counters
+    float* dBound = nullptr;
+    float* dRootBox = nullptr;
+    float* dPartials = nullptr;
+    uint32_t* dCounter = nullptr;
+    uint32_t* dErr = nullptr;
+    unsigned long long* dCrossings = nullptr;
+    unsigned long long* dCount = nullptr;
+    void* dSmall = nullptr;
+
+    // grid
+    uint32_t* gridOwned = nullptr; size_t gridCap = 0;
+    uint32_t* gridTarget = nullptr; size_t gridTargetBytes = 0;
+    uint32_t* texels = nullptr; size_t texCap = 0;
+    uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
+    uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
+    bool haveGrid = false, haveTexels = false;
+
+    cudaEvent_t copyDone = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace
+{
+int fail(dxrv_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else globalError() = msg;
+    return code;
+}
+
+int cudaFail(dxrv_ctx* c, cudaError_t e, const char* what)
+{
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();  // clear the non-sticky error state
+    return fail(c, e == cudaErrorMemoryAllocation ? DXRV_ERR_OOM : DXRV_ERR_CUDA, buf);
+}
+
+#define DXRV_CUDA(call)                                                   \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return cudaFail(ctx, e_, #call);           \
+    } while (0)
+
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+cudaError_t ensure(T*& p, size_t& cap, size_t need)
+{
+    if (need <= cap && p) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t grow = need + need / 8;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), grow ? grow : 16);
+    if (e == cudaSuccess) cap = grow ? grow : 16;
+    return e;
+}
+
+size_t slabWords(uint32_t N, uint32_t z0, uint32_t z1) { return (size_t)(z1 - z0) * N * ((N + 31) / 32); }
+
+int checkDeviceError(dxrv_ctx* ctx)
+{
+    uint32_t e = 0;
+    DXRV_CUDA(cudaMemcpyAsync(&e, ctx->dErr, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e == kErrNone) return DXRV_OK;
+    cudaMemsetAsync(ctx->dErr, 0, sizeof(uint32_t), ctx->stream);
+    if (e == kErrBadIndex) return fail(ctx, DXRV_ERR_INVALID_ARG, "index buffer references a vertex >= numVerts");
+    return fail(ctx, DXRV_ERR_CUDA, "traversal stack overflow / corrupt hierarchy");
+}
+
+int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
+{
+    const MeshView& m = ctx->mesh;
+    const uint32_t T = m.numTris;
+    ctx->haveBvh = false;
+    ctx->haveGrid = false;
+    if (T > ctx->capTris || !ctx->nodes)
+    {
+        const size_t cap = T + T / 8 + 16;
+        uint32_t** u32s[] = {&ctx->keysA, &ctx->keysB, &ctx->valsA, &ctx->valsB, &ctx->nodeParent, &ctx->leafParent, &ctx->flags};
+        for (auto pp : u32s) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+        if (ctx->nodes) cudaFree(ctx->nodes); ctx->nodes = nullptr;
+        if (ctx->tris) cudaFree(ctx->tris); ctx->tris = nullptr;
+        ctx->capTris = 0;
+        for (auto pp : u32s) DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(pp), sizeof(uint32_t) * cap));
+        DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->nodes), sizeof(BvhNode) * cap));
+        DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tris), sizeof(Tri48) * cap));
+        DXRV_CUDA(cudaMemsetAsync(ctx->flags, 0, sizeof(uint32_t) * cap, ctx->stream));
+        ctx->capTris = cap;
+    }
+    {
+        size_t need = SortTemp::bytesFor(T);
+        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->sortTemp), ctx->sortTempCap, need);
+        if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(sort temp)");
+    }
+
+    cudaStream_t s = ctx->stream;
+    if (bound) { launchSetBound(s, bound[0], bound[1], bound[2], bound[3], ctx->dBound); }
+    else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
+    ctx->launches += 1;
+    if (T > 0)
+    {
+        launchMorton(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->dErr);
+        ctx->launches += 1;
+        ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, T);
+        if (T > 1) { launchHierarchy(s, ctx->keysA, T, ctx->nodes, ctx->nodeParent, ctx->leafParent); ctx->launches += 1; }
+        launchRefit(s, m, ctx->dBound, ctx->valsA, ctx->nodes, ctx->nodeParent, ctx->leafParent, ctx->flags, ctx->tris,
+                    ctx->dRootBox, ctx->dErr);
+        ctx->launches += 1;
+    }
+    DXRV_CUDA(cudaGetLastError());
+    ctx->haveBvh = true;
+    return DXRV_OK;
+}
+
+int validateMeshArgs(dxrv_ctx* ctx, const void* v, uint32_t numVerts, uint32_t stride, const uint32_t* idx, uint32_t numIndices,
+                     const float bound[4])
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    if (!v || numVerts == 0) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh: no vertices");
+    if (stride < 12 || (stride & 3u)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh: strideBytes must be >= 12 and a multiple of 4");
+    if (numIndices % 3u) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh: numIndices must be a multiple of 3");
+    if (numIndices && !idx) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh: null index buffer");
+    if (bound && !(bound[3] > 0.0f)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh: bound[3] (half extent) must be > 0");
+    return DXRV_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dxrv_create(dxrv_ctx** out, int cuda_device)
+{
+    if (!out) return fail(nullptr, DXRV_ERR_INVALID_ARG, "dxrv_create: null out");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(nullptr, DXRV_ERR_CUDA, std::string("dxrv_create: no CUDA device (") + cudaGetErrorString(e) +
+                                                "); this library has no CPU fallback");
+    }
+    if (cuda_device < 0 || cuda_device >= count) return fail(nullptr, DXRV_ERR_INVALID_ARG, "dxrv_create: bad device ordinal");
+    dxrv_ctx* ctx = new (std::nothrow) dxrv_ctx();
+    if (!ctx) return fail(nullptr, DXRV_ERR_OOM, "dxrv_create: out of memory");
+    ctx->device = cuda_device;
+    DeviceGuard g(cuda_device);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cuda_device)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaGetDeviceProperties"); }
+    if (prop.major < 10)
+    {
+        delete ctx;
+        return fail(nullptr, DXRV_ERR_UNSUPPORTED, "dxrv_create: kernels are built for sm_100a (Blackwell) only");
+    }
+    ctx->smCount = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
+    ctx->stream = ctx->ownStream;
+    if ((e = cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaEventCreate"); }
+    const size_t smallBytes = 64 * sizeof(float) + 6 * kBoundsMaxBlocks * sizeof(float);
+    if ((e = cudaMalloc(&ctx->dSmall, smallBytes)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaMalloc"); }
+    cudaMemset(ctx->dSmall, 0, smallBytes);
+    float* f = static_cast<float*>(ctx->dSmall);
+    ctx->dBound = f;                                                   // 4 floats
+    ctx->dRootBox = f + 4;                                             // 6 floats
+    ctx->dCounter = reinterpret_cast<uint32_t*>(f + 12);
+    ctx->dErr = reinterpret_cast<uint32_t*>(f + 13);
+    ctx->dCrossings = reinterpret_cast<unsigned long long*>(f + 16);   // 8-byte aligned
+    ctx->dCount = reinterpret_cast<unsigned long long*>(f + 18);
+    ctx->dPartials = f + 64;
+    *out = ctx;
+    return DXRV_OK;
+}
+
+void dxrv_destroy(dxrv_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
+                    ctx->nodeParent, ctx->leafParent, ctx->flags, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char* dxrv_last_error(const dxrv_ctx* ctx) { return ctx ? ctx->err.c_str() : globalError().c_str(); }
+
+int dxrv_set_stream(dxrv_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->ownStream;
+    return DXRV_OK;
+}
+
+int dxrv_synchronize(dxrv_ctx* ctx)
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return checkDeviceError(ctx);
+}
+
+int dxrv_build_bvh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts, uint32_t strideBytes, const uint32_t* indices,
+                   uint32_t numIndices, const float bound[4])
+{
+    int rc = validateMeshArgs(ctx, vertices, numVerts, strideBytes, indices, numIndices, bound);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    const size_t vBytes = (size_t)numVerts * strideBytes, iBytes = (size_t)numIndices * sizeof(uint32_t);
+    cudaError_t e = ensure(ctx->vertsOwned, ctx->vertsCap, vBytes);
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(vertices)");
+    e = ensure(reinterpret_cast<uint8_t*&>(ctx->idxOwned), ctx->idxCap, iBytes);
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(indices)");
+    // upload heaps of Voxelizer::createVB / createIB (Voxelizer.cpp:115-138)
+    DXRV_CUDA(cudaMemcpyAsync(ctx->vertsOwned, vertices, vBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (iBytes) DXRV_CUDA(cudaMemcpyAsync(ctx->idxOwned, indices, iBytes, cudaMemcpyHostToDevice, ctx->stream));
+    DXRV_CUDA(cudaEventRecord(ctx->copyDone, ctx->stream));
+    ctx->mesh = MeshView{ctx->vertsOwned, numVerts, strideBytes, ctx->idxOwned, numIndices / 3u};
+    rc = buildOnDevice(ctx, bound);
+    // the host arrays are only borrowed for the duration of this call: wait for the uploads (not the build)
+    cudaError_t ce = cudaEventSynchronize(ctx->copyDone);
+    if (ce != cudaSuccess) return cudaFail(ctx, ce, "upload");
+    return rc;
+}
+
+int dxrv_build_bvh_device(dxrv_ctx* ctx, const void* d_vertices, uint32_t numVerts, uint32_t strideBytes,
+                          const uint32_t* d_indices, uint32_t numIndices, const float bound[4])
+{
+    int rc = validateMeshArgs(ctx, d_vertices, numVerts, strideBytes, d_indices, numIndices, bound);
+    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(d_vertices) & 3u) || (reinterpret_cast<uintptr_t>(d_indices) & 3u))
+        return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh_device: buffers must be 4-byte aligned");
+    DeviceGuard g(ctx->device);
+    ctx->mesh = MeshView{static_cast<const uint8_t*>(d_vertices), numVerts, strideBytes, d_indices, numIndices / 3u};
+    return buildOnDevice(ctx, bound);
+}
+
+int dxrv_get_bound(dxrv_ctx* ctx, float bound[4])
+{
+    if (!ctx || !bound) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveBvh) return fail(ctx, DXRV_ERR_NO_BVH, "dxrv_get_bound: no acceleration structure built");
+    DeviceGuard g(ctx->device);
+    DXRV_CUDA(cudaMemcpyAsync(bound, ctx->dBound, 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DXRV_OK;
+}
+
+int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd)
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveBvh) return fail(ctx, DXRV_ERR_NO_BVH, "dxrv_voxelize: call dxrv_build_bvh first");
+    const uint32_t algo = mode & DXRV_MODE_MASK;
+    const bool wantTexels = (mode & DXRV_EMIT_TEXELS) != 0;
+    if (algo != DXRV_MODE_SHADER && algo != DXRV_MODE_PARITY) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: unknown mode");
+    if (mode & ~(uint32_t)(DXRV_MODE_MASK | DXRV_EMIT_TEXELS)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: unknown mode flags");
+    if (wantTexels && algo != DXRV_MODE_SHADER) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: DXRV_EMIT_TEXELS needs DXRV_MODE_SHADER");
+    if (N == 0 || N > 8192) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: N must be in [1, 8192]");
+    if (slabBegin >= slabEnd || slabEnd > N) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: need 0 <= slabBegin < slabEnd <= N");
+    if (algo == DXRV_MODE_SHADER && ctx->mesh.stride < 24)
+        return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: MODE_SHADER needs vertex normals (strideBytes >= 24)");
+    DeviceGuard g(ctx->device);
+
+    const size_t bytes = slabWords(N, slabBegin, slabEnd) * sizeof(uint32_t);
+    uint32_t* grid = nullptr;
+    if (ctx->gridTarget)
+    {
+        if (ctx->gridTargetBytes < bytes) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: grid target too small for this slab");
+        grid = ctx->gridTarget;
+    }
+    else
+    {
+        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->gridOwned), ctx->gridCap, bytes);
+        if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(grid)");
+        grid = ctx->gridOwned;
+    }
+    uint32_t* texels = nullptr;
+    if (wantTexels)
+    {
+        const size_t tb = (size_t)(slabEnd - slabBegin) * N * N * sizeof(uint32_t);
+        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->texels), ctx->texCap, tb);
+        if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(texels)");
+        texels = ctx->texels;
+    }
+
+    BvhView bvh{ctx->nodes, ctx->tris, ctx->dRootBox, ctx->mesh.numTris};
+    if (algo == DXRV_MODE_PARITY)
+        launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->dCrossings, ctx->dErr, ctx->smCount);
+    else
+        launchTraceShader(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr);
+    ctx->launches += 1;
+    DXRV_CUDA(cudaGetLastError());
+    ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
+    ctx->haveGrid = true; ctx->haveTexels = wantTexels;
+    return DXRV_OK;
+}
+
+int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format)
+{
+    if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_fetch_grid: call dxrv_voxelize first");
+    DeviceGuard g(ctx->device);
+    const uint32_t* grid = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
+    const uint32_t layers = ctx->z1 - ctx->z0;
+    const void* src = nullptr;
+    size_t need = 0;
+    if (format == DXRV_FORMAT_BITS) { src = grid; need = slabWords(ctx->N, ctx->z0, ctx->z1) * sizeof(uint32_t); }
+    else if (format == DXRV_FORMAT_U8)
+    {
+        need = (size_t)layers * ctx->N * ctx->N;
+        cudaError_t e = ensure(ctx->u8Temp, ctx->u8Cap, need);
+        if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(u8)");
+        launchBitsToU8(ctx->stream, grid, ctx->N, layers, ctx->u8Temp);
+        ctx->launches += 1;
+        src = ctx->u8Temp;
+    }
+    else if (format == DXRV_FORMAT_R10G10B10A2)
+    {
+        if (!ctx->haveTexels) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_fetch_grid: texels need DXRV_MODE_SHADER | DXRV_EMIT_TEXELS");
+        src = ctx->texels; need = (size_t)layers * ctx->N * ctx->N * sizeof(uint32_t);
+    }
+    else return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid: unknown format");
+    if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid: bytes does not match the slab size in this format");
+    DXRV_CUDA(cudaMemcpyAsync(hostDst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    return checkDeviceError(ctx);
+}
+
+int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes)
+{
+    if (!ctx || !d_ptr || !bytes) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_grid_device: call dxrv_voxelize first");
+    *d_ptr = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
+    *bytes = slabWords(ctx->N, ctx->z0, ctx->z1) * sizeof(uint32_t);
+    return DXRV_OK;
+}
+
+int dxrv_set_grid_target(dxrv_ctx* ctx, void* d_ptr, size_t bytes)
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    if (d_ptr && (reinterpret_cast<uintptr_t>(d_ptr) & 15u)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_set_grid_target: pointer must be 16-byte aligned");
+    ctx->gridTarget = static_cast<uint32_t*>(d_ptr);
+    ctx->gridTargetBytes = d_ptr ? bytes : 0;
+    ctx->haveGrid = false;
+    return DXRV_OK;
+}
+
+int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count)
+{
+    if (!ctx || !count) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_count_inside: call dxrv_voxelize first");
+    DeviceGuard g(ctx->device);
+    const uint32_t* grid = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
+    launchPopcount(ctx->stream, grid, slabWords(ctx->N, ctx->z0, ctx->z1), ctx->dCount);
+    ctx->launches += 1;
+    unsigned long long c = 0;
+    DXRV_CUDA(cudaMemcpyAsync(&c, ctx->dCount, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = checkDeviceError(ctx);
+    *count = c;
+    return rc;
+}
+
+int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value)
+{
+    if (!ctx || !value) return DXRV_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    switch (what)
+    {
+    case DXRV_INFO_NUM_TRIANGLES: *value = ctx->haveBvh ? ctx->mesh.numTris : 0; return DXRV_OK;
+    case DXRV_INFO_NUM_NODES: *value = (ctx->haveBvh && ctx->mesh.numTris) ? 2ull * ctx->mesh.numTris - 1 : 0; return DXRV_OK;
+    case DXRV_INFO_KERNEL_LAUNCHES: *value = ctx->launches; return DXRV_OK;
+    case DXRV_INFO_SM_COUNT: *value = (uint64_t)ctx->smCount; return DXRV_OK;
+    case DXRV_INFO_CROSSINGS:
+    {
+        unsigned long long c = 0;
+        DXRV_CUDA(cudaMemcpyAsync(&c, ctx->dCrossings, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+        *value = c;
+        return DXRV_OK;
+    }
+    default: return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_get_info: unknown query");
+    }
+}
+
+int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes)
+{
+    if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveBvh) return fail(ctx, DXRV_ERR_NO_BVH, "dxrv_debug_read: no acceleration structure built");
+    DeviceGuard g(ctx->device);
+    const size_t T = ctx->mesh.numTris;
+    const void* src = nullptr; size_t need = 0;
+    switch (what)
+    {
+    case DXRV_DBG_MORTON_SORTED: src = ctx->keysA; need = T * 4; break;
+    case DXRV_DBG_PRIM_SORTED: src = ctx->valsA; need = T * 4; break;
+    case DXRV_DBG_NODES: src = ctx->nodes; need = (T ? T - 1 : 0) * sizeof(BvhNode); break;
+    case DXRV_DBG_TRIS: src = ctx->tris; need = T * sizeof(Tri48); break;
+    case DXRV_DBG_ROOT_BOX: src = ctx->dRootBox; need = 6 * sizeof(float); break;
+    case DXRV_DBG_PARENTS:
+    {
+        // [nodeParent (T-1) | leafParent (T)]
+        need = (T ? 2 * T - 1 : 0) * 4;
+        if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: size mismatch");
+        if (T > 1) DXRV_CUDA(cudaMemcpyAsync(hostDst, ctx->nodeParent, (T - 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (T > 0) DXRV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(hostDst) + (T - 1) * 4, ctx->leafParent, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+        return DXRV_OK;
+    }
+    default: return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: unknown buffer");
+    }
+    if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: size mismatch");
+    if (need) DXRV_CUDA(cudaMemcpyAsync(hostDst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DXRV_OK;
+}
+
+int dxrv_debug_sort_pairs(dxrv_ctx* ctx, uint32_t* keys, uint32_t* values, uint32_t n)
+{
+    if (!ctx || (n && (!keys || !values))) return DXRV_ERR_INVALID_ARG;
+    if (n == 0) return DXRV_OK;
+    DeviceGuard g(ctx->device);
+    uint32_t* buf = nullptr;
+    void* temp = nullptr;
+    DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), sizeof(uint32_t) * 4 * (size_t)n));
+    cudaError_t e = cudaMalloc(&temp, SortTemp::bytesFor(n));
+    if (e != cudaSuccess) { cudaFree(buf); return cudaFail(ctx, e, "cudaMalloc(sort temp)"); }
+    uint32_t *kA = buf, *vA = buf + n, *kB = buf + 2 * (size_t)n, *vB = buf + 3 * (size_t)n;
+    cudaMemcpyAsync(kA, keys, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(vA, values, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+    ctx->launches += (uint64_t)radixSortPairs(ctx->stream, temp, kA, vA, kB, vB, n);
+    cudaMemcpyAsync(keys, kA, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(values, vA, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf); cudaFree(temp);
+    if (e != cudaSuccess) return cudaFail(ctx, e, "radix sort");
+    return DXRV_OK;
+}
+
+void* dxrv_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void dxrv_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int dxrv_ipc_export_grid(dxrv_ctx* ctx, size_t fullBytes, void* handle64, void** d_ptr)
+{
+    if (!ctx || !handle64 || !d_ptr || !fullBytes) return DXRV_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(ctx->device);
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gridCap < fullBytes || !ctx->gridOwned)
+    {
+        // exact, stand-alone allocation: IPC handles cover whole cudaMalloc allocations
+        if (ctx->gridOwned) cudaFree(ctx->gridOwned);
+        ctx->gridOwned = nullptr; ctx->gridCap = 0;
+        DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->gridOwned), fullBytes));
+        ctx->gridCap = fullBytes;
+        ctx->haveGrid = false;
+    }
+    cudaIpcMemHandle_t h;
+    DXRV_CUDA(cudaIpcGetMemHandle(&h, ctx->gridOwned));
+    std::memcpy(handle64, &h, sizeof(h));
+    *d_ptr = ctx->gridOwned;
+    return DXRV_OK;
+}
+
+int dxrv_ipc_open(dxrv_ctx* ctx, const void* handle64, void** d_ptr)
+{
+    if (!ctx || !handle64 || !d_ptr) return DXRV_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    DXRV_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DXRV_OK;
+}
+
+int dxrv_ipc_close(dxrv_ctx* ctx, void* d_ptr)
+{
+    if (!ctx || !d_ptr) return DXRV_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    DXRV_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return DXRV_OK;
+}
+
+}  // extern "C"

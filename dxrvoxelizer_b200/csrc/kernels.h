@@ -1,0 +1,70 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to libdxrv.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace dxrv
+{
+struct MeshView
+{
+    const uint8_t* verts;     // device, interleaved, float3 position first
+    uint32_t numVerts;
+    uint32_t stride;          // bytes
+    const uint32_t* indices;  // device
+    uint32_t numTris;
+};
+
+// ---- lbvh.cu ------------------------------------------------------------------------------------
+constexpr int kBoundsMaxBlocks = 1024;
+// scratch: 6 * kBoundsMaxBlocks floats + 1 counter (zero before first use; self-resetting)
+void launchBounds(cudaStream_t s, const MeshView& m, float* dBound, float* dPartials, uint32_t* dCounter);
+void launchSetBound(cudaStream_t s, float cx, float cy, float cz, float w, float* dBound);
+void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32_t* keys, uint32_t* vals,
+                  uint32_t* dErr);
+void launchHierarchy(cudaStream_t s, const uint32_t* sortedKeys, uint32_t numTris, BvhNode* nodes,
+                     uint32_t* nodeParent, uint32_t* leafParent);
+// flags: one uint32 per internal node; must be all-even on entry (memset 0 once; each completed
+// refit adds exactly 2 to every flag).
+void launchRefit(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedPrims,
+                 BvhNode* nodes, const uint32_t* nodeParent, const uint32_t* leafParent, uint32_t* flags,
+                 Tri48* tris, float* rootBox, uint32_t* dErr);
+
+// ---- onesweep.cu --------------------------------------------------------------------------------
+struct SortTemp
+{
+    uint32_t* hist;         // [4][256]   digit histograms -> exclusive digit bases
+    uint32_t* tileCounter;  // [4]
+    uint32_t* lookback;     // [4][tiles][256]
+    uint32_t tilesCapacity;
+    static size_t bytesFor(uint32_t n);
+    static uint32_t tilesFor(uint32_t n);
+};
+// Stable LSD radix sort of (key,value) pairs, 4 passes of 8 bits; result ends in keysA/valsA.
+// tempBase: device memory of SortTemp::bytesFor(n) bytes.  Returns the number of kernels launched.
+int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* valsA, uint32_t* keysB,
+                   uint32_t* valsB, uint32_t n);
+
+// ---- trace_parity.cu ----------------------------------------------------------------------------
+struct BvhView
+{
+    const BvhNode* nodes;
+    const Tri48* tris;
+    const float* rootBox;   // lo.xyz hi.xyz
+    uint32_t numTris;
+};
+// MODE_PARITY: +x column rays for layers z in [z0,z1); writes every word of the slab exactly once.
+void launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1,
+                            uint32_t* grid, unsigned long long* dCrossings, uint32_t* dErr, int smCount);
+
+// ---- trace_shader.cu ----------------------------------------------------------------------------
+// MODE_SHADER: one radial closest-hit ray per voxel (DXRVoxelizer.hlsl raygenMain/closestHitMain).
+// texels may be null.  verts/indices are the ORIGINAL buffers (normals at byte offset 12).
+void launchTraceShader(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0,
+                       uint32_t z1, uint32_t* grid, uint32_t* texels, uint32_t* dErr);
+
+// ---- misc (lbvh.cu) -----------------------------------------------------------------------------
+void launchPopcount(cudaStream_t s, const uint32_t* words, size_t numWords, unsigned long long* dCount);
+void launchBitsToU8(cudaStream_t s, const uint32_t* words, uint32_t N, uint32_t layers, uint8_t* out);
+}  // namespace dxrv

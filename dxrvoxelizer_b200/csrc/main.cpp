@@ -1,0 +1,124 @@
+// main.cpp -- headless CLI: the reference's `DXRVoxelizer.exe -mesh <path> [x y z scale]` without
+// the window.  Argument grammar follows DXRVoxelizer::ParseCommandLineArgs
+// (reference DXRVoxelizer.cpp:363-408): '-' or '/' prefixes, case-insensitive names, a value may
+// start with '-' only when a digit or '.' follows; defaults Assets/bunny.obj and posScale (0,0,0,1)
+// (DXRVoxelizer.cpp:36-37).  -warp / -uma select D3D adapters in the reference and are accepted and
+// ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity, -device k,
+// -slab z0 z1, -frames n, -out file.bin (raw DXRV_FORMAT_BITS words).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "voxelizer_host.h"
+
+namespace
+{
+std::string lower(std::string s)
+{
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    return s;
+}
+
+struct Args
+{
+    int argc;
+    char** argv;
+    bool matches(int i, const char* name) const
+    {
+        const char* a = argv[i];
+        return (a[0] == '-' || a[0] == '/') && lower(a + 1) == lower(name);  // DXRVoxelizer.cpp:372-378
+    }
+    // One deviation from the reference: there every '/'-prefixed token is an option; on Linux that
+    // would swallow absolute paths, so '/' only introduces an option when a known name follows.
+    static bool knownOption(const char* name)
+    {
+        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode"};
+        for (const char* n : names) if (lower(name) == n) return true;
+        return false;
+    }
+    bool hasValue(int i) const
+    {
+        if (i + 1 >= argc) return false;
+        const char* a = argv[i + 1];
+        if (a[0] == '/') return !knownOption(a + 1);
+        return a[0] != '-' || (a[1] >= '0' && a[1] <= '9') || a[1] == '.';
+    }
+};
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    std::string mesh = "Assets/bunny.obj", out;
+    float posScale[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+    uint32_t grid = 64, slab0 = 0, slab1 = 0;
+    int device = 0, frames = 1;
+    DXRVoxelizer::Mode mode = DXRVoxelizer::MODE_PARITY;
+
+    Args a{argc, argv};
+    for (int i = 1; i < argc; ++i)
+    {
+        if (a.matches(i, "warp") || a.matches(i, "uma")) continue;
+        else if (a.matches(i, "mesh"))
+        {
+            if (a.hasValue(i)) mesh = argv[++i];
+            for (int k = 0; k < 4; ++k)
+                if (a.hasValue(i)) i += std::sscanf(argv[i + 1], "%f", &posScale[k]) == 1 ? 1 : 0;
+        }
+        else if (a.matches(i, "grid") && a.hasValue(i)) grid = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
+        else if (a.matches(i, "device") && a.hasValue(i)) device = std::atoi(argv[++i]);
+        else if (a.matches(i, "frames") && a.hasValue(i)) frames = std::atoi(argv[++i]);
+        else if (a.matches(i, "out") && a.hasValue(i)) out = argv[++i];
+        else if (a.matches(i, "slab") && a.hasValue(i))
+        {
+            slab0 = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
+            if (a.hasValue(i)) slab1 = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
+        }
+        else if (a.matches(i, "mode") && a.hasValue(i))
+        {
+            const std::string m = lower(argv[++i]);
+            if (m == "shader") mode = DXRVoxelizer::MODE_SHADER;
+            else if (m == "parity") mode = DXRVoxelizer::MODE_PARITY;
+            else { std::fprintf(stderr, "unknown -mode %s (shader|parity)\n", m.c_str()); return 2; }
+        }
+    }
+
+    DXRVoxelizer vox;
+    vox.SetDevice(device);
+    vox.SetMode(mode);
+    vox.SetSlab(slab0, slab1);
+    using clock = std::chrono::steady_clock;
+    auto t0 = clock::now();
+    if (!vox.Init(mesh.c_str(), grid, posScale)) { std::fprintf(stderr, "Init failed: %s\n", vox.LastError()); return 1; }
+    auto t1 = clock::now();
+    uint64_t inside = 0;
+    double best = 1e30;
+    for (int f = 0; f < (frames < 1 ? 1 : frames); ++f)
+    {
+        auto s = clock::now();
+        if (!vox.BuildAccelerationStructures() || !vox.Voxelize() || !vox.CountInside(inside))
+        {
+            std::fprintf(stderr, "Voxelize failed: %s\n", vox.LastError());
+            return 1;
+        }
+        best = std::min(best, std::chrono::duration<double, std::milli>(clock::now() - s).count());
+    }
+    const double voxels = (double)vox.GridWords() * 32.0;
+    std::printf("{\"mesh\": \"%s\", \"triangles\": %u, \"grid\": %u, \"mode\": \"%s\", \"bound\": [%g, %g, %g, %g], "
+                "\"inside\": %llu, \"init_ms\": %.3f, \"build_plus_voxelize_ms\": %.4f, \"gvoxels_per_s\": %.2f}\n",
+                mesh.c_str(), vox.NumTriangles(), grid, mode == DXRVoxelizer::MODE_SHADER ? "shader" : "parity",
+                vox.Bound()[0], vox.Bound()[1], vox.Bound()[2], vox.Bound()[3], (unsigned long long)inside,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), best, voxels / best * 1e-6);
+    if (!out.empty())
+    {
+        const uint32_t* g = vox.Grid();
+        if (!g) { std::fprintf(stderr, "fetch failed: %s\n", vox.LastError()); return 1; }
+        FILE* f = std::fopen(out.c_str(), "wb");
+        if (!f) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
+        std::fwrite(g, sizeof(uint32_t), vox.GridWords(), f);
+        std::fclose(f);
+    }
+    return 0;
+}

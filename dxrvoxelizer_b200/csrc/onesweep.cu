@@ -1,0 +1,232 @@
+// onesweep.cu -- stable LSD radix sort of (Morton key, triangle index) pairs for sm_100a.
+//
+// Single-pass-per-digit "onesweep" (Adinets & Merrill 2022): one kernel computes the histograms of
+// all four 8-bit digits, and each digit pass then reads every pair ONCE and writes it ONCE; the
+// cross-tile prefix is resolved inside the pass by decoupled look-back over per-tile
+// {flag, count} words.  Algorithmic HBM traffic: 4 B (histogram read) + 4 passes x 16 B per pair.
+//
+// Tile = 256 threads x 16 items.  Ranking inside a tile is warp-synchronous (match.any), which keeps
+// the sort stable: order of equal digits = (warp, item, lane) = input order.
+#include "kernels.h"
+
+namespace dxrv
+{
+namespace
+{
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;   // 256
+constexpr int kPasses = 4;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItems = 16;
+constexpr int kTile = kSortThreads * kItems;  // 4096 pairs
+
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagInclusive = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1u;
+
+// ---- digit histograms for all passes ----------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_histogram(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t sh[kPasses][kRadix];
+    for (int i = threadIdx.x; i < kPasses * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t k = __ldg(keys + i);
+        atomicAdd(&sh[0][k & 255u], 1u);
+        atomicAdd(&sh[1][(k >> 8) & 255u], 1u);
+        atomicAdd(&sh[2][(k >> 16) & 255u], 1u);
+        atomicAdd(&sh[3][k >> 24], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPasses * kRadix; i += blockDim.x)
+    {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix
+__device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* warpSums /* [8] shared */)
+{
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) warpSums[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w)
+        if ((uint32_t)w < warp) base += warpSums[w];
+    __syncthreads();
+    return base + inc - v;
+}
+
+// hist[p][d] (counts) -> exclusive digit bases, one block per pass
+__global__ void __launch_bounds__(kRadix)
+k_radix_scan(uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t warpSums[kSortWarps];
+    uint32_t* h = hist + blockIdx.x * kRadix;
+    const uint32_t v = h[threadIdx.x];
+    const uint32_t ex = blockExclusiveScan256(v, warpSums);
+    h[threadIdx.x] = ex;
+}
+
+// ---- one digit pass ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n, int shift,
+                const uint32_t* __restrict__ digitBase, volatile uint32_t* __restrict__ lookback,
+                uint32_t* __restrict__ tileCounter)
+{
+    __shared__ uint32_t warpHist[kSortWarps][kRadix];  // 8 KB
+    __shared__ uint32_t binStart[kRadix];
+    __shared__ uint32_t globalBase[kRadix];
+    __shared__ uint32_t sKeys[kTile];                  // 16 KB
+    __shared__ uint32_t sVals[kTile];                  // 16 KB
+    __shared__ uint32_t warpSums[kSortWarps];
+    __shared__ uint32_t sTile;
+
+    const uint32_t tid = threadIdx.x, lane = laneId(), warp = tid >> 5;
+    // Tiles are numbered in the order blocks START, so every lower-numbered tile is already running
+    // (or done) when this one looks back: the look-back can never wait on an unscheduled block.
+    if (tid == 0) sTile = atomicAdd(tileCounter, 1u);
+    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&warpHist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t base = tile * (uint32_t)kTile;
+    const uint32_t valid = min((uint32_t)kTile, n - base);
+
+    // ---- load (warp-striped: item i of lane l is element warp*512 + i*32 + l) ----
+    uint32_t key[kItems], val[kItems], rank[kItems];
+    const uint32_t warpBase = warp * (32u * kItems);
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t local = warpBase + i * 32u + lane;
+        const bool ok = local < valid;
+        key[i] = ok ? __ldg(keysIn + base + local) : 0xffffffffu;
+        val[i] = ok ? __ldg(valsIn + base + local) : 0u;
+    }
+
+    // ---- rank within the warp ----
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if ((int)lane == leader)
+        {
+            old = warpHist[warp][d];
+            warpHist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = old + __popc(peers & laneMaskLt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit (thread d): prefix over warps, tile count ----
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w)
+    {
+        const uint32_t c = warpHist[w][tid];
+        warpHist[w][tid] = count;
+        count += c;
+    }
+
+    // ---- decoupled look-back: exclusive count of digit `tid` over all previous tiles ----
+    volatile uint32_t* lb = lookback + (size_t)tile * kRadix;
+    uint32_t prev = 0;
+    if (tile == 0) lb[tid] = kFlagInclusive | count;
+    else
+    {
+        lb[tid] = kFlagAggregate | count;
+        int j = (int)tile - 1;
+        while (true)
+        {
+            const uint32_t v = lookback[(size_t)j * kRadix + tid];
+            const uint32_t flag = v & ~kValueMask;
+            if (flag == 0) continue;  // not published yet
+            prev += v & kValueMask;
+            if (flag == kFlagInclusive) break;
+            --j;
+        }
+        lb[tid] = kFlagInclusive | (prev + count);
+    }
+
+    const uint32_t start = blockExclusiveScan256(count, warpSums);
+    binStart[tid] = start;
+    globalBase[tid] = __ldg(digitBase + tid) + prev - start;
+    __syncthreads();
+
+    // ---- scatter into shared memory in sorted order ----
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t pos = binStart[d] + warpHist[warp][d] + rank[i];
+        sKeys[pos] = key[i];
+        sVals[pos] = val[i];
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out (padding keys sort to the end of the tile: positions >= valid) ----
+    for (uint32_t p = tid; p < valid; p += kSortThreads)
+    {
+        const uint32_t k = sKeys[p];
+        const uint32_t dst = globalBase[(k >> shift) & 255u] + p;
+        keysOut[dst] = k;
+        valsOut[dst] = sVals[p];
+    }
+}
+}  // namespace
+
+uint32_t SortTemp::tilesFor(uint32_t n) { return (n + kTile - 1) / kTile; }
+
+size_t SortTemp::bytesFor(uint32_t n)
+{
+    const size_t tiles = tilesFor(n) ? tilesFor(n) : 1;
+    // [hist 4*256][tileCounter 4 (padded to 64)][lookback 4*tiles*256]
+    return sizeof(uint32_t) * (kPasses * kRadix + 64 + (size_t)kPasses * tiles * kRadix);
+}
+
+int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* valsA, uint32_t* keysB,
+                   uint32_t* valsB, uint32_t n)
+{
+    if (n < 2) return 0;
+    const uint32_t tiles = SortTemp::tilesFor(n);
+    uint32_t* hist = static_cast<uint32_t*>(tempBase);
+    uint32_t* tileCounter = hist + kPasses * kRadix;
+    uint32_t* lookback = tileCounter + 64;
+    cudaMemsetAsync(tempBase, 0, SortTemp::bytesFor(n), s);
+
+    int launches = 0;
+    uint32_t histBlocks = (n + kSortThreads * 16 - 1) / (kSortThreads * 16);
+    if (histBlocks > 148 * 4) histBlocks = 148 * 4;
+    k_radix_histogram<<<histBlocks, kSortThreads, 0, s>>>(keysA, n, hist);
+    k_radix_scan<<<kPasses, kRadix, 0, s>>>(hist);
+    launches += 2;
+    uint32_t *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
+    for (int p = 0; p < kPasses; ++p)
+    {
+        k_onesweep_pass<<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
+                                                       lookback + (size_t)p * tiles * kRadix, tileCounter + p);
+        ++launches;
+        uint32_t* t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    return launches;  // an even number of passes: the result is back in keysA / valsA
+}
+}  // namespace dxrv

@@ -1,0 +1,209 @@
+"""Python face of the voxelization path: a thin mirror of the C++ host class
+(csrc/voxelizer_host.h), which itself mirrors the reference's ``Voxelizer::Init`` / ``voxelize``
+(Content/Voxelizer.h:16-22,90).  Everything goes through the C ABI (include/dxrv.h); numpy is only
+used to hold host buffers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+
+class Mesh:
+    """Output of the OBJ loader (== XUSG::ObjLoader::Import(file, true, true))."""
+
+    def __init__(self, vertices, indices, stride, aabb=None, bound=None):
+        self.vertex_bytes = np.ascontiguousarray(vertices).view(np.uint8).reshape(-1)
+        self.indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        self.stride = int(stride)
+        self.aabb = aabb
+        self.bound = bound
+
+    @property
+    def num_vertices(self):
+        return self.vertex_bytes.size // self.stride
+
+    @property
+    def num_triangles(self):
+        return self.indices.size // 3
+
+    @property
+    def vertices(self):
+        """float32 view [numVerts, stride/4]: columns 0..2 position, 3..5 normal."""
+        return self.vertex_bytes.view(np.float32).reshape(self.num_vertices, self.stride // 4)
+
+    @staticmethod
+    def from_arrays(positions, triangles, normals=None):
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        if normals is None:
+            vb = pos
+        else:
+            vb = np.concatenate([pos, np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)], axis=1)
+        vb = np.ascontiguousarray(vb)
+        return Mesh(vb, triangles, vb.shape[1] * 4)
+
+
+def load_obj(path):
+    lib = L.lib()
+    h = ctypes.c_void_p()
+    rc = lib.dxrv_obj_load(str(path).encode(), ctypes.byref(h))
+    if rc != L.OK:
+        raise L.DxrvError(rc, lib.dxrv_last_error(None).decode())
+    try:
+        nv, ni, st = lib.dxrv_obj_num_vertices(h), lib.dxrv_obj_num_indices(h), lib.dxrv_obj_vertex_stride(h)
+        vb = np.ctypeslib.as_array(ctypes.cast(lib.dxrv_obj_vertices(h), ctypes.POINTER(ctypes.c_uint8)), (nv * st,)).copy() \
+            if nv else np.zeros(0, np.uint8)
+        ib = np.ctypeslib.as_array(ctypes.cast(lib.dxrv_obj_indices(h), ctypes.POINTER(ctypes.c_uint32)), (ni,)).copy() \
+            if ni else np.zeros(0, np.uint32)
+        aabb = np.zeros(6, np.float32)
+        bound = np.zeros(4, np.float32)
+        lib.dxrv_obj_aabb(h, aabb.ctypes.data)
+        lib.dxrv_obj_bound(h, bound.ctypes.data)
+    finally:
+        lib.dxrv_obj_free(h)
+    return Mesh(vb, ib, st, aabb, bound)
+
+
+class Voxelizer:
+    """One context = one GPU + one stream.  Not thread-safe (same as the C ABI)."""
+
+    MODE_SHADER = L.MODE_SHADER
+    MODE_PARITY = L.MODE_PARITY
+
+    def __init__(self, device=0):
+        self._lib = L.lib()
+        h = ctypes.c_void_p()
+        rc = self._lib.dxrv_create(ctypes.byref(h), int(device))
+        if rc != L.OK:
+            raise L.DxrvError(rc, self._lib.dxrv_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self._shape = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dxrv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != L.OK:
+            raise L.DxrvError(rc, self._lib.dxrv_last_error(self._h).decode())
+
+    # -- Voxelizer::Init's device half: createVB/createIB + buildAccelerationStructures ----------
+    def build_bvh(self, mesh, bound=None):
+        b = None if bound is None else np.ascontiguousarray(bound, dtype=np.float32)
+        self._mesh = mesh  # keep host arrays alive
+        self._check(self._lib.dxrv_build_bvh(self._h, mesh.vertex_bytes.ctypes.data, mesh.num_vertices, mesh.stride,
+                                             mesh.indices.ctypes.data, mesh.indices.size,
+                                             None if b is None else b.ctypes.data))
+
+    def build_bvh_host_ptr(self, vptr, num_verts, stride, iptr, num_indices, bound=None):
+        b = None if bound is None else np.ascontiguousarray(bound, dtype=np.float32)
+        self._check(self._lib.dxrv_build_bvh(self._h, vptr, num_verts, stride, iptr, num_indices,
+                                             None if b is None else b.ctypes.data))
+
+    def build_bvh_device(self, d_vertices, num_verts, stride, d_indices, num_indices, bound=None):
+        b = None if bound is None else np.ascontiguousarray(bound, dtype=np.float32)
+        self._check(self._lib.dxrv_build_bvh_device(self._h, d_vertices, num_verts, stride, d_indices, num_indices,
+                                                    None if b is None else b.ctypes.data))
+
+    def bound(self):
+        out = np.zeros(4, np.float32)
+        self._check(self._lib.dxrv_get_bound(self._h, out.ctypes.data))
+        return out
+
+    # -- Voxelizer::voxelize ------------------------------------------------------------------------
+    def voxelize(self, N, mode=L.MODE_PARITY, z0=0, z1=None, texels=False):
+        z1 = N if z1 is None else z1
+        self._check(self._lib.dxrv_voxelize(self._h, N, mode | (L.EMIT_TEXELS if texels else 0), z0, z1))
+        self._shape = (z1 - z0, N, (N + 31) // 32)
+        self._N = N
+
+    def fetch_bits(self, out=None):
+        """uint32[(z1-z0), N, P] in the DXRV_FORMAT_BITS layout."""
+        if out is None:
+            out = np.empty(self._shape, np.uint32)
+        self._check(self._lib.dxrv_fetch_grid(self._h, out.ctypes.data, out.nbytes, L.FORMAT_BITS))
+        return out
+
+    def fetch_into(self, ptr, nbytes, fmt=L.FORMAT_BITS):
+        self._check(self._lib.dxrv_fetch_grid(self._h, ptr, nbytes, fmt))
+
+    def fetch_u8(self):
+        out = np.empty((self._shape[0], self._N, self._N), np.uint8)
+        self._check(self._lib.dxrv_fetch_grid(self._h, out.ctypes.data, out.nbytes, L.FORMAT_U8))
+        return out
+
+    def fetch_texels(self):
+        out = np.empty((self._shape[0], self._N, self._N), np.uint32)
+        self._check(self._lib.dxrv_fetch_grid(self._h, out.ctypes.data, out.nbytes, L.FORMAT_R10G10B10A2))
+        return out
+
+    def grid_device(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self._lib.dxrv_grid_device(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def set_grid_target(self, d_ptr, nbytes):
+        self._check(self._lib.dxrv_set_grid_target(self._h, d_ptr, nbytes))
+
+    def count_inside(self):
+        c = ctypes.c_uint64()
+        self._check(self._lib.dxrv_count_inside(self._h, ctypes.byref(c)))
+        return int(c.value)
+
+    def info(self, what):
+        v = ctypes.c_uint64()
+        self._check(self._lib.dxrv_get_info(self._h, what, ctypes.byref(v)))
+        return int(v.value)
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.dxrv_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        self._check(self._lib.dxrv_synchronize(self._h))
+
+    def debug_read(self, what, dtype, count):
+        out = np.empty(count, dtype)
+        self._check(self._lib.dxrv_debug_read(self._h, what, out.ctypes.data, out.nbytes))
+        return out
+
+    def debug_sort_pairs(self, keys, values):
+        k = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+        v = np.ascontiguousarray(values, dtype=np.uint32).copy()
+        self._check(self._lib.dxrv_debug_sort_pairs(self._h, k.ctypes.data, v.ctypes.data, k.size))
+        return k, v
+
+    def ipc_export_grid(self, full_bytes):
+        handle = (ctypes.c_ubyte * 64)()
+        p = ctypes.c_void_p()
+        self._check(self._lib.dxrv_ipc_export_grid(self._h, full_bytes, handle, ctypes.byref(p)))
+        return bytes(handle), p.value
+
+    def ipc_open(self, handle):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        p = ctypes.c_void_p()
+        self._check(self._lib.dxrv_ipc_open(self._h, buf, ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, d_ptr):
+        self._check(self._lib.dxrv_ipc_close(self._h, d_ptr))
+
+
+def unpack_bits(bits, N):
+    """uint32[..., P] -> uint8[..., N] occupancy (bit x&31 of word x>>5)."""
+    b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=-1, bitorder="little")
+    return b[..., :N]

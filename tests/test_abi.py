@@ -1,0 +1,71 @@
+"""The drop-in boundary: libdxrv.so loads, exports every symbol that
+include/dxrv.h declares, and -- on a box without a GPU -- fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from dxrvoxelizer_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dxrv.h")).read()
+    return sorted(set(re.findall(r"DXRV_API[^;(]*?\b(dxrv_\w+)\s*\(", text)))
+
+
+def test_header_binding_and_library_agree():
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    assert sorted(L.SIGNATURES) == declared            # the Python binding covers the whole ABI
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (dxrv_\w+)", out)))
+    assert exported == declared                        # nothing undeclared leaks out either
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product path must never route through oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "dxrvoxelizer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), f
+                assert "libdxrv_oracle" not in text and "dxrv_oracle.h" not in text.replace("oracle/dxrv_oracle.h", ""), f
+    deps = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
+
+
+def test_error_convention_without_context():
+    lib = L.lib()
+    assert lib.dxrv_create(None, 0) == L.ERR_INVALID_ARG
+    assert b"null" in lib.dxrv_last_error(None)
+    h = ctypes.c_void_p()
+    assert lib.dxrv_obj_load(b"/nonexistent.obj", ctypes.byref(h)) == L.ERR_IO
+    assert b"cannot open" in lib.dxrv_last_error(None)
+    assert lib.dxrv_voxelize(None, 64, 1, 0, 64) == L.ERR_INVALID_ARG
+    lib.dxrv_destroy(None)   # harmless
+    lib.dxrv_obj_free(None)
+
+
+def test_no_cpu_fallback_when_no_device():
+    """Without a usable CUDA device dxrv_create must fail (there is no CPU path to fall back to)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    code = ("import ctypes,sys; sys.path.insert(0, %r); from dxrvoxelizer_b200 import _lib as L; "
+            "h=ctypes.c_void_p(); rc=L.lib().dxrv_create(ctypes.byref(h),0); "
+            "print(rc, L.lib().dxrv_last_error(None).decode())" % ROOT)
+    out = subprocess.run(["python", "-c", code], capture_output=True, text=True, env=env, check=True).stdout
+    assert out.startswith("-2 ") and "no CPU fallback" in out
+
+
+def test_cli_reports_failure_like_reference_init(tmp_path):
+    exe = os.path.join(ROOT, "dxrvoxelizer_b200", "dxrvoxelizer")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "-mesh", str(tmp_path / "missing.obj"), "0.0", "2.8", "0.0", "0.03"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr   # Init returns false when Import fails

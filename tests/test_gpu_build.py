@@ -1,0 +1,135 @@
+"""LBVH build stages on the GPU: bounds, Morton sort (onesweep),
+Karras hierarchy, atomic refit -- each checked against an independent numpy restatement."""
+import numpy as np
+import pytest
+
+from dxrvoxelizer_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4096, 4097, 100000, 1 << 20, 3000001])
+def test_onesweep_sorts_pairs_stably(vox, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 3] &= np.uint32(0x3FF)          # many duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = vox.debug_sort_pairs(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(v, vals[order])
+
+
+def test_onesweep_all_equal_and_presorted(vox):
+    n = 50000
+    k, v = vox.debug_sort_pairs(np.full(n, 7, np.uint32), np.arange(n, dtype=np.uint32))
+    assert np.array_equal(v, np.arange(n, dtype=np.uint32)) and (k == 7).all()
+    keys = np.arange(n, dtype=np.uint32)[::-1].copy()
+    k, v = vox.debug_sort_pairs(keys, keys)
+    assert np.array_equal(k, np.arange(n, dtype=np.uint32)) and np.array_equal(v, k)
+
+
+def _scene(mesh, bound):
+    p = mesh.vertices[:, :3]
+    b = bound.astype(np.float32)
+    return ((p - b[:3]) / b[3]).astype(np.float32)
+
+
+def _check_tree(vox, mesh):
+    T = mesh.num_triangles
+    bound = vox.bound()
+    keys = vox.debug_read(L.DBG_MORTON_SORTED, np.uint32, T)
+    prims = vox.debug_read(L.DBG_PRIM_SORTED, np.uint32, T)
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
+    assert np.array_equal(np.sort(prims), np.arange(T, dtype=np.uint32))
+    # equal keys keep input order (stable sort)
+    same = keys[1:] == keys[:-1]
+    assert (prims[1:][same] > prims[:-1][same]).all()
+
+    tris = vox.debug_read(L.DBG_TRIS, np.float32, T * 12).reshape(T, 3, 4)
+    assert np.array_equal(tris[:, 0, 3].copy().view(np.uint32), prims)
+    scene = _scene(mesh, bound)
+    want = scene[mesh.indices.reshape(-1, 3)[prims]]
+    assert np.array_equal(tris[:, :, :3], want)          # p' = (p - c) / w, bit exact
+
+    if T < 2:
+        return
+    nodes = vox.debug_read(L.DBG_NODES, np.uint32, (T - 1) * 16).reshape(T - 1, 16)
+    boxes = nodes[:, :12].copy().view(np.float32).reshape(T - 1, 2, 2, 3)   # [node, child, lo/hi, xyz]
+    child = nodes[:, 12:14]
+    is_leaf = (child & 0x80000000) != 0
+    idx = child & 0x7FFFFFFF
+    # every leaf and every inner node (but the root) is referenced exactly once
+    assert np.array_equal(np.sort(idx[is_leaf]), np.arange(T, dtype=np.uint32))
+    assert np.array_equal(np.sort(idx[~is_leaf]), np.arange(1, T - 1, dtype=np.uint32))
+    # boxes: bottom-up restatement (children are exact min/max unions)
+    lo = np.empty((2 * T - 1, 3), np.float32)
+    hi = np.empty((2 * T - 1, 3), np.float32)
+    lo[T - 1:] = tris[:, :, :3].min(1)
+    hi[T - 1:] = tris[:, :, :3].max(1)
+    ref = np.where(is_leaf, idx + (T - 1), idx).astype(np.int64)
+    # process inner nodes in an order where children come first: depth via parent pointers
+    parents = vox.debug_read(L.DBG_PARENTS, np.uint32, 2 * T - 1)
+    node_parent = parents[: T - 1] & 0x7FFFFFFF
+    depth = np.zeros(T - 1, np.int64)
+    order = [0]
+    for i in order:                      # BFS from the root
+        for c in range(2):
+            if not is_leaf[i, c]:
+                j = int(idx[i, c])
+                assert node_parent[j] == i
+                depth[j] = depth[i] + 1
+                order.append(j)
+    assert len(order) == T - 1
+    for i in reversed(order):
+        lo[i] = np.minimum(lo[ref[i, 0]], lo[ref[i, 1]])
+        hi[i] = np.maximum(hi[ref[i, 0]], hi[ref[i, 1]])
+    assert np.array_equal(boxes[:, 0, 0], lo[ref[:, 0]]) and np.array_equal(boxes[:, 0, 1], hi[ref[:, 0]])
+    assert np.array_equal(boxes[:, 1, 0], lo[ref[:, 1]]) and np.array_equal(boxes[:, 1, 1], hi[ref[:, 1]])
+    root = vox.debug_read(L.DBG_ROOT_BOX, np.float32, 6)
+    assert np.array_equal(root[:3], lo[0]) and np.array_equal(root[3:], hi[0])
+    assert depth.max() <= 62
+
+
+@pytest.mark.parametrize("name", ["dragon.obj", "TuringBowl.obj"])
+def test_lbvh_invariants_on_shipped_meshes(vox, assets, name):
+    m = assets(name)
+    vox.build_bvh(m)
+    assert np.array_equal(vox.bound(), m.bound)            # device bound == Voxelizer.cpp:52-57 on the host
+    _check_tree(vox, m)
+    vox.build_bvh(m)                                        # rebuild reuses the flag parity trick
+    _check_tree(vox, m)
+
+
+@pytest.mark.parametrize("tris", [1, 2, 3, 12])
+def test_lbvh_tiny_meshes(vox, meshes_mod, tris):
+    from dxrvoxelizer_b200 import Mesh
+    c = meshes_mod.cube()
+    m = Mesh(c.vertex_bytes, c.indices[: 3 * tris], c.stride)
+    vox.build_bvh(m)
+    _check_tree(vox, m)
+
+
+def test_lbvh_duplicate_keys(vox):
+    """Many triangles with identical Morton keys: the index tie-break must still give a tree."""
+    from dxrvoxelizer_b200 import Mesh
+    rng = np.random.default_rng(0)
+    base = rng.uniform(-1e-4, 1e-4, size=(300, 3)).astype(np.float32)
+    pos = np.concatenate([base, [[-1, -1, -1], [1, 1, 1]]]).astype(np.float32)
+    tri = rng.integers(0, 300, size=(500, 3)).astype(np.uint32)
+    m = Mesh.from_arrays(pos, tri)
+    vox.build_bvh(m)
+    _check_tree(vox, m)
+
+
+def test_bad_index_is_reported(vox, meshes_mod):
+    from dxrvoxelizer_b200 import Mesh, DxrvError
+    c = meshes_mod.cube()
+    idx = c.indices.copy()
+    idx[5] = 1000
+    vox.build_bvh(Mesh(c.vertex_bytes, idx, c.stride))
+    with pytest.raises(DxrvError):
+        vox.synchronize()
+    vox.build_bvh(c)          # the context stays usable
+    vox.synchronize()
