@@ -307,11 +307,13 @@ void launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint
     prm.numTiles = prm.tilesY * ((z1 - z0 + TZ - 1) / TZ);
     prm.grid = grid; prm.crossings = dCrossings; prm.err = dErr;
     const size_t smemBytes = sizeof(uint32_t) * kParityWarps * (32u * prm.Ps + kStackCap + kCandCap + 64u);
-    static bool attrSet = false;
-    if (!attrSet)
+    static bool attrSet[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attrSet[dev])
     {
         cudaFuncSetAttribute(k_trace_fill_columns<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attrSet = true;
+        attrSet[dev] = true;
     }
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
     const uint32_t blocks = (prm.numTiles + kParityWarps - 1) / kParityWarps;

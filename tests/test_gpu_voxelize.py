@@ -127,6 +127,7 @@ def test_external_grid_target_and_device_pointer(vox, assets):
     N = 64
     full = _run(vox, m, N, d.MODE_PARITY)
     buf = torch.full((N * N * 2,), -1, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
     half = N * N * 2 // 2 * 4
     vox.set_grid_target(buf.data_ptr(), half)
     vox.voxelize(N, d.MODE_PARITY, 0, N // 2)

@@ -23,7 +23,7 @@ def timeit(fn, stream, iters=20, warm=3):
 
 def main():
     torch.cuda.init()
-    s = torch.cuda.current_stream()
+    s = torch.cuda.Stream()
     vox = d.Voxelizer(0)
     vox.set_stream(s.cuda_stream)
     cases = [("dragon", d.load_obj(d.asset_path("dragon.obj"))), ("bowl", d.load_obj(d.asset_path("TuringBowl.obj")))]
