@@ -56,6 +56,7 @@ struct dxrv_ctx
     uint32_t* gridTarget = nullptr; size_t gridTargetBytes = 0;
     uint32_t* texels = nullptr; size_t texCap = 0;
     uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
+    uint32_t* walkBuf = nullptr; size_t walkCap = 0;  // MODE_PARITY candidate lists
     uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
     bool haveGrid = false, haveTexels = false;
 
@@ -225,7 +226,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
-                    ctx->nodeParent, ctx->leafParent, ctx->flags, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp};
+                    ctx->nodeParent, ctx->leafParent, ctx->flags, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -336,10 +337,20 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
 
     BvhView bvh{ctx->nodes, ctx->tris, ctx->dRootBox, ctx->mesh.numTris};
     if (algo == DXRV_MODE_PARITY)
-        launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->dCrossings, ctx->dErr, ctx->smCount);
+    {
+        uint32_t numTiles = 0, candCap = 0;
+        parityTileCounts(N, slabBegin, slabEnd, numTiles, candCap);
+        const size_t walkBytes = sizeof(uint32_t) * ((size_t)((numTiles + 31u) & ~31u) + (size_t)numTiles * candCap);
+        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->walkBuf), ctx->walkCap, walkBytes);
+        if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(walk lists)");
+        ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
+                                                          ctx->dCrossings, ctx->dErr);
+    }
     else
+    {
         launchTraceShader(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr);
-    ctx->launches += 1;
+        ctx->launches += 1;
+    }
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels;

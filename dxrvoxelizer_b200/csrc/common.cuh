@@ -18,13 +18,15 @@ constexpr float kFltMax = 3.402823466e+38f;
 
 // ---- HBM layout ---------------------------------------------------------------------------------
 // Internal node i (0 <= i < T-1; node 0 is the root).  64 bytes = two 32 B sectors, fetched as
-// four 128-bit loads.  Each node stores the boxes of its two CHILDREN, so one fetch decides both.
-//   f[0..2]  = child0.lo.xyz   f[3..5]  = child0.hi.xyz
-//   f[6..8]  = child1.lo.xyz   f[9..11] = child1.hi.xyz
-//   c0, c1   = child references: kLeafFlag | sortedTriangleSlot, or internal node index
+// 128-bit loads.  Each node stores the boxes of its two CHILDREN, so one fetch decides both.  The
+// (y,z) extents come first: the column tracer (rays along x) needs only yz0, yz1 and the child
+// references (three loads), the closest-hit tracer reads all four.
+//   yz0 = child0 (ylo, yhi, zlo, zhi)      yz1 = child1 (ylo, yhi, zlo, zhi)
+//   x01 = (child0 xlo, child0 xhi, child1 xlo, child1 xhi)
+//   c0, c1 = child references: kLeafFlag | sortedTriangleSlot, or internal node index
 struct __align__(16) BvhNode
 {
-    float f[12];
+    float4 yz0, yz1, x01;
     uint32_t c0, c1;
     uint32_t pad0, pad1;
 };

@@ -55,8 +55,11 @@ struct BvhView
     uint32_t numTris;
 };
 // MODE_PARITY: +x column rays for layers z in [z0,z1); writes every word of the slab exactly once.
-void launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1,
-                            uint32_t* grid, unsigned long long* dCrossings, uint32_t* dErr, int smCount);
+// walkBuf: device scratch of (roundUp32(numTiles) + numTiles * candCap) uint32 (see parityTileCounts).
+// Returns the number of kernels launched.
+void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, uint32_t& candCap);
+int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1,
+                           uint32_t* grid, uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr);
 
 // ---- trace_shader.cu ----------------------------------------------------------------------------
 // MODE_SHADER: one radial closest-hit ray per voxel (DXRVoxelizer.hlsl raygenMain/closestHitMain).

@@ -251,26 +251,32 @@ k_refit(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __restri
     }
 
     uint32_t p = __ldg(leafParent + j);
-    while (true)
+    for (int level = 0; level < 128; ++level)  // depth <= 62; the bound only guards against a corrupt tree
     {
         const uint32_t pi = p & 0x7fffffffu, slot = p >> 31;
-        float* dst = nodes[pi].f + 6 * slot;
-        dst[0] = lo[0]; dst[1] = lo[1]; dst[2] = lo[2];
-        dst[3] = hi[0]; dst[4] = hi[1]; dst[5] = hi[2];
-        __threadfence();
+        const uint32_t up = (pi != 0u) ? __ldg(nodeParent + pi) : 0u;  // issued early: overlaps the atomic
+        BvhNode* n = nodes + pi;
+        float4* yz = slot ? &n->yz1 : &n->yz0;
+        float2* xx = reinterpret_cast<float2*>(&n->x01) + slot;
+        *yz = make_float4(lo[1], hi[1], lo[2], hi[2]);
+        *xx = make_float2(lo[0], hi[0]);
+        __threadfence();  // release: the box must be visible before the arrival counter moves
         const uint32_t old = atomicAdd(flags + pi, 1u);
         if ((old & 1u) == 0u) return;  // first child to arrive: the sibling will carry on
-        __threadfence();
-        const float* src = nodes[pi].f + 6 * (1u - slot);
-        lo[0] = fminf(lo[0], __ldcg(src + 0)); lo[1] = fminf(lo[1], __ldcg(src + 1)); lo[2] = fminf(lo[2], __ldcg(src + 2));
-        hi[0] = fmaxf(hi[0], __ldcg(src + 3)); hi[1] = fmaxf(hi[1], __ldcg(src + 4)); hi[2] = fmaxf(hi[2], __ldcg(src + 5));
+        // second arrival: the sibling's box was released before its increment; read it past L1
+        const float4 syz = __ldcg(slot ? &n->yz0 : &n->yz1);
+        const float2 sxx = __ldcg(reinterpret_cast<const float2*>(&n->x01) + (1u - slot));
+        lo[0] = fminf(lo[0], sxx.x); hi[0] = fmaxf(hi[0], sxx.y);
+        lo[1] = fminf(lo[1], syz.x); hi[1] = fmaxf(hi[1], syz.y);
+        lo[2] = fminf(lo[2], syz.z); hi[2] = fmaxf(hi[2], syz.w);
         if (pi == 0)
         {
             for (int q = 0; q < 3; ++q) { rootBox[q] = lo[q]; rootBox[3 + q] = hi[q]; }
             return;
         }
-        p = __ldg(nodeParent + pi);
+        p = up;
     }
+    atomicMax(err, (uint32_t)kErrStackOverflow);
 }
 
 // ---- small utilities -------------------------------------------------------------------------------

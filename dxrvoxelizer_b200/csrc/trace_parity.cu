@@ -4,34 +4,50 @@
 // Content/Shaders/DXRVoxelizer.hlsl:58-85) for the column-parity formulation of the solid test.
 // The per-(column, triangle) arithmetic is Spec H / MODE_PARITY of oracle/dxrv_oracle.h.
 //
-// One warp owns a tile of TY x TZ = 32 voxel columns (y,z) and ALL their voxels along x:
-//   1. warp-cooperative BVH walk: every lane pops a different node from a shared-memory stack,
-//      tests both child boxes against the tile's (y,z) rectangle (exact compares: a crossing implies
-//      the column lies inside every ancestor box), pushes inner children, queues leaf children;
-//   2. queued triangles are processed 32 at a time, one triangle per lane: each covered column gets
-//      the exact crossing test and toggles ONE bit (first voxel whose centre is beyond the crossing)
-//      in the tile's shared-memory bit rows -- XOR makes the order of crossings irrelevant, so no
-//      per-column hit list or sort is needed;
-//   3. the toggles become occupancy by an inclusive prefix-XOR along x (in-register per 128-bit
-//      group, ballot carry across lanes) and every word of the slab is written exactly once with
-//      coalesced 128-bit stores -- no clear pass, no scatter to HBM.
-// HBM traffic is the grid (N^3/8 bytes, written once) plus node/triangle reads that mostly hit L2.
+// The grid is cut into super-tiles of SY x SZ voxel columns (y,z); a super-tile owns ALL voxels of its
+// columns along x.  Two kernels, each with the occupancy its phase needs:
+//
+//   k_walk_columns       latency bound, almost no shared memory, 64 warps / SM.  One WARP per
+//                        super-tile walks the LBVH cooperatively: every lane pops a different node
+//                        from a shared-memory stack, tests both child boxes against the super-tile's
+//                        (y,z) rectangle (exact compares: a crossing implies the column lies inside
+//                        every ancestor box), pushes inner children and appends leaf children to the
+//                        super-tile's candidate list in HBM.  All walks of a 1024^2-column grid are in
+//                        flight at once, so the kernel takes about one root-to-leaf latency chain.
+//   k_trace_fill_columns HBM-write bound.  One CTA per super-tile: one candidate triangle per thread,
+//                        each covered column gets the exact crossing test and toggles ONE bit (the
+//                        first voxel whose centre is beyond the crossing) in shared-memory bit rows --
+//                        XOR makes the order of crossings irrelevant, so no per-column hit list or sort
+//                        is needed; the toggles become occupancy by an inclusive prefix-XOR along x (in
+//                        registers per 128-bit group, ballot carry across lanes) and every word of the
+//                        slab is written exactly once with coalesced 128-bit stores -- no clear pass,
+//                        no scatter to HBM.  A super-tile whose candidate list overflowed (huge meshes)
+//                        walks the tree itself, CTA-cooperatively, instead of reading a list.
 #include "kernels.h"
 
 namespace dxrv
 {
 namespace
 {
-constexpr int kParityWarps = 4;
-constexpr int kParityThreads = kParityWarps * 32;
-constexpr int kStackCap = 512;   // entries per warp
-constexpr int kStackSlack = 96;  // switch to depth-first popping above kStackCap - kStackSlack
-constexpr int kCandCap = 128;    // queued leaf references per warp
+constexpr int kStackGuard = 64;   // >= LBVH depth bound (62): head-room kept for depth-first popping
+constexpr int kWalkStack = 512;   // per-warp stack of k_walk_columns
+constexpr int kWalkWarps = 4;     // warps (= super-tiles) per CTA of k_walk_columns
+constexpr int kStackCap = 1024;   // per-CTA stack of the in-kernel fallback walk
+constexpr int kCandCap = 768;     // per-CTA leaf ring of the fallback walk (>= 3 * threads per CTA)
 
 __device__ __forceinline__ uint32_t prefixXor32(uint32_t v)
 {
     v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
     return v;
+}
+
+// centre(i) of Spec H.  For a power-of-two grid dividing by N is exact scaling, so multiplying by
+// 1/N is bit-identical to the IEEE division and several times cheaper.
+__device__ __forceinline__ float centreOf(uint32_t i, float fN, float invNPow2)
+{
+    const float h = __fadd_rn((float)i, 0.5f);
+    const float q = (invNPow2 != 0.0f) ? __fmul_rn(h, invNPow2) : __fdiv_rn(h, fN);
+    return __fsub_rn(__fmul_rn(q, 2.0f), 1.0f);
 }
 
 // exact sign of edge(P,Q) = P.p*Q.q - P.q*Q.p including the (+e, +e^2) tie rule, given the exactly
@@ -47,7 +63,7 @@ __device__ __forceinline__ int edgeSignExact(double e, float Pp, float Pq, float
 // Spec H, MODE_PARITY: does the line {(s, Y, Z)} cross triangle (a,b,c)?  On a crossing returns the
 // first toggled voxel ix in [0, N].
 __device__ __forceinline__ bool columnCrossing(const float4& a, const float4& b, const float4& c, float Y, float Z,
-                                               uint32_t N, float fN, uint32_t& ixOut)
+                                               uint32_t N, float fN, float invNPow2, uint32_t& ixOut)
 {
     const float Ap = __fsub_rn(a.y, Y), Aq = __fsub_rn(a.z, Z);
     const float Bp = __fsub_rn(b.y, Y), Bq = __fsub_rn(b.z, Z);
@@ -81,8 +97,8 @@ __device__ __forceinline__ bool columnCrossing(const float4& a, const float4& b,
     if (!(g > 0.0f)) g = 0.0f;
     if (g > fN) g = fN;
     uint32_t ix = (uint32_t)g;
-    while (ix > 0 && voxelCentre(ix - 1, fN) > d) --ix;
-    while (ix < N && !(voxelCentre(ix, fN) > d)) ++ix;
+    while (ix > 0 && centreOf(ix - 1, fN, invNPow2) > d) --ix;
+    while (ix < N && !(centreOf(ix, fN, invNPow2) > d)) ++ix;
     ixOut = ix;
     return true;
 }
@@ -92,172 +108,351 @@ struct ParityParams
     const BvhNode* nodes;
     const Tri48* tris;
     uint32_t numTris;
-    uint32_t N, P, Ps;      // grid size, words per global row, words per shared row
+    uint32_t N, P, Ps;       // grid size, words per global row, words per shared row
+    uint32_t gprShift;       // log2(Ps / 4) when Ps <= 128 (Ps is then a power of two)
     uint32_t z0, z1;
-    uint32_t tilesY, numTiles;
+    uint32_t tilesY;         // super-tiles along y
+    uint32_t numTiles;
+    float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
+    uint32_t* candCount;     // [numTiles]  leaves found by k_walk_columns; > candCap = overflow
+    uint32_t* candList;      // [numTiles][candCap]
+    uint32_t candCap;
     unsigned long long* crossings;
     uint32_t* err;
 };
 
-template <int TY>
-__global__ void __launch_bounds__(kParityThreads)
+// (y,z) rectangle of a super-tile, from the exact column centres
+template <int SY, int SZ>
+__device__ __forceinline__ void tileRect(const ParityParams& prm, uint32_t sy0, uint32_t sz0, float& rYmin, float& rYmax,
+                                         float& rZmin, float& rZmax)
+{
+    const float fN = (float)prm.N;
+    const uint32_t yLast = min(sy0 + SY - 1, prm.N - 1), zLast = min(sz0 + SZ - 1, prm.z1 - 1);
+    rYmax = -centreOf(sy0, fN, prm.invNPow2);   // scene Y decreases with y
+    rYmin = -centreOf(yLast, fN, prm.invNPow2);
+    rZmin = centreOf(sz0, fN, prm.invNPow2);
+    rZmax = centreOf(zLast, fN, prm.invNPow2);
+}
+
+// both children of `ni` against the rectangle
+__device__ __forceinline__ void testNode(const BvhNode* __restrict__ nodes, uint32_t ni, float rYmin, float rYmax,
+                                         float rZmin, float rZmax, bool& ov0, bool& ov1, uint32_t& c0, uint32_t& c1)
+{
+    const float4* q = reinterpret_cast<const float4*>(nodes + ni);
+    const float4 b0 = __ldg(q), b1 = __ldg(q + 1);                       // (ylo, yhi, zlo, zhi) of child 0 / 1
+    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(q + 3));
+    ov0 = b0.x <= rYmax && b0.y >= rYmin && b0.z <= rZmax && b0.w >= rZmin;
+    ov1 = b1.x <= rYmax && b1.y >= rYmin && b1.z <= rZmax && b1.w >= rZmin;
+    c0 = ch.x; c1 = ch.y;
+}
+
+// ---- kernel A: one warp per super-tile walks the tree and lists the leaves it may cross ---------
+template <int SY, int SZ>
+__global__ void __launch_bounds__(32 * kWalkWarps)
+k_walk_columns(const ParityParams prm)
+{
+    __shared__ uint32_t sStack[kWalkWarps][kWalkStack];
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * kWalkWarps + warp;
+    if (tile >= prm.numTiles) return;
+    uint32_t* list = prm.candList + (size_t)tile * prm.candCap;
+    if (prm.numTris <= 1)
+    {
+        if (lane == 0) { prm.candCount[tile] = prm.numTris; if (prm.numTris) list[0] = 0; }
+        return;
+    }
+    const uint32_t sy0 = (tile % prm.tilesY) * SY;
+    const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
+    float rYmin, rYmax, rZmin, rZmax;
+    tileRect<SY, SZ>(prm, sy0, sz0, rYmin, rYmax, rZmin, rZmax);
+
+    uint32_t* stack = sStack[warp];
+    uint32_t sp = 1, count = 0, guard = 0;  // warp-uniform
+    if (lane == 0) stack[0] = 0;
+    __syncwarp();
+    const uint32_t lt = laneMaskLt();
+    while (sp > 0)
+    {
+        // pop up to 32 nodes from the top; keep kStackGuard entries of head-room so that the depth-first
+        // tail (k == 1) can never overflow: pushes <= 2k, depth <= 62
+        const int room = kWalkStack - kStackGuard - (int)sp;
+        const uint32_t k = room >= 1 ? min(min(32u, sp), (uint32_t)room) : 1u;
+        sp -= k;
+        uint32_t c0 = 0, c1 = 0;
+        bool ov0 = false, ov1 = false;
+        if (lane < k) testNode(prm.nodes, stack[sp + lane], rYmin, rYmax, rZmin, rZmax, ov0, ov1, c0, c1);
+        __syncwarp();
+        const bool in0 = ov0 && !(c0 & kLeafFlag), in1 = ov1 && !(c1 & kLeafFlag);
+        const bool lf0 = ov0 && (c0 & kLeafFlag), lf1 = ov1 && (c1 & kLeafFlag);
+        const uint32_t mi0 = __ballot_sync(0xffffffffu, in0), mi1 = __ballot_sync(0xffffffffu, in1);
+        const uint32_t ml0 = __ballot_sync(0xffffffffu, lf0), ml1 = __ballot_sync(0xffffffffu, lf1);
+        const uint32_t nIn = __popc(mi0) + __popc(mi1), nLf = __popc(ml0) + __popc(ml1);
+        if (sp + nIn > (uint32_t)kWalkStack || ++guard > 2u * prm.numTris + 64u)
+        {
+            if (lane == 0) atomicMax(prm.err, (uint32_t)kErrStackOverflow);
+            break;
+        }
+        if (count + nLf > prm.candCap) { count = prm.candCap + 1u; break; }  // overflow: the fill kernel walks itself
+        if (in0) stack[sp + __popc(mi0 & lt)] = c0;
+        if (in1) stack[sp + __popc(mi0) + __popc(mi1 & lt)] = c1;
+        sp += nIn;
+        if (lf0) list[count + __popc(ml0 & lt)] = c0 & ~kLeafFlag;
+        if (lf1) list[count + __popc(ml0) + __popc(ml1 & lt)] = c1 & ~kLeafFlag;
+        count += nLf;
+        __syncwarp();
+    }
+    if (lane == 0) prm.candCount[tile] = count;
+}
+
+// ---- kernel B: W warps per CTA; the super-tile is SY x SZ columns with SY * SZ == 32 * W --------
+template <int W, int SY, int SZ>
+__global__ void __launch_bounds__(32 * W)
 k_trace_fill_columns(const ParityParams prm)
 {
-    constexpr int TZ = 32 / TY;
+    static_assert(SY * SZ == 32 * W, "super-tile must hold one column per thread");
+    constexpr int kThreads = 32 * W;
+    constexpr int kCols = SY * SZ;
     extern __shared__ __align__(16) uint32_t smem[];
-    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * kParityWarps + warp;
-    if (tile >= prm.numTiles) return;
+    __shared__ uint32_t sTop[2];   // fallback walk: stack height, double-buffered by iteration parity
+    __shared__ uint32_t sCand;     // fallback walk: leaves queued so far
 
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t N = prm.N, P = prm.P, Ps = prm.Ps;
-    const float fN = (float)N;
-    const uint32_t perWarp = 32u * Ps + kStackCap + kCandCap + 64u;
-    uint32_t* rows = smem + warp * perWarp;          // [32][Ps] toggle / occupancy bits
-    uint32_t* stack = rows + 32u * Ps;
-    uint32_t* cand = stack + kStackCap;
-    float* tileY = reinterpret_cast<float*>(cand + kCandCap);  // [TY] scene Y of the tile's columns
-    float* tileZ = tileY + 32;                                  // [TZ]
+    const float fN = (float)N, invNPow2 = prm.invNPow2;
 
-    const uint32_t ty0 = (tile % prm.tilesY) * TY;
-    const uint32_t tz0 = prm.z0 + (tile / prm.tilesY) * TZ;
+    uint32_t* rows = smem;                                     // [kCols][Ps] toggle / occupancy bits, column = zl*SY + yl
+    float* tileY = reinterpret_cast<float*>(rows + (uint32_t)kCols * Ps);  // [SY] scene Y of the columns (decreasing)
+    float* tileZ = tileY + SY;                                 // [SZ]
+    uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
+    uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
 
-    // ---- tile setup ----
-    for (uint32_t i = lane; i < 8u * Ps; i += 32u) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
-    if (lane < TY) tileY[lane] = (ty0 + lane < N) ? -voxelCentre(ty0 + lane, fN) : INFINITY;
-    if (lane < TZ) tileZ[lane] = (tz0 + lane < prm.z1) ? voxelCentre(tz0 + lane, fN) : INFINITY;
-    __syncwarp();
-    // scene Y decreases with y; the last VALID column bounds the rectangle
-    const uint32_t yLast = min(ty0 + TY - 1, N - 1) - ty0, zLast = min(tz0 + TZ - 1, prm.z1 - 1) - tz0;
-    const float rYmax = tileY[0], rYmin = tileY[yLast];
-    const float rZmin = tileZ[0], rZmax = tileZ[zLast];
+    const uint32_t tile = blockIdx.x;
+    const uint32_t sy0 = (tile % prm.tilesY) * SY;
+    const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
+    const uint32_t listed = __ldg(prm.candCount + tile);
+    const uint32_t yLast = min(sy0 + SY - 1, N - 1) - sy0, zLast = min(sz0 + SZ - 1, prm.z1 - 1) - sz0;
 
     uint32_t myCrossings = 0;
-
-    // one queued triangle per lane
-    auto processTriangle = [&](uint32_t slot) {
-        const float4* t = reinterpret_cast<const float4*>(prm.tris + slot);
-        const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
-        const float ylo = fminf(fminf(a.y, b.y), c.y), yhi = fmaxf(fmaxf(a.y, b.y), c.y);
-        const float zlo = fminf(fminf(a.z, b.z), c.z), zhi = fmaxf(fmaxf(a.z, b.z), c.z);
-#pragma unroll 1
-        for (int zl = 0; zl < TZ; ++zl)
-        {
-            const float Z = tileZ[zl];
-            if (Z < zlo || Z > zhi) continue;
-#pragma unroll 1
-            for (int yl = 0; yl < TY; ++yl)
-            {
-                const float Y = tileY[yl];
-                if (Y < ylo || Y > yhi) continue;
-                uint32_t ix;
-                if (columnCrossing(a, b, c, Y, Z, N, fN, ix))
-                {
-                    ++myCrossings;
-                    if (ix < N) atomicXor(&rows[(uint32_t)(zl * TY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
-                }
-            }
-        }
-    };
-
-    // ---- 1+2: cooperative walk ----
-    if (prm.numTris == 1)
+    if (listed != 0u)   // an empty super-tile needs no shared memory at all
     {
-        if (lane == 0) processTriangle(0);
-    }
-    else if (prm.numTris > 1)
-    {
-        uint32_t sp = 1, nc = 0;  // warp-uniform
-        if (lane == 0) stack[0] = 0;
-        __syncwarp();
-        uint32_t guard = 0;
-        while (sp > 0)
-        {
-            const uint32_t k = (sp <= (uint32_t)(kStackCap - kStackSlack)) ? min(32u, sp) : 1u;
-            sp -= k;
-            const bool has = lane < k;
-            uint32_t c0 = 0, c1 = 0;
-            bool ov0 = false, ov1 = false;
+        for (uint32_t i = tid; i < (uint32_t)kCols * (Ps >> 2); i += kThreads) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
+        if (tid < SY) tileY[tid] = (sy0 + tid < N) ? -centreOf(sy0 + tid, fN, invNPow2) : INFINITY;
+        if (tid >= 32 && tid < 32 + SZ) tileZ[tid - 32] = (sz0 + tid - 32 < prm.z1) ? centreOf(sz0 + tid - 32, fN, invNPow2) : INFINITY;
+        if (tid == 0) { stack[0] = 0; sTop[0] = 1u; sTop[1] = 0; sCand = 0; }
+        __syncthreads();
+        const float halfN = 0.5f * fN;
+
+        // Up to 32 candidate triangles per call (one per lane; `has` marks real ones), processed by the
+        // whole warp: every lane first finds the EXACT rectangle of columns whose centres lie in its
+        // triangle's (y,z) box, a warp scan turns the rectangle sizes into one flat list of
+        // (triangle, column) pairs, and the pairs are dealt round-robin to the 32 lanes -- a triangle
+        // that spans many columns no longer serialises on one thread while the CTA waits at the barrier.
+        auto processWarpChunk = [&](bool has, uint32_t slot) {
+            float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+            int yA = 0, zA = 0, w = 0, h = 0;
             if (has)
             {
-                const uint32_t ni = stack[sp + lane];
-                const float4* q = reinterpret_cast<const float4*>(prm.nodes + ni);
-                const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-                const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
-                // child0: lo=(q0.x,q0.y,q0.z) hi=(q0.w,q1.x,q1.y); child1: lo=(q1.z,q1.w,q2.x) hi=(q2.y,q2.z,q2.w)
-                ov0 = q0.y <= rYmax && q1.x >= rYmin && q0.z <= rZmax && q1.y >= rZmin;
-                ov1 = q1.w <= rYmax && q2.z >= rYmin && q2.x <= rZmax && q2.w >= rZmin;
-                c0 = q3.x; c1 = q3.y;
+                const float4* t = reinterpret_cast<const float4*>(prm.tris + slot);
+                a = __ldg(t); b = __ldg(t + 1); c = __ldg(t + 2);
+                const float ylo = fminf(fminf(a.y, b.y), c.y), yhi = fmaxf(fmaxf(a.y, b.y), c.y);
+                const float zlo = fminf(fminf(a.z, b.z), c.z), zhi = fmaxf(fmaxf(a.z, b.z), c.z);
+                // float estimate of the index range, then fix-up against the tabulated exact centres
+                // (tileY decreases with yl, tileZ increases with zl)
+                int yB, zB;
+                yA = min(max((int)floorf((1.0f - yhi) * halfN - 0.5f) - (int)sy0, 0), (int)yLast + 1);
+                while (yA > 0 && tileY[yA - 1] <= yhi) --yA;
+                while (yA <= (int)yLast && tileY[yA] > yhi) ++yA;
+                yB = min(max((int)ceilf((1.0f - ylo) * halfN - 0.5f) - (int)sy0, -1), (int)yLast);
+                while (yB < (int)yLast && tileY[yB + 1] >= ylo) ++yB;
+                while (yB >= 0 && tileY[yB] < ylo) --yB;
+                zA = min(max((int)floorf((zlo + 1.0f) * halfN - 0.5f) - (int)sz0, 0), (int)zLast + 1);
+                while (zA > 0 && tileZ[zA - 1] >= zlo) --zA;
+                while (zA <= (int)zLast && tileZ[zA] < zlo) ++zA;
+                zB = min(max((int)ceilf((zhi + 1.0f) * halfN - 0.5f) - (int)sz0, -1), (int)zLast);
+                while (zB < (int)zLast && tileZ[zB + 1] <= zhi) ++zB;
+                while (zB >= 0 && tileZ[zB] > zhi) --zB;
+                w = max(yB - yA + 1, 0); h = max(zB - zA + 1, 0);
             }
-            __syncwarp();
-            const bool in0 = ov0 && !(c0 & kLeafFlag), in1 = ov1 && !(c1 & kLeafFlag);
-            const bool lf0 = ov0 && (c0 & kLeafFlag), lf1 = ov1 && (c1 & kLeafFlag);
-            const uint32_t mi0 = __ballot_sync(0xffffffffu, in0), mi1 = __ballot_sync(0xffffffffu, in1);
-            const uint32_t ml0 = __ballot_sync(0xffffffffu, lf0), ml1 = __ballot_sync(0xffffffffu, lf1);
-            const uint32_t lt = laneMaskLt();
-            const uint32_t pushes = __popc(mi0) + __popc(mi1);
-            if (sp + pushes > (uint32_t)kStackCap || ++guard > 4u * prm.numTris + 64u)
+            const uint32_t n = (uint32_t)(w * h);
+            uint32_t incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                if (lane == 0) atomicMax(prm.err, (uint32_t)kErrStackOverflow);
-                break;
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
             }
-            if (in0) stack[sp + __popc(mi0 & lt)] = c0;
-            if (in1) stack[sp + __popc(mi0) + __popc(mi1 & lt)] = c1;
-            sp += pushes;
-            if (lf0) cand[nc + __popc(ml0 & lt)] = c0 & ~kLeafFlag;
-            if (lf1) cand[nc + __popc(ml0) + __popc(ml1 & lt)] = c1 & ~kLeafFlag;
-            nc += __popc(ml0) + __popc(ml1);
-            __syncwarp();
-            while (nc >= 32u)
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t excl = incl - n;
+#pragma unroll 1
+            for (uint32_t p0 = 0; p0 < total; p0 += 32u)
             {
-                nc -= 32u;
-                processTriangle(cand[nc + lane]);
-                __syncwarp();
+                const uint32_t p = p0 + lane;
+                // owner = the last lane whose exclusive offset is <= p (empty triangles share their offset
+                // with the next lane, so the last one is the one that really owns pair p)
+                uint32_t owner = 0;
+#pragma unroll
+                for (uint32_t step = 16; step > 0; step >>= 1)
+                {
+                    const uint32_t e = __shfl_sync(0xffffffffu, excl, owner + step);
+                    if (e <= p) owner += step;
+                }
+                const uint32_t q = p - __shfl_sync(0xffffffffu, excl, owner);
+                const int ow = __shfl_sync(0xffffffffu, w, owner);
+                const int oyA = __shfl_sync(0xffffffffu, yA, owner), ozA = __shfl_sync(0xffffffffu, zA, owner);
+                float4 ta, tb, tc;
+                ta.x = __shfl_sync(0xffffffffu, a.x, owner); ta.y = __shfl_sync(0xffffffffu, a.y, owner); ta.z = __shfl_sync(0xffffffffu, a.z, owner);
+                tb.x = __shfl_sync(0xffffffffu, b.x, owner); tb.y = __shfl_sync(0xffffffffu, b.y, owner); tb.z = __shfl_sync(0xffffffffu, b.z, owner);
+                tc.x = __shfl_sync(0xffffffffu, c.x, owner); tc.y = __shfl_sync(0xffffffffu, c.y, owner); tc.z = __shfl_sync(0xffffffffu, c.z, owner);
+                if (p < total)
+                {
+                    const uint32_t qz = q / (uint32_t)ow;
+                    const int yl = oyA + (int)(q - qz * (uint32_t)ow), zl = ozA + (int)qz;
+                    uint32_t ix;
+                    if (columnCrossing(ta, tb, tc, tileY[yl], tileZ[zl], N, fN, invNPow2, ix))
+                    {
+                        ++myCrossings;
+                        if (ix < N) atomicXor(&rows[(uint32_t)(zl * SY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
+                    }
+                }
             }
-        }
-        if (lane < nc) processTriangle(cand[lane]);
-    }
-    __syncwarp();
+        };
 
-    // ---- 3: prefix-XOR along x and write-out, 4 words (128 bits) per lane ----
-    const uint32_t groupsPerRow = Ps >> 2;            // 128-bit groups per shared row (power of two or multiple of 32)
-    const uint32_t totalGroups = 32u * groupsPerRow;  // multiple of 32
-    const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
-    uint32_t runCarry = 0;                            // carry along a row spanning several 32-group chunks
-    for (uint32_t g0 = 0; g0 < totalGroups; g0 += 32u)
-    {
-        const uint32_t g = g0 + lane;
-        const uint32_t row = g / groupsPerRow, gi = g - row * groupsPerRow;
-        uint4 t = reinterpret_cast<const uint4*>(rows)[g];
-        uint32_t par = 0;
-        t.x = prefixXor32(t.x); par = t.x >> 31;
-        t.y = prefixXor32(t.y) ^ (0u - par); par = t.y >> 31;
-        t.z = prefixXor32(t.z) ^ (0u - par); par = t.z >> 31;
-        t.w = prefixXor32(t.w) ^ (0u - par); par = t.w >> 31;
-        const uint32_t bal = __ballot_sync(0xffffffffu, par);
-        uint32_t carry;
-        if (groupsPerRow >= 32u)
+        if (listed <= prm.candCap)
         {
-            // the whole chunk is one row segment
-            if ((g0 % groupsPerRow) == 0) runCarry = 0;
-            carry = (__popc(bal & laneMaskLt()) & 1u) ^ runCarry;
-            runCarry ^= (__popc(bal) & 1u);
+            // ---- candidates were listed by k_walk_columns: dealt to the warps in chunks of C (small
+            // chunks when there are few candidates, so that all W warps get some) ----
+            const uint32_t* list = prm.candList + (size_t)tile * prm.candCap;
+            uint32_t C = 32u;
+            while (C > 4u && listed < C * (uint32_t)W * 2u) C >>= 1;
+            for (uint32_t first = warp * C; first < listed; first += (uint32_t)W * C)
+            {
+                const bool has = lane < C && first + lane < listed;
+                processWarpChunk(has, has ? __ldg(list + first + lane) : 0u);
+            }
         }
         else
         {
-            // 32 / groupsPerRow rows per chunk: carry only from lower lanes of the same row.
-            // NOTE `par` of a lane already includes its own lower words, but not lower lanes.
-            const uint32_t segLo = lane - gi;  // first lane of this row
-            const uint32_t segMask = laneMaskLt() & ~((1u << segLo) - 1u);
-            carry = __popc(bal & segMask) & 1u;
+            // ---- fallback: CTA-cooperative walk (every thread pops a different node) ----
+            float rYmin, rYmax, rZmin, rZmax;
+            tileRect<SY, SZ>(prm, sy0, sz0, rYmin, rYmax, rZmin, rZmax);
+            uint32_t parity = 0, guard = 0;
+            uint32_t consumed = 0;  // ring entries already processed (uniform); sCand counts entries produced
+            while (true)
+            {
+                __syncthreads();  // S1: pushes / counters of the previous iteration are visible
+                const uint32_t sp = sTop[parity];
+                const uint32_t produced = sCand;
+                if (sp == 0) break;
+                if (++guard > 2u * prm.numTris + 64u)
+                {
+                    if (tid == 0) atomicMax(prm.err, (uint32_t)kErrStackOverflow);
+                    break;
+                }
+                // drain full batches of queued triangles first: at most kThreads-1 stay queued, so the
+                // 2*kThreads pushes of this iteration always fit the ring (kCandCap >= 3*kThreads)
+                while (produced - consumed >= (uint32_t)kThreads)
+                {
+                    processWarpChunk(true, cand[(consumed + tid) % kCandCap]);
+                    consumed += kThreads;
+                }
+                const int room = kStackCap - kStackGuard - (int)sp;
+                const uint32_t k = room >= 1 ? min(min((uint32_t)kThreads, sp), (uint32_t)room) : 1u;
+                const uint32_t base = sp - k;
+                uint32_t c0 = 0, c1 = 0;
+                bool ov0 = false, ov1 = false;
+                if (tid < k) testNode(prm.nodes, stack[base + tid], rYmin, rYmax, rZmin, rZmax, ov0, ov1, c0, c1);
+                if (tid == 0) sTop[parity ^ 1u] = base;   // nobody reads this word before S2
+                __syncthreads();  // S2: every thread has read its stack / ring entries and both counters
+                if (warp * 32u < k)
+                {
+                    const bool in0 = ov0 && !(c0 & kLeafFlag), in1 = ov1 && !(c1 & kLeafFlag);
+                    const bool lf0 = ov0 && (c0 & kLeafFlag), lf1 = ov1 && (c1 & kLeafFlag);
+                    const uint32_t mi0 = __ballot_sync(0xffffffffu, in0), mi1 = __ballot_sync(0xffffffffu, in1);
+                    const uint32_t ml0 = __ballot_sync(0xffffffffu, lf0), ml1 = __ballot_sync(0xffffffffu, lf1);
+                    const uint32_t lt = laneMaskLt();
+                    const uint32_t nIn = __popc(mi0) + __popc(mi1), nLf = __popc(ml0) + __popc(ml1);
+                    uint32_t offIn = 0, offLf = 0;
+                    if (lane == 0)
+                    {
+                        if (nIn) offIn = atomicAdd(&sTop[parity ^ 1u], nIn);
+                        if (nLf) offLf = atomicAdd(&sCand, nLf);
+                    }
+                    offIn = __shfl_sync(0xffffffffu, offIn, 0);
+                    offLf = __shfl_sync(0xffffffffu, offLf, 0);
+                    if (offIn + nIn > (uint32_t)kStackCap)
+                    {
+                        if (lane == 0) atomicMax(prm.err, (uint32_t)kErrStackOverflow);  // never expected; drop
+                    }
+                    else
+                    {
+                        if (in0) stack[offIn + __popc(mi0 & lt)] = c0;
+                        if (in1) stack[offIn + __popc(mi0) + __popc(mi1 & lt)] = c1;
+                    }
+                    if (lf0) cand[(offLf + __popc(ml0 & lt)) % kCandCap] = c0 & ~kLeafFlag;
+                    if (lf1) cand[(offLf + __popc(ml0) + __popc(ml1 & lt)) % kCandCap] = c1 & ~kLeafFlag;
+                }
+                parity ^= 1u;
+            }
+            __syncthreads();
+            for (uint32_t produced = sCand, i0 = consumed + warp * 32u; i0 < produced; i0 += kThreads)
+            {
+                const bool has = i0 + lane < produced;
+                processWarpChunk(has, has ? cand[(i0 + lane) % kCandCap] : 0u);
+            }
         }
-        // `par` bits were computed without the incoming carry: XOR of the lanes' own parities is
-        // exactly the carry because prefix parity is linear.
-        const uint32_t flip = 0u - carry;
-        t.x ^= flip; t.y ^= flip; t.z ^= flip; t.w ^= flip;
+        __syncthreads();
+    }
 
-        const uint32_t yl = row % TY, zl = row / TY;
-        const uint32_t y = ty0 + yl, z = tz0 + zl;
+    // ---- prefix-XOR along x and write-out, 4 words (128 bits) per lane ----
+    // warp w owns shared rows [32w, 32w+32): for every z of the super-tile SY consecutive y rows,
+    // which are contiguous in the global grid.
+    const uint32_t groupsPerRow = Ps >> 2;            // 128-bit groups per shared row
+    const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
+    const uint4* rows4 = reinterpret_cast<const uint4*>(rows) + (size_t)warp * 32u * groupsPerRow;
+    uint32_t runCarry = 0;                            // carry along a row spanning several 32-group chunks
+    for (uint32_t g0 = 0; g0 < 32u * groupsPerRow; g0 += 32u)
+    {
+        const uint32_t g = g0 + lane;
+        uint32_t rowInWarp, gi;
+        if (groupsPerRow <= 32u) { rowInWarp = g >> prm.gprShift; gi = g & (groupsPerRow - 1u); }
+        else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
+        uint4 t = make_uint4(0, 0, 0, 0);
+        uint32_t carry = 0;
+        if (listed != 0u)
+        {
+            t = rows4[g];
+            const uint32_t dirty = __ballot_sync(0xffffffffu, (t.x | t.y | t.z | t.w) != 0u);
+            if (groupsPerRow >= 32u && (g0 % groupsPerRow) == 0) runCarry = 0;
+            if (dirty)
+            {
+                uint32_t par;
+                t.x = prefixXor32(t.x); par = t.x >> 31;
+                t.y = prefixXor32(t.y) ^ (0u - par); par = t.y >> 31;
+                t.z = prefixXor32(t.z) ^ (0u - par); par = t.z >> 31;
+                t.w = prefixXor32(t.w) ^ (0u - par); par = t.w >> 31;
+                // `par` = parity of this lane's 128 bits (without incoming carry); prefix parity is
+                // linear, so the carry into a lane is the XOR of `par` over the lower lanes of its row
+                const uint32_t bal = __ballot_sync(0xffffffffu, par);
+                if (groupsPerRow >= 32u)
+                {
+                    carry = (__popc(bal & laneMaskLt()) & 1u) ^ runCarry;
+                    runCarry ^= (__popc(bal) & 1u);
+                }
+                else
+                {
+                    const uint32_t segLo = lane - gi;  // first lane of this row
+                    carry = __popc(bal & laneMaskLt() & ~((1u << segLo) - 1u)) & 1u;
+                }
+            }
+            else if (groupsPerRow >= 32u) carry = runCarry;
+            const uint32_t flip = 0u - carry;
+            t.x ^= flip; t.y ^= flip; t.z ^= flip; t.w ^= flip;
+        }
+
+        const uint32_t col = warp * 32u + rowInWarp;
+        const uint32_t yl = col % SY, zl = col / SY;
+        const uint32_t y = sy0 + yl, z = sz0 + zl;
         const uint32_t w0 = gi * 4u;
         if (y < N && z < prm.z1 && w0 < P)
         {
@@ -277,8 +472,11 @@ k_trace_fill_columns(const ParityParams prm)
     }
 
     // ---- statistics ----
-    for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
-    if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
+    if (listed != 0u)
+    {
+        for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
+        if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
+    }
 }
 
 uint32_t sharedRowWords(uint32_t P)
@@ -292,31 +490,51 @@ uint32_t sharedRowWords(uint32_t P)
     }
     return (P + 127u) / 128u * 128u;
 }
-}  // namespace
 
-void launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
-                            unsigned long long* dCrossings, uint32_t* dErr, int smCount)
+template <int W, int SY, int SZ>
+void launchVariant(cudaStream_t s, ParityParams prm)
 {
-    (void)smCount;
-    constexpr int TY = 8, TZ = 32 / TY;
-    ParityParams prm;
-    prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
-    prm.N = N; prm.P = (N + 31) / 32; prm.Ps = sharedRowWords(prm.P);
-    prm.z0 = z0; prm.z1 = z1;
-    prm.tilesY = (N + TY - 1) / TY;
-    prm.numTiles = prm.tilesY * ((z1 - z0 + TZ - 1) / TZ);
-    prm.grid = grid; prm.crossings = dCrossings; prm.err = dErr;
-    const size_t smemBytes = sizeof(uint32_t) * kParityWarps * (32u * prm.Ps + kStackCap + kCandCap + 64u);
+    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + kStackCap + kCandCap);
     static bool attrSet[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attrSet[dev])
     {
-        cudaFuncSetAttribute(k_trace_fill_columns<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_trace_fill_columns<W, SY, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
         attrSet[dev] = true;
     }
+    k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
+    k_trace_fill_columns<W, SY, SZ><<<prm.numTiles, 32 * W, smemBytes, s>>>(prm);
+}
+}  // namespace
+
+void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, uint32_t& candCap)
+{
+    const uint32_t SY = 16, SZ = (N <= 2048) ? 16u : 8u;
+    numTiles = ((N + SY - 1) / SY) * ((z1 - z0 + SZ - 1) / SZ);
+    candCap = 512;
+}
+
+int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
+                           uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr)
+{
+    ParityParams prm;
+    prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
+    prm.N = N; prm.P = (N + 31) / 32; prm.Ps = sharedRowWords(prm.P);
+    prm.gprShift = 0;
+    while ((1u << prm.gprShift) < (prm.Ps >> 2)) ++prm.gprShift;
+    prm.z0 = z0; prm.z1 = z1;
+    prm.tilesY = (N + 15) / 16;
+    parityTileCounts(N, z0, z1, prm.numTiles, prm.candCap);
+    prm.invNPow2 = ((N & (N - 1)) == 0) ? 1.0f / (float)N : 0.0f;
+    prm.grid = grid;
+    prm.candCount = walkBuf;
+    prm.candList = walkBuf + ((prm.numTiles + 31u) & ~31u);
+    prm.crossings = dCrossings; prm.err = dErr;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
-    const uint32_t blocks = (prm.numTiles + kParityWarps - 1) / kParityWarps;
-    k_trace_fill_columns<TY><<<blocks, kParityThreads, smemBytes, s>>>(prm);
+    // 256 columns per CTA while the bit rows fit comfortably (N <= 2048: 64 KB), else 128
+    if (N <= 2048) launchVariant<8, 16, 16>(s, prm);
+    else launchVariant<4, 16, 8>(s, prm);
+    return 2;
 }
 }  // namespace dxrv

@@ -157,11 +157,11 @@ k_trace_shader(const ShaderParams prm)
             while (true)
             {
                 const float4* q = reinterpret_cast<const float4*>(prm.nodes + node);
-                const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                const float4 yz0 = __ldg(q), yz1 = __ldg(q + 1), x01 = __ldg(q + 2);
                 const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
                 float tin0, tout0, tin1, tout1;
-                bool h0 = slabTest(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tin0, tout0) && !(tin0 > best.tc);
-                bool h1 = slabTest(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tin1, tout1) && !(tin1 > best.tc);
+                bool h0 = slabTest(r, x01.x, yz0.x, yz0.z, x01.y, yz0.y, yz0.w, tin0, tout0) && !(tin0 > best.tc);
+                bool h1 = slabTest(r, x01.z, yz1.x, yz1.z, x01.w, yz1.y, yz1.w, tin1, tout1) && !(tin1 > best.tc);
                 if (h0 && (q3.x & kLeafFlag)) { testTriangle(r, prm.tris, q3.x & ~kLeafFlag, best); h0 = false; }
                 if (h1 && (q3.y & kLeafFlag))
                 {

@@ -56,7 +56,12 @@ def _check_tree(vox, mesh):
     if T < 2:
         return
     nodes = vox.debug_read(L.DBG_NODES, np.uint32, (T - 1) * 16).reshape(T - 1, 16)
-    boxes = nodes[:, :12].copy().view(np.float32).reshape(T - 1, 2, 2, 3)   # [node, child, lo/hi, xyz]
+    f = nodes[:, :12].copy().view(np.float32)            # yz0 | yz1 | x01 (csrc/common.cuh BvhNode)
+    boxes = np.empty((T - 1, 2, 2, 3), np.float32)        # [node, child, lo/hi, xyz]
+    for c in range(2):
+        boxes[:, c, 0, 0], boxes[:, c, 1, 0] = f[:, 8 + 2 * c], f[:, 9 + 2 * c]
+        boxes[:, c, 0, 1], boxes[:, c, 1, 1] = f[:, 4 * c + 0], f[:, 4 * c + 1]
+        boxes[:, c, 0, 2], boxes[:, c, 1, 2] = f[:, 4 * c + 2], f[:, 4 * c + 3]
     child = nodes[:, 12:14]
     is_leaf = (child & 0x80000000) != 0
     idx = child & 0x7FFFFFFF
