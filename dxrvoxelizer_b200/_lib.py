@@ -14,7 +14,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_NO_BVH, ERR_NO_GRID, ERR_IO, ERR_OOM, ERR_UNSUPPO
 MODE_SHADER, MODE_PARITY, EMIT_TEXELS = 0, 1, 0x100
 FORMAT_BITS, FORMAT_U8, FORMAT_R10G10B10A2 = 0, 1, 2
 INFO_NUM_TRIANGLES, INFO_NUM_NODES, INFO_KERNEL_LAUNCHES, INFO_CROSSINGS, INFO_SM_COUNT = 0, 1, 2, 3, 4
-DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_PARENTS, DBG_ROOT_BOX = 0, 1, 2, 3, 4, 5
+DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_ROOT_BOX = 0, 1, 2, 3, 5
 
 _c = ctypes
 _vp, _u32, _u64, _sz, _int = _c.c_void_p, _c.c_uint32, _c.c_uint64, _c.c_size_t, _c.c_int

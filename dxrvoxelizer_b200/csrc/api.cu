@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 
 #include "../../include/dxrv.h"
 #include "kernels.h"
@@ -37,7 +38,7 @@ struct dxrv_ctx
     uint32_t *keysA = nullptr, *keysB = nullptr, *valsA = nullptr, *valsB = nullptr;
     BvhNode* nodes = nullptr;
     Tri48* tris = nullptr;
-    uint32_t *nodeParent = nullptr, *leafParent = nullptr, *flags = nullptr;
+    float4* pyramid = nullptr;          // leaf boxes + 16:1 summary levels
     void* sortTemp = nullptr; size_t sortTempCap = 0;
     size_t capTris = 0;
 
@@ -126,15 +127,16 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     if (T > ctx->capTris || !ctx->nodes)
     {
         const size_t cap = T + T / 8 + 16;
-        uint32_t** u32s[] = {&ctx->keysA, &ctx->keysB, &ctx->valsA, &ctx->valsB, &ctx->nodeParent, &ctx->leafParent, &ctx->flags};
+        uint32_t** u32s[] = {&ctx->keysA, &ctx->keysB, &ctx->valsA, &ctx->valsB};
         for (auto pp : u32s) { if (*pp) cudaFree(*pp); *pp = nullptr; }
         if (ctx->nodes) cudaFree(ctx->nodes); ctx->nodes = nullptr;
         if (ctx->tris) cudaFree(ctx->tris); ctx->tris = nullptr;
+        if (ctx->pyramid) cudaFree(ctx->pyramid); ctx->pyramid = nullptr;
         ctx->capTris = 0;
         for (auto pp : u32s) DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(pp), sizeof(uint32_t) * cap));
         DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->nodes), sizeof(BvhNode) * cap));
         DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tris), sizeof(Tri48) * cap));
-        DXRV_CUDA(cudaMemsetAsync(ctx->flags, 0, sizeof(uint32_t) * cap, ctx->stream));
+        DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->pyramid), sizeof(float4) * boxPyramidFloat4s((uint32_t)cap)));
         ctx->capTris = cap;
     }
     {
@@ -149,13 +151,18 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     ctx->launches += 1;
     if (T > 0)
     {
-        launchMorton(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->dErr);
+        // small meshes: 8 bits per axis (24-bit keys, three radix passes); large: all 30 bits
+        const uint32_t keyShift = (T <= (1u << 18)) ? 6u : 0u;
+        const int numPasses = (T <= (1u << 18)) ? 3 : 4;
+        uint32_t* hist = sortClearTemp(s, ctx->sortTemp, T);
+        launchMorton(s, m, ctx->dBound, ctx->keysA, ctx->valsA, keyShift, numPasses, hist, ctx->dErr);
         ctx->launches += 1;
-        ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, T);
-        if (T > 1) { launchHierarchy(s, ctx->keysA, T, ctx->nodes, ctx->nodeParent, ctx->leafParent); ctx->launches += 1; }
-        launchRefit(s, m, ctx->dBound, ctx->valsA, ctx->nodes, ctx->nodeParent, ctx->leafParent, ctx->flags, ctx->tris,
-                    ctx->dRootBox, ctx->dErr);
-        ctx->launches += 1;
+        bool inB = false;
+        ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, T,
+                                                  numPasses, true, &inB);
+        if (inB) { std::swap(ctx->keysA, ctx->keysB); std::swap(ctx->valsA, ctx->valsB); }
+        ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
+                                                            ctx->pyramid, ctx->dRootBox, ctx->dErr);
     }
     DXRV_CUDA(cudaGetLastError());
     ctx->haveBvh = true;
@@ -226,7 +233,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
-                    ctx->nodeParent, ctx->leafParent, ctx->flags, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf};
+                    ctx->pyramid, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -457,16 +464,6 @@ int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes)
     case DXRV_DBG_NODES: src = ctx->nodes; need = (T ? T - 1 : 0) * sizeof(BvhNode); break;
     case DXRV_DBG_TRIS: src = ctx->tris; need = T * sizeof(Tri48); break;
     case DXRV_DBG_ROOT_BOX: src = ctx->dRootBox; need = 6 * sizeof(float); break;
-    case DXRV_DBG_PARENTS:
-    {
-        // [nodeParent (T-1) | leafParent (T)]
-        need = (T ? 2 * T - 1 : 0) * 4;
-        if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: size mismatch");
-        if (T > 1) DXRV_CUDA(cudaMemcpyAsync(hostDst, ctx->nodeParent, (T - 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (T > 0) DXRV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(hostDst) + (T - 1) * 4, ctx->leafParent, T * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
-        return DXRV_OK;
-    }
     default: return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: unknown buffer");
     }
     if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: size mismatch");
@@ -488,7 +485,7 @@ int dxrv_debug_sort_pairs(dxrv_ctx* ctx, uint32_t* keys, uint32_t* values, uint3
     uint32_t *kA = buf, *vA = buf + n, *kB = buf + 2 * (size_t)n, *vB = buf + 3 * (size_t)n;
     cudaMemcpyAsync(kA, keys, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(vA, values, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
-    ctx->launches += (uint64_t)radixSortPairs(ctx->stream, temp, kA, vA, kB, vB, n);
+    ctx->launches += (uint64_t)radixSortPairs(ctx->stream, temp, kA, vA, kB, vB, n, 4, false, nullptr);
     cudaMemcpyAsync(keys, kA, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(values, vA, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);

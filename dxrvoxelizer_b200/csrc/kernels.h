@@ -21,15 +21,17 @@ constexpr int kBoundsMaxBlocks = 1024;
 // scratch: 6 * kBoundsMaxBlocks floats + 1 counter (zero before first use; self-resetting)
 void launchBounds(cudaStream_t s, const MeshView& m, float* dBound, float* dPartials, uint32_t* dCounter);
 void launchSetBound(cudaStream_t s, float cx, float cy, float cz, float w, float* dBound);
+// keys = 30-bit Morton code >> keyShift; also accumulates the digit histograms of `numPasses` radix
+// passes into hist (which must be zero).
 void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32_t* keys, uint32_t* vals,
-                  uint32_t* dErr);
-void launchHierarchy(cudaStream_t s, const uint32_t* sortedKeys, uint32_t numTris, BvhNode* nodes,
-                     uint32_t* nodeParent, uint32_t* leafParent);
-// flags: one uint32 per internal node; must be all-even on entry (memset 0 once; each completed
-// refit adds exactly 2 to every flag).
-void launchRefit(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedPrims,
-                 BvhNode* nodes, const uint32_t* nodeParent, const uint32_t* leafParent, uint32_t* flags,
-                 Tri48* tris, float* rootBox, uint32_t* dErr);
+                  uint32_t keyShift, int numPasses, uint32_t* hist, uint32_t* dErr);
+constexpr int kMaxBoxLevels = 8;
+// float4 entries needed for the leaf-box pyramid of numTris leaves
+size_t boxPyramidFloat4s(uint32_t numTris);
+// k_leaf_setup (+ k_box_level) + k_hierarchy_boxes; returns the number of kernels launched
+int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
+                             const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
+                             float* rootBox, uint32_t* dErr);
 
 // ---- onesweep.cu --------------------------------------------------------------------------------
 struct SortTemp
@@ -41,10 +43,15 @@ struct SortTemp
     static size_t bytesFor(uint32_t n);
     static uint32_t tilesFor(uint32_t n);
 };
-// Stable LSD radix sort of (key,value) pairs, 4 passes of 8 bits; result ends in keysA/valsA.
+// Zero the sort scratch (histograms, tile counters, look-back words); returns the histogram pointer
+// ([4][256] digit counts) for a producer kernel to fill.
+uint32_t* sortClearTemp(cudaStream_t s, void* tempBase, uint32_t n);
+// Stable LSD radix sort of (key,value) pairs, `numPasses` passes of 8 bits from bit 0.  histReady: the
+// digit counts are already in the scratch (sortClearTemp + producer); otherwise they are computed here.
+// The result is in keysB/valsB when numPasses is odd (*resultInB), else in keysA/valsA.
 // tempBase: device memory of SortTemp::bytesFor(n) bytes.  Returns the number of kernels launched.
 int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* valsA, uint32_t* keysB,
-                   uint32_t* valsB, uint32_t n);
+                   uint32_t* valsB, uint32_t n, int numPasses, bool histReady, bool* resultInB);
 
 // ---- trace_parity.cu ----------------------------------------------------------------------------
 struct BvhView

@@ -2,11 +2,15 @@
 //
 // Replaces the driver's BLAS/TLAS build requested by Voxelizer::buildAccelerationStructures
 // (reference Content/Voxelizer.cpp:264-326).  Pipeline (all HBM/latency bound, no tensor work):
-//   k_bounds      min/max of all vertex positions -> {c, w}         (Voxelizer.cpp:52-57)
-//   k_morton      per triangle: scene-space box centre -> 30-bit Morton key
-//   (onesweep.cu) stable radix sort of (key, triangle)
-//   k_hierarchy   Karras 2012 radix tree over the sorted keys (index tie-break for duplicates)
-//   k_refit       leaves: scene-space triangle + box; bottom-up union with one atomic per node
+//   k_bounds          min/max of all vertex positions -> {c, w}     (Voxelizer.cpp:52-57)
+//   k_morton          per triangle: scene-space box centre -> Morton key, fused digit histograms
+//   (onesweep.cu)     stable radix sort of (key, triangle)
+//   k_leaf_setup      per sorted leaf: scene-space triangle, its box, 16- and 256-leaf summary boxes
+//   k_box_level       coarser summary levels (16:1) for big meshes
+//   k_hierarchy_boxes Karras 2012 radix tree over the sorted keys (index tie-break for duplicates);
+//                     each node's child boxes are the unions of CONTIGUOUS leaf ranges, answered from
+//                     the summary pyramid -- no parent pointers, no atomics, no bottom-up latency chain
+//                     (the classic refit walks leaf-to-root with a fence + atomic per level)
 #include "kernels.h"
 
 namespace dxrv
@@ -118,7 +122,7 @@ __global__ void k_set_bound(float cx, float cy, float cz, float w, float* bound)
     bound[0] = cx; bound[1] = cy; bound[2] = cz; bound[3] = w;
 }
 
-// ---- Morton keys -----------------------------------------------------------------------------------
+// ---- Morton keys ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t expandBits10(uint32_t v)
 {
     v = (v * 0x00010001u) & 0xFF0000FFu;
@@ -135,31 +139,221 @@ __device__ __forceinline__ uint32_t quantize10(float c)
     return (uint32_t)q;
 }
 
+// keys[k] = 30-bit Morton code >> keyShift (keyShift = 6 keeps 8 bits per axis: three radix passes are
+// enough for small meshes).  The digit histograms of all `numPasses` radix passes are accumulated here
+// (hist must be zero on entry), so the sort never re-reads the keys for counting.
 __global__ void __launch_bounds__(256)
 k_morton(MeshView m, const float* __restrict__ boundPtr, uint32_t* __restrict__ keys,
-         uint32_t* __restrict__ vals, uint32_t* __restrict__ err)
+         uint32_t* __restrict__ vals, uint32_t keyShift, int numPasses, uint32_t* __restrict__ hist,
+         uint32_t* __restrict__ err)
 {
+    __shared__ uint32_t sh[4][256];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m.numTris) return;
-    const float4 bound = make_float4(__ldg(boundPtr), __ldg(boundPtr + 1), __ldg(boundPtr + 2), __ldg(boundPtr + 3));
-    uint32_t i0 = __ldg(m.indices + 3 * (size_t)k), i1 = __ldg(m.indices + 3 * (size_t)k + 1),
-             i2 = __ldg(m.indices + 3 * (size_t)k + 2);
-    if (i0 >= m.numVerts || i1 >= m.numVerts || i2 >= m.numVerts)
+    if (k < m.numTris)
     {
-        atomicMax(err, (uint32_t)kErrBadIndex);
-        i0 = i1 = i2 = 0;
+        const float4 bound = make_float4(__ldg(boundPtr), __ldg(boundPtr + 1), __ldg(boundPtr + 2), __ldg(boundPtr + 3));
+        uint32_t i0 = __ldg(m.indices + 3 * (size_t)k), i1 = __ldg(m.indices + 3 * (size_t)k + 1),
+                 i2 = __ldg(m.indices + 3 * (size_t)k + 2);
+        if (i0 >= m.numVerts || i1 >= m.numVerts || i2 >= m.numVerts)
+        {
+            atomicMax(err, (uint32_t)kErrBadIndex);
+            i0 = i1 = i2 = 0;
+        }
+        const float3 a = scenePos(m.verts, m.stride, i0, bound);
+        const float3 b = scenePos(m.verts, m.stride, i1, bound);
+        const float3 c = scenePos(m.verts, m.stride, i2, bound);
+        const float cx = 0.5f * (fminf(fminf(a.x, b.x), c.x) + fmaxf(fmaxf(a.x, b.x), c.x));
+        const float cy = 0.5f * (fminf(fminf(a.y, b.y), c.y) + fmaxf(fmaxf(a.y, b.y), c.y));
+        const float cz = 0.5f * (fminf(fminf(a.z, b.z), c.z) + fmaxf(fmaxf(a.z, b.z), c.z));
+        const uint32_t key = ((expandBits10(quantize10(cx)) << 2) | (expandBits10(quantize10(cy)) << 1) |
+                              expandBits10(quantize10(cz))) >> keyShift;
+        keys[k] = key;
+        vals[k] = k;
+        for (int p = 0; p < numPasses; ++p) atomicAdd(&sh[p][(key >> (8 * p)) & 255u], 1u);
     }
-    const float3 a = scenePos(m.verts, m.stride, i0, bound);
-    const float3 b = scenePos(m.verts, m.stride, i1, bound);
-    const float3 c = scenePos(m.verts, m.stride, i2, bound);
-    const float cx = 0.5f * (fminf(fminf(a.x, b.x), c.x) + fmaxf(fmaxf(a.x, b.x), c.x));
-    const float cy = 0.5f * (fminf(fminf(a.y, b.y), c.y) + fmaxf(fmaxf(a.y, b.y), c.y));
-    const float cz = 0.5f * (fminf(fminf(a.z, b.z), c.z) + fmaxf(fmaxf(a.z, b.z), c.z));
-    keys[k] = (expandBits10(quantize10(cx)) << 2) | (expandBits10(quantize10(cy)) << 1) | expandBits10(quantize10(cz));
-    vals[k] = k;
+    __syncthreads();
+    for (int i = threadIdx.x; i < numPasses * 256; i += blockDim.x)
+    {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
 }
 
-// ---- Karras hierarchy ------------------------------------------------------------------------------
+// ---- leaves and the box pyramid ----------------------------------------------------------------------
+// Box of a range of sorted leaves, stored as two float4: (ylo, yhi, zlo, zhi), (xlo, xhi, -, -).
+// Level 0 = the leaves, level l = unions of 16^l consecutive leaves.
+struct RangeBox
+{
+    float ylo, yhi, zlo, zhi, xlo, xhi;
+    __device__ __forceinline__ void clear()
+    {
+        ylo = zlo = xlo = INFINITY;
+        yhi = zhi = xhi = -INFINITY;
+    }
+    __device__ __forceinline__ void add(const float4& yz, const float4& x)
+    {
+        ylo = fminf(ylo, yz.x); yhi = fmaxf(yhi, yz.y);
+        zlo = fminf(zlo, yz.z); zhi = fmaxf(zhi, yz.w);
+        xlo = fminf(xlo, x.x);  xhi = fmaxf(xhi, x.y);
+    }
+    __device__ __forceinline__ void shuffleXor(int o)
+    {
+        ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+        zlo = fminf(zlo, __shfl_xor_sync(0xffffffffu, zlo, o)); zhi = fmaxf(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
+        xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+    }
+    __device__ __forceinline__ void store(float4* dst) const
+    {
+        dst[0] = make_float4(ylo, yhi, zlo, zhi);
+        dst[1] = make_float4(xlo, xhi, 0.0f, 0.0f);
+    }
+};
+
+struct Pyramid
+{
+    float4* level[kMaxBoxLevels];   // level[l][2*i], level[l][2*i+1]
+    uint32_t count[kMaxBoxLevels];  // entries per level
+    int numLevels;
+};
+
+__global__ void __launch_bounds__(256)
+k_leaf_setup(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __restrict__ sortedPrims,
+             Tri48* __restrict__ tris, Pyramid pyr, float* __restrict__ rootBox, uint32_t* __restrict__ err)
+{
+    __shared__ float sBox[8][6];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    RangeBox box;
+    box.clear();
+    if (j < m.numTris)
+    {
+        const float4 bound = make_float4(__ldg(boundPtr), __ldg(boundPtr + 1), __ldg(boundPtr + 2), __ldg(boundPtr + 3));
+        const uint32_t k = __ldg(sortedPrims + j);
+        uint32_t i0 = __ldg(m.indices + 3 * (size_t)k), i1 = __ldg(m.indices + 3 * (size_t)k + 1),
+                 i2 = __ldg(m.indices + 3 * (size_t)k + 2);
+        if (i0 >= m.numVerts || i1 >= m.numVerts || i2 >= m.numVerts)
+        {
+            atomicMax(err, (uint32_t)kErrBadIndex);
+            i0 = i1 = i2 = 0;
+        }
+        const float3 a = scenePos(m.verts, m.stride, i0, bound);
+        const float3 b = scenePos(m.verts, m.stride, i1, bound);
+        const float3 c = scenePos(m.verts, m.stride, i2, bound);
+        Tri48 t;
+        t.a = make_float4(a.x, a.y, a.z, __uint_as_float(k));
+        t.b = make_float4(b.x, b.y, b.z, 0.0f);
+        t.c = make_float4(c.x, c.y, c.z, 0.0f);
+        tris[j] = t;
+        box.ylo = fminf(fminf(a.y, b.y), c.y); box.yhi = fmaxf(fmaxf(a.y, b.y), c.y);
+        box.zlo = fminf(fminf(a.z, b.z), c.z); box.zhi = fmaxf(fmaxf(a.z, b.z), c.z);
+        box.xlo = fminf(fminf(a.x, b.x), c.x); box.xhi = fmaxf(fmaxf(a.x, b.x), c.x);
+        box.store(pyr.level[0] + 2 * (size_t)j);
+        if (m.numTris == 1)
+        {
+            rootBox[0] = box.xlo; rootBox[1] = box.ylo; rootBox[2] = box.zlo;
+            rootBox[3] = box.xhi; rootBox[4] = box.yhi; rootBox[5] = box.zhi;
+        }
+    }
+    // level 1: 16 consecutive leaves = one half-warp
+    box.shuffleXor(1); box.shuffleXor(2); box.shuffleXor(4); box.shuffleXor(8);
+    if (pyr.numLevels > 1 && (threadIdx.x & 15u) == 0u && j < m.numTris) box.store(pyr.level[1] + 2 * (size_t)(j >> 4));
+    // level 2: the 256 leaves of this block
+    if (pyr.numLevels > 2)
+    {
+        box.shuffleXor(16);
+        const int warp = threadIdx.x >> 5;
+        if (laneId() == 0)
+        {
+            sBox[warp][0] = box.ylo; sBox[warp][1] = box.yhi; sBox[warp][2] = box.zlo;
+            sBox[warp][3] = box.zhi; sBox[warp][4] = box.xlo; sBox[warp][5] = box.xhi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            for (int w = 1; w < 8; ++w)
+            {
+                box.ylo = fminf(box.ylo, sBox[w][0]); box.yhi = fmaxf(box.yhi, sBox[w][1]);
+                box.zlo = fminf(box.zlo, sBox[w][2]); box.zhi = fmaxf(box.zhi, sBox[w][3]);
+                box.xlo = fminf(box.xlo, sBox[w][4]); box.xhi = fmaxf(box.xhi, sBox[w][5]);
+            }
+            box.store(pyr.level[2] + 2 * (size_t)blockIdx.x);
+        }
+    }
+}
+
+// level l (>= 3) from level l-1: one thread per entry, 16 children each
+__global__ void __launch_bounds__(128)
+k_box_level(const float4* __restrict__ src, uint32_t srcCount, float4* __restrict__ dst, uint32_t dstCount)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dstCount) return;
+    RangeBox box;
+    box.clear();
+    // all 32 loads are issued before the first min/max: one memory round trip, not sixteen
+    float4 yz[16], xx[16];
+#pragma unroll
+    for (uint32_t q = 0; q < 16u; ++q)
+    {
+        const uint32_t c = min(16u * i + q, srcCount - 1u);   // clamped duplicates do not change a union
+        yz[q] = __ldg(src + 2 * (size_t)c);
+        xx[q] = __ldg(src + 2 * (size_t)c + 1);
+    }
+#pragma unroll
+    for (uint32_t q = 0; q < 16u; ++q) box.add(yz[q], xx[q]);
+    box.store(dst + 2 * (size_t)i);
+}
+
+// union of `n` consecutive entries starting at `first`; loads are issued in batches of 8 entries
+// (16 independent 128-bit loads in flight) instead of one dependent round trip per entry
+__device__ __forceinline__ void addRun(RangeBox& box, const float4* __restrict__ lev, uint32_t first, uint32_t n)
+{
+    if (n <= 2u)   // most nodes are tiny: do not pay for a padded batch
+    {
+        if (n >= 1u) box.add(__ldg(lev + 2 * (size_t)first), __ldg(lev + 2 * (size_t)first + 1));
+        if (n == 2u) box.add(__ldg(lev + 2 * (size_t)first + 2), __ldg(lev + 2 * (size_t)first + 3));
+        return;
+    }
+#pragma unroll 1
+    for (uint32_t base = 0; base < n; base += 8u)
+    {
+        float4 yz[8], xx[8];
+#pragma unroll
+        for (uint32_t q = 0; q < 8u; ++q)
+        {
+            const uint32_t c = first + min(base + q, n - 1u);   // clamped duplicates do not change a union
+            yz[q] = __ldg(lev + 2 * (size_t)c);
+            xx[q] = __ldg(lev + 2 * (size_t)c + 1);
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 8u; ++q) box.add(yz[q], xx[q]);
+    }
+}
+
+// union of the leaf boxes [first, last]: at most 15 + 15 entries per pyramid level (64 at the top)
+__device__ __forceinline__ RangeBox rangeQuery(const Pyramid& pyr, uint32_t first, uint32_t last)
+{
+    RangeBox box;
+    box.clear();
+    uint32_t lo = first, hi = last + 1u;  // half open, in units of level-l entries
+    for (int l = 0; l < pyr.numLevels && lo < hi; ++l)
+    {
+        const float4* lev = pyr.level[l];
+        if (l == pyr.numLevels - 1 || hi - lo <= 15u)
+        {
+            addRun(box, lev, lo, hi - lo);
+            break;
+        }
+        const uint32_t head = (16u - (lo & 15u)) & 15u;   // entries up to the next multiple of 16
+        const uint32_t tail = hi & 15u;                    // entries after the last multiple of 16
+        addRun(box, lev, lo, head);
+        addRun(box, lev, hi - tail, tail);
+        lo = (lo + head) >> 4; hi = (hi - tail) >> 4;
+    }
+    return box;
+}
+
+// ---- Karras hierarchy + child boxes ----------------------------------------------------------------
 // delta(i,j): length of the common prefix of the 64-bit augmented keys (key << 32 | index), -1 when
 // j is out of range.
 __device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int numLeaves, uint32_t ki, int i, int j)
@@ -170,113 +364,84 @@ __device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int numL
     return x ? __clz(x) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
 }
 
-__global__ void __launch_bounds__(256)
-k_hierarchy(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __restrict__ nodes,
-            uint32_t* __restrict__ nodeParent, uint32_t* __restrict__ leafParent)
+__global__ void __launch_bounds__(128, 8)
+k_hierarchy_boxes(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __restrict__ nodes, Pyramid pyr,
+                  float* __restrict__ rootBox)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numLeaves - 1) return;
     const uint32_t ki = __ldg(keys + i);
     const int d = (delta(keys, numLeaves, ki, i, i + 1) - delta(keys, numLeaves, ki, i, i - 1)) < 0 ? -1 : 1;
     const int dMin = delta(keys, numLeaves, ki, i, i - d);
+    // The three searches below are chains of dependent key loads (every probe is an L2 round trip
+    // for the nodes near the root), so each round issues several independent probes at once.
+    // delta(i, i + l*d) > bound is monotone in l: true up to the end of the node's range, false beyond.
+    auto inRange = [&](long long l, int bound) {
+        const long long q = (long long)i + l * d;
+        return q >= 0 && q < numLeaves && delta(keys, numLeaves, ki, i, (int)q) > bound;
+    };
     long long lMax = 2;
     while (true)
     {
-        const long long j = (long long)i + lMax * d;
-        if (j < 0 || j >= numLeaves || delta(keys, numLeaves, ki, i, (int)j) <= dMin) break;
-        lMax <<= 1;
+        const bool p0 = inRange(lMax, dMin), p1 = inRange(lMax * 2, dMin), p2 = inRange(lMax * 4, dMin), p3 = inRange(lMax * 8, dMin);
+        if (!p0) break;
+        if (!p1) { lMax *= 2; break; }
+        if (!p2) { lMax *= 4; break; }
+        if (!p3) { lMax *= 8; break; }
+        lMax *= 16;
     }
+    // largest l < lMax with inRange(l): two bits per round
     long long l = 0;
-    for (long long t = lMax >> 1; t >= 1; t >>= 1)
+    long long t = lMax >> 1;
+    while (t >= 1)
     {
-        const long long j = (long long)i + (l + t) * d;
-        if (j >= 0 && j < numLeaves && delta(keys, numLeaves, ki, i, (int)j) > dMin) l += t;
+        const long long h = t >> 1;
+        const bool a = inRange(l + t, dMin);
+        const bool b0 = h >= 1 && inRange(l + h, dMin), b1 = h >= 1 && inRange(l + t + h, dMin);
+        if (a) { l += t; if (b1) l += h; }
+        else if (b0) l += h;
+        t = h >> 1;
+        if (h < 1) break;
     }
     const int j = i + (int)l * d;
     const int dNode = delta(keys, numLeaves, ki, i, j);
+    // split: largest s in [0, l) with delta(i, i + s*d) > dNode, by the same two-bits-per-round search
+    // over the power-of-two ladder ceil(l/2), ceil(l/4), ... , 1
     long long s = 0;
-    long long t = l;
+    t = l;
     do
     {
         t = (t + 1) >> 1;
-        const long long q = (long long)i + (s + t) * d;
-        if (q >= 0 && q < numLeaves && delta(keys, numLeaves, ki, i, (int)q) > dNode) s += t;
+        const long long t2 = (t > 1) ? ((t + 1) >> 1) : 0;
+        const bool a = inRange(s + t, dNode);
+        const bool b0 = t2 >= 1 && inRange(s + t2, dNode), b1 = t2 >= 1 && inRange(s + t + t2, dNode);
+        if (a) { s += t; if (t2 >= 1 && b1) s += t2; }
+        else if (t2 >= 1 && b0) s += t2;
+        if (t2 >= 1) t = t2;
     } while (t > 1);
     const int gamma = i + (int)s * d + min(d, 0);
 
-    const int lo = min(i, j), hi = max(i, j);
-    const bool leftLeaf = (lo == gamma), rightLeaf = (hi == gamma + 1);
-    nodes[i].c0 = leftLeaf ? (kLeafFlag | (uint32_t)gamma) : (uint32_t)gamma;
-    nodes[i].c1 = rightLeaf ? (kLeafFlag | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-    // parent reference: node index | (1u << 31 when the child is the right one)
-    if (leftLeaf) leafParent[gamma] = (uint32_t)i; else nodeParent[gamma] = (uint32_t)i;
-    if (rightLeaf) leafParent[gamma + 1] = (uint32_t)i | 0x80000000u; else nodeParent[gamma + 1] = (uint32_t)i | 0x80000000u;
-    if (i == 0) nodeParent[0] = 0xffffffffu;
-}
-
-// ---- refit -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_refit(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __restrict__ sortedPrims,
-        BvhNode* __restrict__ nodes, const uint32_t* __restrict__ nodeParent,
-        const uint32_t* __restrict__ leafParent, uint32_t* __restrict__ flags, Tri48* __restrict__ tris,
-        float* __restrict__ rootBox, uint32_t* __restrict__ err)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m.numTris) return;
-    const float4 bound = make_float4(__ldg(boundPtr), __ldg(boundPtr + 1), __ldg(boundPtr + 2), __ldg(boundPtr + 3));
-    const uint32_t k = __ldg(sortedPrims + j);
-    uint32_t i0 = __ldg(m.indices + 3 * (size_t)k), i1 = __ldg(m.indices + 3 * (size_t)k + 1),
-             i2 = __ldg(m.indices + 3 * (size_t)k + 2);
-    if (i0 >= m.numVerts || i1 >= m.numVerts || i2 >= m.numVerts)
+    // node i covers the sorted leaves [first, last]; its children cover [first, gamma] and [gamma+1, last]
+    const int first = min(i, j), last = max(i, j);
+    const bool leftLeaf = (first == gamma), rightLeaf = (last == gamma + 1);
+    const RangeBox b0 = rangeQuery(pyr, (uint32_t)first, (uint32_t)gamma);
+    const RangeBox b1 = rangeQuery(pyr, (uint32_t)gamma + 1u, (uint32_t)last);
+    BvhNode n;
+    n.yz0 = make_float4(b0.ylo, b0.yhi, b0.zlo, b0.zhi);
+    n.yz1 = make_float4(b1.ylo, b1.yhi, b1.zlo, b1.zhi);
+    n.x01 = make_float4(b0.xlo, b0.xhi, b1.xlo, b1.xhi);
+    n.c0 = leftLeaf ? (kLeafFlag | (uint32_t)gamma) : (uint32_t)gamma;
+    n.c1 = rightLeaf ? (kLeafFlag | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    n.pad0 = (uint32_t)first;   // leaf range of the node (debug / tests)
+    n.pad1 = (uint32_t)last;
+    float4* dst = reinterpret_cast<float4*>(nodes + i);
+    dst[0] = n.yz0; dst[1] = n.yz1; dst[2] = n.x01;
+    dst[3] = make_float4(__uint_as_float(n.c0), __uint_as_float(n.c1), __uint_as_float(n.pad0), __uint_as_float(n.pad1));
+    if (i == 0)
     {
-        atomicMax(err, (uint32_t)kErrBadIndex);
-        i0 = i1 = i2 = 0;
+        rootBox[0] = fminf(b0.xlo, b1.xlo); rootBox[1] = fminf(b0.ylo, b1.ylo); rootBox[2] = fminf(b0.zlo, b1.zlo);
+        rootBox[3] = fmaxf(b0.xhi, b1.xhi); rootBox[4] = fmaxf(b0.yhi, b1.yhi); rootBox[5] = fmaxf(b0.zhi, b1.zhi);
     }
-    const float3 a = scenePos(m.verts, m.stride, i0, bound);
-    const float3 b = scenePos(m.verts, m.stride, i1, bound);
-    const float3 c = scenePos(m.verts, m.stride, i2, bound);
-    Tri48 t;
-    t.a = make_float4(a.x, a.y, a.z, __uint_as_float(k));
-    t.b = make_float4(b.x, b.y, b.z, 0.0f);
-    t.c = make_float4(c.x, c.y, c.z, 0.0f);
-    tris[j] = t;
-
-    float lo[3] = {fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z)};
-    float hi[3] = {fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z)};
-
-    if (m.numTris == 1)
-    {
-        for (int q = 0; q < 3; ++q) { rootBox[q] = lo[q]; rootBox[3 + q] = hi[q]; }
-        return;
-    }
-
-    uint32_t p = __ldg(leafParent + j);
-    for (int level = 0; level < 128; ++level)  // depth <= 62; the bound only guards against a corrupt tree
-    {
-        const uint32_t pi = p & 0x7fffffffu, slot = p >> 31;
-        const uint32_t up = (pi != 0u) ? __ldg(nodeParent + pi) : 0u;  // issued early: overlaps the atomic
-        BvhNode* n = nodes + pi;
-        float4* yz = slot ? &n->yz1 : &n->yz0;
-        float2* xx = reinterpret_cast<float2*>(&n->x01) + slot;
-        *yz = make_float4(lo[1], hi[1], lo[2], hi[2]);
-        *xx = make_float2(lo[0], hi[0]);
-        __threadfence();  // release: the box must be visible before the arrival counter moves
-        const uint32_t old = atomicAdd(flags + pi, 1u);
-        if ((old & 1u) == 0u) return;  // first child to arrive: the sibling will carry on
-        // second arrival: the sibling's box was released before its increment; read it past L1
-        const float4 syz = __ldcg(slot ? &n->yz0 : &n->yz1);
-        const float2 sxx = __ldcg(reinterpret_cast<const float2*>(&n->x01) + (1u - slot));
-        lo[0] = fminf(lo[0], sxx.x); hi[0] = fmaxf(hi[0], sxx.y);
-        lo[1] = fminf(lo[1], syz.x); hi[1] = fmaxf(hi[1], syz.y);
-        lo[2] = fminf(lo[2], syz.z); hi[2] = fmaxf(hi[2], syz.w);
-        if (pi == 0)
-        {
-            for (int q = 0; q < 3; ++q) { rootBox[q] = lo[q]; rootBox[3 + q] = hi[q]; }
-            return;
-        }
-        p = up;
-    }
-    atomicMax(err, (uint32_t)kErrStackOverflow);
 }
 
 // ---- small utilities -------------------------------------------------------------------------------
@@ -314,26 +479,57 @@ void launchSetBound(cudaStream_t s, float cx, float cy, float cz, float w, float
     k_set_bound<<<1, 1, 0, s>>>(cx, cy, cz, w, dBound);
 }
 
-void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32_t* keys, uint32_t* vals, uint32_t* dErr)
+void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32_t* keys, uint32_t* vals,
+                  uint32_t keyShift, int numPasses, uint32_t* hist, uint32_t* dErr)
 {
     if (!m.numTris) return;
-    k_morton<<<(m.numTris + 255) / 256, 256, 0, s>>>(m, dBound, keys, vals, dErr);
+    k_morton<<<(m.numTris + 255) / 256, 256, 0, s>>>(m, dBound, keys, vals, keyShift, numPasses, hist, dErr);
 }
 
-void launchHierarchy(cudaStream_t s, const uint32_t* sortedKeys, uint32_t numTris, BvhNode* nodes,
-                     uint32_t* nodeParent, uint32_t* leafParent)
+size_t boxPyramidFloat4s(uint32_t numTris)
 {
-    if (numTris < 2) return;
-    k_hierarchy<<<(numTris - 1 + 255) / 256, 256, 0, s>>>(sortedKeys, (int)numTris, nodes, nodeParent, leafParent);
+    size_t total = 0;
+    uint32_t c = numTris ? numTris : 1;
+    for (int l = 0; l < kMaxBoxLevels; ++l)
+    {
+        total += 2 * (size_t)c + 2;
+        if (c <= 64) break;
+        c = (c + 15) / 16;
+    }
+    return total;
 }
 
-void launchRefit(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedPrims, BvhNode* nodes,
-                 const uint32_t* nodeParent, const uint32_t* leafParent, uint32_t* flags, Tri48* tris, float* rootBox,
-                 uint32_t* dErr)
+int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
+                             const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
+                             float* rootBox, uint32_t* dErr)
 {
-    if (!m.numTris) return;
-    k_refit<<<(m.numTris + 255) / 256, 256, 0, s>>>(m, dBound, sortedPrims, nodes, nodeParent, leafParent, flags, tris,
-                                                   rootBox, dErr);
+    if (!m.numTris) return 0;
+    Pyramid pyr;
+    uint32_t c = m.numTris;
+    float4* p = pyramidMem;
+    pyr.numLevels = 0;
+    for (int l = 0; l < kMaxBoxLevels; ++l)
+    {
+        pyr.level[l] = p; pyr.count[l] = c; pyr.numLevels = l + 1;
+        p += 2 * (size_t)c + 2;
+        if (c <= 64) break;
+        c = (c + 15) / 16;
+    }
+    for (int l = pyr.numLevels; l < kMaxBoxLevels; ++l) { pyr.level[l] = nullptr; pyr.count[l] = 0; }
+    int launches = 0;
+    k_leaf_setup<<<(m.numTris + 255) / 256, 256, 0, s>>>(m, dBound, sortedPrims, tris, pyr, rootBox, dErr);
+    ++launches;
+    for (int l = 3; l < pyr.numLevels; ++l)
+    {
+        k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, s>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l]);
+        ++launches;
+    }
+    if (m.numTris > 1)
+    {
+        k_hierarchy_boxes<<<(m.numTris - 1 + 127) / 128, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, pyr, rootBox);
+        ++launches;
+    }
+    return launches;
 }
 
 void launchPopcount(cudaStream_t s, const uint32_t* words, size_t numWords, unsigned long long* dCount)

@@ -1,12 +1,15 @@
 // onesweep.cu -- stable LSD radix sort of (Morton key, triangle index) pairs for sm_100a.
 //
-// Single-pass-per-digit "onesweep" (Adinets & Merrill 2022): one kernel computes the histograms of
-// all four 8-bit digits, and each digit pass then reads every pair ONCE and writes it ONCE; the
-// cross-tile prefix is resolved inside the pass by decoupled look-back over per-tile
-// {flag, count} words.  Algorithmic HBM traffic: 4 B (histogram read) + 4 passes x 16 B per pair.
+// Single-pass-per-digit "onesweep" (Adinets & Merrill 2022): the digit histograms of all passes are
+// computed up front (by the Morton kernel itself when the sort serves the LBVH build), and each
+// 8-bit digit pass then reads every pair ONCE and writes it ONCE; the cross-tile prefix is resolved
+// inside the pass by decoupled look-back over per-tile {flag, count} words.  Algorithmic HBM
+// traffic: passes x 16 B per pair (+ 4 B per pair when the histogram needs its own read).
 //
-// Tile = 256 threads x 16 items.  Ranking inside a tile is warp-synchronous (match.any), which keeps
-// the sort stable: order of equal digits = (warp, item, lane) = input order.
+// Tile = 256 threads x kItems pairs (16 for bandwidth-bound sizes, 4 for small inputs where the
+// per-tile latency chain matters more than the tile count).  Ranking inside a tile is
+// warp-synchronous (match.any), which keeps the sort stable: order of equal digits =
+// (warp, item, lane) = input order.
 #include "kernels.h"
 
 namespace dxrv
@@ -15,22 +18,21 @@ namespace
 {
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;   // 256
-constexpr int kPasses = 4;
+constexpr int kMaxPasses = 4;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItems = 16;
-constexpr int kTile = kSortThreads * kItems;  // 4096 pairs
+constexpr uint32_t kSmallSort = 1u << 19;  // below this many pairs use the 1024-pair tile
 
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagInclusive = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
 
-// ---- digit histograms for all passes ----------------------------------------------------------------
+// ---- digit histograms for all passes (stand-alone sort only; the LBVH build fuses this into k_morton)
 __global__ void __launch_bounds__(kSortThreads)
 k_radix_histogram(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t sh[kPasses][kRadix];
-    for (int i = threadIdx.x; i < kPasses * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __shared__ uint32_t sh[kMaxPasses][kRadix];
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
@@ -41,7 +43,7 @@ k_radix_histogram(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __res
         atomicAdd(&sh[3][k >> 24], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kPasses * kRadix; i += blockDim.x)
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x)
     {
         const uint32_t c = (&sh[0][0])[i];
         if (c) atomicAdd(hist + i, c);
@@ -69,29 +71,20 @@ __device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* 
     return base + inc - v;
 }
 
-// hist[p][d] (counts) -> exclusive digit bases, one block per pass
-__global__ void __launch_bounds__(kRadix)
-k_radix_scan(uint32_t* __restrict__ hist)
-{
-    __shared__ uint32_t warpSums[kSortWarps];
-    uint32_t* h = hist + blockIdx.x * kRadix;
-    const uint32_t v = h[threadIdx.x];
-    const uint32_t ex = blockExclusiveScan256(v, warpSums);
-    h[threadIdx.x] = ex;
-}
-
 // ---- one digit pass ----------------------------------------------------------------------------------
+template <int kItems>
 __global__ void __launch_bounds__(kSortThreads)
 k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                 uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n, int shift,
-                const uint32_t* __restrict__ digitBase, volatile uint32_t* __restrict__ lookback,
+                const uint32_t* __restrict__ digitCount, volatile uint32_t* __restrict__ lookback,
                 uint32_t* __restrict__ tileCounter)
 {
+    constexpr int kTile = kSortThreads * kItems;
     __shared__ uint32_t warpHist[kSortWarps][kRadix];  // 8 KB
     __shared__ uint32_t binStart[kRadix];
     __shared__ uint32_t globalBase[kRadix];
-    __shared__ uint32_t sKeys[kTile];                  // 16 KB
-    __shared__ uint32_t sVals[kTile];                  // 16 KB
+    __shared__ uint32_t sKeys[kTile];
+    __shared__ uint32_t sVals[kTile];
     __shared__ uint32_t warpSums[kSortWarps];
     __shared__ uint32_t sTile;
 
@@ -100,12 +93,13 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     // (or done) when this one looks back: the look-back can never wait on an unscheduled block.
     if (tid == 0) sTile = atomicAdd(tileCounter, 1u);
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&warpHist[0][0])[i] = 0;
-    __syncthreads();
+    // exclusive digit bases of this pass from the global digit counts (256 values: one block scan)
+    const uint32_t digitBase = blockExclusiveScan256(__ldg(digitCount + tid), warpSums);
     const uint32_t tile = sTile;
     const uint32_t base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - base);
 
-    // ---- load (warp-striped: item i of lane l is element warp*512 + i*32 + l) ----
+    // ---- load (warp-striped: item i of lane l is element warp*32*kItems + i*32 + l) ----
     uint32_t key[kItems], val[kItems], rank[kItems];
     const uint32_t warpBase = warp * (32u * kItems);
 #pragma unroll
@@ -146,7 +140,8 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
         count += c;
     }
 
-    // ---- decoupled look-back: exclusive count of digit `tid` over all previous tiles ----
+    // ---- decoupled look-back: exclusive count of digit `tid` over all previous tiles.  Four
+    // predecessors are fetched at once so the latency chain is a quarter of the tile distance. ----
     volatile uint32_t* lb = lookback + (size_t)tile * kRadix;
     uint32_t prev = 0;
     if (tile == 0) lb[tid] = kFlagInclusive | count;
@@ -154,21 +149,29 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     {
         lb[tid] = kFlagAggregate | count;
         int j = (int)tile - 1;
-        while (true)
+        bool done = false;
+        while (!done)
         {
-            const uint32_t v = lookback[(size_t)j * kRadix + tid];
-            const uint32_t flag = v & ~kValueMask;
-            if (flag == 0) continue;  // not published yet
-            prev += v & kValueMask;
-            if (flag == kFlagInclusive) break;
-            --j;
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = (j - q >= 0) ? lookback[(size_t)(j - q) * kRadix + tid] : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                if (done || j - q < 0) break;
+                uint32_t x = v[q];
+                while ((x & ~kValueMask) == 0u) x = lookback[(size_t)(j - q) * kRadix + tid];  // not published yet
+                prev += x & kValueMask;
+                if ((x & ~kValueMask) == kFlagInclusive) done = true;
+            }
+            j -= 4;
         }
         lb[tid] = kFlagInclusive | (prev + count);
     }
 
     const uint32_t start = blockExclusiveScan256(count, warpSums);
     binStart[tid] = start;
-    globalBase[tid] = __ldg(digitBase + tid) + prev - start;
+    globalBase[tid] = digitBase + prev - start;
     __syncthreads();
 
     // ---- scatter into shared memory in sorted order ----
@@ -191,42 +194,59 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
         valsOut[dst] = sVals[p];
     }
 }
+
+uint32_t tileSizeFor(uint32_t n) { return n < kSmallSort ? kSortThreads * 4u : kSortThreads * 16u; }
 }  // namespace
 
-uint32_t SortTemp::tilesFor(uint32_t n) { return (n + kTile - 1) / kTile; }
+uint32_t SortTemp::tilesFor(uint32_t n) { const uint32_t t = tileSizeFor(n); return (n + t - 1) / t; }
 
 size_t SortTemp::bytesFor(uint32_t n)
 {
     const size_t tiles = tilesFor(n) ? tilesFor(n) : 1;
     // [hist 4*256][tileCounter 4 (padded to 64)][lookback 4*tiles*256]
-    return sizeof(uint32_t) * (kPasses * kRadix + 64 + (size_t)kPasses * tiles * kRadix);
+    return sizeof(uint32_t) * (kMaxPasses * kRadix + 64 + (size_t)kMaxPasses * tiles * kRadix);
+}
+
+uint32_t* sortClearTemp(cudaStream_t s, void* tempBase, uint32_t n)
+{
+    cudaMemsetAsync(tempBase, 0, SortTemp::bytesFor(n), s);
+    return static_cast<uint32_t*>(tempBase);
 }
 
 int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* valsA, uint32_t* keysB,
-                   uint32_t* valsB, uint32_t n)
+                   uint32_t* valsB, uint32_t n, int numPasses, bool histReady, bool* resultInB)
 {
-    if (n < 2) return 0;
+    if (resultInB) *resultInB = false;
+    if (n < 2 || numPasses < 1) return 0;
+    if (numPasses > kMaxPasses) numPasses = kMaxPasses;
     const uint32_t tiles = SortTemp::tilesFor(n);
     uint32_t* hist = static_cast<uint32_t*>(tempBase);
-    uint32_t* tileCounter = hist + kPasses * kRadix;
+    uint32_t* tileCounter = hist + kMaxPasses * kRadix;
     uint32_t* lookback = tileCounter + 64;
-    cudaMemsetAsync(tempBase, 0, SortTemp::bytesFor(n), s);
 
     int launches = 0;
-    uint32_t histBlocks = (n + kSortThreads * 16 - 1) / (kSortThreads * 16);
-    if (histBlocks > 148 * 4) histBlocks = 148 * 4;
-    k_radix_histogram<<<histBlocks, kSortThreads, 0, s>>>(keysA, n, hist);
-    k_radix_scan<<<kPasses, kRadix, 0, s>>>(hist);
-    launches += 2;
-    uint32_t *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
-    for (int p = 0; p < kPasses; ++p)
+    if (!histReady)
     {
-        k_onesweep_pass<<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
-                                                       lookback + (size_t)p * tiles * kRadix, tileCounter + p);
+        sortClearTemp(s, tempBase, n);
+        uint32_t histBlocks = (n + kSortThreads * 16 - 1) / (kSortThreads * 16);
+        if (histBlocks > 148 * 4) histBlocks = 148 * 4;
+        k_radix_histogram<<<histBlocks, kSortThreads, 0, s>>>(keysA, n, hist);
+        ++launches;
+    }
+    uint32_t *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
+    for (int p = 0; p < numPasses; ++p)
+    {
+        if (n < kSmallSort)
+            k_onesweep_pass<4><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
+                                                              lookback + (size_t)p * tiles * kRadix, tileCounter + p);
+        else
+            k_onesweep_pass<16><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
+                                                               lookback + (size_t)p * tiles * kRadix, tileCounter + p);
         ++launches;
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    return launches;  // an even number of passes: the result is back in keysA / valsA
+    if (resultInB) *resultInB = (numPasses & 1) != 0;
+    return launches;
 }
 }  // namespace dxrv

@@ -249,12 +249,11 @@ k_trace_fill_columns(const ParityParams prm)
         // (triangle, column) pairs, and the pairs are dealt round-robin to the 32 lanes -- a triangle
         // that spans many columns no longer serialises on one thread while the CTA waits at the barrier.
         auto processWarpChunk = [&](bool has, uint32_t slot) {
-            float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
             int yA = 0, zA = 0, w = 0, h = 0;
             if (has)
             {
                 const float4* t = reinterpret_cast<const float4*>(prm.tris + slot);
-                a = __ldg(t); b = __ldg(t + 1); c = __ldg(t + 2);
+                const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
                 const float ylo = fminf(fminf(a.y, b.y), c.y), yhi = fmaxf(fmaxf(a.y, b.y), c.y);
                 const float zlo = fminf(fminf(a.z, b.z), c.z), zhi = fmaxf(fmaxf(a.z, b.z), c.z);
                 // float estimate of the index range, then fix-up against the tabulated exact centres
@@ -275,6 +274,10 @@ k_trace_fill_columns(const ParityParams prm)
                 w = max(yB - yA + 1, 0); h = max(zB - zA + 1, 0);
             }
             const uint32_t n = (uint32_t)(w * h);
+            // per-triangle constants of the pair loop, packed for one shuffle: yA | zA << 8 | w << 16, and
+            // ceil(2^16 / w) so that q / w == (q * inv) >> 16 exactly (q < 256, w <= 16)
+            const uint32_t packed = (uint32_t)yA | ((uint32_t)zA << 8) | ((uint32_t)w << 16);
+            const uint32_t inv = w > 0 ? (65535u + (uint32_t)w) / (uint32_t)w : 0u;
             uint32_t incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
@@ -298,21 +301,22 @@ k_trace_fill_columns(const ParityParams prm)
                     if (e <= p) owner += step;
                 }
                 const uint32_t q = p - __shfl_sync(0xffffffffu, excl, owner);
-                const int ow = __shfl_sync(0xffffffffu, w, owner);
-                const int oyA = __shfl_sync(0xffffffffu, yA, owner), ozA = __shfl_sync(0xffffffffu, zA, owner);
-                float4 ta, tb, tc;
-                ta.x = __shfl_sync(0xffffffffu, a.x, owner); ta.y = __shfl_sync(0xffffffffu, a.y, owner); ta.z = __shfl_sync(0xffffffffu, a.z, owner);
-                tb.x = __shfl_sync(0xffffffffu, b.x, owner); tb.y = __shfl_sync(0xffffffffu, b.y, owner); tb.z = __shfl_sync(0xffffffffu, b.z, owner);
-                tc.x = __shfl_sync(0xffffffffu, c.x, owner); tc.y = __shfl_sync(0xffffffffu, c.y, owner); tc.z = __shfl_sync(0xffffffffu, c.z, owner);
+                const uint32_t oPacked = __shfl_sync(0xffffffffu, packed, owner);
+                const uint32_t oInv = __shfl_sync(0xffffffffu, inv, owner);
+                const uint32_t oSlot = __shfl_sync(0xffffffffu, slot, owner);
                 if (p < total)
                 {
-                    const uint32_t qz = q / (uint32_t)ow;
-                    const int yl = oyA + (int)(q - qz * (uint32_t)ow), zl = ozA + (int)qz;
+                    // the owner's triangle was just loaded by the owner lane: these hit L1
+                    const float4* t = reinterpret_cast<const float4*>(prm.tris + oSlot);
+                    const float4 ta = __ldg(t), tb = __ldg(t + 1), tc = __ldg(t + 2);
+                    const uint32_t ow = oPacked >> 16;
+                    const uint32_t qz = (q * oInv) >> 16;
+                    const uint32_t yl = (oPacked & 0xffu) + (q - qz * ow), zl = ((oPacked >> 8) & 0xffu) + qz;
                     uint32_t ix;
                     if (columnCrossing(ta, tb, tc, tileY[yl], tileZ[zl], N, fN, invNPow2, ix))
                     {
                         ++myCrossings;
-                        if (ix < N) atomicXor(&rows[(uint32_t)(zl * SY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
+                        if (ix < N) atomicXor(&rows[(zl * SY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
                     }
                 }
             }
@@ -411,62 +415,87 @@ k_trace_fill_columns(const ParityParams prm)
     const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
     const uint4* rows4 = reinterpret_cast<const uint4*>(rows) + (size_t)warp * 32u * groupsPerRow;
     uint32_t runCarry = 0;                            // carry along a row spanning several 32-group chunks
-    for (uint32_t g0 = 0; g0 < 32u * groupsPerRow; g0 += 32u)
-    {
-        const uint32_t g = g0 + lane;
-        uint32_t rowInWarp, gi;
-        if (groupsPerRow <= 32u) { rowInWarp = g >> prm.gprShift; gi = g & (groupsPerRow - 1u); }
-        else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
-        uint4 t = make_uint4(0, 0, 0, 0);
-        uint32_t carry = 0;
-        if (listed != 0u)
-        {
-            t = rows4[g];
-            const uint32_t dirty = __ballot_sync(0xffffffffu, (t.x | t.y | t.z | t.w) != 0u);
-            if (groupsPerRow >= 32u && (g0 % groupsPerRow) == 0) runCarry = 0;
-            if (dirty)
-            {
-                uint32_t par;
-                t.x = prefixXor32(t.x); par = t.x >> 31;
-                t.y = prefixXor32(t.y) ^ (0u - par); par = t.y >> 31;
-                t.z = prefixXor32(t.z) ^ (0u - par); par = t.z >> 31;
-                t.w = prefixXor32(t.w) ^ (0u - par); par = t.w >> 31;
-                // `par` = parity of this lane's 128 bits (without incoming carry); prefix parity is
-                // linear, so the carry into a lane is the XOR of `par` over the lower lanes of its row
-                const uint32_t bal = __ballot_sync(0xffffffffu, par);
-                if (groupsPerRow >= 32u)
-                {
-                    carry = (__popc(bal & laneMaskLt()) & 1u) ^ runCarry;
-                    runCarry ^= (__popc(bal) & 1u);
-                }
-                else
-                {
-                    const uint32_t segLo = lane - gi;  // first lane of this row
-                    carry = __popc(bal & laneMaskLt() & ~((1u << segLo) - 1u)) & 1u;
-                }
-            }
-            else if (groupsPerRow >= 32u) carry = runCarry;
-            const uint32_t flip = 0u - carry;
-            t.x ^= flip; t.y ^= flip; t.z ^= flip; t.w ^= flip;
-        }
 
-        const uint32_t col = warp * 32u + rowInWarp;
-        const uint32_t yl = col % SY, zl = col / SY;
-        const uint32_t y = sy0 + yl, z = sz0 + zl;
-        const uint32_t w0 = gi * 4u;
-        if (y < N && z < prm.z1 && w0 < P)
+    // toggles of group g (lane's 128 bits of row g / groupsPerRow) -> occupancy bits
+    auto occupancy = [&](uint32_t g0, uint32_t g, uint32_t gi) -> uint4 {
+        uint4 t = rows4[g];
+        uint32_t carry = 0;
+        const uint32_t dirty = __ballot_sync(0xffffffffu, (t.x | t.y | t.z | t.w) != 0u);
+        if (groupsPerRow >= 32u && (g0 % groupsPerRow) == 0) runCarry = 0;
+        if (dirty)
         {
-            uint32_t* dst = prm.grid + ((size_t)(z - prm.z0) * N + y) * P + w0;
-            if (w0 + 4u <= P && (P & 3u) == 0u)
+            uint32_t par;
+            t.x = prefixXor32(t.x); par = t.x >> 31;
+            t.y = prefixXor32(t.y) ^ (0u - par); par = t.y >> 31;
+            t.z = prefixXor32(t.z) ^ (0u - par); par = t.z >> 31;
+            t.w = prefixXor32(t.w) ^ (0u - par); par = t.w >> 31;
+            // `par` = parity of this lane's 128 bits (without incoming carry); prefix parity is
+            // linear, so the carry into a lane is the XOR of `par` over the lower lanes of its row
+            const uint32_t bal = __ballot_sync(0xffffffffu, par);
+            if (groupsPerRow >= 32u)
             {
-                if (w0 + 4u == P) t.w &= tailMask;
-                *reinterpret_cast<uint4*>(dst) = t;
+                carry = (__popc(bal & laneMaskLt()) & 1u) ^ runCarry;
+                runCarry ^= (__popc(bal) & 1u);
             }
             else
             {
-                const uint32_t v[4] = {t.x, t.y, t.z, t.w};
-                for (uint32_t q = 0; q < 4u && w0 + q < P; ++q)
-                    dst[q] = (w0 + q == P - 1u) ? (v[q] & tailMask) : v[q];
+                const uint32_t segLo = lane - gi;  // first lane of this row
+                carry = __popc(bal & laneMaskLt() & ~((1u << segLo) - 1u)) & 1u;
+            }
+        }
+        else if (groupsPerRow >= 32u) carry = runCarry;
+        const uint32_t flip = 0u - carry;
+        t.x ^= flip; t.y ^= flip; t.z ^= flip; t.w ^= flip;
+        return t;
+    };
+
+    const bool interior = SY == 16 && (N & 127u) == 0u && groupsPerRow <= 32u && sy0 + SY <= N && sz0 + SZ <= prm.z1;
+    if (interior)
+    {
+        // fast path (every super-tile of a grid with N % 128 == 0): the warp's 32 rows are two runs of
+        // 16 consecutive y rows (z = 2*warp and 2*warp + 1), each run contiguous in the grid.  The shared
+        // row pitch (Ps, a power of two) may exceed the global one (P): the padding groups are skipped.
+        uint4* base = reinterpret_cast<uint4*>(prm.grid + ((size_t)(sz0 + 2u * warp - prm.z0) * N + sy0) * P);
+        const uint32_t zStride = (uint32_t)(((size_t)N * P) >> 2);
+        const uint32_t gprG = P >> 2;
+        for (uint32_t g0 = 0; g0 < 32u * groupsPerRow; g0 += 32u)
+        {
+            const uint32_t g = g0 + lane;
+            const uint32_t rr = g >> prm.gprShift, gi = g & (groupsPerRow - 1u);
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (listed != 0u) t = occupancy(g0, g, gi);
+            if (gi < gprG) base[(rr >> 4) * zStride + (rr & 15u) * gprG + gi] = t;
+        }
+    }
+    else
+    {
+        for (uint32_t g0 = 0; g0 < 32u * groupsPerRow; g0 += 32u)
+        {
+            const uint32_t g = g0 + lane;
+            uint32_t rowInWarp, gi;
+            if (groupsPerRow <= 32u) { rowInWarp = g >> prm.gprShift; gi = g & (groupsPerRow - 1u); }
+            else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (listed != 0u) t = occupancy(g0, g, gi);
+
+            const uint32_t col = warp * 32u + rowInWarp;
+            const uint32_t yl = col % SY, zl = col / SY;
+            const uint32_t y = sy0 + yl, z = sz0 + zl;
+            const uint32_t w0 = gi * 4u;
+            if (y < N && z < prm.z1 && w0 < P)
+            {
+                uint32_t* dst = prm.grid + ((size_t)(z - prm.z0) * N + y) * P + w0;
+                if (w0 + 4u <= P && (P & 3u) == 0u)
+                {
+                    if (w0 + 4u == P) t.w &= tailMask;
+                    *reinterpret_cast<uint4*>(dst) = t;
+                }
+                else
+                {
+                    const uint32_t v[4] = {t.x, t.y, t.z, t.w};
+                    for (uint32_t q = 0; q < 4u && w0 + q < P; ++q)
+                        dst[q] = (w0 + q == P - 1u) ? (v[q] & tailMask) : v[q];
+                }
             }
         }
     }

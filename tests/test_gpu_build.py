@@ -74,18 +74,22 @@ def _check_tree(vox, mesh):
     lo[T - 1:] = tris[:, :, :3].min(1)
     hi[T - 1:] = tris[:, :, :3].max(1)
     ref = np.where(is_leaf, idx + (T - 1), idx).astype(np.int64)
-    # process inner nodes in an order where children come first: depth via parent pointers
-    parents = vox.debug_read(L.DBG_PARENTS, np.uint32, 2 * T - 1)
-    node_parent = parents[: T - 1] & 0x7FFFFFFF
+    # process inner nodes in an order where children come first (BFS from the root, then reversed);
+    # every node also records the contiguous range of sorted leaves it covers
+    rng = nodes[:, 14:16].astype(np.int64)
     depth = np.zeros(T - 1, np.int64)
     order = [0]
-    for i in order:                      # BFS from the root
+    assert tuple(rng[0]) == (0, T - 1)
+    for i in order:
+        split = [int(idx[i, 0]), int(idx[i, 1])]
         for c in range(2):
             if not is_leaf[i, c]:
                 j = int(idx[i, c])
-                assert node_parent[j] == i
                 depth[j] = depth[i] + 1
                 order.append(j)
+                want_rng = (rng[i, 0], split[0]) if c == 0 else (split[1], rng[i, 1])
+                assert tuple(rng[j]) == tuple(want_rng)
+        assert split[1] == split[0] + 1 and rng[i, 0] <= split[0] < rng[i, 1]
     assert len(order) == T - 1
     for i in reversed(order):
         lo[i] = np.minimum(lo[ref[i, 0]], lo[ref[i, 1]])
