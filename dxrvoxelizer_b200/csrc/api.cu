@@ -57,7 +57,7 @@ struct dxrv_ctx
     uint32_t* gridTarget = nullptr; size_t gridTargetBytes = 0;
     uint32_t* texels = nullptr; size_t texCap = 0;
     uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
-    uint32_t* walkBuf = nullptr; size_t walkCap = 0;  // MODE_PARITY candidate lists
+    uint32_t* walkBuf = nullptr; size_t walkCap = 0, walkZeroed = 0;  // MODE_PARITY candidate lists + split-tile scratch
     uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
     bool haveGrid = false, haveTexels = false;
 
@@ -114,6 +114,7 @@ int checkDeviceError(dxrv_ctx* ctx)
     DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
     if (e == kErrNone) return DXRV_OK;
     cudaMemsetAsync(ctx->dErr, 0, sizeof(uint32_t), ctx->stream);
+    ctx->walkZeroed = 0;  // a kernel that bailed out may have left the split-tile scratch dirty
     if (e == kErrBadIndex) return fail(ctx, DXRV_ERR_INVALID_ARG, "index buffer references a vertex >= numVerts");
     return fail(ctx, DXRV_ERR_CUDA, "traversal stack overflow / corrupt hierarchy");
 }
@@ -345,11 +346,17 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     BvhView bvh{ctx->nodes, ctx->tris, ctx->dRootBox, ctx->mesh.numTris};
     if (algo == DXRV_MODE_PARITY)
     {
-        uint32_t numTiles = 0, candCap = 0;
-        parityTileCounts(N, slabBegin, slabEnd, numTiles, candCap);
-        const size_t walkBytes = sizeof(uint32_t) * ((size_t)((numTiles + 31u) & ~31u) + (size_t)numTiles * candCap);
+        const size_t walkBytes = sizeof(uint32_t) * parityScratchWords(N, slabBegin, slabEnd);
+        const size_t zeroBytes = sizeof(uint32_t) * parityScratchZeroWords(N);
+        uint32_t* before = ctx->walkBuf;
         cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->walkBuf), ctx->walkCap, walkBytes);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(walk lists)");
+        if (ctx->walkBuf != before || zeroBytes != ctx->walkZeroed)
+        {
+            // the split-tile scratch is self-cleaning; it only needs zeroing when (re)allocated or grown
+            DXRV_CUDA(cudaMemsetAsync(ctx->walkBuf, 0, zeroBytes, ctx->stream));
+            ctx->walkZeroed = zeroBytes;
+        }
         ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
                                                           ctx->dCrossings, ctx->dErr);
     }

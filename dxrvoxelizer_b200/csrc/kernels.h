@@ -62,9 +62,12 @@ struct BvhView
     uint32_t numTris;
 };
 // MODE_PARITY: +x column rays for layers z in [z0,z1); writes every word of the slab exactly once.
-// walkBuf: device scratch of (roundUp32(numTiles) + numTiles * candCap) uint32 (see parityTileCounts).
+// walkBuf: device scratch of parityScratchWords() uint32; its first parityScratchZeroWords() words
+// must be zero the first time it is used (the kernels leave them zero again).
 // Returns the number of kernels launched.
 void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, uint32_t& candCap);
+size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1);
+size_t parityScratchZeroWords(uint32_t N);
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1,
                            uint32_t* grid, uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr);
 

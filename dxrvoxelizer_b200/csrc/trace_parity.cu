@@ -115,6 +115,12 @@ struct ParityParams
     uint32_t numTiles;
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
+    uint32_t* bucketCount;   // [0] heavy entries, [1] light tiles, [2] empty tiles, [3] heavy slots, [4] extra parts
+    uint32_t* lightTiles;    // [numTiles]
+    uint32_t* emptyTiles;    // [numTiles]
+    uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}
+    uint32_t* heavyArrive;   // [kHeavySlots] parts of a split tile that have merged (self-resetting)
+    uint32_t* heavyScratch;  // [kHeavySlots][128 * Ps] merged toggle rows of split tiles (self-cleaning)
     uint32_t* candCount;     // [numTiles]  leaves found by k_walk_columns; > candCap = overflow
     uint32_t* candList;      // [numTiles][candCap]
     uint32_t candCap;
@@ -148,6 +154,37 @@ __device__ __forceinline__ void testNode(const BvhNode* __restrict__ nodes, uint
 }
 
 // ---- kernel A: one warp per super-tile walks the tree and lists the leaves it may cross ---------
+// The tile is then filed as "heavy", "light" or "empty".  The fill kernel takes its CTAs in that order,
+// and a heavy tile is SPLIT: several CTAs each rasterise a share of its candidate list and merge their
+// toggle rows through a scratch buffer with atomicXor (XOR commutes); the last one to arrive fills.
+// Real meshes leave most of the (y,z) plane empty and put hundreds of triangles into a few tiles
+// (surfaces seen edge-on): without the split those few CTAs are the kernel's critical path.
+constexpr uint32_t kHeavyTile = 192;    // candidates from which a tile is scheduled first
+constexpr uint32_t kSplitTile = 768;    // candidates from which a tile is split ...
+constexpr uint32_t kPartSize = 384;     // ... into parts of about this many candidates
+constexpr uint32_t kMaxParts = 12;
+constexpr uint32_t kHeavySlots = 1024;  // tiles that can be split per launch
+constexpr uint32_t kExtraParts = 2048;  // extra CTAs (beyond one per tile) a launch provides
+
+__device__ __forceinline__ void fileTile(const ParityParams& prm, uint32_t tile, uint32_t count)
+{
+    prm.candCount[tile] = count;
+    if (count == 0u) { prm.emptyTiles[atomicAdd(prm.bucketCount + 2, 1u)] = tile; return; }
+    if (count < kHeavyTile) { prm.lightTiles[atomicAdd(prm.bucketCount + 1, 1u)] = tile; return; }
+    uint32_t parts = 1u, slot = 0xffffu;
+    if (count <= prm.candCap)   // (an overflowed list is not split: that CTA walks the tree itself)
+    {
+        if (count >= kSplitTile) parts = min((count + kPartSize - 1u) / kPartSize, kMaxParts);
+        if (parts > 1u)
+        {
+            slot = atomicAdd(prm.bucketCount + 3, 1u);
+            if (slot >= kHeavySlots || atomicAdd(prm.bucketCount + 4, parts - 1u) + parts - 1u > kExtraParts) { parts = 1u; slot = 0xffffu; }
+        }
+    }
+    const uint32_t pos = atomicAdd(prm.bucketCount, parts);
+    for (uint32_t part = 0; part < parts; ++part) prm.heavyEntries[pos + part] = make_uint2(tile, part | (parts << 8) | (slot << 16));
+}
+
 template <int SY, int SZ>
 __global__ void __launch_bounds__(32 * kWalkWarps)
 k_walk_columns(const ParityParams prm)
@@ -159,7 +196,7 @@ k_walk_columns(const ParityParams prm)
     uint32_t* list = prm.candList + (size_t)tile * prm.candCap;
     if (prm.numTris <= 1)
     {
-        if (lane == 0) { prm.candCount[tile] = prm.numTris; if (prm.numTris) list[0] = 0; }
+        if (lane == 0) { if (prm.numTris) list[0] = 0; fileTile(prm, tile, prm.numTris); }
         return;
     }
     const uint32_t sy0 = (tile % prm.tilesY) * SY;
@@ -202,7 +239,7 @@ k_walk_columns(const ParityParams prm)
         count += nLf;
         __syncwarp();
     }
-    if (lane == 0) prm.candCount[tile] = count;
+    if (lane == 0) fileTile(prm, tile, count);
 }
 
 // ---- kernel B: W warps per CTA; the super-tile is SY x SZ columns with SY * SZ == 32 * W --------
@@ -227,7 +264,19 @@ k_trace_fill_columns(const ParityParams prm)
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
 
-    const uint32_t tile = blockIdx.x;
+    // CTAs take the work heavy parts first, then light tiles, then empty tiles (see fileTile)
+    __shared__ uint32_t sIsLast;
+    const uint32_t nHeavy = __ldg(prm.bucketCount), nLight = __ldg(prm.bucketCount + 1), nEmpty = __ldg(prm.bucketCount + 2);
+    const uint32_t bIdx = blockIdx.x;
+    if (bIdx >= nHeavy + nLight + nEmpty) return;
+    uint32_t tile, part = 0, parts = 1, hslot = 0xffffu;
+    if (bIdx < nHeavy)
+    {
+        const uint2 e = __ldg(prm.heavyEntries + bIdx);
+        tile = e.x; part = e.y & 0xffu; parts = (e.y >> 8) & 0xffu; hslot = e.y >> 16;
+    }
+    else if (bIdx < nHeavy + nLight) tile = __ldg(prm.lightTiles + (bIdx - nHeavy));
+    else tile = __ldg(prm.emptyTiles + (bIdx - nHeavy - nLight));
     const uint32_t sy0 = (tile % prm.tilesY) * SY;
     const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
     const uint32_t listed = __ldg(prm.candCount + tile);
@@ -326,12 +375,14 @@ k_trace_fill_columns(const ParityParams prm)
         {
             // ---- candidates were listed by k_walk_columns: dealt to the warps in chunks of C (small
             // chunks when there are few candidates, so that all W warps get some) ----
-            const uint32_t* list = prm.candList + (size_t)tile * prm.candCap;
+            const uint32_t partBegin = (uint32_t)(((uint64_t)listed * part) / parts);
+            const uint32_t mine = (uint32_t)(((uint64_t)listed * (part + 1u)) / parts) - partBegin;   // this CTA's share
+            const uint32_t* list = prm.candList + (size_t)tile * prm.candCap + partBegin;
             uint32_t C = 32u;
-            while (C > 4u && listed < C * (uint32_t)W * 2u) C >>= 1;
-            for (uint32_t first = warp * C; first < listed; first += (uint32_t)W * C)
+            while (C > 4u && mine < C * (uint32_t)W * 2u) C >>= 1;
+            for (uint32_t first = warp * C; first < mine; first += (uint32_t)W * C)
             {
-                const bool has = lane < C && first + lane < listed;
+                const bool has = lane < C && first + lane < mine;
                 processWarpChunk(has, has ? __ldg(list + first + lane) : 0u);
             }
         }
@@ -406,6 +457,37 @@ k_trace_fill_columns(const ParityParams prm)
             }
         }
         __syncthreads();
+
+        if (parts > 1u)
+        {
+            // ---- split tile: merge this part's toggles into the tile's scratch rows; the last part to
+            // arrive takes the merged rows back and carries on to the fill, the others are done ----
+            uint32_t* scratch = prm.heavyScratch + (size_t)hslot * kCols * Ps;
+            for (uint32_t i = tid; i < (uint32_t)kCols * Ps; i += kThreads)
+            {
+                const uint32_t v = rows[i];
+                if (v) atomicXor(scratch + i, v);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sIsLast = (atomicAdd(prm.heavyArrive + hslot, 1u) == parts - 1u) ? 1u : 0u;
+            __syncthreads();
+            if (!sIsLast)
+            {
+                for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
+                if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
+                return;
+            }
+            __threadfence();
+            for (uint32_t i = tid; i < (uint32_t)kCols * (Ps >> 2); i += kThreads)
+            {
+                uint4* src = reinterpret_cast<uint4*>(scratch) + i;
+                reinterpret_cast<uint4*>(rows)[i] = __ldcg(src);
+                *src = make_uint4(0, 0, 0, 0);          // leave the scratch clean for the next launch
+            }
+            if (tid == 0) prm.heavyArrive[hslot] = 0;
+            __syncthreads();
+        }
     }
 
     // ---- prefix-XOR along x and write-out, 4 words (128 bits) per lane ----
@@ -533,15 +615,34 @@ void launchVariant(cudaStream_t s, ParityParams prm)
         attrSet[dev] = true;
     }
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
-    k_trace_fill_columns<W, SY, SZ><<<prm.numTiles, 32 * W, smemBytes, s>>>(prm);
+    k_trace_fill_columns<W, SY, SZ><<<prm.numTiles + kExtraParts, 32 * W, smemBytes, s>>>(prm);
 }
 }  // namespace
 
+// super-tile shape: 16 x 8 columns, 4 warps per CTA (9 CTAs / SM at N = 1024).  Smaller tiles than the
+// obvious 16 x 16 spread the dense tiles of a real mesh over more SMs.
 void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, uint32_t& candCap)
 {
-    const uint32_t SY = 16, SZ = (N <= 2048) ? 16u : 8u;
+    const uint32_t SY = 16, SZ = 8;
     numTiles = ((N + SY - 1) / SY) * ((z1 - z0 + SZ - 1) / SZ);
-    candCap = 512;
+    candCap = 2048;
+}
+
+// words of device scratch launchTraceFillColumns needs (see the layout below); the region up to
+// parityScratchZeroWords() must be zero when first used (it is self-cleaning afterwards)
+size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
+{
+    uint32_t numTiles, candCap;
+    parityTileCounts(N, z0, z1, numTiles, candCap);
+    const size_t tilesPad = (numTiles + 31u) & ~31u;
+    const size_t Ps = sharedRowWords((N + 31) / 32);
+    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + 3 * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
+}
+
+size_t parityScratchZeroWords(uint32_t N)
+{
+    const size_t Ps = sharedRowWords((N + 31) / 32);
+    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * Ps;
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
@@ -557,13 +658,20 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     parityTileCounts(N, z0, z1, prm.numTiles, prm.candCap);
     prm.invNPow2 = ((N & (N - 1)) == 0) ? 1.0f / (float)N : 0.0f;
     prm.grid = grid;
-    prm.candCount = walkBuf;
-    prm.candList = walkBuf + ((prm.numTiles + 31u) & ~31u);
+    const size_t tilesPad = (prm.numTiles + 31u) & ~31u;
+    uint32_t* p = walkBuf;
+    prm.bucketCount = p;  p += 32;
+    prm.heavyArrive = p;  p += kHeavySlots;
+    prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * prm.Ps;      // 16-byte aligned: all sizes are multiples of 4 words
+    prm.lightTiles = p;   p += tilesPad;
+    prm.emptyTiles = p;   p += tilesPad;
+    prm.candCount = p;    p += tilesPad;
+    prm.heavyEntries = reinterpret_cast<uint2*>(p); p += 2 * (tilesPad + kExtraParts);
+    prm.candList = p;
     prm.crossings = dCrossings; prm.err = dErr;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
-    // 256 columns per CTA while the bit rows fit comfortably (N <= 2048: 64 KB), else 128
-    if (N <= 2048) launchVariant<8, 16, 16>(s, prm);
-    else launchVariant<4, 16, 8>(s, prm);
+    cudaMemsetAsync(prm.bucketCount, 0, 32 * sizeof(uint32_t), s);
+    launchVariant<4, 16, 8>(s, prm);
     return 2;
 }
 }  // namespace dxrv
