@@ -6,3 +6,4 @@ from ._lib import (MODE_PARITY, MODE_SHADER, FORMAT_BITS, FORMAT_R10G10B10A2, FO
                    LIB_PATH)
 from .voxelizer import Mesh, Voxelizer, load_obj, unpack_bits  # noqa: F401
 from .assets import asset_path  # noqa: F401
+from . import sharding  # noqa: F401,E402

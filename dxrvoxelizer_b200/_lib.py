@@ -14,6 +14,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_NO_BVH, ERR_NO_GRID, ERR_IO, ERR_OOM, ERR_UNSUPPO
 MODE_SHADER, MODE_PARITY, EMIT_TEXELS = 0, 1, 0x100
 FORMAT_BITS, FORMAT_U8, FORMAT_R10G10B10A2 = 0, 1, 2
 INFO_NUM_TRIANGLES, INFO_NUM_NODES, INFO_KERNEL_LAUNCHES, INFO_CROSSINGS, INFO_SM_COUNT = 0, 1, 2, 3, 4
+INFO_LAST_WALK_NS, INFO_LAST_FILL_NS = 5, 6
 DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_ROOT_BOX = 0, 1, 2, 3, 5
 
 _c = ctypes
@@ -35,6 +36,7 @@ SIGNATURES = {
     "dxrv_set_grid_target": (_int, [_vp, _vp, _sz]),
     "dxrv_count_inside": (_int, [_vp, _c.POINTER(_u64)]),
     "dxrv_get_info": (_int, [_vp, _u32, _c.POINTER(_u64)]),
+    "dxrv_set_profiling": (_int, [_vp, _int]),
     "dxrv_debug_read": (_int, [_vp, _u32, _vp, _sz]),
     "dxrv_debug_sort_pairs": (_int, [_vp, _vp, _vp, _u32]),
     "dxrv_obj_load": (_int, [_c.c_char_p, _c.POINTER(_vp)]),

@@ -62,6 +62,8 @@ struct dxrv_ctx
     bool haveGrid = false, haveTexels = false;
 
     cudaEvent_t copyDone = nullptr;
+    cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};  // MODE_PARITY kernel timing (dxrv_set_profiling)
+    bool profiling = false, profValid = false;
     uint64_t launches = 0;
 };
 
@@ -237,6 +239,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
                     ctx->pyramid, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
+    for (cudaEvent_t e : ctx->prof) if (e) cudaEventDestroy(e);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     cudaGetLastError();
     delete ctx;
@@ -250,6 +253,18 @@ int dxrv_set_stream(dxrv_ctx* ctx, void* cuda_stream)
     DeviceGuard g(ctx->device);
     DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->ownStream;
+    return DXRV_OK;
+}
+
+int dxrv_set_profiling(dxrv_ctx* ctx, int enable)
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    if (enable)
+        for (cudaEvent_t& e : ctx->prof)
+            if (!e) DXRV_CUDA(cudaEventCreate(&e));
+    ctx->profiling = enable != 0;
+    ctx->profValid = false;
     return DXRV_OK;
 }
 
@@ -358,7 +373,8 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
             ctx->walkZeroed = zeroBytes;
         }
         ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
-                                                          ctx->dCrossings, ctx->dErr);
+                                                          ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr);
+        ctx->profValid = ctx->profiling;
     }
     else
     {
@@ -445,6 +461,17 @@ int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value)
     case DXRV_INFO_NUM_NODES: *value = (ctx->haveBvh && ctx->mesh.numTris) ? 2ull * ctx->mesh.numTris - 1 : 0; return DXRV_OK;
     case DXRV_INFO_KERNEL_LAUNCHES: *value = ctx->launches; return DXRV_OK;
     case DXRV_INFO_SM_COUNT: *value = (uint64_t)ctx->smCount; return DXRV_OK;
+    case DXRV_INFO_LAST_WALK_NS:
+    case DXRV_INFO_LAST_FILL_NS:
+    {
+        if (!ctx->profValid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_get_info: enable dxrv_set_profiling and run a MODE_PARITY voxelize first");
+        DXRV_CUDA(cudaEventSynchronize(ctx->prof[2]));
+        float ms = 0.0f;
+        const int a = what == DXRV_INFO_LAST_WALK_NS ? 0 : 1;
+        DXRV_CUDA(cudaEventElapsedTime(&ms, ctx->prof[a], ctx->prof[a + 1]));
+        *value = (uint64_t)(ms * 1e6f + 0.5f);
+        return DXRV_OK;
+    }
     case DXRV_INFO_CROSSINGS:
     {
         unsigned long long c = 0;

@@ -69,7 +69,8 @@ void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, 
 size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1);
 size_t parityScratchZeroWords(uint32_t N);
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1,
-                           uint32_t* grid, uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr);
+                           uint32_t* grid, uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr,
+                           cudaEvent_t* ev /* nullable: {before walk, between, after fill} */);
 
 // ---- trace_shader.cu ----------------------------------------------------------------------------
 // MODE_SHADER: one radial closest-hit ray per voxel (DXRVoxelizer.hlsl raygenMain/closestHitMain).

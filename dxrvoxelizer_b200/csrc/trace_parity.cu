@@ -603,7 +603,7 @@ uint32_t sharedRowWords(uint32_t P)
 }
 
 template <int W, int SY, int SZ>
-void launchVariant(cudaStream_t s, ParityParams prm)
+void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 {
     const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + kStackCap + kCandCap);
     static bool attrSet[64] = {};
@@ -614,8 +614,11 @@ void launchVariant(cudaStream_t s, ParityParams prm)
         cudaFuncSetAttribute(k_trace_fill_columns<W, SY, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
         attrSet[dev] = true;
     }
+    if (ev) cudaEventRecord(ev[0], s);
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
+    if (ev) cudaEventRecord(ev[1], s);
     k_trace_fill_columns<W, SY, SZ><<<prm.numTiles + kExtraParts, 32 * W, smemBytes, s>>>(prm);
+    if (ev) cudaEventRecord(ev[2], s);
 }
 }  // namespace
 
@@ -646,7 +649,7 @@ size_t parityScratchZeroWords(uint32_t N)
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
-                           uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr)
+                           uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr, cudaEvent_t* ev)
 {
     ParityParams prm;
     prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
@@ -671,7 +674,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.crossings = dCrossings; prm.err = dErr;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
     cudaMemsetAsync(prm.bucketCount, 0, 32 * sizeof(uint32_t), s);
-    launchVariant<4, 16, 8>(s, prm);
+    launchVariant<4, 16, 8>(s, prm, ev);
     return 2;
 }
 }  // namespace dxrv

@@ -170,6 +170,9 @@ class Voxelizer:
         self._check(self._lib.dxrv_get_info(self._h, what, ctypes.byref(v)))
         return int(v.value)
 
+    def set_profiling(self, enable=True):
+        self._check(self._lib.dxrv_set_profiling(self._h, 1 if enable else 0))
+
     def set_stream(self, cuda_stream):
         self._check(self._lib.dxrv_set_stream(self._h, cuda_stream))
 

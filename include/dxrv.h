@@ -138,9 +138,13 @@ enum dxrv_info
     DXRV_INFO_NUM_NODES = 1,
     DXRV_INFO_KERNEL_LAUNCHES = 2, /* kernels launched by this context so far */
     DXRV_INFO_CROSSINGS = 3,       /* MODE_PARITY: surface crossings found by the last voxelize */
-    DXRV_INFO_SM_COUNT = 4
+    DXRV_INFO_SM_COUNT = 4,
+    DXRV_INFO_LAST_WALK_NS = 5,    /* device time of the last k_walk_columns (needs dxrv_set_profiling) */
+    DXRV_INFO_LAST_FILL_NS = 6     /* device time of the last k_trace_fill_columns                       */
 };
 DXRV_API int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value);
+/* Record CUDA events around the MODE_PARITY kernels of every dxrv_voxelize (for roofline reporting). */
+DXRV_API int dxrv_set_profiling(dxrv_ctx* ctx, int enable);
 
 /* Read back an internal device buffer for tests (synchronises).  `what`: */
 enum dxrv_debug_buffer
