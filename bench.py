@@ -98,6 +98,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun pins OMP_NUM_THREADS=1, so ask the OS instead)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def load_workload():
     import dxrvoxelizer_b200 as d
     return d.load_obj(d.asset_path("dragon.obj"))
@@ -115,16 +123,16 @@ def run_reference(args):
     mesh = load_workload()
     world = args.gpus
     N = grid_for(world)
-    threads = oracle.max_threads()
+    threads = host_threads()
     # bounded sample: the central z-slab one GPU owns (N/world layers ~ 1024^3 voxels; the whole grid
     # at N=1), ~0.5 s per step on 8 cores
     layers = max(1, N // world)
     z0 = (N - layers) // 2
     for _ in range(args.warmup):
-        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers)
+        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers)
+        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = layers * N * N / dt * 1e-9
     sample = "central z-slab of %d layers of the %d^3 dragon grid per step (MODE_PARITY, own yz-bin build included)" % (layers, N)
@@ -349,15 +357,15 @@ def ncu_traffic():
 def cpu_baseline(mesh, N, world):
     """The CPU oracle (a port of the reference's algorithm) on the box's host cores, bounded sample."""
     import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()
     layers = max(1, N // world)
     z0 = (N - layers) // 2
-    oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers)
+    oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
     best = 1e30
     t_all = time.perf_counter()
     for _ in range(3):
         t = time.perf_counter()
-        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers)
+        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
         best = min(best, time.perf_counter() - t)
         if time.perf_counter() - t_all > 25:
             break

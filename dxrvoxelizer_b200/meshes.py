@@ -35,7 +35,7 @@ def _displace(unit_dirs, seed, amplitude=0.15, waves=4):
     return r
 
 
-def icosphere(subdivisions, seed=1234, amplitude=0.15, rotate=False):
+def icosphere(subdivisions, seed=1234, amplitude=0.15, rotate=False, normals=True):
     """20 * 4**k triangles, 10 * 4**k + 2 vertices, outward winding, closed 2-manifold."""
     t = (1.0 + 5.0 ** 0.5) / 2.0
     v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
@@ -68,10 +68,10 @@ def icosphere(subdivisions, seed=1234, amplitude=0.15, rotate=False):
         pos = pos @ q.T
     pos = pos.astype(np.float32)
     tri = f.astype(np.uint32)
-    return Mesh.from_arrays(pos, tri, _vertex_normals(pos, tri))
+    return Mesh.from_arrays(pos, tri, _vertex_normals(pos, tri) if normals else None)
 
 
-def torus_knot(nu, nv, p=2, q=3, tube=0.18, seed=1234, amplitude=0.1):
+def torus_knot(nu, nv, p=2, q=3, tube=0.18, seed=1234, amplitude=0.1, normals=True):
     """Tube around a (p,q) torus knot: 2*nu*nv triangles, nu*nv vertices, closed 2-manifold."""
     u = np.linspace(0, 2 * np.pi, nu, endpoint=False)
     r = np.cos(q * u) + 2.0
@@ -94,7 +94,7 @@ def torus_knot(nu, nv, p=2, q=3, tube=0.18, seed=1234, amplitude=0.1):
     i1, j1 = (i + 1) % nu, (j + 1) % nv
     a, b, c2, d = i * nv + j, i1 * nv + j, i1 * nv + j1, i * nv + j1
     tri = np.concatenate([np.stack([a, c2, b], -1).reshape(-1, 3), np.stack([a, d, c2], -1).reshape(-1, 3)], 0).astype(np.uint32)
-    return Mesh.from_arrays(pos, tri, _vertex_normals(pos, tri))
+    return Mesh.from_arrays(pos, tri, _vertex_normals(pos, tri) if normals else None)
 
 
 def cube(half=0.75):
