@@ -92,13 +92,21 @@ __device__ __forceinline__ bool columnCrossing(const float4& a, const float4& b,
     if (det == 0.0f) return false;
     const float d = __fdiv_rn(weighted3(U, a.x, V, b.x, W, c.x), det);
 
-    // smallest x with centre(x) > d: estimate, then fix up with the exact predicate
-    float g = floorf((d + 1.0f) * 0.5f * fN + 0.5f);
+    // smallest x with centre(x) > d: estimate, then fix up with the exact predicate.  The estimate's
+    // error is far below 1/64 of a voxel for every supported N, so the (exact, but costlier) fix-up is
+    // only needed when d sits that close to a voxel centre.
+    const float gf = (d + 1.0f) * 0.5f * fN + 0.5f;
+    float g = floorf(gf);
+    const float fr = gf - g;
+    const bool nearCentre = !(fr > 0.015625f && fr < 0.984375f);   // also true for NaN / inf
     if (!(g > 0.0f)) g = 0.0f;
     if (g > fN) g = fN;
     uint32_t ix = (uint32_t)g;
-    while (ix > 0 && centreOf(ix - 1, fN, invNPow2) > d) --ix;
-    while (ix < N && !(centreOf(ix, fN, invNPow2) > d)) ++ix;
+    if (nearCentre)
+    {
+        while (ix > 0 && centreOf(ix - 1, fN, invNPow2) > d) --ix;
+        while (ix < N && !(centreOf(ix, fN, invNPow2) > d)) ++ix;
+    }
     ixOut = ix;
     return true;
 }
@@ -297,7 +305,7 @@ k_trace_fill_columns(const ParityParams prm)
         // triangle's (y,z) box, a warp scan turns the rectangle sizes into one flat list of
         // (triangle, column) pairs, and the pairs are dealt round-robin to the 32 lanes -- a triangle
         // that spans many columns no longer serialises on one thread while the CTA waits at the barrier.
-        auto processWarpChunk = [&](bool has, uint32_t slot) {
+        auto processWarpChunk = [&](bool has, uint32_t slot, uint32_t chunk) {
             int yA = 0, zA = 0, w = 0, h = 0;
             if (has)
             {
@@ -343,8 +351,8 @@ k_trace_fill_columns(const ParityParams prm)
                 // owner = the last lane whose exclusive offset is <= p (empty triangles share their offset
                 // with the next lane, so the last one is the one that really owns pair p)
                 uint32_t owner = 0;
-#pragma unroll
-                for (uint32_t step = 16; step > 0; step >>= 1)
+#pragma unroll 1
+                for (uint32_t step = chunk >> 1; step > 0; step >>= 1)   // triangles live in lanes [0, chunk)
                 {
                     const uint32_t e = __shfl_sync(0xffffffffu, excl, owner + step);
                     if (e <= p) owner += step;
@@ -383,7 +391,7 @@ k_trace_fill_columns(const ParityParams prm)
             for (uint32_t first = warp * C; first < mine; first += (uint32_t)W * C)
             {
                 const bool has = lane < C && first + lane < mine;
-                processWarpChunk(has, has ? __ldg(list + first + lane) : 0u);
+                processWarpChunk(has, has ? __ldg(list + first + lane) : 0u, C);
             }
         }
         else
@@ -408,7 +416,7 @@ k_trace_fill_columns(const ParityParams prm)
                 // 2*kThreads pushes of this iteration always fit the ring (kCandCap >= 3*kThreads)
                 while (produced - consumed >= (uint32_t)kThreads)
                 {
-                    processWarpChunk(true, cand[(consumed + tid) % kCandCap]);
+                    processWarpChunk(true, cand[(consumed + tid) % kCandCap], 32u);
                     consumed += kThreads;
                 }
                 const int room = kStackCap - kStackGuard - (int)sp;
@@ -453,7 +461,7 @@ k_trace_fill_columns(const ParityParams prm)
             for (uint32_t produced = sCand, i0 = consumed + warp * 32u; i0 < produced; i0 += kThreads)
             {
                 const bool has = i0 + lane < produced;
-                processWarpChunk(has, has ? cand[(i0 + lane) % kCandCap] : 0u);
+                processWarpChunk(has, has ? cand[(i0 + lane) % kCandCap] : 0u, 32u);
             }
         }
         __syncthreads();

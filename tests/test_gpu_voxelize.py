@@ -165,3 +165,52 @@ def test_shader_mode_slab_at_512_matches_oracle(vox, assets, oracle_mod):
         vox.voxelize(N, d.MODE_SHADER, z0, z0 + 2)
         ref = oracle_mod.voxelize(m.vertices, m.indices, N, oracle_mod.MODE_SHADER, z0=z0, z1=z0 + 2)
         assert popcount(vox.fetch_bits() ^ ref["bits"]) == 0
+
+
+def test_kernel_timing_api(vox, assets):
+    m = assets("bunny.obj")
+    vox.build_bvh(m)
+    with pytest.raises(d.DxrvError):
+        vox.info(L.INFO_LAST_FILL_NS)          # profiling not enabled yet
+    vox.set_profiling(True)
+    vox.voxelize(256, d.MODE_PARITY)
+    walk, fill = vox.info(L.INFO_LAST_WALK_NS), vox.info(L.INFO_LAST_FILL_NS)
+    vox.set_profiling(False)
+    assert 0 < walk < 50_000_000 and 0 < fill < 50_000_000
+
+
+def test_independent_contexts_and_streams(meshes_mod, oracle_mod):
+    """C5 shape: several contexts (one per stream) on one GPU, different meshes in flight at once."""
+    ctxs = [d.Voxelizer(0) for _ in range(4)]
+    ms = [meshes_mod.icosphere(4, seed=i, rotate=True) for i in range(8)]
+    N = 64
+    for round_ in range(2):
+        for i, c in enumerate(ctxs):
+            c.build_bvh(ms[round_ * 4 + i])
+            c.voxelize(N, d.MODE_PARITY)
+        for i, c in enumerate(ctxs):
+            m = ms[round_ * 4 + i]
+            assert popcount(c.fetch_bits() ^ oracle_mod.voxelize(m.vertices, m.indices, N, 1)["bits"]) == 0
+    for c in ctxs:
+        c.close()
+
+
+def test_large_synthetic_mesh_dense_tiles(vox, meshes_mod, oracle_mod):
+    """Build-dominated regime in miniature: 327k triangles at 128^3 puts thousands of candidates into
+    every super-tile (candidate-list overflow -> in-kernel walk) and at 512^3 exercises split tiles."""
+    m = meshes_mod.icosphere(7, seed=3, normals=False)
+    for N in (128, 512):
+        got = _run(vox, m, N, d.MODE_PARITY)
+        ref = oracle_mod.voxelize(m.vertices, m.indices, N, 1)
+        assert ref["odd_columns"] == 0
+        assert popcount(got ^ ref["bits"]) == 0
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"]
+
+
+def test_rebuild_is_deterministic(vox, assets):
+    m = assets("TuringBowl.obj")
+    a = _run(vox, m, 256, d.MODE_PARITY)
+    k1 = vox.debug_read(L.DBG_PRIM_SORTED, np.uint32, m.num_triangles)
+    b = _run(vox, m, 256, d.MODE_PARITY)
+    k2 = vox.debug_read(L.DBG_PRIM_SORTED, np.uint32, m.num_triangles)
+    assert np.array_equal(a, b) and np.array_equal(k1, k2)
