@@ -9,6 +9,8 @@
 #include <new>
 #include <string>
 #include <utility>
+#include <vector>
+#include <cstdlib>
 
 #include "../../include/dxrv.h"
 #include "kernels.h"
@@ -60,6 +62,13 @@ struct dxrv_ctx
     uint32_t* walkBuf = nullptr; size_t walkCap = 0, walkZeroed = 0;  // MODE_PARITY candidate lists + split-tile scratch
     uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
     bool haveGrid = false, haveTexels = false;
+
+    // CUDA graphs: the kernel sequence of a build / voxelize call is captured once per distinct
+    // parameter set and replayed afterwards (the per-launch gaps matter at 100 k triangles)
+    struct GraphEntry { std::vector<uint8_t> key; cudaGraphExec_t exec = nullptr; uint64_t launches = 0, lastUse = 0; };
+    std::vector<GraphEntry> graphs;
+    uint64_t graphClock = 0;
+    bool useGraphs = true;
 
     cudaEvent_t copyDone = nullptr;
     cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};  // MODE_PARITY kernel timing (dxrv_set_profiling)
@@ -121,6 +130,67 @@ int checkDeviceError(dxrv_ctx* ctx)
     return fail(ctx, DXRV_ERR_CUDA, "traversal stack overflow / corrupt hierarchy");
 }
 
+// Run `enqueue` (which only launches kernels / memsets on ctx->stream) through a cached CUDA graph.
+template <class F>
+int runCaptured(dxrv_ctx* ctx, const std::vector<uint8_t>& key, F&& enqueue)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (!ctx->useGraphs || ctx->profiling || cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone)
+    {
+        cudaGetLastError();
+        enqueue();
+        return DXRV_OK;
+    }
+    ++ctx->graphClock;
+    for (auto& g : ctx->graphs)
+        if (g.key == key)
+        {
+            g.lastUse = ctx->graphClock;
+            DXRV_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches += g.launches;
+            return DXRV_OK;
+        }
+    const uint64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok)
+    {
+        enqueue();
+        ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok)
+    {
+        // capture is an optimisation only: fall back to plain stream launches
+        cudaGetLastError();
+        ctx->launches = before;
+        ctx->useGraphs = false;
+        enqueue();
+        return DXRV_OK;
+    }
+    if (ctx->graphs.size() >= 8)
+    {
+        size_t victim = 0;
+        for (size_t i = 1; i < ctx->graphs.size(); ++i) if (ctx->graphs[i].lastUse < ctx->graphs[victim].lastUse) victim = i;
+        cudaGraphExecDestroy(ctx->graphs[victim].exec);
+        ctx->graphs.erase(ctx->graphs.begin() + victim);
+    }
+    dxrv_ctx::GraphEntry e;
+    e.key = key; e.exec = exec; e.launches = ctx->launches - before; e.lastUse = ctx->graphClock;
+    ctx->graphs.push_back(e);
+    DXRV_CUDA(cudaGraphLaunch(exec, ctx->stream));
+    return DXRV_OK;
+}
+
+template <class T>
+void keyPush(std::vector<uint8_t>& k, const T& v)
+{
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+    k.insert(k.end(), p, p + sizeof(T));
+}
+
 int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
 {
     const MeshView& m = ctx->mesh;
@@ -149,24 +219,40 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     }
 
     cudaStream_t s = ctx->stream;
-    if (bound) { launchSetBound(s, bound[0], bound[1], bound[2], bound[3], ctx->dBound); }
-    else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
-    ctx->launches += 1;
-    if (T > 0)
-    {
-        // small meshes: 8 bits per axis (24-bit keys, three radix passes); large: all 30 bits
-        const uint32_t keyShift = (T <= (1u << 18)) ? 6u : 0u;
-        const int numPasses = (T <= (1u << 18)) ? 3 : 4;
-        uint32_t* hist = sortClearTemp(s, ctx->sortTemp, T);
-        launchMorton(s, m, ctx->dBound, ctx->keysA, ctx->valsA, keyShift, numPasses, hist, ctx->dErr);
+    // small meshes: 8 bits per axis (24-bit keys, three radix passes); large: all 30 bits
+    const uint32_t keyShift = (T <= (1u << 18)) ? 6u : 0u;
+    const int numPasses = (T <= (1u << 18)) ? 3 : 4;
+    // with an odd number of passes start in the B buffers, so that the sorted result is always in A
+    // (a single triangle is not sorted at all: it stays where the Morton kernel wrote it)
+    const bool startInB = (numPasses & 1) && T >= 2;
+    uint32_t* k0 = startInB ? ctx->keysB : ctx->keysA;
+    uint32_t* v0 = startInB ? ctx->valsB : ctx->valsA;
+    uint32_t* k1 = startInB ? ctx->keysA : ctx->keysB;
+    uint32_t* v1 = startInB ? ctx->valsA : ctx->valsB;
+    const float bnd[4] = {bound ? bound[0] : 0.0f, bound ? bound[1] : 0.0f, bound ? bound[2] : 0.0f, bound ? bound[3] : 0.0f};
+    const bool haveBound = bound != nullptr;
+
+    std::vector<uint8_t> key;
+    keyPush(key, (uint32_t)0xB01Du);
+    keyPush(key, m.verts); keyPush(key, m.numVerts); keyPush(key, m.stride); keyPush(key, m.indices); keyPush(key, m.numTris);
+    keyPush(key, (uint32_t)haveBound); keyPush(key, bnd);
+    keyPush(key, ctx->keysA); keyPush(key, ctx->keysB); keyPush(key, ctx->valsA); keyPush(key, ctx->valsB);
+    keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp);
+    const int rc = runCaptured(ctx, key, [&]() {
+        if (haveBound) { launchSetBound(s, bnd[0], bnd[1], bnd[2], bnd[3], ctx->dBound); }
+        else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
         ctx->launches += 1;
-        bool inB = false;
-        ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, T,
-                                                  numPasses, true, &inB);
-        if (inB) { std::swap(ctx->keysA, ctx->keysB); std::swap(ctx->valsA, ctx->valsB); }
-        ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
-                                                            ctx->pyramid, ctx->dRootBox, ctx->dErr);
-    }
+        if (T > 0)
+        {
+            uint32_t* hist = sortClearTemp(s, ctx->sortTemp, T);
+            launchMorton(s, m, ctx->dBound, k0, v0, keyShift, numPasses, hist, ctx->dErr);
+            ctx->launches += 1;
+            ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, k0, v0, k1, v1, T, numPasses, true, nullptr);
+            ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
+                                                                ctx->pyramid, ctx->dRootBox, ctx->dErr);
+        }
+    });
+    if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
     ctx->haveBvh = true;
     return DXRV_OK;
@@ -212,6 +298,7 @@ int dxrv_create(dxrv_ctx** out, int cuda_device)
         return fail(nullptr, DXRV_ERR_UNSUPPORTED, "dxrv_create: kernels are built for sm_100a (Blackwell) only");
     }
     ctx->smCount = prop.multiProcessorCount;
+    if (const char* ng = std::getenv("DXRV_NO_GRAPHS")) ctx->useGraphs = !(ng[0] && ng[0] != '0');
     if ((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
     ctx->stream = ctx->ownStream;
     if ((e = cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaEventCreate"); }
@@ -238,6 +325,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
                     ctx->pyramid, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     for (cudaEvent_t e : ctx->prof) if (e) cudaEventDestroy(e);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -368,19 +456,31 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(walk lists)");
         if (ctx->walkBuf != before || zeroBytes != ctx->walkZeroed)
         {
-            // the split-tile scratch is self-cleaning; it only needs zeroing when (re)allocated or grown
+            // the split-tile scratch is self-cleaning; it only needs zeroing when (re)allocated or resized
             DXRV_CUDA(cudaMemsetAsync(ctx->walkBuf, 0, zeroBytes, ctx->stream));
             ctx->walkZeroed = zeroBytes;
         }
-        ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
-                                                          ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr);
-        ctx->profValid = ctx->profiling;
     }
-    else
-    {
-        launchTraceShader(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr);
-        ctx->launches += 1;
-    }
+    std::vector<uint8_t> key;
+    keyPush(key, (uint32_t)0x70C5u);
+    keyPush(key, N); keyPush(key, mode); keyPush(key, slabBegin); keyPush(key, slabEnd);
+    keyPush(key, grid); keyPush(key, texels); keyPush(key, ctx->walkBuf);
+    keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
+    keyPush(key, ctx->mesh.verts); keyPush(key, ctx->mesh.numVerts); keyPush(key, ctx->mesh.stride); keyPush(key, ctx->mesh.indices); keyPush(key, ctx->mesh.numTris);
+    const int rc = runCaptured(ctx, key, [&]() {
+        if (algo == DXRV_MODE_PARITY)
+        {
+            ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
+                                                              ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr);
+            ctx->profValid = ctx->profiling;
+        }
+        else
+        {
+            launchTraceShader(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr);
+            ctx->launches += 1;
+        }
+    });
+    if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels;
