@@ -6,7 +6,7 @@ A step = one pass of the hot path over one mesh: LBVH build (bounds, Morton, one
 hierarchy, refit) + MODE_PARITY trace/fill of the bit-packed grid.  Workload: the reference's
 Stanford dragon (Bin/Assets/dragon.obj via Dragon.bat) at 1024^3 voxels PER GPU:
   N=1      1024^3 grid, one GPU does all of it (BASELINE configs[2] at one GPU).
-  N=2,4,8  z-slab sharding, weak scaling: the grid grows to 1280^3 / 1632^3 / 2048^3 so every rank
+  N=2,4,8  z-slab sharding, weak scaling: the grid grows to 1280^3 / 1664^3 / 2048^3 so every rank
            still fills ~1024^3 voxels (its own z-slab); the mesh/BVH is replicated, no data-path
            collective in the timed region.  ("zslab_1024" in the JSON additionally reports the
            strong-scaling number: ONE 1024^3 grid split into N slabs.)
@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "gvoxels_per_s_incl_bvh_build"
 UNIT = "Gvoxel/s"
-GRID_FOR_GPUS = {1: 1024, 2: 1280, 4: 1632, 8: 2048}   # ~1024^3 voxels per GPU
+GRID_FOR_GPUS = {1: 1024, 2: 1280, 4: 1664, 8: 2048}   # ~1024^3 voxels per GPU
 
 
 def grid_for(n_gpus):

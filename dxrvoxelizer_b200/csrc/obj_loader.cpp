@@ -3,10 +3,12 @@
 #include "obj_loader.h"
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace dxrv
 {
@@ -268,9 +270,26 @@ void ObjMesh::bound(float out[4]) const
     out[3] = std::max(ex, std::max(ey, ez)) / 2.0f;
 }
 
+// shared tail of both parsers: validation + the order-dependent post-import steps
+static bool finishMesh(ObjMesh& m, const std::vector<float>& normals, const std::vector<uint32_t>& nrmIdx, bool fileHasNormals,
+                       std::string& err)
+{
+    // Out-of-range references would be out-of-bounds reads in the reference; reject instead.
+    const uint32_t numVert = m.numVertices();
+    for (uint32_t i : m.indices)
+        if (i >= numVert) { err = "OBJ face references a vertex that does not exist"; return false; }
+    for (uint32_t i : nrmIdx)
+        if (3 * static_cast<size_t>(i) + 2 >= normals.size()) { err = "OBJ face references a normal that does not exist"; return false; }
+
+    assignFileNormals(m, normals, nrmIdx);
+    std::reverse(m.indices.begin(), m.indices.end());
+    if (!fileHasNormals) faceNormals(m);
+    boundingBox(m);
+    return true;
+}
+
 bool parseObj(const char* text, size_t size, ObjMesh& m, std::string& err)
 {
-    (void)err;
     const Counts k = countRecords(text, size);
 
     m = ObjMesh();
@@ -309,19 +328,242 @@ bool parseObj(const char* text, size_t size, ObjMesh& m, std::string& err)
         }
         else c.restOfLine();
     }
+    return finishMesh(m, normals, nrmIdx, k.normals != 0, err);
+}
 
-    // Out-of-range references would be out-of-bounds reads in the reference; reject instead.
-    const uint32_t numVert = m.numVertices();
-    for (uint32_t i : m.indices)
-        if (i >= numVert) { err = "OBJ face references a vertex that does not exist"; return false; }
-    for (uint32_t i : nrmIdx)
-        if (3 * static_cast<size_t>(i) + 2 >= normals.size()) { err = "OBJ face references a normal that does not exist"; return false; }
+// ---- fast path ---------------------------------------------------------------------------------------
+// Multi-threaded parser for WELL-FORMED files (one record per line; `v x y z`, `vn x y z`, `vt ...`,
+// `f` with >= 3 corners whose syntax matches the file: v, v/vt, v//vn or v/vt/vn; plain decimal
+// numbers; no line longer than 255 characters).  For such files the reference's fscanf grammar reduces
+// to per-line parsing, so the text is cut at newlines and the chunks are parsed concurrently with
+// std::from_chars (correctly rounded, like fscanf's %f).  Anything else -- a face continued on the
+// next line, `vp` records, hexadecimal floats, ... -- makes it return false WITHOUT an error, and the
+// caller falls back to parseObj, which follows the reference's grammar token by token.
+namespace
+{
+struct Chunk
+{
+    const char* begin; const char* end;
+    Counts counts;
+    bool odd = false;
+};
 
-    assignFileNormals(m, normals, nrmIdx);
-    std::reverse(m.indices.begin(), m.indices.end());
-    if (!k.normals) faceNormals(m);
-    boundingBox(m);
+inline bool isBlank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+inline bool fastReal(const char*& p, const char* end, float& out)
+{
+    while (p < end && isBlank(*p)) ++p;
+    const char* q = p;
+    if (q < end && *q == '+') ++q;
+    const char* d = q;
+    if (d < end && *d == '-') ++d;
+    if (d >= end || !((*d >= '0' && *d <= '9') || *d == '.')) return false;   // inf / nan / hex: not here
+    auto r = std::from_chars(q, end, out);
+    if (r.ec != std::errc() || r.ptr == q) return false;
+    if (r.ptr < end && !isBlank(*r.ptr)) return false;                          // e.g. 0x10, 1.5f
+    p = r.ptr;
     return true;
+}
+
+inline bool fastInt(const char*& p, const char* end, long long& out)
+{
+    const char* q = p;
+    bool neg = false;
+    if (q < end && (*q == '-' || *q == '+')) neg = (*q++ == '-');
+    if (q >= end || *q < '0' || *q > '9') return false;
+    long long v = 0;
+    while (q < end && *q >= '0' && *q <= '9') v = v * 10 + (*q++ - '0');
+    out = neg ? -v : v;
+    p = q;
+    return true;
+}
+
+// One pass over a chunk.  kStore = false: count records and detect anything unusual.
+template <bool kStore>
+void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8_t* vb, uint32_t stride, float* normals,
+               uint32_t* indices, uint32_t* nrmIdx, Counts base)
+{
+    const char* p = ch.begin;
+    Counts k;
+    while (p < ch.end)
+    {
+        const char* eol = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(ch.end - p)));
+        if (!eol) eol = ch.end;
+        if (eol - p > 255) { ch.odd = true; return; }
+        const char* q = p;
+        while (q < eol && isBlank(*q)) ++q;
+        const char* tok = q;
+        while (q < eol && !isBlank(*q)) ++q;
+        const size_t len = static_cast<size_t>(q - tok);
+        if (len == 0) { p = eol + 1; continue; }
+        const char c0 = tok[0];
+        if (c0 == 'v')
+        {
+            if (len == 1 || (len == 2 && tok[1] == 'n'))
+            {
+                float v[3];
+                if (!(fastReal(q, eol, v[0]) && fastReal(q, eol, v[1]) && fastReal(q, eol, v[2]))) { ch.odd = true; return; }
+                // whatever follows on the line (vertex colours, w) must not look like a record
+                while (q < eol && isBlank(*q)) ++q;
+                if (q < eol && (*q == 'f' || *q == 'v')) { ch.odd = true; return; }
+                if (len == 1)
+                {
+                    if (kStore)
+                    {
+                        float* dst = reinterpret_cast<float*>(vb + static_cast<size_t>(stride) * (base.positions + k.positions));
+                        dst[0] = v[0]; dst[1] = v[1]; dst[2] = -v[2];
+                    }
+                    ++k.positions;
+                }
+                else
+                {
+                    if (kStore)
+                    {
+                        float* dst = normals + 3 * static_cast<size_t>(base.normals + k.normals);
+                        dst[0] = v[0]; dst[1] = v[1]; dst[2] = -v[2];
+                    }
+                    ++k.normals;
+                }
+            }
+            else if (len == 2 && tok[1] == 't')
+            {
+                // the reference skips the record token by token; a sane vt line is numbers only
+                while (q < eol && isBlank(*q)) ++q;
+                if (q >= eol || !((*q >= '0' && *q <= '9') || *q == '-' || *q == '+' || *q == '.')) { ch.odd = true; return; }
+                ++k.texcoords;
+            }
+            else { ch.odd = true; return; }
+        }
+        else if (c0 == 'f')
+        {
+            if (len != 1) { ch.odd = true; return; }
+            uint32_t v0 = 0, n0 = 0, vPrev = 0, nPrev = 0, corners = 0;
+            while (true)
+            {
+                while (q < eol && isBlank(*q)) ++q;
+                if (q >= eol) break;
+                long long vi = 0, ti = 0, ni = 0;
+                if (!fastInt(q, eol, vi)) { ch.odd = true; return; }
+                if (hasTexc)
+                {
+                    if (q >= eol || *q != '/') { ch.odd = true; return; }
+                    ++q;
+                    if (hasNorm && q < eol && *q == '/') { ch.odd = true; return; }   // "v//vn" in a file with vt: stale-value semantics
+                    if (!fastInt(q, eol, ti)) { ch.odd = true; return; }
+                }
+                if (hasNorm)
+                {
+                    if (q >= eol || *q != '/') { ch.odd = true; return; }
+                    ++q;
+                    if (!hasTexc) { if (q >= eol || *q != '/') { ch.odd = true; return; } ++q; }
+                    if (!fastInt(q, eol, ni)) { ch.odd = true; return; }
+                }
+                if (q < eol && !isBlank(*q)) { ch.odd = true; return; }
+                const uint32_t v = CornerReader::resolve(vi, total.positions);
+                const uint32_t n = hasNorm ? CornerReader::resolve(ni, total.normals) : 0u;
+                ++corners;
+                if (corners == 1) { v0 = v; n0 = n; }
+                else if (corners >= 3)
+                {
+                    if (kStore)
+                    {
+                        const size_t t = 3 * static_cast<size_t>(base.triangles + k.triangles);
+                        indices[t] = v0; indices[t + 1] = vPrev; indices[t + 2] = v;
+                        if (hasNorm) { nrmIdx[t] = n0; nrmIdx[t + 1] = nPrev; nrmIdx[t + 2] = n; }
+                    }
+                    ++k.triangles;
+                }
+                vPrev = v; nPrev = n;
+            }
+            if (corners < 3) { ch.odd = true; return; }
+        }
+        else if ((c0 >= '0' && c0 <= '9') || c0 == '-' || c0 == '+')
+        {
+            ch.odd = true; return;   // could be the continuation of a face on the previous line
+        }
+        p = eol + 1;
+    }
+    ch.counts = k;
+}
+}  // namespace
+
+bool parseObjFast(const char* text, size_t size, ObjMesh& m, std::string& err, unsigned threads)
+{
+    if (threads == 0) threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t minChunk = 1u << 16;
+    size_t numChunks = std::max<size_t>(1, std::min<size_t>(threads, size / minChunk));
+    std::vector<Chunk> chunks(numChunks);
+    const char* cursor = text;
+    for (size_t i = 0; i < numChunks; ++i)
+    {
+        const char* target = (i + 1 == numChunks) ? text + size : text + size * (i + 1) / numChunks;
+        if (target < cursor) target = cursor;
+        if (i + 1 < numChunks)
+        {
+            const char* nl = static_cast<const char*>(std::memchr(target, '\n', static_cast<size_t>(text + size - target)));
+            target = nl ? nl + 1 : text + size;
+        }
+        chunks[i].begin = cursor; chunks[i].end = target;
+        cursor = target;
+    }
+
+    auto parallelFor = [&](auto&& body) {
+        std::vector<std::thread> pool;
+        for (size_t i = 1; i < numChunks; ++i) pool.emplace_back([&, i]() { body(i); });
+        body(0);
+        for (auto& t : pool) t.join();
+    };
+
+    // pass A: counts + well-formedness (corner syntax is checked with "has everything" semantics off: it needs
+    // the file-level flags, so it is checked in pass B)
+    Counts dummy;
+    parallelFor([&](size_t i) { scanChunk<false>(chunks[i], false, false, dummy, nullptr, 0, nullptr, nullptr, nullptr, Counts()); });
+    // pass A parsed corners as bare integers; files with '/' need the flags first: recount with them
+    Counts total;
+    bool sawOdd = false;
+    for (auto& ch : chunks) sawOdd |= ch.odd;
+    if (sawOdd)
+    {
+        // maybe only because corners carry '/' parts: count v/vt/vn cheaply, then redo pass A with the flags
+        Counts recs;
+        for (const char* p = text; p < text + size;)
+        {
+            const char* eol = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(text + size - p)));
+            if (!eol) eol = text + size;
+            const char* q = p;
+            while (q < eol && isBlank(*q)) ++q;
+            if (q + 1 < eol && q[0] == 'v' && q[1] == 't' && (q + 2 == eol || isBlank(q[2]))) ++recs.texcoords;
+            else if (q + 1 < eol && q[0] == 'v' && q[1] == 'n' && (q + 2 == eol || isBlank(q[2]))) ++recs.normals;
+            p = eol + 1;
+        }
+        if (!recs.texcoords && !recs.normals) return false;
+        for (auto& ch : chunks) { ch.odd = false; ch.counts = Counts(); }
+        parallelFor([&](size_t i) { scanChunk<false>(chunks[i], recs.texcoords != 0, recs.normals != 0, dummy, nullptr, 0, nullptr, nullptr, nullptr, Counts()); });
+        for (auto& ch : chunks) if (ch.odd) return false;
+    }
+    std::vector<Counts> base(numChunks);
+    for (size_t i = 0; i < numChunks; ++i)
+    {
+        base[i] = total;
+        total.positions += chunks[i].counts.positions; total.texcoords += chunks[i].counts.texcoords;
+        total.normals += chunks[i].counts.normals; total.triangles += chunks[i].counts.triangles;
+    }
+    const bool hasTexc = total.texcoords != 0, hasNorm = total.normals != 0;
+
+    m = ObjMesh();
+    m.stride = 24 + (hasTexc ? 8 : 0);
+    m.vertices.assign(static_cast<size_t>(m.stride) * total.positions, 0);
+    m.indices.assign(3 * static_cast<size_t>(total.triangles), 0);
+    std::vector<float> normals(3 * static_cast<size_t>(total.normals));
+    std::vector<uint32_t> nrmIdx(hasNorm ? 3 * static_cast<size_t>(total.triangles) : 0);
+
+    // pass B: parse and store at the chunk's offsets
+    parallelFor([&](size_t i) {
+        scanChunk<true>(chunks[i], hasTexc, hasNorm, total, m.vertices.data(), m.stride, normals.data(), m.indices.data(),
+                        nrmIdx.data(), base[i]);
+    });
+    for (auto& ch : chunks) if (ch.odd) return false;
+    return finishMesh(m, normals, nrmIdx, hasNorm, err);
 }
 
 bool loadObj(const char* path, ObjMesh& mesh, std::string& err)
@@ -333,6 +575,10 @@ bool loadObj(const char* path, ObjMesh& mesh, std::string& err)
     size_t n;
     while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
     std::fclose(f);
+    // well-formed files take the multi-threaded parser; anything unusual is parsed exactly like the reference does
+    std::string fastErr;
+    if (parseObjFast(text.c_str(), text.size(), mesh, fastErr, 0)) return true;
+    if (!fastErr.empty()) { err = fastErr; return false; }
     return parseObj(text.c_str(), text.size(), mesh, err);
 }
 }  // namespace dxrv

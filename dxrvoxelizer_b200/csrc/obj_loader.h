@@ -39,6 +39,9 @@ struct ObjMesh
 // Returns false (and fills err) when the file cannot be read -- the reference returns false
 // from Import when fopen fails (XUSGObjLoader.cpp:21-23).
 bool loadObj(const char* path, ObjMesh& mesh, std::string& err);
-// Same, from a memory buffer holding the OBJ text.
+// Same, from a memory buffer holding the OBJ text (follows the reference's fscanf grammar token by token).
 bool parseObj(const char* text, size_t size, ObjMesh& mesh, std::string& err);
+// Multi-threaded parser for well-formed files; returns false with an empty `err` when the text needs the
+// exact grammar of parseObj instead (loadObj falls back automatically).  threads = 0: one per core, <= 16.
+bool parseObjFast(const char* text, size_t size, ObjMesh& mesh, std::string& err, unsigned threads);
 }  // namespace dxrv

@@ -13,7 +13,7 @@ from dxrvoxelizer_b200.sharding import slab_range, slab_words
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("N", [1, 7, 64, 100, 1024, 1632])
+@pytest.mark.parametrize("N", [1, 7, 64, 100, 1024, 1664])
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_slabs_partition_the_grid(N, world):
     ranges = [slab_range(r, world, N) for r in range(world)]
