@@ -451,10 +451,11 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     {
         const size_t walkBytes = sizeof(uint32_t) * parityScratchWords(N, slabBegin, slabEnd);
         const size_t zeroBytes = sizeof(uint32_t) * parityScratchZeroWords(N);
-        uint32_t* before = ctx->walkBuf;
+        // (a re-allocation may hand back the very same address, so compare capacities, not pointers)
+        const bool reallocated = !ctx->walkBuf || walkBytes > ctx->walkCap;
         cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->walkBuf), ctx->walkCap, walkBytes);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(walk lists)");
-        if (ctx->walkBuf != before || zeroBytes != ctx->walkZeroed)
+        if (reallocated || zeroBytes != ctx->walkZeroed)
         {
             // the split-tile scratch is self-cleaning; it only needs zeroing when (re)allocated or resized
             DXRV_CUDA(cudaMemsetAsync(ctx->walkBuf, 0, zeroBytes, ctx->stream));
