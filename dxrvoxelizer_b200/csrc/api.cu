@@ -59,6 +59,8 @@ struct dxrv_ctx
     uint32_t* gridTarget = nullptr; size_t gridTargetBytes = 0;
     uint32_t* texels = nullptr; size_t texCap = 0;
     uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
+    uint32_t* mips = nullptr; size_t mipCap = 0;      // occupancy pyramid levels 1.. (concatenated)
+    uint32_t mipLevels = 0;                            // levels incl. level 0; 0 = not built for the current grid
     uint32_t* walkBuf = nullptr; size_t walkCap = 0, walkZeroed = 0;  // MODE_PARITY candidate lists + split-tile scratch
     uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
     bool haveGrid = false, haveTexels = false;
@@ -323,7 +325,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
-                    ctx->pyramid, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf};
+                    ctx->pyramid, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -484,7 +486,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
-    ctx->haveGrid = true; ctx->haveTexels = wantTexels;
+    ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
     return DXRV_OK;
 }
 
@@ -535,6 +537,57 @@ int dxrv_set_grid_target(dxrv_ctx* ctx, void* d_ptr, size_t bytes)
     ctx->gridTargetBytes = d_ptr ? bytes : 0;
     ctx->haveGrid = false;
     return DXRV_OK;
+}
+
+static size_t mipWords(uint32_t N, uint32_t layers, uint32_t level)
+{
+    const uint32_t n = N >> level, l = layers >> level;
+    return (size_t)l * n * ((n + 31) / 32);
+}
+
+int dxrv_build_mips(dxrv_ctx* ctx, uint32_t* numLevels)
+{
+    if (!ctx || !numLevels) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_build_mips: call dxrv_voxelize first");
+    DeviceGuard g(ctx->device);
+    const uint32_t layers = ctx->z1 - ctx->z0;
+    uint32_t levels = 1;
+    size_t words = 0;
+    while (((ctx->N >> (levels - 1)) & 1u) == 0u && ((layers >> (levels - 1)) & 1u) == 0u && (ctx->N >> levels) >= 1u && (layers >> levels) >= 1u)
+    {
+        words += mipWords(ctx->N, layers, levels);
+        ++levels;
+    }
+    cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->mips), ctx->mipCap, words * sizeof(uint32_t));
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(mips)");
+    const uint32_t* src = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
+    uint32_t* dst = ctx->mips;
+    for (uint32_t l = 1; l < levels; ++l)
+    {
+        launchMipReduce(ctx->stream, src, ctx->N >> (l - 1), layers >> (l - 1), dst);
+        ctx->launches += 1;
+        src = dst;
+        dst += mipWords(ctx->N, layers, l);
+    }
+    DXRV_CUDA(cudaGetLastError());
+    ctx->mipLevels = levels;
+    *numLevels = levels;
+    return DXRV_OK;
+}
+
+int dxrv_fetch_mip(dxrv_ctx* ctx, uint32_t level, void* hostDst, size_t bytes)
+{
+    if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveGrid || ctx->mipLevels == 0) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_fetch_mip: call dxrv_build_mips first");
+    if (level < 1 || level >= ctx->mipLevels) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_mip: no such level (level 0 is dxrv_fetch_grid)");
+    DeviceGuard g(ctx->device);
+    const uint32_t layers = ctx->z1 - ctx->z0;
+    const uint32_t* src = ctx->mips;
+    for (uint32_t l = 1; l < level; ++l) src += mipWords(ctx->N, layers, l);
+    const size_t need = mipWords(ctx->N, layers, level) * sizeof(uint32_t);
+    if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_mip: bytes does not match the level size");
+    DXRV_CUDA(cudaMemcpyAsync(hostDst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    return checkDeviceError(ctx);
 }
 
 int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count)

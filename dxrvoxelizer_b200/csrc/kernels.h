@@ -80,5 +80,7 @@ void launchTraceShader(cudaStream_t s, const BvhView& bvh, const MeshView& m, ui
 
 // ---- misc (lbvh.cu) -----------------------------------------------------------------------------
 void launchPopcount(cudaStream_t s, const uint32_t* words, size_t numWords, unsigned long long* dCount);
+// dst = next level of the occupancy pyramid of src (Ns^2 x layersSrc voxels; Ns and layersSrc even)
+void launchMipReduce(cudaStream_t s, const uint32_t* src, uint32_t Ns, uint32_t layersSrc, uint32_t* dst);
 void launchBitsToU8(cudaStream_t s, const uint32_t* words, uint32_t N, uint32_t layers, uint8_t* out);
 }  // namespace dxrv

@@ -455,6 +455,43 @@ k_popcount(const uint32_t* __restrict__ words, size_t numWords, unsigned long lo
     if (laneId() == 0 && c) atomicAdd(total, c);
 }
 
+// One level of the occupancy pyramid: a voxel of the coarser level is set when any of its 2x2x2
+// children is (conservative: safe for empty-space skipping).  One thread per destination word:
+// 64 source voxels along x (two words) of 2 rows and 2 layers are OR-ed and pair-compacted.
+__device__ __forceinline__ uint32_t compactPairs(uint32_t x)
+{
+    x = (x | (x >> 1)) & 0x55555555u;          // OR of each bit pair, kept in the even bit
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+k_mip_reduce(const uint32_t* __restrict__ src, uint32_t Ns, uint32_t Ps, uint32_t* __restrict__ dst, uint32_t Nd,
+             uint32_t Pd, uint32_t layersDst)
+{
+    const size_t total = (size_t)layersDst * Nd * Pd;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const uint32_t w = (uint32_t)(i % Pd);
+        const size_t row = i / Pd;
+        const uint32_t y = (uint32_t)(row % Nd), z = (uint32_t)(row / Nd);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (uint32_t dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (uint32_t dy = 0; dy < 2; ++dy)
+            {
+                const uint32_t* r = src + ((size_t)(2 * z + dz) * Ns + (2 * y + dy)) * Ps;
+                if (2 * w < Ps) lo |= __ldg(r + 2 * w);
+                if (2 * w + 1 < Ps) hi |= __ldg(r + 2 * w + 1);
+            }
+        dst[i] = compactPairs(lo) | (compactPairs(hi) << 16);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_bits_to_u8(const uint32_t* __restrict__ words, uint32_t N, uint32_t P, size_t numVoxels, uint8_t* __restrict__ out)
 {
@@ -539,6 +576,16 @@ void launchPopcount(cudaStream_t s, const uint32_t* words, size_t numWords, unsi
     size_t blocks = (numWords + 256 * 8 - 1) / (256 * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_popcount<<<(unsigned)blocks, 256, 0, s>>>(words, numWords, dCount);
+}
+
+void launchMipReduce(cudaStream_t s, const uint32_t* src, uint32_t Ns, uint32_t layersSrc, uint32_t* dst)
+{
+    const uint32_t Nd = Ns / 2, layersDst = layersSrc / 2;
+    const size_t total = (size_t)layersDst * Nd * ((Nd + 31) / 32);
+    if (!total) return;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_mip_reduce<<<(unsigned)blocks, 256, 0, s>>>(src, Ns, (Ns + 31) / 32, dst, Nd, (Nd + 31) / 32, layersDst);
 }
 
 void launchBitsToU8(cudaStream_t s, const uint32_t* words, uint32_t N, uint32_t layers, uint8_t* out)

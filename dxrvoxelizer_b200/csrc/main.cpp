@@ -4,7 +4,7 @@
 // start with '-' only when a digit or '.' follows; defaults Assets/bunny.obj and posScale (0,0,0,1)
 // (DXRVoxelizer.cpp:36-37).  -warp / -uma select D3D adapters in the reference and are accepted and
 // ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity, -device k,
-// -slab z0 z1, -frames n, -out file.bin (raw DXRV_FORMAT_BITS words).
+// -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -35,7 +35,7 @@ struct Args
     // would swallow absolute paths, so '/' only introduces an option when a known name follows.
     static bool knownOption(const char* name)
     {
-        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode"};
+        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus"};
         for (const char* n : names) if (lower(name) == n) return true;
         return false;
     }
@@ -54,7 +54,7 @@ int main(int argc, char** argv)
     std::string mesh = "Assets/bunny.obj", out;
     float posScale[4] = {0.0f, 0.0f, 0.0f, 1.0f};
     uint32_t grid = 64, slab0 = 0, slab1 = 0;
-    int device = 0, frames = 1;
+    int device = 0, frames = 1, gpus = 1;
     DXRVoxelizer::Mode mode = DXRVoxelizer::MODE_PARITY;
 
     Args a{argc, argv};
@@ -70,6 +70,7 @@ int main(int argc, char** argv)
         else if (a.matches(i, "grid") && a.hasValue(i)) grid = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
         else if (a.matches(i, "device") && a.hasValue(i)) device = std::atoi(argv[++i]);
         else if (a.matches(i, "frames") && a.hasValue(i)) frames = std::atoi(argv[++i]);
+        else if (a.matches(i, "gpus") && a.hasValue(i)) gpus = std::atoi(argv[++i]);
         else if (a.matches(i, "out") && a.hasValue(i)) out = argv[++i];
         else if (a.matches(i, "slab") && a.hasValue(i))
         {
@@ -87,6 +88,7 @@ int main(int argc, char** argv)
 
     DXRVoxelizer vox;
     vox.SetDevice(device);
+    vox.SetGpuCount(gpus);
     vox.SetMode(mode);
     vox.SetSlab(slab0, slab1);
     using clock = std::chrono::steady_clock;

@@ -80,6 +80,9 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
                 uint32_t* __restrict__ tileCounter)
 {
     constexpr int kTile = kSortThreads * kItems;
+    // predecessor tiles fetched per round trip of the look-back: the small-tile variant is latency bound
+    // (many tiles, few keys), the big-tile variant is register bound
+    constexpr int kLookbackWindow = kItems >= 16 ? 4 : 12;
     __shared__ uint32_t warpHist[kSortWarps][kRadix];  // 8 KB
     __shared__ uint32_t binStart[kRadix];
     __shared__ uint32_t globalBase[kRadix];
@@ -140,8 +143,8 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
         count += c;
     }
 
-    // ---- decoupled look-back: exclusive count of digit `tid` over all previous tiles.  Four
-    // predecessors are fetched at once so the latency chain is a quarter of the tile distance. ----
+    // ---- decoupled look-back: exclusive count of digit `tid` over all previous tiles.  A window of
+    // predecessors is fetched at once, so the latency chain is 1/window of the tile distance. ----
     volatile uint32_t* lb = lookback + (size_t)tile * kRadix;
     uint32_t prev = 0;
     if (tile == 0) lb[tid] = kFlagInclusive | count;
@@ -152,11 +155,11 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
         bool done = false;
         while (!done)
         {
-            uint32_t v[4];
+            uint32_t v[kLookbackWindow];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = (j - q >= 0) ? lookback[(size_t)(j - q) * kRadix + tid] : 0u;
+            for (int q = 0; q < kLookbackWindow; ++q) v[q] = (j - q >= 0) ? lookback[(size_t)(j - q) * kRadix + tid] : 0u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kLookbackWindow; ++q)
             {
                 if (done || j - q < 0) break;
                 uint32_t x = v[q];
@@ -164,7 +167,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
                 prev += x & kValueMask;
                 if ((x & ~kValueMask) == kFlagInclusive) done = true;
             }
-            j -= 4;
+            j -= kLookbackWindow;
         }
         lb[tid] = kFlagInclusive | (prev + count);
     }

@@ -31,7 +31,7 @@ namespace
 {
 constexpr int kStackGuard = 64;   // >= LBVH depth bound (62): head-room kept for depth-first popping
 constexpr int kWalkStack = 512;   // per-warp stack of k_walk_columns
-constexpr int kWalkWarps = 4;     // warps (= super-tiles) per CTA of k_walk_columns
+constexpr int kWalkWarps = 8;     // warps (= super-tiles) per CTA of k_walk_columns (<= 32)
 constexpr int kStackCap = 1024;   // per-CTA stack of the in-kernel fallback walk
 constexpr int kCandCap = 768;     // per-CTA leaf ring of the fallback walk (>= 3 * threads per CTA)
 
@@ -174,23 +174,48 @@ constexpr uint32_t kMaxParts = 12;
 constexpr uint32_t kHeavySlots = 1024;  // tiles that can be split per launch
 constexpr uint32_t kExtraParts = 2048;  // extra CTAs (beyond one per tile) a launch provides
 
-__device__ __forceinline__ void fileTile(const ParityParams& prm, uint32_t tile, uint32_t count)
+// File the (up to 32) tiles of a CTA: one atomicAdd per bucket per CTA instead of one per tile -- with
+// thousands of tiles hammering three counters the serialised atomics were a third of the kernel.
+// Called by one full warp; lane i files tile firstTile + i (count == 0xffffffff: no such tile).
+__device__ __forceinline__ void fileTiles(const ParityParams& prm, uint32_t firstTile, uint32_t count)
 {
-    prm.candCount[tile] = count;
-    if (count == 0u) { prm.emptyTiles[atomicAdd(prm.bucketCount + 2, 1u)] = tile; return; }
-    if (count < kHeavyTile) { prm.lightTiles[atomicAdd(prm.bucketCount + 1, 1u)] = tile; return; }
-    uint32_t parts = 1u, slot = 0xffffu;
-    if (count <= prm.candCap)   // (an overflowed list is not split: that CTA walks the tree itself)
+    const uint32_t lane = laneId(), lt = laneMaskLt();
+    const uint32_t tile = firstTile + lane;
+    const bool active = count != 0xffffffffu;
+    if (active) prm.candCount[tile] = count;
+    const bool isEmpty = active && count == 0u, isLight = active && count > 0u && count < kHeavyTile;
+    const bool isHeavy = active && count >= kHeavyTile;
+    const uint32_t mE = __ballot_sync(0xffffffffu, isEmpty), mL = __ballot_sync(0xffffffffu, isLight);
+    uint32_t baseE = 0, baseL = 0;
+    if (lane == 0)
     {
-        if (count >= kSplitTile) parts = min((count + kPartSize - 1u) / kPartSize, kMaxParts);
-        if (parts > 1u)
-        {
-            slot = atomicAdd(prm.bucketCount + 3, 1u);
-            if (slot >= kHeavySlots || atomicAdd(prm.bucketCount + 4, parts - 1u) + parts - 1u > kExtraParts) { parts = 1u; slot = 0xffffu; }
-        }
+        if (mE) baseE = atomicAdd(prm.bucketCount + 2, __popc(mE));
+        if (mL) baseL = atomicAdd(prm.bucketCount + 1, __popc(mL));
     }
-    const uint32_t pos = atomicAdd(prm.bucketCount, parts);
-    for (uint32_t part = 0; part < parts; ++part) prm.heavyEntries[pos + part] = make_uint2(tile, part | (parts << 8) | (slot << 16));
+    baseE = __shfl_sync(0xffffffffu, baseE, 0);
+    baseL = __shfl_sync(0xffffffffu, baseL, 0);
+    if (isEmpty) prm.emptyTiles[baseE + __popc(mE & lt)] = tile;
+    if (isLight) prm.lightTiles[baseL + __popc(mL & lt)] = tile;
+
+    uint32_t parts = isHeavy ? 1u : 0u, slot = 0xffffu;
+    if (isHeavy && count <= prm.candCap && count >= kSplitTile)   // (an overflowed list is not split: that CTA walks itself)
+    {
+        parts = min((count + kPartSize - 1u) / kPartSize, kMaxParts);
+        slot = atomicAdd(prm.bucketCount + 3, 1u);
+        if (slot >= kHeavySlots || atomicAdd(prm.bucketCount + 4, parts - 1u) + parts - 1u > kExtraParts) { parts = 1u; slot = 0xffffu; }
+    }
+    uint32_t incl = parts;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t totalParts = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t baseH = 0;
+    if (lane == 0 && totalParts) baseH = atomicAdd(prm.bucketCount, totalParts);
+    baseH = __shfl_sync(0xffffffffu, baseH, 0) + incl - parts;
+    for (uint32_t part = 0; part < parts; ++part) prm.heavyEntries[baseH + part] = make_uint2(tile, part | (parts << 8) | (slot << 16));
 }
 
 template <int SY, int SZ>
@@ -198,56 +223,68 @@ __global__ void __launch_bounds__(32 * kWalkWarps)
 k_walk_columns(const ParityParams prm)
 {
     __shared__ uint32_t sStack[kWalkWarps][kWalkStack];
+    __shared__ uint32_t sCount[32];
     const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x * kWalkWarps + warp;
-    if (tile >= prm.numTiles) return;
-    uint32_t* list = prm.candList + (size_t)tile * prm.candCap;
-    if (prm.numTris <= 1)
+    if (threadIdx.x < 32) sCount[threadIdx.x] = 0xffffffffu;
+    __syncthreads();
+    uint32_t count = 0xffffffffu;
+    if (tile < prm.numTiles)
     {
-        if (lane == 0) { if (prm.numTris) list[0] = 0; fileTile(prm, tile, prm.numTris); }
-        return;
-    }
-    const uint32_t sy0 = (tile % prm.tilesY) * SY;
-    const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
-    float rYmin, rYmax, rZmin, rZmax;
-    tileRect<SY, SZ>(prm, sy0, sz0, rYmin, rYmax, rZmin, rZmax);
-
-    uint32_t* stack = sStack[warp];
-    uint32_t sp = 1, count = 0, guard = 0;  // warp-uniform
-    if (lane == 0) stack[0] = 0;
-    __syncwarp();
-    const uint32_t lt = laneMaskLt();
-    while (sp > 0)
-    {
-        // pop up to 32 nodes from the top; keep kStackGuard entries of head-room so that the depth-first
-        // tail (k == 1) can never overflow: pushes <= 2k, depth <= 62
-        const int room = kWalkStack - kStackGuard - (int)sp;
-        const uint32_t k = room >= 1 ? min(min(32u, sp), (uint32_t)room) : 1u;
-        sp -= k;
-        uint32_t c0 = 0, c1 = 0;
-        bool ov0 = false, ov1 = false;
-        if (lane < k) testNode(prm.nodes, stack[sp + lane], rYmin, rYmax, rZmin, rZmax, ov0, ov1, c0, c1);
-        __syncwarp();
-        const bool in0 = ov0 && !(c0 & kLeafFlag), in1 = ov1 && !(c1 & kLeafFlag);
-        const bool lf0 = ov0 && (c0 & kLeafFlag), lf1 = ov1 && (c1 & kLeafFlag);
-        const uint32_t mi0 = __ballot_sync(0xffffffffu, in0), mi1 = __ballot_sync(0xffffffffu, in1);
-        const uint32_t ml0 = __ballot_sync(0xffffffffu, lf0), ml1 = __ballot_sync(0xffffffffu, lf1);
-        const uint32_t nIn = __popc(mi0) + __popc(mi1), nLf = __popc(ml0) + __popc(ml1);
-        if (sp + nIn > (uint32_t)kWalkStack || ++guard > 2u * prm.numTris + 64u)
+        uint32_t* list = prm.candList + (size_t)tile * prm.candCap;
+        if (prm.numTris <= 1)
         {
-            if (lane == 0) atomicMax(prm.err, (uint32_t)kErrStackOverflow);
-            break;
+            count = prm.numTris;
+            if (lane == 0 && prm.numTris) list[0] = 0;
         }
-        if (count + nLf > prm.candCap) { count = prm.candCap + 1u; break; }  // overflow: the fill kernel walks itself
-        if (in0) stack[sp + __popc(mi0 & lt)] = c0;
-        if (in1) stack[sp + __popc(mi0) + __popc(mi1 & lt)] = c1;
-        sp += nIn;
-        if (lf0) list[count + __popc(ml0 & lt)] = c0 & ~kLeafFlag;
-        if (lf1) list[count + __popc(ml0) + __popc(ml1 & lt)] = c1 & ~kLeafFlag;
-        count += nLf;
-        __syncwarp();
+        else
+        {
+            const uint32_t sy0 = (tile % prm.tilesY) * SY;
+            const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
+            float rYmin, rYmax, rZmin, rZmax;
+            tileRect<SY, SZ>(prm, sy0, sz0, rYmin, rYmax, rZmin, rZmax);
+
+            uint32_t* stack = sStack[warp];
+            uint32_t sp = 1, guard = 0;  // warp-uniform
+            count = 0;
+            if (lane == 0) stack[0] = 0;
+            __syncwarp();
+            const uint32_t lt = laneMaskLt();
+            while (sp > 0)
+            {
+                // pop up to 32 nodes from the top; keep kStackGuard entries of head-room so that the
+                // depth-first tail (k == 1) can never overflow: pushes <= 2k, depth <= 62
+                const int room = kWalkStack - kStackGuard - (int)sp;
+                const uint32_t k = room >= 1 ? min(min(32u, sp), (uint32_t)room) : 1u;
+                sp -= k;
+                uint32_t c0 = 0, c1 = 0;
+                bool ov0 = false, ov1 = false;
+                if (lane < k) testNode(prm.nodes, stack[sp + lane], rYmin, rYmax, rZmin, rZmax, ov0, ov1, c0, c1);
+                __syncwarp();
+                const bool in0 = ov0 && !(c0 & kLeafFlag), in1 = ov1 && !(c1 & kLeafFlag);
+                const bool lf0 = ov0 && (c0 & kLeafFlag), lf1 = ov1 && (c1 & kLeafFlag);
+                const uint32_t mi0 = __ballot_sync(0xffffffffu, in0), mi1 = __ballot_sync(0xffffffffu, in1);
+                const uint32_t ml0 = __ballot_sync(0xffffffffu, lf0), ml1 = __ballot_sync(0xffffffffu, lf1);
+                const uint32_t nIn = __popc(mi0) + __popc(mi1), nLf = __popc(ml0) + __popc(ml1);
+                if (sp + nIn > (uint32_t)kWalkStack || ++guard > 2u * prm.numTris + 64u)
+                {
+                    if (lane == 0) atomicMax(prm.err, (uint32_t)kErrStackOverflow);
+                    break;
+                }
+                if (count + nLf > prm.candCap) { count = prm.candCap + 1u; break; }  // overflow: the fill kernel walks itself
+                if (in0) stack[sp + __popc(mi0 & lt)] = c0;
+                if (in1) stack[sp + __popc(mi0) + __popc(mi1 & lt)] = c1;
+                sp += nIn;
+                if (lf0) list[count + __popc(ml0 & lt)] = c0 & ~kLeafFlag;
+                if (lf1) list[count + __popc(ml0) + __popc(ml1 & lt)] = c1 & ~kLeafFlag;
+                count += nLf;
+                __syncwarp();
+            }
+        }
     }
-    if (lane == 0) fileTile(prm, tile, count);
+    if (lane == 0) sCount[warp] = count;
+    __syncthreads();
+    if (warp == 0) fileTiles(prm, blockIdx.x * kWalkWarps, sCount[lane]);
 }
 
 // ---- kernel B: W warps per CTA; the super-tile is SY x SZ columns with SY * SZ == 32 * W --------

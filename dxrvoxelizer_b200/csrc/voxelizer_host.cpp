@@ -8,6 +8,7 @@ DXRVoxelizer::DXRVoxelizer() {}
 DXRVoxelizer::~DXRVoxelizer()
 {
     if (m_ctx) dxrv_destroy(m_ctx);
+    for (dxrv_ctx* c : m_more) dxrv_destroy(c);
     if (m_mesh) dxrv_obj_free(m_mesh);
 }
 
@@ -43,6 +44,16 @@ bool DXRVoxelizer::Init(const void* vertices, uint32_t numVerts, uint32_t stride
         m_error = dxrv_last_error(nullptr);
         return false;
     }
+    while (static_cast<int>(m_more.size()) + 1 < m_gpus)
+    {
+        dxrv_ctx* c = nullptr;
+        if (dxrv_create(&c, m_device + 1 + static_cast<int>(m_more.size())) != DXRV_OK)
+        {
+            m_error = dxrv_last_error(nullptr);
+            return false;
+        }
+        m_more.push_back(c);
+    }
     return BuildAccelerationStructures();
 }
 
@@ -52,8 +63,24 @@ bool DXRVoxelizer::BuildAccelerationStructures()
     // bound = NULL: extracted on the device as Voxelizer.cpp:52-57 does on the host
     if (dxrv_build_bvh(m_ctx, m_vertices, m_numVerts, m_stride, m_indices, m_numIndices, nullptr) != DXRV_OK)
         return fail("dxrv_build_bvh");
+    // every further GPU builds the identical tree from the same host arrays (calls are asynchronous:
+    // the builds run concurrently)
+    for (dxrv_ctx* c : m_more)
+        if (dxrv_build_bvh(c, m_vertices, m_numVerts, m_stride, m_indices, m_numIndices, nullptr) != DXRV_OK)
+        {
+            m_error = std::string("dxrv_build_bvh: ") + dxrv_last_error(c);
+            return false;
+        }
     if (dxrv_get_bound(m_ctx, m_bound) != DXRV_OK) return fail("dxrv_get_bound");
     return true;
+}
+
+// z-slab of GPU g out of k over [begin, end): contiguous, disjoint, sizes differ by at most one layer
+static void slabOf(uint32_t begin, uint32_t end, int g, int k, uint32_t& z0, uint32_t& z1)
+{
+    const uint32_t layers = end - begin;
+    z0 = begin + static_cast<uint32_t>(static_cast<uint64_t>(layers) * g / k);
+    z1 = begin + static_cast<uint32_t>(static_cast<uint64_t>(layers) * (g + 1) / k);
 }
 
 bool DXRVoxelizer::Voxelize()
@@ -61,7 +88,19 @@ bool DXRVoxelizer::Voxelize()
     if (!m_ctx) { m_error = "Init has not been called"; return false; }
     const uint32_t end = m_slabEnd ? m_slabEnd : m_gridSize;
     m_gridFetched = false;
-    if (dxrv_voxelize(m_ctx, m_gridSize, m_mode, m_slabBegin, end) != DXRV_OK) return fail("dxrv_voxelize");
+    const int k = 1 + static_cast<int>(m_more.size());
+    for (int g = 0; g < k; ++g)
+    {
+        uint32_t z0, z1;
+        slabOf(m_slabBegin, end, g, k, z0, z1);
+        if (z0 == z1) continue;
+        dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
+        if (dxrv_voxelize(c, m_gridSize, m_mode, z0, z1) != DXRV_OK)
+        {
+            m_error = std::string("dxrv_voxelize: ") + dxrv_last_error(c);
+            return false;
+        }
+    }
     return true;
 }
 
@@ -77,10 +116,21 @@ const uint32_t* DXRVoxelizer::Grid()
     if (!m_gridFetched)
     {
         m_grid.resize(GridWords());
-        if (dxrv_fetch_grid(m_ctx, m_grid.data(), m_grid.size() * sizeof(uint32_t), DXRV_FORMAT_BITS) != DXRV_OK)
+        const uint32_t end = m_slabEnd ? m_slabEnd : m_gridSize;
+        const size_t wordsPerLayer = static_cast<size_t>(m_gridSize) * ((m_gridSize + 31) / 32);
+        const int k = 1 + static_cast<int>(m_more.size());
+        for (int g = 0; g < k; ++g)   // gather: every GPU's slab lands at its offset of the host grid
         {
-            fail("dxrv_fetch_grid");
-            return nullptr;
+            uint32_t z0, z1;
+            slabOf(m_slabBegin, end, g, k, z0, z1);
+            if (z0 == z1) continue;
+            dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
+            if (dxrv_fetch_grid(c, m_grid.data() + (z0 - m_slabBegin) * wordsPerLayer, (z1 - z0) * wordsPerLayer * sizeof(uint32_t),
+                                DXRV_FORMAT_BITS) != DXRV_OK)
+            {
+                m_error = std::string("dxrv_fetch_grid: ") + dxrv_last_error(c);
+                return nullptr;
+            }
         }
         m_gridFetched = true;
     }
@@ -90,6 +140,22 @@ const uint32_t* DXRVoxelizer::Grid()
 bool DXRVoxelizer::CountInside(uint64_t& count)
 {
     if (!m_ctx) { m_error = "Init has not been called"; return false; }
-    if (dxrv_count_inside(m_ctx, &count) != DXRV_OK) return fail("dxrv_count_inside");
+    count = 0;
+    const uint32_t end = m_slabEnd ? m_slabEnd : m_gridSize;
+    const int k = 1 + static_cast<int>(m_more.size());
+    for (int g = 0; g < k; ++g)
+    {
+        uint32_t z0, z1;
+        slabOf(m_slabBegin, end, g, k, z0, z1);
+        if (z0 == z1) continue;
+        dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
+        uint64_t part = 0;
+        if (dxrv_count_inside(c, &part) != DXRV_OK)
+        {
+            m_error = std::string("dxrv_count_inside: ") + dxrv_last_error(c);
+            return false;
+        }
+        count += part;
+    }
     return true;
 }

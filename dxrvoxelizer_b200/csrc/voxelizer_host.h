@@ -32,6 +32,9 @@ public:
     DXRVoxelizer& operator=(const DXRVoxelizer&) = delete;
 
     void SetDevice(int cudaDevice) { m_device = cudaDevice; }
+    // Shard the grid into z-slabs over `count` GPUs (devices m_device .. m_device+count-1), one context
+    // each, mesh/BVH replicated.  Call before Init.  (New: the reference is single-GPU.)
+    void SetGpuCount(int count) { m_gpus = count < 1 ? 1 : count; }
     void SetMode(Mode mode) { m_mode = mode; }
     // z-slab [begin, end) computed by Voxelize(); end = 0 means the whole grid.
     void SetSlab(uint32_t begin, uint32_t end) { m_slabBegin = begin; m_slabEnd = end; }
@@ -62,7 +65,9 @@ public:
 private:
     bool fail(const char* what);
 
-    dxrv_ctx* m_ctx = nullptr;
+    dxrv_ctx* m_ctx = nullptr;            // context of the first GPU
+    std::vector<dxrv_ctx*> m_more;        // contexts of GPUs 2..k
+    int m_gpus = 1;
     dxrv_mesh* m_mesh = nullptr;
     const void* m_vertices = nullptr;
     const uint32_t* m_indices = nullptr;

@@ -160,6 +160,18 @@ class Voxelizer:
     def set_grid_target(self, d_ptr, nbytes):
         self._check(self._lib.dxrv_set_grid_target(self._h, d_ptr, nbytes))
 
+    def build_mips(self):
+        """Occupancy pyramid (OR of 2x2x2 children); returns the number of levels incl. level 0."""
+        n = ctypes.c_uint32()
+        self._check(self._lib.dxrv_build_mips(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def fetch_mip(self, level):
+        layers, N = self._shape[0] >> level, self._N >> level
+        out = np.empty((layers, N, (N + 31) // 32), np.uint32)
+        self._check(self._lib.dxrv_fetch_mip(self._h, level, out.ctypes.data, out.nbytes))
+        return out
+
     def count_inside(self):
         c = ctypes.c_uint64()
         self._check(self._lib.dxrv_count_inside(self._h, ctypes.byref(c)))

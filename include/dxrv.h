@@ -128,6 +128,15 @@ DXRV_API int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);
  * (may be peer-mapped memory of another GPU: the fill kernel's 128-bit stores then go over
  * NVLink, fusing the slab gather into the write).  NULL restores the internal grid. */
 DXRV_API int dxrv_set_grid_target(dxrv_ctx* ctx, void* d_ptr, size_t bytes);
+/* Occupancy pyramid of the slab of the last voxelize (BITS layout per level): level 0 is the grid itself,
+ * a voxel of level l+1 is set when any of its 2x2x2 children in level l is.  Levels are built while the
+ * grid size and the slab's layer count stay even; *numLevels receives how many exist (>= 1).  The reference
+ * samples its grid texture at mip SHOW_MIP (Content/SharedConst.h:5, PSRayCast.hlsl:106-108) and never
+ * builds the chain; this is the consumer-side format for empty-space skipping. */
+DXRV_API int dxrv_build_mips(dxrv_ctx* ctx, uint32_t* numLevels);
+/* Copy level `level` (1 <= level < numLevels; level 0 is dxrv_fetch_grid) to host memory.  bytes must be
+ * layers_l * N_l * ceil(N_l / 32) * 4 with N_l = N >> level, layers_l = (slabEnd - slabBegin) >> level. */
+DXRV_API int dxrv_fetch_mip(dxrv_ctx* ctx, uint32_t level, void* hostDst, size_t bytes);
 /* Number of set voxels in the slab of the last voxelize (device popcount; synchronises). */
 DXRV_API int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count);
 

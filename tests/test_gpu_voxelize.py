@@ -214,3 +214,44 @@ def test_rebuild_is_deterministic(vox, assets):
     b = _run(vox, m, 256, d.MODE_PARITY)
     k2 = vox.debug_read(L.DBG_PRIM_SORTED, np.uint32, m.num_triangles)
     assert np.array_equal(a, b) and np.array_equal(k1, k2)
+
+
+@pytest.mark.parametrize("N,z0,z1", [(64, 0, 64), (96, 32, 64), (100, 0, 100), (256, 0, 256)])
+def test_occupancy_pyramid(vox, assets, N, z0, z1):
+    """dxrv_build_mips: a coarse voxel is set iff any of its 2x2x2 children is (numpy restatement)."""
+    m = assets("bunny.obj")
+    vox.build_bvh(m)
+    vox.voxelize(N, d.MODE_PARITY, z0, z1)
+    level0 = d.unpack_bits(vox.fetch_bits(), N).astype(bool)
+    levels = vox.build_mips()
+    want_levels, n, l = 1, N, z1 - z0
+    while n % 2 == 0 and l % 2 == 0:
+        n //= 2; l //= 2; want_levels += 1
+    assert levels == want_levels
+    cur = level0
+    for lev in range(1, levels):
+        lz, ly, lx = cur.shape
+        cur = cur.reshape(lz // 2, 2, ly // 2, 2, lx // 2, 2).any(axis=(1, 3, 5))
+        got = vox.fetch_mip(lev)
+        assert got.shape[:2] == cur.shape[:2]
+        assert np.array_equal(d.unpack_bits(got, cur.shape[2]).astype(bool), cur)
+        pad = np.unpackbits(got.view(np.uint8), axis=-1, bitorder="little")[..., cur.shape[2]:]
+        assert not pad.any()                       # bits beyond N_l stay clear
+    with pytest.raises(d.DxrvError):
+        vox.fetch_mip(levels)
+
+
+def test_cli_matches_oracle(tmp_path, oracle_mod, assets):
+    """The headless CLI (Bin/TuringBowl.bat argument list + new flags) end to end, raw grid dump."""
+    import os, subprocess, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "grid.bin"
+    r = subprocess.run([os.path.join(root, "dxrvoxelizer_b200", "dxrvoxelizer"), "-mesh", d.asset_path("TuringBowl.obj"),
+                        "0.0", "2.8", "0.0", "0.03", "-GRID", "128", "/mode", "parity", "-out", str(out)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout)
+    m = assets("TuringBowl.obj")
+    ref = oracle_mod.voxelize(m.vertices, m.indices, 128, 1)["bits"]
+    got = np.fromfile(out, np.uint32).reshape(ref.shape)
+    assert popcount(got ^ ref) == 0 and info["inside"] == popcount(ref) and info["triangles"] == m.num_triangles
