@@ -255,3 +255,16 @@ def test_cli_matches_oracle(tmp_path, oracle_mod, assets):
     ref = oracle_mod.voxelize(m.vertices, m.indices, 128, 1)["bits"]
     got = np.fromfile(out, np.uint32).reshape(ref.shape)
     assert popcount(got ^ ref) == 0 and info["inside"] == popcount(ref) and info["triangles"] == m.num_triangles
+
+
+@pytest.mark.parametrize("N", [384, 1280, 1664])
+def test_weak_scaling_grid_sizes_slab(vox, assets, oracle_mod, N):
+    """Grids of the multi-GPU bench (N % 128 == 0 but not a power of two: shared row pitch > global pitch,
+    IEEE division in centre()): a few z-slabs against the oracle."""
+    m = assets("dragon.obj")
+    vox.build_bvh(m)
+    for z0 in (N // 2 - 8, N // 2 + 40):
+        vox.voxelize(N, d.MODE_PARITY, z0, z0 + 16)
+        ref = oracle_mod.voxelize(m.vertices, m.indices, N, 1, z0=z0, z1=z0 + 16)
+        assert popcount(vox.fetch_bits() ^ ref["bits"]) == 0
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"]
