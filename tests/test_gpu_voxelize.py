@@ -268,3 +268,24 @@ def test_weak_scaling_grid_sizes_slab(vox, assets, oracle_mod, N):
         ref = oracle_mod.voxelize(m.vertices, m.indices, N, 1, z0=z0, z1=z0 + 16)
         assert popcount(vox.fetch_bits() ^ ref["bits"]) == 0
         assert vox.info(L.INFO_CROSSINGS) == ref["crossings"]
+
+
+def test_degenerate_inputs_do_not_hang(vox, meshes_mod, oracle_mod):
+    base = meshes_mod.icosphere(2, seed=8)
+    # zero-area and duplicated triangles (finite coordinates): still bit-exact against the oracle
+    idx = base.indices.reshape(-1, 3).copy()
+    extra = np.array([[0, 0, 0], [1, 1, 2], [3, 4, 3], idx[5], idx[5]], np.uint32)
+    m = d.Mesh(base.vertex_bytes, np.concatenate([idx, extra]).reshape(-1), base.stride)
+    for mode in (d.MODE_PARITY, d.MODE_SHADER):
+        got = _run(vox, m, 40, mode)
+        assert popcount(got ^ oracle_mod.voxelize(m.vertices, m.indices, 40, mode)["bits"]) == 0
+    # all vertices identical: w = 0, scene coordinates are NaN -> nothing can be hit, nothing may hang
+    v = base.vertices.copy(); v[:, :3] = 1.5
+    flat = d.Mesh(v, base.indices, base.stride)
+    for mode in (d.MODE_PARITY, d.MODE_SHADER):
+        assert popcount(_run(vox, flat, 32, mode)) == 0
+    # a NaN vertex: the call must complete (results near the NaN triangles are unspecified)
+    v = base.vertices.copy(); v[7, :3] = np.nan
+    vox.build_bvh(d.Mesh(v, base.indices, base.stride))
+    vox.voxelize(32, d.MODE_PARITY); vox.fetch_bits()
+    vox.voxelize(32, d.MODE_SHADER); vox.fetch_bits()
