@@ -590,6 +590,26 @@ int dxrv_fetch_mip(dxrv_ctx* ctx, uint32_t level, void* hostDst, size_t bytes)
     return checkDeviceError(ctx);
 }
 
+int dxrv_render_view(dxrv_ctx* ctx, uint32_t width, uint32_t height, const float screenToLocal[16], const float eye[3],
+                     const float light[3], void* hostRGBA, size_t bytes)
+{
+    if (!ctx || !screenToLocal || !eye || !light || !hostRGBA) return DXRV_ERR_INVALID_ARG;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_render_view: call dxrv_voxelize first");
+    if (ctx->z0 != 0 || ctx->z1 != ctx->N) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_render_view: needs the full grid (slab [0, N))");
+    if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_render_view: bad target size");
+    const size_t need = (size_t)width * height * 4;
+    if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_render_view: bytes must be width * height * 4");
+    DeviceGuard g(ctx->device);
+    cudaError_t e = ensure(ctx->u8Temp, ctx->u8Cap, need);
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(image)");
+    const uint32_t* grid = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
+    launchRaycastView(ctx->stream, grid, ctx->N, width, height, screenToLocal, eye, light, reinterpret_cast<uint32_t*>(ctx->u8Temp));
+    ctx->launches += 1;
+    DXRV_CUDA(cudaGetLastError());
+    DXRV_CUDA(cudaMemcpyAsync(hostRGBA, ctx->u8Temp, need, cudaMemcpyDeviceToHost, ctx->stream));
+    return checkDeviceError(ctx);
+}
+
 int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count)
 {
     if (!ctx || !count) return DXRV_ERR_INVALID_ARG;

@@ -78,6 +78,10 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
 void launchTraceShader(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0,
                        uint32_t z1, uint32_t* grid, uint32_t* texels, uint32_t* dErr);
 
+// ---- view.cu (headless port of the reference's viewer pass, PSRayCast.hlsl) -----------------------------
+void launchRaycastView(cudaStream_t s, const uint32_t* grid, uint32_t N, uint32_t width, uint32_t height,
+                       const float screenToLocal[16], const float eye[3], const float light[3], uint32_t* image);
+
 // ---- misc (lbvh.cu) -----------------------------------------------------------------------------
 void launchPopcount(cudaStream_t s, const uint32_t* words, size_t numWords, unsigned long long* dCount);
 // dst = next level of the occupancy pyramid of src (Ns^2 x layersSrc voxels; Ns and layersSrc even)

@@ -4,13 +4,15 @@
 // start with '-' only when a digit or '.' follows; defaults Assets/bunny.obj and posScale (0,0,0,1)
 // (DXRVoxelizer.cpp:36-37).  -warp / -uma select D3D adapters in the reference and are accepted and
 // ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity, -device k,
-// -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words).
+// -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words),
+// -view file.ppm (the reference's viewer pass, 1280 x 720).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "voxelizer_host.h"
 
@@ -35,7 +37,7 @@ struct Args
     // would swallow absolute paths, so '/' only introduces an option when a known name follows.
     static bool knownOption(const char* name)
     {
-        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus"};
+        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus", "view"};
         for (const char* n : names) if (lower(name) == n) return true;
         return false;
     }
@@ -51,7 +53,7 @@ struct Args
 
 int main(int argc, char** argv)
 {
-    std::string mesh = "Assets/bunny.obj", out;
+    std::string mesh = "Assets/bunny.obj", out, view;
     float posScale[4] = {0.0f, 0.0f, 0.0f, 1.0f};
     uint32_t grid = 64, slab0 = 0, slab1 = 0;
     int device = 0, frames = 1, gpus = 1;
@@ -72,6 +74,7 @@ int main(int argc, char** argv)
         else if (a.matches(i, "frames") && a.hasValue(i)) frames = std::atoi(argv[++i]);
         else if (a.matches(i, "gpus") && a.hasValue(i)) gpus = std::atoi(argv[++i]);
         else if (a.matches(i, "out") && a.hasValue(i)) out = argv[++i];
+        else if (a.matches(i, "view") && a.hasValue(i)) view = argv[++i];
         else if (a.matches(i, "slab") && a.hasValue(i))
         {
             slab0 = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
@@ -120,6 +123,17 @@ int main(int argc, char** argv)
         FILE* f = std::fopen(out.c_str(), "wb");
         if (!f) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
         std::fwrite(g, sizeof(uint32_t), vox.GridWords(), f);
+        std::fclose(f);
+    }
+    if (!view.empty())
+    {
+        // what the reference's window shows (1280 x 720, Main.cpp:17), as a binary PPM
+        std::vector<uint8_t> rgba;
+        if (!vox.RenderView(1280, 720, rgba)) { std::fprintf(stderr, "view failed: %s\n", vox.LastError()); return 1; }
+        FILE* f = std::fopen(view.c_str(), "wb");
+        if (!f) { std::fprintf(stderr, "cannot write %s\n", view.c_str()); return 1; }
+        std::fprintf(f, "P6\n1280 720\n255\n");
+        for (size_t i = 0; i < rgba.size(); i += 4) std::fwrite(&rgba[i], 1, 3, f);
         std::fclose(f);
     }
     return 0;

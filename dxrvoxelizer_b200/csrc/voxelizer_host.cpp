@@ -159,3 +159,19 @@ bool DXRVoxelizer::CountInside(uint64_t& count)
     }
     return true;
 }
+
+bool DXRVoxelizer::RenderView(uint32_t width, uint32_t height, std::vector<uint8_t>& rgba)
+{
+    if (!m_ctx) { m_error = "Init has not been called"; return false; }
+    if (!m_more.empty()) { m_error = "RenderView needs the whole grid on one GPU"; return false; }
+    float screenToLocal[16], eye[3], light[3];
+    if (dxrv_default_view(m_bound, m_posScale, width, height, screenToLocal, eye, light) != DXRV_OK)
+    {
+        m_error = "dxrv_default_view: invalid arguments";
+        return false;
+    }
+    rgba.resize(static_cast<size_t>(width) * height * 4);
+    if (dxrv_render_view(m_ctx, width, height, screenToLocal, eye, light, rgba.data(), rgba.size()) != DXRV_OK)
+        return fail("dxrv_render_view");
+    return true;
+}

@@ -54,6 +54,9 @@ public:
     const uint32_t* Grid();
     size_t GridWords() const;
     bool CountInside(uint64_t& count);
+    // The reference's viewer pass (Render -> renderRayCast, Content/Voxelizer.cpp:371-399) into an RGBA8 image
+    // with the reference's camera; single-GPU, full grid.
+    bool RenderView(uint32_t width, uint32_t height, std::vector<uint8_t>& rgba);
 
     uint32_t GridSize() const { return m_gridSize; }
     uint32_t NumTriangles() const { return m_numIndices / 3; }

@@ -65,6 +65,19 @@ def load_obj(path):
     return Mesh(vb, ib, st, aabb, bound)
 
 
+def default_view(bound, width=1280, height=720, pos_scale=None):
+    """(screenToLocal[4,4], eye[3], light[3]) of the reference's camera for this bound (dxrv_default_view)."""
+    lib = L.lib()
+    b = np.ascontiguousarray(bound, dtype=np.float32)
+    ps = None if pos_scale is None else np.ascontiguousarray(pos_scale, dtype=np.float32)
+    m, eye, light = np.zeros(16, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+    rc = lib.dxrv_default_view(b.ctypes.data, None if ps is None else ps.ctypes.data, width, height,
+                               m.ctypes.data, eye.ctypes.data, light.ctypes.data)
+    if rc != L.OK:
+        raise L.DxrvError(rc, "dxrv_default_view: invalid arguments")
+    return m.reshape(4, 4), eye, light
+
+
 class Voxelizer:
     """One context = one GPU + one stream.  Not thread-safe (same as the C ABI)."""
 
@@ -170,6 +183,16 @@ class Voxelizer:
         layers, N = self._shape[0] >> level, self._N >> level
         out = np.empty((layers, N, (N + 31) // 32), np.uint32)
         self._check(self._lib.dxrv_fetch_mip(self._h, level, out.ctypes.data, out.nbytes))
+        return out
+
+    def render_view(self, width, height, screen_to_local, eye, light):
+        """RGBA8 image [height, width, 4] of the reference's viewer pass over the last (full) grid."""
+        m = np.ascontiguousarray(screen_to_local, dtype=np.float32).reshape(16)
+        e = np.ascontiguousarray(eye, dtype=np.float32)
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        out = np.empty((height, width, 4), np.uint8)
+        self._check(self._lib.dxrv_render_view(self._h, width, height, m.ctypes.data, e.ctypes.data, l.ctypes.data,
+                                               out.ctypes.data, out.nbytes))
         return out
 
     def count_inside(self):

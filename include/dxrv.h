@@ -137,6 +137,18 @@ DXRV_API int dxrv_build_mips(dxrv_ctx* ctx, uint32_t* numLevels);
 /* Copy level `level` (1 <= level < numLevels; level 0 is dxrv_fetch_grid) to host memory.  bytes must be
  * layers_l * N_l * ceil(N_l / 32) * 4 with N_l = N >> level, layers_l = (slabEnd - slabBegin) >> level. */
 DXRV_API int dxrv_fetch_mip(dxrv_ctx* ctx, uint32_t level, void* hostDst, size_t bytes);
+/* ---- viewer pass (the step right after the path; headless) ---------------------------------------------
+ * Camera of the reference (DXRVoxelizer.cpp:19-23,222-234) and the per-object constants of
+ * Voxelizer::UpdateFrame (Content/Voxelizer.cpp:81-106) for a width x height target: screenToLocal in the
+ * row-vector convention (p' = (x,y,z,1) * M, as PSRayCast.hlsl:63 uses it), eye and light point in the
+ * grid's local space.  posScale may be NULL (0,0,0,1).  Pure host code. */
+DXRV_API int dxrv_default_view(const float bound[4], const float posScale[4], uint32_t width, uint32_t height,
+                               float screenToLocal[16], float eye[3], float light[3]);
+/* Ray-march the FULL grid of the last dxrv_voxelize (slab [0, N)) exactly like PSRayCast.hlsl:117-187
+ * (128 steps, 32 light steps, trilinear LINEAR_CLAMP sampling of the occupancy) into an R8G8B8A8 image
+ * (row-major, y down, bytes = width * height * 4).  Synchronises. */
+DXRV_API int dxrv_render_view(dxrv_ctx* ctx, uint32_t width, uint32_t height, const float screenToLocal[16],
+                              const float eye[3], const float light[3], void* hostRGBA, size_t bytes);
 /* Number of set voxels in the slab of the last voxelize (device popcount; synchronises). */
 DXRV_API int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count);
 

@@ -42,6 +42,9 @@ def _lib():
             ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         L.oracle_voxelize.restype = ctypes.c_int
         L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_render_view.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.oracle_render_view.restype = ctypes.c_int
         _LIB = L
     return _LIB
 
@@ -84,6 +87,20 @@ def voxelize(vertices, indices, N, mode, z0=0, z1=None, tier=TIER_ACCEL, threads
     if rc != 0:
         raise ValueError("oracle_voxelize: invalid arguments")
     return {"bits": bits, "texels": tex, "crossings": int(cr.value), "odd_columns": int(odd.value)}
+
+
+def render_view(bits, N, width, height, screen_to_local, eye, light, threads=0):
+    """RGBA8 image [height, width, 4] of the viewer pass (PSRayCast.hlsl) over a full bit grid."""
+    b = np.ascontiguousarray(bits, dtype=np.uint32)
+    m = np.ascontiguousarray(screen_to_local, dtype=np.float32).reshape(16)
+    e = np.ascontiguousarray(eye, dtype=np.float32)
+    l = np.ascontiguousarray(light, dtype=np.float32)
+    out = np.empty((height, width, 4), np.uint8)
+    rc = _lib().oracle_render_view(b.ctypes.data, N, width, height, m.ctypes.data, e.ctypes.data, l.ctypes.data,
+                                   out.ctypes.data, threads)
+    if rc != 0:
+        raise ValueError("oracle_render_view: invalid arguments")
+    return out
 
 
 # ---- the reference's own ObjLoader (compiled from /root/reference into oracle/_ref) -------------

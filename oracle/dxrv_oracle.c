@@ -559,3 +559,124 @@ int oracle_voxelize(const void* vertices, uint32_t numVerts, uint32_t stride, co
     bvh_free(&bvh); bins_free(&bins); scene_free(&s);
     return 0;
 }
+
+/* ---- viewer pass ----------------------------------------------------------------
+ * Restatement of Content/Shaders/PSRayCast.hlsl:61-187 over the bit grid: ScreenToLocal (:61-66),
+ * ComputeStartPoint (:71-99), GetSample = trilinear LINEAR_CLAMP fetch of the alpha channel, min(d*8,16)
+ * (:104-111), main (:117-187).  min16float evaluated as float.  The GPU kernel is compared with a
+ * tolerance on the 8-bit image: normalize/sqrt precision and the sampler's filter weights are
+ * implementation defined in the reference. */
+static float occ_at(const uint32_t* bits, int N, int P, int x, int y, int z)
+{
+    x = x < 0 ? 0 : (x > N - 1 ? N - 1 : x);
+    y = y < 0 ? 0 : (y > N - 1 ? N - 1 : y);
+    z = z < 0 ? 0 : (z > N - 1 ? N - 1 : z);
+    return (float)((bits[((size_t)z * N + y) * P + (x >> 5)] >> (x & 31)) & 1u);
+}
+
+static float get_sample(const uint32_t* bits, int N, int P, float tx, float ty, float tz)
+{
+    const float ux = tx * (float)N - 0.5f, uy = ty * (float)N - 0.5f, uz = tz * (float)N - 0.5f;
+    const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+    const float fx = ux - x0, fy = uy - y0, fz = uz - z0;
+    const int ix = (int)x0, iy = (int)y0, iz = (int)z0;
+    float c[2][2][2];
+    for (int k = 0; k < 2; ++k) for (int j = 0; j < 2; ++j) for (int i = 0; i < 2; ++i) c[k][j][i] = occ_at(bits, N, P, ix + i, iy + j, iz + k);
+    float cz[2];
+    for (int k = 0; k < 2; ++k)
+    {
+        const float a = c[k][0][0] + fx * (c[k][0][1] - c[k][0][0]);
+        const float b = c[k][1][0] + fx * (c[k][1][1] - c[k][1][0]);
+        cz[k] = a + fy * (b - a);
+    }
+    const float d = cz[0] + fz * (cz[1] - cz[0]);
+    return d * 8.0f < 16.0f ? d * 8.0f : 16.0f;
+}
+
+static float sat(float a) { return a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a); }
+static uint32_t unorm8(float a) { return (uint32_t)(sat(a) * 255.0f + 0.5f); }
+
+int oracle_render_view(const uint32_t* bits, uint32_t N, uint32_t width, uint32_t height, const float m[16],
+                       const float eye[3], const float light[3], uint32_t* image, int threads)
+{
+    if (!bits || !m || !eye || !light || !image || !N || !width || !height) return -1;
+    const int P = (int)((N + 31) / 32);
+    const float clear[3] = { 0.0f, 0.2f, 0.4f };
+    const float maxDist = 2.0f * sqrtf(3.0f);
+    const float stepScale = maxDist / 128.0f, lightStepScale = maxDist / 32.0f;
+    const float ll = sqrtf(light[0] * light[0] + light[1] * light[1] + light[2] * light[2]);
+    const float ls[3] = { light[0] / ll * lightStepScale, light[1] / ll * lightStepScale, light[2] / ll * lightStepScale };
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#else
+    threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+    for (int64_t py = 0; py < (int64_t)height; ++py)
+        for (uint32_t px = 0; px < width; ++px)
+        {
+            const float sx = (float)px + 0.5f, sy = (float)py + 0.5f;
+            float h[4];
+            for (int c = 0; c < 4; ++c) h[c] = sx * m[c] + sy * m[4 + c] + m[12 + c];
+            float pos[3] = { h[0] / h[3], h[1] / h[3], h[2] / h[3] };
+            float dir[3] = { pos[0] - eye[0], pos[1] - eye[1], pos[2] - eye[2] };
+            const float dl = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+            dir[0] /= dl; dir[1] /= dl; dir[2] /= dl;
+            int hit = 1;
+            if (!(fabsf(pos[0]) <= 1.0f && fabsf(pos[1]) <= 1.0f && fabsf(pos[2]) <= 1.0f))
+            {
+                float U = 3.402823466e+38f;
+                hit = 0;
+                for (int i = 0; i < 3; ++i)
+                {
+                    const float sg = dir[i] > 0.0f ? 1.0f : (dir[i] < 0.0f ? -1.0f : 0.0f);
+                    const float u = (-sg - pos[i]) / dir[i];
+                    if (u < 0.0f) continue;
+                    const int j = (i + 1) % 3, k = (i + 2) % 3;
+                    if (fabsf(dir[j] * u + pos[j]) > 1.0f) continue;
+                    if (fabsf(dir[k] * u + pos[k]) > 1.0f) continue;
+                    if (u < U) { U = u; hit = 1; }
+                }
+                for (int i = 0; i < 3; ++i)
+                {
+                    float v = dir[i] * U + pos[i];
+                    pos[i] = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+                }
+            }
+            uint32_t* out = image + (size_t)py * width + px;
+            if (!hit) { *out = unorm8(clear[0]) | (unorm8(clear[1]) << 8) | (unorm8(clear[2]) << 16); continue; }
+            float transmit = 1.0f, scatter = 0.0f;
+            for (int i = 0; i < 128; ++i)
+            {
+                if (fabsf(pos[0]) > 1.0f || fabsf(pos[1]) > 1.0f || fabsf(pos[2]) > 1.0f) break;
+                const float density = get_sample(bits, (int)N, P, 0.5f * pos[0] + 0.5f, -0.5f * pos[1] + 0.5f, 0.5f * pos[2] + 0.5f);
+                if (density > 0.01f)
+                {
+                    const float scaled = density * stepScale;
+                    transmit *= sat(1.0f - scaled * 1.0f);
+                    if (transmit < 0.01f) break;
+                    float lt = 1.0f;
+                    float lp[3] = { pos[0] + ls[0], pos[1] + ls[1], pos[2] + ls[2] };
+                    for (int j = 0; j < 32; ++j)
+                    {
+                        if (fabsf(lp[0]) > 1.0f || fabsf(lp[1]) > 1.0f || fabsf(lp[2]) > 1.0f) break;
+                        const float ld = get_sample(bits, (int)N, P, 0.5f * lp[0] + 0.5f, -0.5f * lp[1] + 0.5f, 0.5f * lp[2] + 0.5f);
+                        lt *= sat(1.0f - 1.0f * lightStepScale * ld);
+                        if (lt < 0.01f) break;
+                        lp[0] += ls[0]; lp[1] += ls[1]; lp[2] += ls[2];
+                    }
+                    scatter += lt * transmit * scaled;
+                }
+                pos[0] += dir[0] * stepScale; pos[1] += dir[1] * stepScale; pos[2] += dir[2] * stepScale;
+            }
+            uint32_t rgba = 0xff000000u;
+            for (int c = 0; c < 3; ++c)
+            {
+                float r = scatter * 0.8f + 0.2f;
+                r = r + transmit * (clear[c] * clear[c] - r);
+                rgba |= unorm8(sqrtf(r)) << (8 * c);
+            }
+            *out = rgba;
+        }
+    return 0;
+}

@@ -93,6 +93,11 @@ int oracle_voxelize(const void* vertices, uint32_t numVerts, uint32_t strideByte
 
 int oracle_max_threads(void);
 
+/* Viewer pass (Content/Shaders/PSRayCast.hlsl:61-187) over a FULL bit grid (N^3, DXRV_FORMAT_BITS layout):
+ * image = width*height RGBA8 (R in the low byte).  m = screenToLocal (row-vector convention). */
+int oracle_render_view(const uint32_t* bits, uint32_t N, uint32_t width, uint32_t height, const float m[16],
+                       const float eye[3], const float light[3], uint32_t* image, int threads);
+
 #ifdef __cplusplus
 }
 #endif
