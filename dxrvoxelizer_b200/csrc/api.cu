@@ -41,6 +41,7 @@ struct dxrv_ctx
     BvhNode* nodes = nullptr;
     Tri48* tris = nullptr;
     float4* pyramid = nullptr;          // leaf boxes + 16:1 summary levels
+    uint32_t* refitScratch = nullptr; size_t refitCap = 0;   // parents + arrival flags (large meshes only)
     void* sortTemp = nullptr; size_t sortTempCap = 0;
     size_t capTris = 0;
 
@@ -214,6 +215,11 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
         DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->pyramid), sizeof(float4) * boxPyramidFloat4s((uint32_t)cap)));
         ctx->capTris = cap;
     }
+    if (useAtomicRefit(T))
+    {
+        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->refitScratch), ctx->refitCap, sizeof(uint32_t) * 3 * (size_t)T);
+        if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(refit scratch)");
+    }
     {
         size_t need = SortTemp::bytesFor(T);
         cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->sortTemp), ctx->sortTempCap, need);
@@ -239,7 +245,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     keyPush(key, m.verts); keyPush(key, m.numVerts); keyPush(key, m.stride); keyPush(key, m.indices); keyPush(key, m.numTris);
     keyPush(key, (uint32_t)haveBound); keyPush(key, bnd);
     keyPush(key, ctx->keysA); keyPush(key, ctx->keysB); keyPush(key, ctx->valsA); keyPush(key, ctx->valsB);
-    keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp);
+    keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp); keyPush(key, ctx->refitScratch);
     const int rc = runCaptured(ctx, key, [&]() {
         if (haveBound) { launchSetBound(s, bnd[0], bnd[1], bnd[2], bnd[3], ctx->dBound); }
         else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
@@ -251,7 +257,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
             ctx->launches += 1;
             ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, k0, v0, k1, v1, T, numPasses, true, nullptr);
             ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
-                                                                ctx->pyramid, ctx->dRootBox, ctx->dErr);
+                                                                ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr);
         }
     });
     if (rc) return rc;
@@ -325,7 +331,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
-                    ctx->pyramid, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips};
+                    ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);

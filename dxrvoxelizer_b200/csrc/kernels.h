@@ -28,10 +28,13 @@ void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32
 constexpr int kMaxBoxLevels = 8;
 // float4 entries needed for the leaf-box pyramid of numTris leaves
 size_t boxPyramidFloat4s(uint32_t numTris);
-// k_leaf_setup (+ k_box_level) + k_hierarchy_boxes; returns the number of kernels launched
+// k_leaf_setup (+ k_box_level) + k_hierarchy_boxes (small meshes: child boxes by range union) or
+// k_hierarchy_boxes + k_refit_atomic (large meshes: bottom-up refit with atomics); returns the number of
+// kernels launched.  refitScratch: 3 * numTris uint32, only touched when useAtomicRefit(numTris).
+bool useAtomicRefit(uint32_t numTris);
 int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
                              const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
-                             float* rootBox, uint32_t* dErr);
+                             uint32_t* refitScratch, float* rootBox, uint32_t* dErr);
 
 // ---- onesweep.cu --------------------------------------------------------------------------------
 struct SortTemp

@@ -364,9 +364,14 @@ __device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int numL
     return x ? __clz(x) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
 }
 
+// kBoxes = true : child boxes by range union from the pyramid (no dependency chain; best for small meshes,
+//                  where everything is latency bound -- 100 k triangles)
+// kBoxes = false: topology + parent references only; k_refit_atomic then fits the boxes bottom-up (O(T) traffic
+//                  instead of O(T log T) pyramid reads; best for millions of triangles, where throughput counts)
+template <bool kBoxes>
 __global__ void __launch_bounds__(128, 8)
 k_hierarchy_boxes(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __restrict__ nodes, Pyramid pyr,
-                  float* __restrict__ rootBox)
+                  float* __restrict__ rootBox, uint32_t* __restrict__ nodeParent, uint32_t* __restrict__ leafParent)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numLeaves - 1) return;
@@ -380,68 +385,134 @@ k_hierarchy_boxes(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __r
         const long long q = (long long)i + l * d;
         return q >= 0 && q < numLeaves && delta(keys, numLeaves, ki, i, (int)q) > bound;
     };
-    long long lMax = 2;
-    while (true)
+    long long l = 0, s = 0;
+    int j, dNode;
+    if (kBoxes)
     {
-        const bool p0 = inRange(lMax, dMin), p1 = inRange(lMax * 2, dMin), p2 = inRange(lMax * 4, dMin), p3 = inRange(lMax * 8, dMin);
-        if (!p0) break;
-        if (!p1) { lMax *= 2; break; }
-        if (!p2) { lMax *= 4; break; }
-        if (!p3) { lMax *= 8; break; }
-        lMax *= 16;
+        // latency regime (small meshes): several independent probes per round
+        long long lMax = 2;
+        while (true)
+        {
+            const bool p0 = inRange(lMax, dMin), p1 = inRange(lMax * 2, dMin), p2 = inRange(lMax * 4, dMin), p3 = inRange(lMax * 8, dMin);
+            if (!p0) break;
+            if (!p1) { lMax *= 2; break; }
+            if (!p2) { lMax *= 4; break; }
+            if (!p3) { lMax *= 8; break; }
+            lMax *= 16;
+        }
+        // largest l < lMax with inRange(l): two bits per round
+        l = 0;
+        long long t = lMax >> 1;
+        while (t >= 1)
+        {
+            const long long h = t >> 1;
+            const bool a = inRange(l + t, dMin);
+            const bool b0 = h >= 1 && inRange(l + h, dMin), b1 = h >= 1 && inRange(l + t + h, dMin);
+            if (a) { l += t; if (b1) l += h; }
+            else if (b0) l += h;
+            t = h >> 1;
+            if (h < 1) break;
+        }
+        j = i + (int)l * d;
+        dNode = delta(keys, numLeaves, ki, i, j);
+        // split: largest s in [0, l) with delta(i, i + s*d) > dNode, by the same two-bits-per-round search
+        // over the power-of-two ladder ceil(l/2), ceil(l/4), ... , 1
+        s = 0;
+        t = l;
+        do
+        {
+            t = (t + 1) >> 1;
+            const long long t2 = (t > 1) ? ((t + 1) >> 1) : 0;
+            const bool a = inRange(s + t, dNode);
+            const bool b0 = t2 >= 1 && inRange(s + t2, dNode), b1 = t2 >= 1 && inRange(s + t + t2, dNode);
+            if (a) { s += t; if (t2 >= 1 && b1) s += t2; }
+            else if (t2 >= 1 && b0) s += t2;
+            if (t2 >= 1) t = t2;
+        } while (t > 1);
     }
-    // largest l < lMax with inRange(l): two bits per round
-    long long l = 0;
-    long long t = lMax >> 1;
-    while (t >= 1)
+    else
     {
-        const long long h = t >> 1;
-        const bool a = inRange(l + t, dMin);
-        const bool b0 = h >= 1 && inRange(l + h, dMin), b1 = h >= 1 && inRange(l + t + h, dMin);
-        if (a) { l += t; if (b1) l += h; }
-        else if (b0) l += h;
-        t = h >> 1;
-        if (h < 1) break;
+        // throughput regime (millions of nodes, mostly tiny ranges): the classic one-probe-per-step searches
+        long long lMax = 2;
+        while (inRange(lMax, dMin)) lMax <<= 1;
+        for (long long t = lMax >> 1; t >= 1; t >>= 1)
+            if (inRange(l + t, dMin)) l += t;
+        j = i + (int)l * d;
+        dNode = delta(keys, numLeaves, ki, i, j);
+        long long t = l;
+        do
+        {
+            t = (t + 1) >> 1;
+            if (inRange(s + t, dNode)) s += t;
+        } while (t > 1);
     }
-    const int j = i + (int)l * d;
-    const int dNode = delta(keys, numLeaves, ki, i, j);
-    // split: largest s in [0, l) with delta(i, i + s*d) > dNode, by the same two-bits-per-round search
-    // over the power-of-two ladder ceil(l/2), ceil(l/4), ... , 1
-    long long s = 0;
-    t = l;
-    do
-    {
-        t = (t + 1) >> 1;
-        const long long t2 = (t > 1) ? ((t + 1) >> 1) : 0;
-        const bool a = inRange(s + t, dNode);
-        const bool b0 = t2 >= 1 && inRange(s + t2, dNode), b1 = t2 >= 1 && inRange(s + t + t2, dNode);
-        if (a) { s += t; if (t2 >= 1 && b1) s += t2; }
-        else if (t2 >= 1 && b0) s += t2;
-        if (t2 >= 1) t = t2;
-    } while (t > 1);
     const int gamma = i + (int)s * d + min(d, 0);
 
     // node i covers the sorted leaves [first, last]; its children cover [first, gamma] and [gamma+1, last]
     const int first = min(i, j), last = max(i, j);
     const bool leftLeaf = (first == gamma), rightLeaf = (last == gamma + 1);
-    const RangeBox b0 = rangeQuery(pyr, (uint32_t)first, (uint32_t)gamma);
-    const RangeBox b1 = rangeQuery(pyr, (uint32_t)gamma + 1u, (uint32_t)last);
-    BvhNode n;
-    n.yz0 = make_float4(b0.ylo, b0.yhi, b0.zlo, b0.zhi);
-    n.yz1 = make_float4(b1.ylo, b1.yhi, b1.zlo, b1.zhi);
-    n.x01 = make_float4(b0.xlo, b0.xhi, b1.xlo, b1.xhi);
-    n.c0 = leftLeaf ? (kLeafFlag | (uint32_t)gamma) : (uint32_t)gamma;
-    n.c1 = rightLeaf ? (kLeafFlag | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-    n.pad0 = (uint32_t)first;   // leaf range of the node (debug / tests)
-    n.pad1 = (uint32_t)last;
+    const uint32_t c0 = leftLeaf ? (kLeafFlag | (uint32_t)gamma) : (uint32_t)gamma;
+    const uint32_t c1 = rightLeaf ? (kLeafFlag | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
     float4* dst = reinterpret_cast<float4*>(nodes + i);
-    dst[0] = n.yz0; dst[1] = n.yz1; dst[2] = n.x01;
-    dst[3] = make_float4(__uint_as_float(n.c0), __uint_as_float(n.c1), __uint_as_float(n.pad0), __uint_as_float(n.pad1));
-    if (i == 0)
+    // child references + the node's leaf range (debug / tests)
+    dst[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float((uint32_t)first), __uint_as_float((uint32_t)last));
+    if (kBoxes)
     {
-        rootBox[0] = fminf(b0.xlo, b1.xlo); rootBox[1] = fminf(b0.ylo, b1.ylo); rootBox[2] = fminf(b0.zlo, b1.zlo);
-        rootBox[3] = fmaxf(b0.xhi, b1.xhi); rootBox[4] = fmaxf(b0.yhi, b1.yhi); rootBox[5] = fmaxf(b0.zhi, b1.zhi);
+        const RangeBox b0 = rangeQuery(pyr, (uint32_t)first, (uint32_t)gamma);
+        const RangeBox b1 = rangeQuery(pyr, (uint32_t)gamma + 1u, (uint32_t)last);
+        dst[0] = make_float4(b0.ylo, b0.yhi, b0.zlo, b0.zhi);
+        dst[1] = make_float4(b1.ylo, b1.yhi, b1.zlo, b1.zhi);
+        dst[2] = make_float4(b0.xlo, b0.xhi, b1.xlo, b1.xhi);
+        if (i == 0)
+        {
+            rootBox[0] = fminf(b0.xlo, b1.xlo); rootBox[1] = fminf(b0.ylo, b1.ylo); rootBox[2] = fminf(b0.zlo, b1.zlo);
+            rootBox[3] = fmaxf(b0.xhi, b1.xhi); rootBox[4] = fmaxf(b0.yhi, b1.yhi); rootBox[5] = fmaxf(b0.zhi, b1.zhi);
+        }
     }
+    else
+    {
+        // parent reference: node index | (1u << 31 when the child is the right one)
+        if (leftLeaf) leafParent[gamma] = (uint32_t)i; else nodeParent[gamma] = (uint32_t)i;
+        if (rightLeaf) leafParent[gamma + 1] = (uint32_t)i | 0x80000000u; else nodeParent[gamma + 1] = (uint32_t)i | 0x80000000u;
+    }
+}
+
+// ---- bottom-up refit with one atomic per node (large meshes) -----------------------------------------
+// Every leaf starts with its box (pyramid level 0), stores it into its parent's slot, and the SECOND child
+// to arrive at a node (atomic arrival counter, zeroed per build) unions both boxes and carries on upwards.
+__global__ void __launch_bounds__(256)
+k_refit_atomic(int numLeaves, const float4* __restrict__ leafBoxes, BvhNode* __restrict__ nodes,
+               const uint32_t* __restrict__ nodeParent, const uint32_t* __restrict__ leafParent, uint32_t* __restrict__ flags,
+               float* __restrict__ rootBox, uint32_t* __restrict__ err)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= numLeaves) return;
+    float4 yz = __ldg(leafBoxes + 2 * (size_t)j);
+    float4 xx = __ldg(leafBoxes + 2 * (size_t)j + 1);
+    uint32_t p = __ldg(leafParent + j);
+    for (int level = 0; level < 128; ++level)  // depth <= 62; the bound only guards against a corrupt tree
+    {
+        const uint32_t pi = p & 0x7fffffffu, slot = p >> 31;
+        const uint32_t up = (pi != 0u) ? __ldg(nodeParent + pi) : 0u;  // issued early: overlaps the atomic
+        BvhNode* n = nodes + pi;
+        *(slot ? &n->yz1 : &n->yz0) = yz;
+        *(reinterpret_cast<float2*>(&n->x01) + slot) = make_float2(xx.x, xx.y);
+        __threadfence();  // release: the box must be visible before the arrival counter moves
+        if (atomicAdd(flags + pi, 1u) == 0u) return;  // first child to arrive: the sibling will carry on
+        // second arrival: the sibling's box was released before its increment; read it past L1
+        const float4 syz = __ldcg(slot ? &n->yz0 : &n->yz1);
+        const float2 sxx = __ldcg(reinterpret_cast<const float2*>(&n->x01) + (1u - slot));
+        yz = make_float4(fminf(yz.x, syz.x), fmaxf(yz.y, syz.y), fminf(yz.z, syz.z), fmaxf(yz.w, syz.w));
+        xx.x = fminf(xx.x, sxx.x); xx.y = fmaxf(xx.y, sxx.y);
+        if (pi == 0)
+        {
+            rootBox[0] = xx.x; rootBox[1] = yz.x; rootBox[2] = yz.z;
+            rootBox[3] = xx.y; rootBox[4] = yz.y; rootBox[5] = yz.w;
+            return;
+        }
+        p = up;
+    }
+    atomicMax(err, (uint32_t)kErrStackOverflow);
 }
 
 // ---- small utilities -------------------------------------------------------------------------------
@@ -538,9 +609,10 @@ size_t boxPyramidFloat4s(uint32_t numTris)
 
 int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
                              const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
-                             float* rootBox, uint32_t* dErr)
+                             uint32_t* refitScratch, float* rootBox, uint32_t* dErr)
 {
     if (!m.numTris) return 0;
+    const bool atomicRefit = useAtomicRefit(m.numTris);
     Pyramid pyr;
     uint32_t c = m.numTris;
     float4* p = pyramidMem;
@@ -549,7 +621,7 @@ int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBo
     {
         pyr.level[l] = p; pyr.count[l] = c; pyr.numLevels = l + 1;
         p += 2 * (size_t)c + 2;
-        if (c <= 64) break;
+        if (c <= 64 || atomicRefit) break;   // the bottom-up refit only needs the leaf boxes (level 0)
         c = (c + 15) / 16;
     }
     for (int l = pyr.numLevels; l < kMaxBoxLevels; ++l) { pyr.level[l] = nullptr; pyr.count[l] = 0; }
@@ -563,11 +635,29 @@ int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBo
     }
     if (m.numTris > 1)
     {
-        k_hierarchy_boxes<<<(m.numTris - 1 + 127) / 128, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, pyr, rootBox);
-        ++launches;
+        const uint32_t blocks = (m.numTris - 1 + 127) / 128;
+        if (!atomicRefit)
+        {
+            k_hierarchy_boxes<true><<<blocks, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, pyr, rootBox, nullptr, nullptr);
+            ++launches;
+        }
+        else
+        {
+            // refitScratch = [nodeParent T][leafParent T][flags T]
+            uint32_t* nodeParent = refitScratch;
+            uint32_t* leafParent = refitScratch + m.numTris;
+            uint32_t* flags = refitScratch + 2 * (size_t)m.numTris;
+            cudaMemsetAsync(flags, 0, sizeof(uint32_t) * m.numTris, s);
+            k_hierarchy_boxes<false><<<blocks, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, pyr, rootBox, nodeParent, leafParent);
+            k_refit_atomic<<<(m.numTris + 255) / 256, 256, 0, s>>>((int)m.numTris, pyr.level[0], nodes, nodeParent, leafParent, flags,
+                                                                   rootBox, dErr);
+            launches += 2;
+        }
     }
     return launches;
 }
+
+bool useAtomicRefit(uint32_t numTris) { return numTris > (1u << 19); }
 
 void launchPopcount(cudaStream_t s, const uint32_t* words, size_t numWords, unsigned long long* dCount)
 {

@@ -289,3 +289,21 @@ def test_degenerate_inputs_do_not_hang(vox, meshes_mod, oracle_mod):
     vox.build_bvh(d.Mesh(v, base.indices, base.stride))
     vox.voxelize(32, d.MODE_PARITY); vox.fetch_bits()
     vox.voxelize(32, d.MODE_SHADER); vox.fetch_bits()
+
+
+def test_million_triangle_mesh_uses_atomic_refit(vox, meshes_mod, oracle_mod):
+    """C4 regime: 1.3 M triangles (> 2^19: 30-bit keys, four radix passes with the big tile, bottom-up refit
+    with atomics instead of range unions) -- still bit-exact, and the root box is the scene box."""
+    m = meshes_mod.icosphere(8, seed=1234, normals=False)
+    assert m.num_triangles == 1310720
+    got = _run(vox, m, 256, d.MODE_PARITY)
+    ref = oracle_mod.voxelize(m.vertices, m.indices, 256, 1)
+    assert ref["odd_columns"] == 0
+    assert popcount(got ^ ref["bits"]) == 0
+    assert vox.info(L.INFO_CROSSINGS) == ref["crossings"]
+    root = vox.debug_read(L.DBG_ROOT_BOX, np.float32, 6)
+    b = vox.bound()
+    scene = ((m.vertices[:, :3] - b[:3]) / b[3]).astype(np.float32)
+    assert np.array_equal(root[:3], scene.min(0)) and np.array_equal(root[3:], scene.max(0))
+    keys = vox.debug_read(L.DBG_MORTON_SORTED, np.uint32, m.num_triangles)
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
