@@ -22,6 +22,7 @@ constexpr int kMaxPasses = 4;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr uint32_t kSmallSort = 1u << 19;  // below this many pairs use the 1024-pair tile
+constexpr int kBigItems = 16;              // items per thread of the bandwidth-bound variant
 
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagInclusive = 2u << 30;
@@ -82,7 +83,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     constexpr int kTile = kSortThreads * kItems;
     // predecessor tiles fetched per round trip of the look-back: the small-tile variant is latency bound
     // (many tiles, few keys), the big-tile variant is register bound
-    constexpr int kLookbackWindow = kItems >= 16 ? 4 : 12;
+    constexpr int kLookbackWindow = kItems >= 8 ? 4 : 12;
     __shared__ uint32_t warpHist[kSortWarps][kRadix];  // 8 KB
     __shared__ uint32_t binStart[kRadix];
     __shared__ uint32_t globalBase[kRadix];
@@ -198,7 +199,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     }
 }
 
-uint32_t tileSizeFor(uint32_t n) { return n < kSmallSort ? kSortThreads * 4u : kSortThreads * 16u; }
+uint32_t tileSizeFor(uint32_t n) { return n < kSmallSort ? kSortThreads * 4u : kSortThreads * (uint32_t)kBigItems; }
 }  // namespace
 
 uint32_t SortTemp::tilesFor(uint32_t n) { const uint32_t t = tileSizeFor(n); return (n + t - 1) / t; }
@@ -243,7 +244,7 @@ int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* va
             k_onesweep_pass<4><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
                                                               lookback + (size_t)p * tiles * kRadix, tileCounter + p);
         else
-            k_onesweep_pass<16><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
+            k_onesweep_pass<kBigItems><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
                                                                lookback + (size_t)p * tiles * kRadix, tileCounter + p);
         ++launches;
         uint32_t* t = kin; kin = kout; kout = t;
