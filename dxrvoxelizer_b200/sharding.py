@@ -24,6 +24,43 @@ def slab_range(rank, world, N):
     return N * rank // world, N * (rank + 1) // world
 
 
+def balanced_slabs(mesh, N, world, bound=None, compute_weight=1.5):
+    """Cost-balanced z-slabs: [(z0, z1)] * world, contiguous and covering [0, N).
+
+    Equal slabs are only balanced for a mesh that fills the grid evenly; a real mesh is thin along some
+    axis (the dragon occupies a quarter of the z range), so the ranks owning its layers do all the
+    crossing tests while the others only stream zeros.  The cost of layer z is modelled as
+    1 (the stores) + compute_weight * t(z) / mean(t), t(z) = triangles whose z extent overlaps the layer,
+    and the cut points split the cumulative cost evenly.  Pure host code (numpy), deterministic: every
+    rank computes the same partition from the replicated mesh."""
+    if world < 1 or N < 1:
+        raise ValueError("bad world/N")
+    if world == 1:
+        return [(0, N)]
+    pos = mesh.vertices[:, :3].astype(np.float64)
+    if bound is None:
+        mn, mx = pos.min(0), pos.max(0)
+        bound = np.concatenate([(mx + mn) / 2, [(mx - mn).max() / 2]])
+    tri = mesh.indices.reshape(-1, 3)
+    z = (pos[:, 2][tri] - bound[2]) / bound[3]                      # scene z of the three corners
+    lo = np.clip(np.floor((z.min(1) + 1.0) * 0.5 * N - 0.5).astype(np.int64), 0, N - 1)
+    hi = np.clip(np.ceil((z.max(1) + 1.0) * 0.5 * N - 0.5).astype(np.int64), 0, N - 1)
+    diff = np.zeros(N + 1, np.float64)
+    np.add.at(diff, lo, 1.0)
+    np.add.at(diff, hi + 1, -1.0)
+    t = np.cumsum(diff[:N])
+    cost = 1.0 + (compute_weight * t / t.mean() if t.sum() > 0 else 0.0)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        zc = int(np.searchsorted(cum, target))
+        zc = max(cuts[-1] + 1, min(zc, N - (world - r)))             # every rank keeps at least one layer
+        cuts.append(zc)
+    cuts.append(N)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def slab_words(N, z0, z1):
     return (z1 - z0) * N * ((N + 31) // 32)
 

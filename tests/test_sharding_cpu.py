@@ -67,3 +67,26 @@ def test_broadcast_and_gather_over_gloo(world, tmp_path):
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, out
         assert "rank %d ok" % r in out
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_balanced_slabs_cover_grid_and_balance_the_dragon(world, assets):
+    from dxrvoxelizer_b200.sharding import balanced_slabs
+    m = assets("dragon.obj")
+    N = 1024
+    slabs = balanced_slabs(m, N, world)
+    assert slabs[0][0] == 0 and slabs[-1][1] == N and len(slabs) == world
+    assert all(a1 == b0 and a0 < a1 for (a0, a1), (b0, b1) in zip(slabs[:-1], slabs[1:]))
+    if world > 1:
+        # triangles per layer (same proxy the function uses): the heaviest rank must carry clearly less than
+        # with equal slabs, where the few ranks owning the dragon's thin z range do all the work
+        b = m.bound
+        z = (m.vertices[:, 2][m.indices.reshape(-1, 3)] - b[2]) / b[3]
+        layer = np.clip(((z.mean(1) + 1) * 0.5 * N).astype(int), 0, N - 1)
+        hist = np.bincount(layer, minlength=N).astype(float)
+        cost = 1.0 + 1.5 * hist / hist.mean()
+        def worst(parts):
+            return max(cost[a:b].sum() for a, b in parts)
+        equal = [slab_range(r, world, N) for r in range(world)]
+        assert worst(slabs) <= worst(equal) * (1.05 if world == 2 else 0.8)
+        assert worst(slabs) <= 1.35 * cost.sum() / world
