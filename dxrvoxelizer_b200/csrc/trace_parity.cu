@@ -23,7 +23,9 @@
 //                        slab is written exactly once with coalesced 128-bit stores -- no clear pass,
 //                        no scatter to HBM.  A super-tile whose candidate list overflowed (huge meshes)
 //                        walks the tree itself, CTA-cooperatively, instead of reading a list.
+#include <cstdlib>
 #include "kernels.h"
+#include "timeline_debug.cuh"
 
 namespace dxrv
 {
@@ -121,10 +123,13 @@ struct ParityParams
     uint32_t z0, z1;
     uint32_t tilesY;         // super-tiles along y
     uint32_t numTiles;
+    uint32_t tilesPad;       // numTiles rounded up to a multiple of 32
+    uint32_t tuneSplit, tunePart, tuneHeavy;
+    uint32_t numWriters;     // leading CTAs of the fill kernel that only write the empty super-tiles
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
-    uint32_t* bucketCount;   // [0] heavy entries, [1] light tiles, [2] empty tiles, [3] heavy slots, [4] extra parts
-    uint32_t* lightTiles;    // [numTiles]
+    uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [8..11] light tiles per class
+    uint32_t* lightTiles;    // [kLightClasses][tilesPad]  light tiles, classed by candidate count
     uint32_t* emptyTiles;    // [numTiles]
     uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}
     uint32_t* heavyArrive;   // [kHeavySlots] parts of a split tile that have merged (self-resetting)
@@ -168,6 +173,9 @@ __device__ __forceinline__ void testNode(const BvhNode* __restrict__ nodes, uint
 // Real meshes leave most of the (y,z) plane empty and put hundreds of triangles into a few tiles
 // (surfaces seen edge-on): without the split those few CTAs are the kernel's critical path.
 constexpr uint32_t kHeavyTile = 192;    // candidates from which a tile is scheduled first
+constexpr int kLightClasses = 4;        // light tiles are scheduled by halving classes of candidate count:
+                                        // [96,192) [48,96) [24,48) [1,24) -- longest work first, so that the
+                                        // kernel's tail is made of its smallest work items
 constexpr uint32_t kSplitTile = 768;    // candidates from which a tile is split ...
 constexpr uint32_t kPartSize = 384;     // ... into parts of about this many candidates
 constexpr uint32_t kMaxParts = 12;
@@ -183,24 +191,34 @@ __device__ __forceinline__ void fileTiles(const ParityParams& prm, uint32_t firs
     const uint32_t tile = firstTile + lane;
     const bool active = count != 0xffffffffu;
     if (active) prm.candCount[tile] = count;
-    const bool isEmpty = active && count == 0u, isLight = active && count > 0u && count < kHeavyTile;
-    const bool isHeavy = active && count >= kHeavyTile;
-    const uint32_t mE = __ballot_sync(0xffffffffu, isEmpty), mL = __ballot_sync(0xffffffffu, isLight);
-    uint32_t baseE = 0, baseL = 0;
+    const bool isEmpty = active && count == 0u, isLight = active && count > 0u && count < prm.tuneHeavy;
+    const bool isHeavy = active && count >= prm.tuneHeavy;
+    int cls = -1;
+    if (isLight) cls = count >= prm.tuneHeavy / 2 ? 0 : count >= prm.tuneHeavy / 4 ? 1 : count >= prm.tuneHeavy / 8 ? 2 : 3;
+    const uint32_t mE = __ballot_sync(0xffffffffu, isEmpty);
+    uint32_t mC[kLightClasses], baseC[kLightClasses], baseE = 0;
+#pragma unroll
+    for (int k = 0; k < kLightClasses; ++k) { mC[k] = __ballot_sync(0xffffffffu, cls == k); baseC[k] = 0; }
     if (lane == 0)
     {
         if (mE) baseE = atomicAdd(prm.bucketCount + 2, __popc(mE));
-        if (mL) baseL = atomicAdd(prm.bucketCount + 1, __popc(mL));
+#pragma unroll
+        for (int k = 0; k < kLightClasses; ++k)
+            if (mC[k]) baseC[k] = atomicAdd(prm.bucketCount + 8 + k, __popc(mC[k]));
     }
     baseE = __shfl_sync(0xffffffffu, baseE, 0);
-    baseL = __shfl_sync(0xffffffffu, baseL, 0);
     if (isEmpty) prm.emptyTiles[baseE + __popc(mE & lt)] = tile;
-    if (isLight) prm.lightTiles[baseL + __popc(mL & lt)] = tile;
+#pragma unroll
+    for (int k = 0; k < kLightClasses; ++k)
+    {
+        const uint32_t b = __shfl_sync(0xffffffffu, baseC[k], 0);
+        if (cls == k) prm.lightTiles[(size_t)k * prm.tilesPad + b + __popc(mC[k] & lt)] = tile;
+    }
 
     uint32_t parts = isHeavy ? 1u : 0u, slot = 0xffffu;
-    if (isHeavy && count <= prm.candCap && count >= kSplitTile)   // (an overflowed list is not split: that CTA walks itself)
+    if (isHeavy && count <= prm.candCap && count >= prm.tuneSplit)   // (an overflowed list is not split: that CTA walks itself)
     {
-        parts = min((count + kPartSize - 1u) / kPartSize, kMaxParts);
+        parts = min((count + prm.tunePart - 1u) / prm.tunePart, kMaxParts);
         slot = atomicAdd(prm.bucketCount + 3, 1u);
         if (slot >= kHeavySlots || atomicAdd(prm.bucketCount + 4, parts - 1u) + parts - 1u > kExtraParts) { parts = 1u; slot = 0xffffu; }
     }
@@ -287,17 +305,67 @@ k_walk_columns(const ParityParams prm)
     if (warp == 0) fileTiles(prm, blockIdx.x * kWalkWarps, sCount[lane]);
 }
 
+// ---- empty super-tiles: nothing to trace, 16 KB of zeros to write.  A few dedicated "writer" CTAs
+// (the first blocks of the fill kernel, one per SM) stream all of them with fire-and-forget 128-bit
+// stores while the other CTAs of the same SMs rasterise: the write stream of the ~80 % of a real
+// grid that is empty overlaps the issue-bound tracing instead of following it.  One warp can keep
+// an SM's share of the HBM write bandwidth busy as long as it never waits: the tile numbers are
+// fetched 32 at a time, one per lane, a batch ahead.
+template <int SY, int SZ>
+__device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_t writerWarp, uint32_t numWriterWarps)
+{
+    const uint32_t lane = laneId();
+    const uint32_t nEmpty = __ldg(prm.bucketCount + 2);
+    const uint32_t N = prm.N, P = prm.P;
+    const size_t layerWords = (size_t)N * P;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    // this warp's tiles: entries writerWarp + k * numWriterWarps of the list; lane j holds entry k0 + j
+    auto fetch = [&](uint32_t k0) -> uint32_t {
+        const uint64_t e = (uint64_t)writerWarp + (uint64_t)(k0 + lane) * numWriterWarps;
+        return e < nEmpty ? __ldg(prm.emptyTiles + e) : 0xffffffffu;
+    };
+    uint32_t next = fetch(0);
+    for (uint32_t k0 = 0; ; k0 += 32u)
+    {
+        const uint32_t mine = next;
+        if (__shfl_sync(0xffffffffu, mine, 0) == 0xffffffffu) break;
+        next = fetch(k0 + 32u);
+        for (uint32_t j = 0; j < 32u; ++j)
+        {
+            const uint32_t tile = __shfl_sync(0xffffffffu, mine, j);
+            if (tile == 0xffffffffu) break;
+            const uint32_t sy0 = (tile % prm.tilesY) * SY, sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
+            const uint32_t runWords = min((uint32_t)SY, N - sy0) * P;   // the tile's rows of one layer are contiguous
+            const uint32_t nz = min((uint32_t)SZ, prm.z1 - sz0);
+            uint32_t* run = prm.grid + ((size_t)(sz0 - prm.z0) * N + sy0) * P;
+            if ((P & 3u) == 0u)
+            {
+                const uint32_t run4 = runWords >> 2;
+                for (uint32_t z = 0; z < nz; ++z, run += layerWords)
+                    for (uint32_t i = lane; i < run4; i += 32u) reinterpret_cast<uint4*>(run)[i] = zero4;
+            }
+            else
+            {
+                for (uint32_t z = 0; z < nz; ++z, run += layerWords)
+                    for (uint32_t i = lane; i < runWords; i += 32u) run[i] = 0u;
+            }
+        }
+    }
+}
+
 // ---- kernel B: W warps per CTA; the super-tile is SY x SZ columns with SY * SZ == 32 * W --------
 template <int W, int SY, int SZ>
 __global__ void __launch_bounds__(32 * W)
 k_trace_fill_columns(const ParityParams prm)
 {
+    DXRV_TL_SCOPE();
     static_assert(SY * SZ == 32 * W, "super-tile must hold one column per thread");
     constexpr int kThreads = 32 * W;
     constexpr int kCols = SY * SZ;
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sTop[2];   // fallback walk: stack height, double-buffered by iteration parity
     __shared__ uint32_t sCand;     // fallback walk: leaves queued so far
+    __shared__ uint32_t sNext;     // listed candidates: next chunk to hand out
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t N = prm.N, P = prm.P, Ps = prm.Ps;
@@ -308,32 +376,48 @@ k_trace_fill_columns(const ParityParams prm)
     float* tileZ = tileY + SY;                                 // [SZ]
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
+    float4* stage = reinterpret_cast<float4*>(stack);          // [W][32 x 3]  triangle records of the listed-candidates path
+    static_assert((kStackCap + kCandCap) * 4 >= W * 32 * 48, "staging area must fit the fallback walk's buffers");
 
-    // CTAs take the work heavy parts first, then light tiles, then empty tiles (see fileTile)
+    // the first CTAs write the empty tiles; the others take the work heavy parts first, then light
+    // tiles (see fileTiles)
     __shared__ uint32_t sIsLast;
-    const uint32_t nHeavy = __ldg(prm.bucketCount), nLight = __ldg(prm.bucketCount + 1), nEmpty = __ldg(prm.bucketCount + 2);
-    const uint32_t bIdx = blockIdx.x;
-    if (bIdx >= nHeavy + nLight + nEmpty) return;
+    if (blockIdx.x < prm.numWriters)
+    {
+        DXRV_TL_ROLE(1);
+        writeEmptyTiles<SY, SZ>(prm, blockIdx.x * (uint32_t)W + warp, prm.numWriters * (uint32_t)W);
+        return;
+    }
+    const uint32_t nHeavy = __ldg(prm.bucketCount);
+    const uint4 nLight = __ldg(reinterpret_cast<const uint4*>(prm.bucketCount + 8));
+    uint32_t bIdx = blockIdx.x - prm.numWriters;
     uint32_t tile, part = 0, parts = 1, hslot = 0xffffu;
     if (bIdx < nHeavy)
     {
+        DXRV_TL_ROLE(2);
         const uint2 e = __ldg(prm.heavyEntries + bIdx);
         tile = e.x; part = e.y & 0xffu; parts = (e.y >> 8) & 0xffu; hslot = e.y >> 16;
     }
-    else if (bIdx < nHeavy + nLight) tile = __ldg(prm.lightTiles + (bIdx - nHeavy));
-    else tile = __ldg(prm.emptyTiles + (bIdx - nHeavy - nLight));
+    else
+    {
+        bIdx -= nHeavy;
+        uint32_t cls = 0;
+        if (bIdx >= nLight.x) { bIdx -= nLight.x; cls = 1; if (bIdx >= nLight.y) { bIdx -= nLight.y; cls = 2; if (bIdx >= nLight.z) { bIdx -= nLight.z; cls = 3; } } }
+        if (cls == 3 && bIdx >= nLight.w) return;
+        DXRV_TL_ROLE(3);
+        tile = __ldg(prm.lightTiles + (size_t)cls * prm.tilesPad + bIdx);
+    }
     const uint32_t sy0 = (tile % prm.tilesY) * SY;
     const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
     const uint32_t listed = __ldg(prm.candCount + tile);
     const uint32_t yLast = min(sy0 + SY - 1, N - 1) - sy0, zLast = min(sz0 + SZ - 1, prm.z1 - 1) - sz0;
 
     uint32_t myCrossings = 0;
-    if (listed != 0u)   // an empty super-tile needs no shared memory at all
     {
         for (uint32_t i = tid; i < (uint32_t)kCols * (Ps >> 2); i += kThreads) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
         if (tid < SY) tileY[tid] = (sy0 + tid < N) ? -centreOf(sy0 + tid, fN, invNPow2) : INFINITY;
         if (tid >= 32 && tid < 32 + SZ) tileZ[tid - 32] = (sz0 + tid - 32 < prm.z1) ? centreOf(sz0 + tid - 32, fN, invNPow2) : INFINITY;
-        if (tid == 0) { stack[0] = 0; sTop[0] = 1u; sTop[1] = 0; sCand = 0; }
+        if (tid == 0) { stack[0] = 0; sTop[0] = 1u; sTop[1] = 0; sCand = 0; sNext = 0; }
         __syncthreads();
         const float halfN = 0.5f * fN;
 
@@ -342,36 +426,108 @@ k_trace_fill_columns(const ParityParams prm)
         // triangle's (y,z) box, a warp scan turns the rectangle sizes into one flat list of
         // (triangle, column) pairs, and the pairs are dealt round-robin to the 32 lanes -- a triangle
         // that spans many columns no longer serialises on one thread while the CTA waits at the barrier.
-        auto processWarpChunk = [&](bool has, uint32_t slot, uint32_t chunk) {
-            int yA = 0, zA = 0, w = 0, h = 0;
+        // columnRange: rectangle of lane's triangle -> yA | zA << 8 | w << 16 and the pair count w * h.
+        auto columnRange = [&](const float4& a, const float4& b, const float4& c, uint32_t& packed, uint32_t& n) {
+            const float ylo = fminf(fminf(a.y, b.y), c.y), yhi = fmaxf(fmaxf(a.y, b.y), c.y);
+            const float zlo = fminf(fminf(a.z, b.z), c.z), zhi = fmaxf(fmaxf(a.z, b.z), c.z);
+            // float estimate of the index range, then fix-up against the tabulated exact centres
+            // (tileY decreases with yl, tileZ increases with zl)
+            int yA, zA, yB, zB;
+            yA = min(max((int)floorf((1.0f - yhi) * halfN - 0.5f) - (int)sy0, 0), (int)yLast + 1);
+            while (yA > 0 && tileY[yA - 1] <= yhi) --yA;
+            while (yA <= (int)yLast && tileY[yA] > yhi) ++yA;
+            yB = min(max((int)ceilf((1.0f - ylo) * halfN - 0.5f) - (int)sy0, -1), (int)yLast);
+            while (yB < (int)yLast && tileY[yB + 1] >= ylo) ++yB;
+            while (yB >= 0 && tileY[yB] < ylo) --yB;
+            zA = min(max((int)floorf((zlo + 1.0f) * halfN - 0.5f) - (int)sz0, 0), (int)zLast + 1);
+            while (zA > 0 && tileZ[zA - 1] >= zlo) --zA;
+            while (zA <= (int)zLast && tileZ[zA] < zlo) ++zA;
+            zB = min(max((int)ceilf((zhi + 1.0f) * halfN - 0.5f) - (int)sz0, -1), (int)zLast);
+            while (zB < (int)zLast && tileZ[zB + 1] <= zhi) ++zB;
+            while (zB >= 0 && tileZ[zB] > zhi) --zB;
+            const int w = max(yB - yA + 1, 0), h = max(zB - zA + 1, 0);
+            n = (uint32_t)(w * h);
+            packed = (uint32_t)yA | ((uint32_t)zA << 8) | ((uint32_t)w << 16);
+        };
+        // one (triangle, column) pair: q-th column of the rectangle `packed`; inv = ceil(2^16 / w), so
+        // that q / w == (q * inv) >> 16 exactly (q < 256, w <= 16)
+        auto testPair = [&](const float4& ta, const float4& tb, const float4& tc, uint32_t packed, uint32_t inv, uint32_t q) {
+            const uint32_t ow = packed >> 16;
+            const uint32_t qz = (q * inv) >> 16;
+            const uint32_t yl = (packed & 0xffu) + (q - qz * ow), zl = ((packed >> 8) & 0xffu) + qz;
+            uint32_t ix;
+            if (columnCrossing(ta, tb, tc, tileY[yl], tileZ[zl], N, fN, invNPow2, ix))
+            {
+                ++myCrossings;
+                if (ix < N) atomicXor(&rows[(zl * SY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
+            }
+        };
+
+        // Staged variant (the normal path): the triangles with a non-empty rectangle are compacted into a
+        // per-warp shared-memory table of 48-byte records {a.xyz, packed | b.xyz, first pair | c.xyz, inv},
+        // so a pair needs three LDS.128 and nothing else.  The record that owns pair p is found without a
+        // search: records start at increasing pair numbers, so with `starts` = bit mask of the records
+        // starting inside the current window of 32 pairs (one warp-wide OR),
+        //   owner(p) = #records started before the window + popc(starts up to p's lane) - 1.
+        auto processWarpChunkStaged = [&](bool has, uint32_t slot) {
+            float4* tab = stage + warp * 96u;   // 32 records x 3 float4
+            float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+            uint32_t packed = 0, n = 0;
             if (has)
             {
                 const float4* t = reinterpret_cast<const float4*>(prm.tris + slot);
-                const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
-                const float ylo = fminf(fminf(a.y, b.y), c.y), yhi = fmaxf(fmaxf(a.y, b.y), c.y);
-                const float zlo = fminf(fminf(a.z, b.z), c.z), zhi = fmaxf(fmaxf(a.z, b.z), c.z);
-                // float estimate of the index range, then fix-up against the tabulated exact centres
-                // (tileY decreases with yl, tileZ increases with zl)
-                int yB, zB;
-                yA = min(max((int)floorf((1.0f - yhi) * halfN - 0.5f) - (int)sy0, 0), (int)yLast + 1);
-                while (yA > 0 && tileY[yA - 1] <= yhi) --yA;
-                while (yA <= (int)yLast && tileY[yA] > yhi) ++yA;
-                yB = min(max((int)ceilf((1.0f - ylo) * halfN - 0.5f) - (int)sy0, -1), (int)yLast);
-                while (yB < (int)yLast && tileY[yB + 1] >= ylo) ++yB;
-                while (yB >= 0 && tileY[yB] < ylo) --yB;
-                zA = min(max((int)floorf((zlo + 1.0f) * halfN - 0.5f) - (int)sz0, 0), (int)zLast + 1);
-                while (zA > 0 && tileZ[zA - 1] >= zlo) --zA;
-                while (zA <= (int)zLast && tileZ[zA] < zlo) ++zA;
-                zB = min(max((int)ceilf((zhi + 1.0f) * halfN - 0.5f) - (int)sz0, -1), (int)zLast);
-                while (zB < (int)zLast && tileZ[zB + 1] <= zhi) ++zB;
-                while (zB >= 0 && tileZ[zB] > zhi) --zB;
-                w = max(yB - yA + 1, 0); h = max(zB - zA + 1, 0);
+                a = __ldg(t); b = __ldg(t + 1); c = __ldg(t + 2);
+                columnRange(a, b, c, packed, n);
             }
-            const uint32_t n = (uint32_t)(w * h);
-            // per-triangle constants of the pair loop, packed for one shuffle: yA | zA << 8 | w << 16, and
-            // ceil(2^16 / w) so that q / w == (q * inv) >> 16 exactly (q < 256, w <= 16)
-            const uint32_t packed = (uint32_t)yA | ((uint32_t)zA << 8) | ((uint32_t)w << 16);
-            const uint32_t inv = w > 0 ? (65535u + (uint32_t)w) / (uint32_t)w : 0u;
+            uint32_t incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t nz = __ballot_sync(0xffffffffu, n != 0u);
+            if (n != 0u)
+            {
+                const uint32_t ow = packed >> 16;
+                float4* r = tab + __popc(nz & laneMaskLt()) * 3u;
+                a.w = __uint_as_float(packed); b.w = __uint_as_float(incl - n); c.w = __uint_as_float((65535u + ow) / ow);
+                r[0] = a; r[1] = b; r[2] = c;
+            }
+            __syncwarp();
+            const uint32_t myStart = lane < (uint32_t)__popc(nz) ? __float_as_uint(tab[lane * 3u + 1u].w) : 0xffffffffu;
+            const uint32_t le = laneMaskLt() | (1u << lane);
+            uint32_t before = 0;   // records that start before the current window
+#pragma unroll 1
+            for (uint32_t p0 = 0; p0 < total; p0 += 32u)
+            {
+                const uint32_t rel = myStart - p0;   // < 32 iff my record starts inside this window
+                const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+                const uint32_t owner = before + __popc(starts & le) - 1u;
+                before += __popc(starts);
+                const uint32_t p = p0 + lane;
+                if (p < total)
+                {
+                    const float4* r = tab + owner * 3u;
+                    const float4 ta = r[0], tb = r[1], tc = r[2];
+                    testPair(ta, tb, tc, __float_as_uint(ta.w), __float_as_uint(tc.w), p - __float_as_uint(tb.w));
+                }
+            }
+            __syncwarp();   // the table is rewritten by the next chunk
+        };
+
+        // Direct variant (fallback walk only, where the staging area holds the walk's stack): records stay
+        // in the registers of the lanes that loaded them and are fetched with shuffles.
+        auto processWarpChunk = [&](bool has, uint32_t slot, uint32_t chunk) {
+            uint32_t packed = 0, n = 0;
+            if (has)
+            {
+                const float4* t = reinterpret_cast<const float4*>(prm.tris + slot);
+                columnRange(__ldg(t), __ldg(t + 1), __ldg(t + 2), packed, n);
+            }
+            const uint32_t ow0 = packed >> 16;
+            const uint32_t inv = ow0 > 0 ? (65535u + ow0) / ow0 : 0u;
             uint32_t incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
@@ -402,16 +558,7 @@ k_trace_fill_columns(const ParityParams prm)
                 {
                     // the owner's triangle was just loaded by the owner lane: these hit L1
                     const float4* t = reinterpret_cast<const float4*>(prm.tris + oSlot);
-                    const float4 ta = __ldg(t), tb = __ldg(t + 1), tc = __ldg(t + 2);
-                    const uint32_t ow = oPacked >> 16;
-                    const uint32_t qz = (q * oInv) >> 16;
-                    const uint32_t yl = (oPacked & 0xffu) + (q - qz * ow), zl = ((oPacked >> 8) & 0xffu) + qz;
-                    uint32_t ix;
-                    if (columnCrossing(ta, tb, tc, tileY[yl], tileZ[zl], N, fN, invNPow2, ix))
-                    {
-                        ++myCrossings;
-                        if (ix < N) atomicXor(&rows[(zl * SY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
-                    }
+                    testPair(__ldg(t), __ldg(t + 1), __ldg(t + 2), oPacked, oInv, q);
                 }
             }
         };
@@ -425,10 +572,14 @@ k_trace_fill_columns(const ParityParams prm)
             const uint32_t* list = prm.candList + (size_t)tile * prm.candCap + partBegin;
             uint32_t C = 32u;
             while (C > 4u && mine < C * (uint32_t)W * 2u) C >>= 1;
-            for (uint32_t first = warp * C; first < mine; first += (uint32_t)W * C)
+            for (;;)   // the warps take chunks as they become free: pair counts per chunk vary a lot
             {
+                uint32_t first = 0;
+                if (lane == 0) first = atomicAdd(&sNext, C);
+                first = __shfl_sync(0xffffffffu, first, 0);
+                if (first >= mine) break;
                 const bool has = lane < C && first + lane < mine;
-                processWarpChunk(has, has ? __ldg(list + first + lane) : 0u, C);
+                processWarpChunkStaged(has, has ? __ldg(list + first + lane) : 0u);
             }
         }
         else
@@ -521,6 +672,7 @@ k_trace_fill_columns(const ParityParams prm)
             {
                 for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
                 if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
+                DXRV_TL_ROLE(4);
                 return;
             }
             __threadfence();
@@ -589,8 +741,7 @@ k_trace_fill_columns(const ParityParams prm)
         {
             const uint32_t g = g0 + lane;
             const uint32_t rr = g >> prm.gprShift, gi = g & (groupsPerRow - 1u);
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (listed != 0u) t = occupancy(g0, g, gi);
+            uint4 t = occupancy(g0, g, gi);
             if (gi < gprG) base[(rr >> 4) * zStride + (rr & 15u) * gprG + gi] = t;
         }
     }
@@ -602,8 +753,7 @@ k_trace_fill_columns(const ParityParams prm)
             uint32_t rowInWarp, gi;
             if (groupsPerRow <= 32u) { rowInWarp = g >> prm.gprShift; gi = g & (groupsPerRow - 1u); }
             else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (listed != 0u) t = occupancy(g0, g, gi);
+            uint4 t = occupancy(g0, g, gi);
 
             const uint32_t col = warp * 32u + rowInWarp;
             const uint32_t yl = col % SY, zl = col / SY;
@@ -628,11 +778,8 @@ k_trace_fill_columns(const ParityParams prm)
     }
 
     // ---- statistics ----
-    if (listed != 0u)
-    {
-        for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
-        if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
-    }
+    for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
+    if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
 }
 
 uint32_t sharedRowWords(uint32_t P)
@@ -652,18 +799,30 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 {
     const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + kStackCap + kCandCap);
     static bool attrSet[64] = {};
+    static int smCount[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attrSet[dev])
     {
         cudaFuncSetAttribute(k_trace_fill_columns<W, SY, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+        cudaDeviceGetAttribute(&smCount[dev], cudaDevAttrMultiProcessorCount, dev);
         attrSet[dev] = true;
     }
+    // one writer CTA per SM: blocks are handed out breadth-first, so the first smCount blocks land on distinct SMs
+    prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 0) ? (uint32_t)smCount[dev] : 148u;
+    prm.tuneSplit = kSplitTile; prm.tunePart = kPartSize; prm.tuneHeavy = kHeavyTile;
+    if (const char* w = std::getenv("DXRV_SPLIT")) prm.tuneSplit = atoi(w);
+    if (const char* w = std::getenv("DXRV_PART")) prm.tunePart = atoi(w);
+    if (const char* w = std::getenv("DXRV_HEAVY")) prm.tuneHeavy = atoi(w);
+    if (const char* w = std::getenv("DXRV_WRITERS")) prm.numWriters = (uint32_t)atoi(w) > 0 ? (uint32_t)atoi(w) : prm.numWriters;
     if (ev) cudaEventRecord(ev[0], s);
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
     if (ev) cudaEventRecord(ev[1], s);
-    k_trace_fill_columns<W, SY, SZ><<<prm.numTiles + kExtraParts, 32 * W, smemBytes, s>>>(prm);
+    k_trace_fill_columns<W, SY, SZ><<<prm.numWriters + prm.numTiles + kExtraParts, 32 * W, smemBytes, s>>>(prm);
     if (ev) cudaEventRecord(ev[2], s);
+    static const char* const kRoles[5] = {"surplus", "writer", "heavy part", "light tile", "merged part"};
+    (void)kRoles;
+    DXRV_TL_REPORT(s, prm.numWriters + prm.numTiles + kExtraParts, kRoles, 5);
 }
 }  // namespace
 
@@ -684,7 +843,7 @@ size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
     parityTileCounts(N, z0, z1, numTiles, candCap);
     const size_t tilesPad = (numTiles + 31u) & ~31u;
     const size_t Ps = sharedRowWords((N + 31) / 32);
-    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + 3 * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
+    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
 }
 
 size_t parityScratchZeroWords(uint32_t N)
@@ -707,11 +866,12 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.invNPow2 = ((N & (N - 1)) == 0) ? 1.0f / (float)N : 0.0f;
     prm.grid = grid;
     const size_t tilesPad = (prm.numTiles + 31u) & ~31u;
+    prm.tilesPad = (uint32_t)tilesPad;
     uint32_t* p = walkBuf;
     prm.bucketCount = p;  p += 32;
     prm.heavyArrive = p;  p += kHeavySlots;
     prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * prm.Ps;      // 16-byte aligned: all sizes are multiples of 4 words
-    prm.lightTiles = p;   p += tilesPad;
+    prm.lightTiles = p;   p += kLightClasses * tilesPad;
     prm.emptyTiles = p;   p += tilesPad;
     prm.candCount = p;    p += tilesPad;
     prm.heavyEntries = reinterpret_cast<uint2*>(p); p += 2 * (tilesPad + kExtraParts);
