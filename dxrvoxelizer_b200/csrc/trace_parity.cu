@@ -119,6 +119,7 @@ struct ParityParams
     const Tri48* tris;
     uint32_t numTris;
     uint32_t N, P, Ps;       // grid size, words per global row, words per shared row
+    uint32_t Mw;             // words of the per-row word mask: ceil(Ps / 32)
     uint32_t gprShift;       // log2(Ps / 4) when Ps <= 128 (Ps is then a power of two)
     uint32_t z0, z1;
     uint32_t tilesY;         // super-tiles along y
@@ -133,7 +134,7 @@ struct ParityParams
     uint32_t* emptyTiles;    // [numTiles]
     uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}
     uint32_t* heavyArrive;   // [kHeavySlots] parts of a split tile that have merged (self-resetting)
-    uint32_t* heavyScratch;  // [kHeavySlots][128 * Ps] merged toggle rows of split tiles (self-cleaning)
+    uint32_t* heavyScratch;  // [kHeavySlots][128 * (Ps + Mw)] merged toggle rows + word masks of split tiles (self-cleaning)
     uint32_t* candCount;     // [numTiles]  leaves found by k_walk_columns; > candCap = overflow
     uint32_t* candList;      // [numTiles][candCap]
     uint32_t candCap;
@@ -368,11 +369,16 @@ k_trace_fill_columns(const ParityParams prm)
     __shared__ uint32_t sNext;     // listed candidates: next chunk to hand out
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t N = prm.N, P = prm.P, Ps = prm.Ps;
+    const uint32_t N = prm.N, P = prm.P, Ps = prm.Ps, Mw = prm.Mw;
     const float fN = (float)N, invNPow2 = prm.invNPow2;
 
-    uint32_t* rows = smem;                                     // [kCols][Ps] toggle / occupancy bits, column = zl*SY + yl
-    float* tileY = reinterpret_cast<float*>(rows + (uint32_t)kCols * Ps);  // [SY] scene Y of the columns (decreasing)
+    // A crossing whose first inside voxel is ix flips every voxel >= ix of its column.  Inside the word of
+    // ix that is one XOR with a suffix mask; for the words after it, it is one bit in the column's WORD
+    // MASK, and the write-out flips word w when the mask has an odd number of bits below w.  (A single
+    // toggle bit per crossing + a 128-bit prefix-XOR at write-out costs four times the ALU work.)
+    uint32_t* rows = smem;                                     // [kCols][Ps] occupancy bits, column = zl*SY + yl
+    uint32_t* wmask = rows + (uint32_t)kCols * Ps;             // [kCols][Mw] word masks
+    float* tileY = reinterpret_cast<float*>(wmask + (uint32_t)kCols * Mw);  // [SY] scene Y of the columns (decreasing)
     float* tileZ = tileY + SY;                                 // [SZ]
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
@@ -414,7 +420,7 @@ k_trace_fill_columns(const ParityParams prm)
 
     uint32_t myCrossings = 0;
     {
-        for (uint32_t i = tid; i < (uint32_t)kCols * (Ps >> 2); i += kThreads) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < ((uint32_t)kCols * (Ps + Mw)) >> 2; i += kThreads) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
         if (tid < SY) tileY[tid] = (sy0 + tid < N) ? -centreOf(sy0 + tid, fN, invNPow2) : INFINITY;
         if (tid >= 32 && tid < 32 + SZ) tileZ[tid - 32] = (sz0 + tid - 32 < prm.z1) ? centreOf(sz0 + tid - 32, fN, invNPow2) : INFINITY;
         if (tid == 0) { stack[0] = 0; sTop[0] = 1u; sTop[1] = 0; sCand = 0; sNext = 0; }
@@ -459,7 +465,12 @@ k_trace_fill_columns(const ParityParams prm)
             if (columnCrossing(ta, tb, tc, tileY[yl], tileZ[zl], N, fN, invNPow2, ix))
             {
                 ++myCrossings;
-                if (ix < N) atomicXor(&rows[(zl * SY + yl) * Ps + (ix >> 5)], 1u << (ix & 31u));
+                if (ix < N)
+                {
+                    const uint32_t col = zl * SY + yl, w = ix >> 5;
+                    atomicXor(&rows[col * Ps + w], 0xffffffffu << (ix & 31u));
+                    atomicXor(&wmask[col * Mw + (w >> 5)], 1u << (w & 31u));
+                }
             }
         };
 
@@ -658,8 +669,8 @@ k_trace_fill_columns(const ParityParams prm)
         {
             // ---- split tile: merge this part's toggles into the tile's scratch rows; the last part to
             // arrive takes the merged rows back and carries on to the fill, the others are done ----
-            uint32_t* scratch = prm.heavyScratch + (size_t)hslot * kCols * Ps;
-            for (uint32_t i = tid; i < (uint32_t)kCols * Ps; i += kThreads)
+            uint32_t* scratch = prm.heavyScratch + (size_t)hslot * kCols * (Ps + Mw);
+            for (uint32_t i = tid; i < (uint32_t)kCols * (Ps + Mw); i += kThreads)
             {
                 const uint32_t v = rows[i];
                 if (v) atomicXor(scratch + i, v);
@@ -676,7 +687,7 @@ k_trace_fill_columns(const ParityParams prm)
                 return;
             }
             __threadfence();
-            for (uint32_t i = tid; i < (uint32_t)kCols * (Ps >> 2); i += kThreads)
+            for (uint32_t i = tid; i < ((uint32_t)kCols * (Ps + Mw)) >> 2; i += kThreads)
             {
                 uint4* src = reinterpret_cast<uint4*>(scratch) + i;
                 reinterpret_cast<uint4*>(rows)[i] = __ldcg(src);
@@ -687,44 +698,25 @@ k_trace_fill_columns(const ParityParams prm)
         }
     }
 
-    // ---- prefix-XOR along x and write-out, 4 words (128 bits) per lane ----
+    // ---- write-out, 4 words (128 bits) per lane: flip the words behind each crossing's word ----
     // warp w owns shared rows [32w, 32w+32): for every z of the super-tile SY consecutive y rows,
     // which are contiguous in the global grid.
     const uint32_t groupsPerRow = Ps >> 2;            // 128-bit groups per shared row
     const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
     const uint4* rows4 = reinterpret_cast<const uint4*>(rows) + (size_t)warp * 32u * groupsPerRow;
-    uint32_t runCarry = 0;                            // carry along a row spanning several 32-group chunks
+    const uint32_t* wmaskW = wmask + warp * 32u * Mw;
 
-    // toggles of group g (lane's 128 bits of row g / groupsPerRow) -> occupancy bits
-    auto occupancy = [&](uint32_t g0, uint32_t g, uint32_t gi) -> uint4 {
+    // occupancy bits of group gi (words 4gi .. 4gi+3) of the warp's row rowInWarp; g = the group's index
+    auto occupancy = [&](uint32_t g, uint32_t rowInWarp, uint32_t gi) -> uint4 {
         uint4 t = rows4[g];
-        uint32_t carry = 0;
-        const uint32_t dirty = __ballot_sync(0xffffffffu, (t.x | t.y | t.z | t.w) != 0u);
-        if (groupsPerRow >= 32u && (g0 % groupsPerRow) == 0) runCarry = 0;
-        if (dirty)
-        {
-            uint32_t par;
-            t.x = prefixXor32(t.x); par = t.x >> 31;
-            t.y = prefixXor32(t.y) ^ (0u - par); par = t.y >> 31;
-            t.z = prefixXor32(t.z) ^ (0u - par); par = t.z >> 31;
-            t.w = prefixXor32(t.w) ^ (0u - par); par = t.w >> 31;
-            // `par` = parity of this lane's 128 bits (without incoming carry); prefix parity is
-            // linear, so the carry into a lane is the XOR of `par` over the lower lanes of its row
-            const uint32_t bal = __ballot_sync(0xffffffffu, par);
-            if (groupsPerRow >= 32u)
-            {
-                carry = (__popc(bal & laneMaskLt()) & 1u) ^ runCarry;
-                runCarry ^= (__popc(bal) & 1u);
-            }
-            else
-            {
-                const uint32_t segLo = lane - gi;  // first lane of this row
-                carry = __popc(bal & laneMaskLt() & ~((1u << segLo) - 1u)) & 1u;
-            }
-        }
-        else if (groupsPerRow >= 32u) carry = runCarry;
-        const uint32_t flip = 0u - carry;
-        t.x ^= flip; t.y ^= flip; t.z ^= flip; t.w ^= flip;
+        const uint32_t w0 = gi * 4u, mw = w0 >> 5;     // the group's four words share one mask word
+        const uint32_t* m = wmaskW + rowInWarp * Mw;
+        uint32_t below = 0;                              // XOR of the mask words before mw (none up to N = 1024)
+        for (uint32_t k = 0; k < mw; ++k) below ^= m[k];
+        // bit j of e: parity of the mask bits below word 32*mw + j
+        const uint32_t e = (prefixXor32(m[mw]) << 1) ^ (0u - (__popc(below) & 1u));
+        const uint32_t f = e >> (w0 & 31u);
+        t.x ^= 0u - (f & 1u); t.y ^= 0u - ((f >> 1) & 1u); t.z ^= 0u - ((f >> 2) & 1u); t.w ^= 0u - ((f >> 3) & 1u);
         return t;
     };
 
@@ -741,7 +733,7 @@ k_trace_fill_columns(const ParityParams prm)
         {
             const uint32_t g = g0 + lane;
             const uint32_t rr = g >> prm.gprShift, gi = g & (groupsPerRow - 1u);
-            uint4 t = occupancy(g0, g, gi);
+            uint4 t = occupancy(g, rr, gi);
             if (gi < gprG) base[(rr >> 4) * zStride + (rr & 15u) * gprG + gi] = t;
         }
     }
@@ -753,7 +745,7 @@ k_trace_fill_columns(const ParityParams prm)
             uint32_t rowInWarp, gi;
             if (groupsPerRow <= 32u) { rowInWarp = g >> prm.gprShift; gi = g & (groupsPerRow - 1u); }
             else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
-            uint4 t = occupancy(g0, g, gi);
+            uint4 t = occupancy(g, rowInWarp, gi);
 
             const uint32_t col = warp * 32u + rowInWarp;
             const uint32_t yl = col % SY, zl = col / SY;
@@ -797,7 +789,7 @@ uint32_t sharedRowWords(uint32_t P)
 template <int W, int SY, int SZ>
 void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 {
-    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + kStackCap + kCandCap);
+    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * (prm.Ps + prm.Mw) + SY + SZ + kStackCap + kCandCap);
     static bool attrSet[64] = {};
     static int smCount[64] = {};
     int dev = 0;
@@ -842,14 +834,14 @@ size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
     uint32_t numTiles, candCap;
     parityTileCounts(N, z0, z1, numTiles, candCap);
     const size_t tilesPad = (numTiles + 31u) & ~31u;
-    const size_t Ps = sharedRowWords((N + 31) / 32);
-    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
+    const size_t Ps = sharedRowWords((N + 31) / 32), Mw = (Ps + 31) / 32;
+    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw) + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
 }
 
 size_t parityScratchZeroWords(uint32_t N)
 {
-    const size_t Ps = sharedRowWords((N + 31) / 32);
-    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * Ps;
+    const size_t Ps = sharedRowWords((N + 31) / 32), Mw = (Ps + 31) / 32;
+    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw);
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
@@ -857,7 +849,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
 {
     ParityParams prm;
     prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
-    prm.N = N; prm.P = (N + 31) / 32; prm.Ps = sharedRowWords(prm.P);
+    prm.N = N; prm.P = (N + 31) / 32; prm.Ps = sharedRowWords(prm.P); prm.Mw = (prm.Ps + 31) / 32;
     prm.gprShift = 0;
     while ((1u << prm.gprShift) < (prm.Ps >> 2)) ++prm.gprShift;
     prm.z0 = z0; prm.z1 = z1;
@@ -870,7 +862,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     uint32_t* p = walkBuf;
     prm.bucketCount = p;  p += 32;
     prm.heavyArrive = p;  p += kHeavySlots;
-    prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * prm.Ps;      // 16-byte aligned: all sizes are multiples of 4 words
+    prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * (prm.Ps + prm.Mw);      // 16-byte aligned: all sizes are multiples of 4 words
     prm.lightTiles = p;   p += kLightClasses * tilesPad;
     prm.emptyTiles = p;   p += tilesPad;
     prm.candCount = p;    p += tilesPad;
