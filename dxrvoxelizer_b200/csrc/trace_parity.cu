@@ -23,6 +23,7 @@
 //                        slab is written exactly once with coalesced 128-bit stores -- no clear pass,
 //                        no scatter to HBM.  A super-tile whose candidate list overflowed (huge meshes)
 //                        walks the tree itself, CTA-cooperatively, instead of reading a list.
+#include <algorithm>
 #include <cstdlib>
 #include "kernels.h"
 #include "timeline_debug.cuh"
@@ -34,8 +35,9 @@ namespace
 constexpr int kStackGuard = 64;   // >= LBVH depth bound (62): head-room kept for depth-first popping
 constexpr int kWalkStack = 512;   // per-warp stack of k_walk_columns
 constexpr int kWalkWarps = 8;     // warps (= super-tiles) per CTA of k_walk_columns (<= 32)
-constexpr int kStackCap = 1024;   // per-CTA stack of the in-kernel fallback walk
-constexpr int kCandCap = 768;     // per-CTA leaf ring of the fallback walk (>= 3 * threads per CTA)
+// in-kernel fallback walk of the fill kernel, per thread of the CTA: stack entries and leaf-ring entries (>= 3)
+constexpr int kStackPerThread = 8;
+constexpr int kCandPerThread = 6;
 
 __device__ __forceinline__ uint32_t prefixXor32(uint32_t v)
 {
@@ -127,6 +129,7 @@ struct ParityParams
     uint32_t tilesPad;       // numTiles rounded up to a multiple of 32
     uint32_t tuneSplit, tunePart, tuneHeavy;
     uint32_t numWriters;     // leading CTAs of the fill kernel that only write the empty super-tiles
+    uint32_t writerTilesPerWork;  // empty tiles those CTAs take per busy work item
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
     uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [8..11] light tiles per class
@@ -177,8 +180,8 @@ constexpr uint32_t kHeavyTile = 192;    // candidates from which a tile is sched
 constexpr int kLightClasses = 4;        // light tiles are scheduled by halving classes of candidate count:
                                         // [96,192) [48,96) [24,48) [1,24) -- longest work first, so that the
                                         // kernel's tail is made of its smallest work items
-constexpr uint32_t kSplitTile = 768;    // candidates from which a tile is split ...
-constexpr uint32_t kPartSize = 384;     // ... into parts of about this many candidates
+constexpr uint32_t kSplitTile = 512;    // candidates from which a tile is split ...
+constexpr uint32_t kPartSize = 256;     // ... into parts of about this many candidates
 constexpr uint32_t kMaxParts = 12;
 constexpr uint32_t kHeavySlots = 1024;  // tiles that can be split per launch
 constexpr uint32_t kExtraParts = 2048;  // extra CTAs (beyond one per tile) a launch provides
@@ -307,23 +310,55 @@ k_walk_columns(const ParityParams prm)
 }
 
 // ---- empty super-tiles: nothing to trace, 16 KB of zeros to write.  A few dedicated "writer" CTAs
-// (the first blocks of the fill kernel, one per SM) stream all of them with fire-and-forget 128-bit
-// stores while the other CTAs of the same SMs rasterise: the write stream of the ~80 % of a real
-// grid that is empty overlaps the issue-bound tracing instead of following it.  One warp can keep
-// an SM's share of the HBM write bandwidth busy as long as it never waits: the tile numbers are
-// fetched 32 at a time, one per lane, a batch ahead.
+// (the first blocks of the fill kernel) stream them with fire-and-forget 128-bit stores while the
+// other CTAs of the same SMs rasterise: the write stream of the ~80 % of a real grid that is empty
+// overlaps the issue-bound tracing instead of following it.  The writers take as many empty tiles as
+// they can stream while the busy tiles are traced (kWriterBytesPerWork per busy work item); what is
+// left -- everything, for a mostly empty grid -- is written one tile per CTA by the launch's surplus
+// CTAs (there is one CTA per tile, and empty tiles need none), i.e. by the whole machine.
+constexpr uint32_t kWriterBytesPerWork = 160u << 10;
+
+// zero layers zFirst, zFirst + zStep, ... of an empty tile (one warp)
 template <int SY, int SZ>
-__device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_t writerWarp, uint32_t numWriterWarps)
+__device__ __forceinline__ void zeroTileLayers(const ParityParams& prm, uint32_t tile, uint32_t zFirst, uint32_t zStep)
 {
     const uint32_t lane = laneId();
-    const uint32_t nEmpty = __ldg(prm.bucketCount + 2);
     const uint32_t N = prm.N, P = prm.P;
     const size_t layerWords = (size_t)N * P;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    // this warp's tiles: entries writerWarp + k * numWriterWarps of the list; lane j holds entry k0 + j
+    const uint32_t sy0 = (tile % prm.tilesY) * SY, sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
+    const uint32_t runWords = min((uint32_t)SY, N - sy0) * P;   // the tile's rows of one layer are contiguous
+    const uint32_t nz = min((uint32_t)SZ, prm.z1 - sz0);
+    uint32_t* run = prm.grid + ((size_t)(sz0 - prm.z0 + zFirst) * N + sy0) * P;
+    if ((P & 3u) == 0u)
+    {
+        // stores issued back to back from independent address registers (a store whose address register
+        // is still being read by the previous one would stall the warp)
+        const uint32_t run4 = runWords >> 2;
+        for (uint32_t z = zFirst; z < nz; z += zStep, run += zStep * layerWords)
+        {
+            uint4* q = reinterpret_cast<uint4*>(run) + lane;
+            uint32_t i = 0;
+            for (; i + 128u <= run4; i += 128u) { q[i] = zero4; q[i + 32u] = zero4; q[i + 64u] = zero4; q[i + 96u] = zero4; }
+            for (i += lane; i < run4; i += 32u) reinterpret_cast<uint4*>(run)[i] = zero4;
+        }
+    }
+    else
+    {
+        for (uint32_t z = zFirst; z < nz; z += zStep, run += zStep * layerWords)
+            for (uint32_t i = lane; i < runWords; i += 32u) run[i] = 0u;
+    }
+}
+
+// dedicated writer warp `writerWarp` of `numWriterWarps`: entries writerWarp + k * numWriterWarps of the first
+// nDedicated entries of the empty list; the tile numbers are fetched 32 at a time, one per lane, a batch ahead
+template <int SY, int SZ>
+__device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_t nDedicated, uint32_t writerWarp, uint32_t numWriterWarps)
+{
+    const uint32_t lane = laneId();
     auto fetch = [&](uint32_t k0) -> uint32_t {
         const uint64_t e = (uint64_t)writerWarp + (uint64_t)(k0 + lane) * numWriterWarps;
-        return e < nEmpty ? __ldg(prm.emptyTiles + e) : 0xffffffffu;
+        return e < nDedicated ? __ldg(prm.emptyTiles + e) : 0xffffffffu;
     };
     uint32_t next = fetch(0);
     for (uint32_t k0 = 0; ; k0 += 32u)
@@ -335,34 +370,24 @@ __device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_
         {
             const uint32_t tile = __shfl_sync(0xffffffffu, mine, j);
             if (tile == 0xffffffffu) break;
-            const uint32_t sy0 = (tile % prm.tilesY) * SY, sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
-            const uint32_t runWords = min((uint32_t)SY, N - sy0) * P;   // the tile's rows of one layer are contiguous
-            const uint32_t nz = min((uint32_t)SZ, prm.z1 - sz0);
-            uint32_t* run = prm.grid + ((size_t)(sz0 - prm.z0) * N + sy0) * P;
-            if ((P & 3u) == 0u)
-            {
-                const uint32_t run4 = runWords >> 2;
-                for (uint32_t z = 0; z < nz; ++z, run += layerWords)
-                    for (uint32_t i = lane; i < run4; i += 32u) reinterpret_cast<uint4*>(run)[i] = zero4;
-            }
-            else
-            {
-                for (uint32_t z = 0; z < nz; ++z, run += layerWords)
-                    for (uint32_t i = lane; i < runWords; i += 32u) run[i] = 0u;
-            }
+            zeroTileLayers<SY, SZ>(prm, tile, 0u, 1u);
         }
     }
 }
 
-// ---- kernel B: W warps per CTA; the super-tile is SY x SZ columns with SY * SZ == 32 * W --------
+// ---- kernel B: W warps per CTA on a super-tile of SY x SZ columns.  W = 4 up to N = 1024; larger grids
+// have longer bit rows, i.e. more shared memory per tile and fewer CTAs per SM, and get more warps per
+// CTA instead (the tracing is dealt to warps in chunks, the write-out in rows: neither cares) --------
 template <int W, int SY, int SZ>
-__global__ void __launch_bounds__(32 * W)
+__global__ void __launch_bounds__(32 * W, W == 4 ? 9 : W == 8 ? 4 : 2)
 k_trace_fill_columns(const ParityParams prm)
 {
     DXRV_TL_SCOPE();
-    static_assert(SY * SZ == 32 * W, "super-tile must hold one column per thread");
     constexpr int kThreads = 32 * W;
     constexpr int kCols = SY * SZ;
+    constexpr int kRowsPerWarp = kCols / W;
+    constexpr int kStackCap = kStackPerThread * kThreads, kCandCap = kCandPerThread * kThreads;
+    static_assert(kCols % W == 0 && SY == 16, "rows are dealt to the warps in equal runs");
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sTop[2];   // fallback walk: stack height, double-buffered by iteration parity
     __shared__ uint32_t sCand;     // fallback walk: leaves queued so far
@@ -383,19 +408,21 @@ k_trace_fill_columns(const ParityParams prm)
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
     float4* stage = reinterpret_cast<float4*>(stack);          // [W][32 x 3]  triangle records of the listed-candidates path
-    static_assert((kStackCap + kCandCap) * 4 >= W * 32 * 48, "staging area must fit the fallback walk's buffers");
+    static_assert((kStackPerThread + kCandPerThread) * 4 >= 48, "staging area must fit the fallback walk's buffers");
 
     // the first CTAs write the empty tiles; the others take the work heavy parts first, then light
     // tiles (see fileTiles)
     __shared__ uint32_t sIsLast;
+    const uint32_t nHeavy = __ldg(prm.bucketCount), nEmpty = __ldg(prm.bucketCount + 2);
+    const uint4 nLight = __ldg(reinterpret_cast<const uint4*>(prm.bucketCount + 8));
+    const uint32_t nWork = nHeavy + nLight.x + nLight.y + nLight.z + nLight.w;
+    const uint32_t nDedicated = (uint32_t)min((uint64_t)nEmpty, (uint64_t)nWork * prm.writerTilesPerWork);
     if (blockIdx.x < prm.numWriters)
     {
         DXRV_TL_ROLE(1);
-        writeEmptyTiles<SY, SZ>(prm, blockIdx.x * (uint32_t)W + warp, prm.numWriters * (uint32_t)W);
+        writeEmptyTiles<SY, SZ>(prm, nDedicated, blockIdx.x * (uint32_t)W + warp, prm.numWriters * (uint32_t)W);
         return;
     }
-    const uint32_t nHeavy = __ldg(prm.bucketCount);
-    const uint4 nLight = __ldg(reinterpret_cast<const uint4*>(prm.bucketCount + 8));
     uint32_t bIdx = blockIdx.x - prm.numWriters;
     uint32_t tile, part = 0, parts = 1, hslot = 0xffffu;
     if (bIdx < nHeavy)
@@ -409,7 +436,13 @@ k_trace_fill_columns(const ParityParams prm)
         bIdx -= nHeavy;
         uint32_t cls = 0;
         if (bIdx >= nLight.x) { bIdx -= nLight.x; cls = 1; if (bIdx >= nLight.y) { bIdx -= nLight.y; cls = 2; if (bIdx >= nLight.z) { bIdx -= nLight.z; cls = 3; } } }
-        if (cls == 3 && bIdx >= nLight.w) return;
+        if (cls == 3 && bIdx >= nLight.w)
+        {
+            // surplus CTA: one of the empty tiles the writers do not take, a quarter of its layers per warp
+            const uint32_t e = nDedicated + (bIdx - nLight.w);
+            if (e < nEmpty) zeroTileLayers<SY, SZ>(prm, __ldg(prm.emptyTiles + e), warp, (uint32_t)W);
+            return;
+        }
         DXRV_TL_ROLE(3);
         tile = __ldg(prm.lightTiles + (size_t)cls * prm.tilesPad + bIdx);
     }
@@ -703,8 +736,9 @@ k_trace_fill_columns(const ParityParams prm)
     // which are contiguous in the global grid.
     const uint32_t groupsPerRow = Ps >> 2;            // 128-bit groups per shared row
     const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
-    const uint4* rows4 = reinterpret_cast<const uint4*>(rows) + (size_t)warp * 32u * groupsPerRow;
-    const uint32_t* wmaskW = wmask + warp * 32u * Mw;
+    const uint4* rows4 = reinterpret_cast<const uint4*>(rows) + (size_t)warp * kRowsPerWarp * groupsPerRow;
+    const uint32_t* wmaskW = wmask + warp * (uint32_t)kRowsPerWarp * Mw;
+    const uint32_t warpGroups = (uint32_t)kRowsPerWarp * groupsPerRow;   // a multiple of 32 for every (W, Ps) launched
 
     // occupancy bits of group gi (words 4gi .. 4gi+3) of the warp's row rowInWarp; g = the group's index
     auto occupancy = [&](uint32_t g, uint32_t rowInWarp, uint32_t gi) -> uint4 {
@@ -723,23 +757,24 @@ k_trace_fill_columns(const ParityParams prm)
     const bool interior = SY == 16 && (N & 127u) == 0u && groupsPerRow <= 32u && sy0 + SY <= N && sz0 + SZ <= prm.z1;
     if (interior)
     {
-        // fast path (every super-tile of a grid with N % 128 == 0): the warp's 32 rows are two runs of
-        // 16 consecutive y rows (z = 2*warp and 2*warp + 1), each run contiguous in the grid.  The shared
-        // row pitch (Ps, a power of two) may exceed the global one (P): the padding groups are skipped.
-        uint4* base = reinterpret_cast<uint4*>(prm.grid + ((size_t)(sz0 + 2u * warp - prm.z0) * N + sy0) * P);
+        // fast path (every super-tile of a grid with N % 128 == 0): the warp's rows are runs of up to 16
+        // consecutive y rows of one z layer, each run contiguous in the grid.  The shared row pitch
+        // (Ps, a power of two) may exceed the global one (P): the padding groups are skipped.
+        uint4* base = reinterpret_cast<uint4*>(prm.grid + ((size_t)(sz0 - prm.z0) * N + sy0) * P);
         const uint32_t zStride = (uint32_t)(((size_t)N * P) >> 2);
         const uint32_t gprG = P >> 2;
-        for (uint32_t g0 = 0; g0 < 32u * groupsPerRow; g0 += 32u)
+        for (uint32_t g0 = 0; g0 < warpGroups; g0 += 32u)
         {
             const uint32_t g = g0 + lane;
             const uint32_t rr = g >> prm.gprShift, gi = g & (groupsPerRow - 1u);
+            const uint32_t col = warp * (uint32_t)kRowsPerWarp + rr;
             uint4 t = occupancy(g, rr, gi);
-            if (gi < gprG) base[(rr >> 4) * zStride + (rr & 15u) * gprG + gi] = t;
+            if (gi < gprG) base[(col >> 4) * zStride + (col & 15u) * gprG + gi] = t;
         }
     }
     else
     {
-        for (uint32_t g0 = 0; g0 < 32u * groupsPerRow; g0 += 32u)
+        for (uint32_t g0 = 0; g0 < warpGroups; g0 += 32u)
         {
             const uint32_t g = g0 + lane;
             uint32_t rowInWarp, gi;
@@ -747,7 +782,7 @@ k_trace_fill_columns(const ParityParams prm)
             else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
             uint4 t = occupancy(g, rowInWarp, gi);
 
-            const uint32_t col = warp * 32u + rowInWarp;
+            const uint32_t col = warp * (uint32_t)kRowsPerWarp + rowInWarp;
             const uint32_t yl = col % SY, zl = col / SY;
             const uint32_t y = sy0 + yl, z = sz0 + zl;
             const uint32_t w0 = gi * 4u;
@@ -789,7 +824,7 @@ uint32_t sharedRowWords(uint32_t P)
 template <int W, int SY, int SZ>
 void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 {
-    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * (prm.Ps + prm.Mw) + SY + SZ + kStackCap + kCandCap);
+    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * (prm.Ps + prm.Mw) + SY + SZ + (size_t)(kStackPerThread + kCandPerThread) * 32 * W);
     static bool attrSet[64] = {};
     static int smCount[64] = {};
     int dev = 0;
@@ -800,12 +835,18 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
         cudaDeviceGetAttribute(&smCount[dev], cudaDevAttrMultiProcessorCount, dev);
         attrSet[dev] = true;
     }
-    // one writer CTA per SM: blocks are handed out breadth-first, so the first smCount blocks land on distinct SMs
-    prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 0) ? (uint32_t)smCount[dev] : 148u;
+    // a writer CTA on every other SM (blocks are handed out breadth-first, so the first blocks land on distinct
+    // SMs): measured best -- more writers take CTA slots from the tracing, fewer cannot keep up with it
+    prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 1) ? (uint32_t)smCount[dev] / 2u : 74u;
     prm.tuneSplit = kSplitTile; prm.tunePart = kPartSize; prm.tuneHeavy = kHeavyTile;
     if (const char* w = std::getenv("DXRV_SPLIT")) prm.tuneSplit = atoi(w);
     if (const char* w = std::getenv("DXRV_PART")) prm.tunePart = atoi(w);
     if (const char* w = std::getenv("DXRV_HEAVY")) prm.tuneHeavy = atoi(w);
+    {
+        const uint64_t tileBytes = (uint64_t)SY * SZ * prm.P * 4u;
+        prm.writerTilesPerWork = (uint32_t)std::max<uint64_t>(1u, kWriterBytesPerWork / tileBytes);
+        if (const char* w = std::getenv("DXRV_WBPW")) prm.writerTilesPerWork = (uint32_t)std::max<uint64_t>(1u, ((uint64_t)atoi(w) << 10) / tileBytes);
+    }
     if (const char* w = std::getenv("DXRV_WRITERS")) prm.numWriters = (uint32_t)atoi(w) > 0 ? (uint32_t)atoi(w) : prm.numWriters;
     if (ev) cudaEventRecord(ev[0], s);
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
@@ -871,7 +912,11 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.crossings = dCrossings; prm.err = dErr;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
     cudaMemsetAsync(prm.bucketCount, 0, 32 * sizeof(uint32_t), s);
-    launchVariant<4, 16, 8>(s, prm, ev);
+    // warps per CTA by row length (see k_trace_fill_columns); every choice keeps rows-per-warp x groups-per-row
+    // a multiple of 32
+    if (prm.Ps <= 32) launchVariant<4, 16, 8>(s, prm, ev);
+    else if (prm.Ps <= 64) launchVariant<8, 16, 8>(s, prm, ev);
+    else launchVariant<16, 16, 8>(s, prm, ev);
     return 2;
 }
 }  // namespace dxrv
