@@ -129,10 +129,9 @@ struct ParityParams
     uint32_t tilesPad;       // numTiles rounded up to a multiple of 32
     uint32_t tuneSplit, tunePart, tuneHeavy;
     uint32_t numWriters;     // leading CTAs of the fill kernel that only write the empty super-tiles
-    uint32_t writerTilesPerWork;  // empty tiles those CTAs take per busy work item
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
-    uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [8..11] light tiles per class
+    uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [5] cursor of the empty-tile writers, [8..11] light tiles per class, [32 + smid] writer claim of an SM
     uint32_t* lightTiles;    // [kLightClasses][tilesPad]  light tiles, classed by candidate count
     uint32_t* emptyTiles;    // [numTiles]
     uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}
@@ -316,7 +315,9 @@ k_walk_columns(const ParityParams prm)
 // they can stream while the busy tiles are traced (kWriterBytesPerWork per busy work item); what is
 // left -- everything, for a mostly empty grid -- is written one tile per CTA by the launch's surplus
 // CTAs (there is one CTA per tile, and empty tiles need none), i.e. by the whole machine.
-constexpr uint32_t kWriterBytesPerWork = 160u << 10;
+constexpr uint32_t kCounterWords = 32 + 1024;   // bucketCount[32] + one writer claim per SM (%smid < 1024)
+constexpr uint32_t kFillWaves = 4;               // CTAs of the fill kernel per resident CTA slot of the machine
+constexpr uint32_t kWriterBatch = 4;             // empty tiles a writer warp takes per grab
 
 // zero layers zFirst, zFirst + zStep, ... of an empty tile (one warp)
 template <int SY, int SZ>
@@ -352,43 +353,72 @@ __device__ __forceinline__ void zeroTileLayers(const ParityParams& prm, uint32_t
 
 // dedicated writer warp `writerWarp` of `numWriterWarps`: entries writerWarp + k * numWriterWarps of the first
 // nDedicated entries of the empty list; the tile numbers are fetched 32 at a time, one per lane, a batch ahead
+// The stores are TMA bulk copies out of a zeroed shared-memory buffer (cp.async.bulk, one per layer of a
+// tile, issued by one lane each): a warp's ordinary stores top out at a few GB/s -- a handful of warps per SM
+// cannot keep the SM's share of the HBM write bandwidth busy -- while the bulk-copy engine has no such limit.
 template <int SY, int SZ>
-__device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_t nDedicated, uint32_t writerWarp, uint32_t numWriterWarps)
+__device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_t nDedicated,
+                                                uint32_t* zeros /* shared, >= SY * P words, 16-byte aligned */)
 {
     const uint32_t lane = laneId();
-    auto fetch = [&](uint32_t k0) -> uint32_t {
-        const uint64_t e = (uint64_t)writerWarp + (uint64_t)(k0 + lane) * numWriterWarps;
-        return e < nDedicated ? __ldg(prm.emptyTiles + e) : 0xffffffffu;
+    const uint32_t N = prm.N, P = prm.P;
+    const bool bulk = (P & 3u) == 0u;
+    if (bulk)
+    {
+        for (uint32_t i = threadIdx.x; i < ((uint32_t)SY * P) >> 2; i += blockDim.x) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> visible to the bulk-copy engine
+        __syncthreads();
+    }
+    const uint32_t zerosAddr = (uint32_t)__cvta_generic_to_shared(zeros);
+    // kWriterBatch tiles per grab of the cursor, one grab ahead; lane j < kWriterBatch holds tile j of the batch
+    auto grab = [&]() -> uint32_t {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(prm.bucketCount + 5, kWriterBatch);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        return (lane < kWriterBatch && first < nDedicated && first + lane < nDedicated) ? __ldg(prm.emptyTiles + first + lane) : 0xffffffffu;
     };
-    uint32_t next = fetch(0);
-    for (uint32_t k0 = 0; ; k0 += 32u)
+    uint32_t next = grab();
+    for (;;)
     {
         const uint32_t mine = next;
         if (__shfl_sync(0xffffffffu, mine, 0) == 0xffffffffu) break;
-        next = fetch(k0 + 32u);
-        for (uint32_t j = 0; j < 32u; ++j)
+        next = grab();
+        for (uint32_t j = 0; j < kWriterBatch; ++j)
         {
             const uint32_t tile = __shfl_sync(0xffffffffu, mine, j);
             if (tile == 0xffffffffu) break;
-            zeroTileLayers<SY, SZ>(prm, tile, 0u, 1u);
+            if (!bulk) { zeroTileLayers<SY, SZ>(prm, tile, 0u, 1u); continue; }
+            const uint32_t sy0 = (tile % prm.tilesY) * SY, sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
+            const uint32_t runBytes = min((uint32_t)SY, N - sy0) * P * 4u;   // the tile's rows of one layer are contiguous
+            const uint32_t nz = min((uint32_t)SZ, prm.z1 - sz0);
+            if (lane < nz)
+            {
+                uint32_t* dst = prm.grid + ((size_t)(sz0 - prm.z0 + lane) * N + sy0) * P;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zerosAddr), "r"(runBytes) : "memory");
+            }
+        }
+        if (bulk)
+        {
+            // one group per batch of tiles; keep a few batches in flight
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
         }
     }
+    if (bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the zeros must outlive the copies
 }
 
 // ---- kernel B: W warps per CTA on a super-tile of SY x SZ columns.  W = 4 up to N = 1024; larger grids
 // have longer bit rows, i.e. more shared memory per tile and fewer CTAs per SM, and get more warps per
 // CTA instead (the tracing is dealt to warps in chunks, the write-out in rows: neither cares) --------
+// One work item (a light tile, or one part of a heavy tile): trace its candidates, then write its rows out.
 template <int W, int SY, int SZ>
-__global__ void __launch_bounds__(32 * W, W == 4 ? 9 : W == 8 ? 4 : 2)
-k_trace_fill_columns(const ParityParams prm)
+__device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t bIdx, uint32_t nHeavy, const uint4& nLight, uint32_t* smem)
 {
-    DXRV_TL_SCOPE();
     constexpr int kThreads = 32 * W;
     constexpr int kCols = SY * SZ;
     constexpr int kRowsPerWarp = kCols / W;
     constexpr int kStackCap = kStackPerThread * kThreads, kCandCap = kCandPerThread * kThreads;
     static_assert(kCols % W == 0 && SY == 16, "rows are dealt to the warps in equal runs");
-    extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t sTop[2];   // fallback walk: stack height, double-buffered by iteration parity
     __shared__ uint32_t sCand;     // fallback walk: leaves queued so far
     __shared__ uint32_t sNext;     // listed candidates: next chunk to hand out
@@ -410,24 +440,11 @@ k_trace_fill_columns(const ParityParams prm)
     float4* stage = reinterpret_cast<float4*>(stack);          // [W][32 x 3]  triangle records of the listed-candidates path
     static_assert((kStackPerThread + kCandPerThread) * 4 >= 48, "staging area must fit the fallback walk's buffers");
 
-    // the first CTAs write the empty tiles; the others take the work heavy parts first, then light
-    // tiles (see fileTiles)
+    // work items are numbered heavy parts first, then the light tiles class by class (see fileTiles)
     __shared__ uint32_t sIsLast;
-    const uint32_t nHeavy = __ldg(prm.bucketCount), nEmpty = __ldg(prm.bucketCount + 2);
-    const uint4 nLight = __ldg(reinterpret_cast<const uint4*>(prm.bucketCount + 8));
-    const uint32_t nWork = nHeavy + nLight.x + nLight.y + nLight.z + nLight.w;
-    const uint32_t nDedicated = (uint32_t)min((uint64_t)nEmpty, (uint64_t)nWork * prm.writerTilesPerWork);
-    if (blockIdx.x < prm.numWriters)
-    {
-        DXRV_TL_ROLE(1);
-        writeEmptyTiles<SY, SZ>(prm, nDedicated, blockIdx.x * (uint32_t)W + warp, prm.numWriters * (uint32_t)W);
-        return;
-    }
-    uint32_t bIdx = blockIdx.x - prm.numWriters;
     uint32_t tile, part = 0, parts = 1, hslot = 0xffffu;
     if (bIdx < nHeavy)
     {
-        DXRV_TL_ROLE(2);
         const uint2 e = __ldg(prm.heavyEntries + bIdx);
         tile = e.x; part = e.y & 0xffu; parts = (e.y >> 8) & 0xffu; hslot = e.y >> 16;
     }
@@ -436,14 +453,6 @@ k_trace_fill_columns(const ParityParams prm)
         bIdx -= nHeavy;
         uint32_t cls = 0;
         if (bIdx >= nLight.x) { bIdx -= nLight.x; cls = 1; if (bIdx >= nLight.y) { bIdx -= nLight.y; cls = 2; if (bIdx >= nLight.z) { bIdx -= nLight.z; cls = 3; } } }
-        if (cls == 3 && bIdx >= nLight.w)
-        {
-            // surplus CTA: one of the empty tiles the writers do not take, a quarter of its layers per warp
-            const uint32_t e = nDedicated + (bIdx - nLight.w);
-            if (e < nEmpty) zeroTileLayers<SY, SZ>(prm, __ldg(prm.emptyTiles + e), warp, (uint32_t)W);
-            return;
-        }
-        DXRV_TL_ROLE(3);
         tile = __ldg(prm.lightTiles + (size_t)cls * prm.tilesPad + bIdx);
     }
     const uint32_t sy0 = (tile % prm.tilesY) * SY;
@@ -490,10 +499,7 @@ k_trace_fill_columns(const ParityParams prm)
         };
         // one (triangle, column) pair: q-th column of the rectangle `packed`; inv = ceil(2^16 / w), so
         // that q / w == (q * inv) >> 16 exactly (q < 256, w <= 16)
-        auto testPair = [&](const float4& ta, const float4& tb, const float4& tc, uint32_t packed, uint32_t inv, uint32_t q) {
-            const uint32_t ow = packed >> 16;
-            const uint32_t qz = (q * inv) >> 16;
-            const uint32_t yl = (packed & 0xffu) + (q - qz * ow), zl = ((packed >> 8) & 0xffu) + qz;
+        auto testPairAt = [&](const float4& ta, const float4& tb, const float4& tc, uint32_t yl, uint32_t zl) {
             uint32_t ix;
             if (columnCrossing(ta, tb, tc, tileY[yl], tileZ[zl], N, fN, invNPow2, ix))
             {
@@ -506,59 +512,136 @@ k_trace_fill_columns(const ParityParams prm)
                 }
             }
         };
+        auto testPair = [&](const float4& ta, const float4& tb, const float4& tc, uint32_t packed, uint32_t inv, uint32_t q) {
+            const uint32_t ow = packed >> 16;
+            const uint32_t qz = (q * inv) >> 16;
+            testPairAt(ta, tb, tc, (packed & 0xffu) + (q - qz * ow), ((packed >> 8) & 0xffu) + qz);
+        };
 
-        // Staged variant (the normal path): the triangles with a non-empty rectangle are compacted into a
-        // per-warp shared-memory table of 48-byte records {a.xyz, packed | b.xyz, first pair | c.xyz, inv},
-        // so a pair needs three LDS.128 and nothing else.  The record that owns pair p is found without a
-        // search: records start at increasing pair numbers, so with `starts` = bit mask of the records
-        // starting inside the current window of 32 pairs (one warp-wide OR),
-        //   owner(p) = #records started before the window + popc(starts up to p's lane) - 1.
+        // Staged variant (the normal path).  Work is flattened twice, so that all 32 lanes stay busy whatever
+        // the triangles' shapes: triangles -> ROW UNITS (one z row of one triangle's columns) -> PAIRS
+        // (row unit, column).  A row unit gets a conservative y interval of the triangle inside its row
+        // (rowInterval), so only about one pair in ten is tested in vain -- the bounding rectangle of a
+        // triangle holds three times more columns than the triangle crosses.  Triangles with rows are
+        // compacted into a per-warp shared-memory table of 48-byte records {a.xyz, zA | h << 8 | b.xyz,
+        // first row unit | c.xyz}, the row units of the current window into {record | zl << 8 | ya << 16,
+        // first pair}.  The record that owns item p is found without a search: records start at increasing
+        // item numbers, so with `starts` = bit mask of the records starting inside the current window of
+        // 32 items (one warp-wide OR),  owner(p) = #records started before the window + popc(starts up to
+        // p's lane) - 1.
+        const float idxSlack = 0.02f;   // index units; covers the rounding of the index estimates below for any N
+        // Conservative y extent of triangle (a,b,c) within the row z = Zc.  A crossing of column (Y, Zc)
+        // means (0,0) lies in the triangle of the ROUNDED differences (a.y - Y, a.z - Zc)..., whose
+        // vertices are within 2^-23 of the exact ones: so some point of the exact triangle lies within
+        // 2^-23 of (Y, Zc) in y and in z, i.e. Y is within 2^-23 of the y extent of the triangle inside the
+        // slab |z - Zc| <= m (m = 1e-6 > 2^-23).  That extent is spanned by the parts of the edges inside
+        // the slab: a steep edge (|dz| >= 64 m) stays within |dy| / 64 of its point at Zc there, a shallow
+        // one is taken whole.  1e-5 on top covers the float evaluation.
+        auto rowInterval = [&](const float4& a, const float4& b, const float4& c, float Zc, float& lo, float& hi) {
+            const float m = 1e-6f;
+            lo = INFINITY; hi = -INFINITY;
+            auto edge = [&](const float4& P, const float4& Q) {
+                if (fmaxf(P.z, Q.z) < Zc - m || fminf(P.z, Q.z) > Zc + m) return;
+                const float dz = Q.z - P.z, dy = Q.y - P.y;
+                float l = fminf(P.y, Q.y), u = fmaxf(P.y, Q.y);
+                if (fabsf(dz) >= 64.0f * m)
+                {
+                    const float t = fminf(fmaxf(__fdividef(Zc - P.z, dz), 0.0f), 1.0f);
+                    const float yc = P.y + t * dy, e = fabsf(dy) * (1.0f / 64.0f);
+                    l = yc - e; u = yc + e;
+                }
+                lo = fminf(lo, l); hi = fmaxf(hi, u);
+            };
+            edge(a, b); edge(b, c); edge(c, a);
+            lo -= 1e-5f; hi += 1e-5f;
+        };
         auto processWarpChunkStaged = [&](bool has, uint32_t slot) {
-            float4* tab = stage + warp * 96u;   // 32 records x 3 float4
+            float4* tab = stage + warp * 112u;                           // 32 records x 3 float4 ...
+            uint2* units = reinterpret_cast<uint2*>(tab + 96);            // ... and 32 row units
+            const uint32_t lt = laneMaskLt(), le = lt | (1u << lane);
             float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-            uint32_t packed = 0, n = 0;
+            uint32_t zA = 0, h = 0;
             if (has)
             {
                 const float4* t = reinterpret_cast<const float4*>(prm.tris + slot);
                 a = __ldg(t); b = __ldg(t + 1); c = __ldg(t + 2);
-                columnRange(a, b, c, packed, n);
+                // rows whose centre may lie in [zlo, zhi] (tileZ increases with zl)
+                const float zlo = fminf(fminf(a.z, b.z), c.z), zhi = fmaxf(fmaxf(a.z, b.z), c.z);
+                const int z0i = min(max((int)ceilf((zlo + 1.0f) * halfN - 0.5f - idxSlack) - (int)sz0, 0), (int)zLast + 1);
+                const int z1i = min(max((int)floorf((zhi + 1.0f) * halfN - 0.5f + idxSlack) - (int)sz0, -1), (int)zLast);
+                zA = (uint32_t)z0i; h = (uint32_t)max(z1i - z0i + 1, 0);
             }
-            uint32_t incl = n;
+            uint32_t incl = h;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
             {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= (uint32_t)o) incl += v;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t nz = __ballot_sync(0xffffffffu, n != 0u);
-            if (n != 0u)
+            const uint32_t totalRows = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t nzA = __ballot_sync(0xffffffffu, h != 0u);
+            if (h != 0u)
             {
-                const uint32_t ow = packed >> 16;
-                float4* r = tab + __popc(nz & laneMaskLt()) * 3u;
-                a.w = __uint_as_float(packed); b.w = __uint_as_float(incl - n); c.w = __uint_as_float((65535u + ow) / ow);
+                float4* r = tab + __popc(nzA & lt) * 3u;
+                a.w = __uint_as_float(zA | (h << 8)); b.w = __uint_as_float(incl - h);
                 r[0] = a; r[1] = b; r[2] = c;
             }
             __syncwarp();
-            const uint32_t myStart = lane < (uint32_t)__popc(nz) ? __float_as_uint(tab[lane * 3u + 1u].w) : 0xffffffffu;
-            const uint32_t le = laneMaskLt() | (1u << lane);
-            uint32_t before = 0;   // records that start before the current window
+            const uint32_t myStartA = lane < (uint32_t)__popc(nzA) ? __float_as_uint(tab[lane * 3u + 1u].w) : 0xffffffffu;
+            uint32_t beforeA = 0;   // records that start before the current window of row units
 #pragma unroll 1
-            for (uint32_t p0 = 0; p0 < total; p0 += 32u)
+            for (uint32_t r0 = 0; r0 < totalRows; r0 += 32u)
             {
-                const uint32_t rel = myStart - p0;   // < 32 iff my record starts inside this window
-                const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
-                const uint32_t owner = before + __popc(starts & le) - 1u;
-                before += __popc(starts);
-                const uint32_t p = p0 + lane;
-                if (p < total)
+                const uint32_t relA = myStartA - r0;   // < 32 iff my record starts inside this window
+                const uint32_t startsA = __reduce_or_sync(0xffffffffu, relA < 32u ? 1u << relA : 0u);
+                const uint32_t ownerA = beforeA + __popc(startsA & le) - 1u;
+                beforeA += __popc(startsA);
+                uint32_t cnt = 0, unit = 0;
+                if (r0 + lane < totalRows)
                 {
-                    const float4* r = tab + owner * 3u;
+                    const float4* r = tab + ownerA * 3u;
                     const float4 ta = r[0], tb = r[1], tc = r[2];
-                    testPair(ta, tb, tc, __float_as_uint(ta.w), __float_as_uint(tc.w), p - __float_as_uint(tb.w));
+                    const uint32_t zl = (__float_as_uint(ta.w) & 0xffu) + (r0 + lane - __float_as_uint(tb.w));
+                    float lo, hi;
+                    rowInterval(ta, tb, tc, tileZ[zl], lo, hi);
+                    // columns whose centre may lie in [lo, hi] (tileY decreases with yl)
+                    const int ya = min(max((int)ceilf((1.0f - hi) * halfN - 0.5f - idxSlack) - (int)sy0, 0), (int)yLast + 1);
+                    const int yb = min(max((int)floorf((1.0f - lo) * halfN - 0.5f + idxSlack) - (int)sy0, -1), (int)yLast);
+                    cnt = (uint32_t)max(yb - ya + 1, 0);
+                    unit = ownerA | (zl << 8) | ((uint32_t)ya << 16);
                 }
+                uint32_t inclB = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inclB, o);
+                    if (lane >= (uint32_t)o) inclB += v;
+                }
+                const uint32_t totalPairs = __shfl_sync(0xffffffffu, inclB, 31);
+                const uint32_t nzB = __ballot_sync(0xffffffffu, cnt != 0u);
+                if (cnt != 0u) units[__popc(nzB & lt)] = make_uint2(unit, inclB - cnt);
+                __syncwarp();
+                const uint32_t myStartB = lane < (uint32_t)__popc(nzB) ? units[lane].y : 0xffffffffu;
+                uint32_t beforeB = 0;
+#pragma unroll 1
+                for (uint32_t p0 = 0; p0 < totalPairs; p0 += 32u)
+                {
+                    const uint32_t relB = myStartB - p0;
+                    const uint32_t startsB = __reduce_or_sync(0xffffffffu, relB < 32u ? 1u << relB : 0u);
+                    const uint32_t ownerB = beforeB + __popc(startsB & le) - 1u;
+                    beforeB += __popc(startsB);
+                    const uint32_t p = p0 + lane;
+                    if (p < totalPairs)
+                    {
+                        const uint2 u = units[ownerB];
+                        const float4* r = tab + (u.x & 0xffu) * 3u;
+                        const float4 ta = r[0], tb = r[1], tc = r[2];
+                        testPairAt(ta, tb, tc, (u.x >> 16) + (p - u.y), (u.x >> 8) & 0xffu);
+                    }
+                }
+                __syncwarp();   // the row units are rewritten by the next window
             }
-            __syncwarp();   // the table is rewritten by the next chunk
+            __syncwarp();       // the table is rewritten by the next chunk
         };
 
         // Direct variant (fallback walk only, where the staging area holds the walk's stack): records stay
@@ -716,7 +799,6 @@ k_trace_fill_columns(const ParityParams prm)
             {
                 for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
                 if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
-                DXRV_TL_ROLE(4);
                 return;
             }
             __threadfence();
@@ -809,6 +891,42 @@ k_trace_fill_columns(const ParityParams prm)
     if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
 }
 
+// The first CTAs of the launch write the empty tiles (one writer per SM); the others take the work items
+// in order -- heavy parts first -- and, when there are more items than CTAs, further ones at a stride.
+template <int W, int SY, int SZ>
+__global__ void __launch_bounds__(32 * W, W == 4 ? 9 : W == 8 ? 4 : 2)
+k_trace_fill_columns(const ParityParams prm)
+{
+    DXRV_TL_SCOPE();
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t sDuplicate;
+    const uint32_t nHeavy = __ldg(prm.bucketCount), nEmpty = __ldg(prm.bucketCount + 2);
+    const uint4 nLight = __ldg(reinterpret_cast<const uint4*>(prm.bucketCount + 8));
+    const uint32_t nWork = nHeavy + nLight.x + nLight.y + nLight.z + nLight.w;
+    if (blockIdx.x < prm.numWriters)
+    {
+        // one writer per SM: an SM's write bandwidth is its share of the machine's, whoever issues the
+        // stores, so a second writer CTA on the same SM would only take a CTA slot from the tracing.
+        // (Twice as many writers as SMs are launched so that nearly every SM gets one.)
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) sDuplicate = atomicExch(prm.bucketCount + 32 + (smid & 1023u), 1u);
+        __syncthreads();
+        if (sDuplicate != 0u) return;
+        DXRV_TL_ROLE(1);
+        writeEmptyTiles<SY, SZ>(prm, nEmpty, smem);
+        return;
+    }
+    const uint32_t stride = gridDim.x - prm.numWriters;
+    uint32_t item = blockIdx.x - prm.numWriters;
+    if (item < nWork) DXRV_TL_ROLE(item < nHeavy ? 2 : 3);
+    for (bool first = true; item < nWork; item += stride, first = false)
+    {
+        if (!first) __syncthreads();   // the previous item's write-out has read the shared rows
+        traceFillItem<W, SY, SZ>(prm, item, nHeavy, nLight, smem);
+    }
+}
+
 uint32_t sharedRowWords(uint32_t P)
 {
     if (P <= 4) return 4;
@@ -835,27 +953,25 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
         cudaDeviceGetAttribute(&smCount[dev], cudaDevAttrMultiProcessorCount, dev);
         attrSet[dev] = true;
     }
-    // a writer CTA on every other SM (blocks are handed out breadth-first, so the first blocks land on distinct
-    // SMs): measured best -- more writers take CTA slots from the tracing, fewer cannot keep up with it
-    prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 1) ? (uint32_t)smCount[dev] / 2u : 74u;
+    prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 0) ? 2u * (uint32_t)smCount[dev] : 296u;
     prm.tuneSplit = kSplitTile; prm.tunePart = kPartSize; prm.tuneHeavy = kHeavyTile;
     if (const char* w = std::getenv("DXRV_SPLIT")) prm.tuneSplit = atoi(w);
     if (const char* w = std::getenv("DXRV_PART")) prm.tunePart = atoi(w);
     if (const char* w = std::getenv("DXRV_HEAVY")) prm.tuneHeavy = atoi(w);
-    {
-        const uint64_t tileBytes = (uint64_t)SY * SZ * prm.P * 4u;
-        prm.writerTilesPerWork = (uint32_t)std::max<uint64_t>(1u, kWriterBytesPerWork / tileBytes);
-        if (const char* w = std::getenv("DXRV_WBPW")) prm.writerTilesPerWork = (uint32_t)std::max<uint64_t>(1u, ((uint64_t)atoi(w) << 10) / tileBytes);
-    }
     if (const char* w = std::getenv("DXRV_WRITERS")) prm.numWriters = (uint32_t)atoi(w) > 0 ? (uint32_t)atoi(w) : prm.numWriters;
     if (ev) cudaEventRecord(ev[0], s);
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
     if (ev) cudaEventRecord(ev[1], s);
-    k_trace_fill_columns<W, SY, SZ><<<prm.numWriters + prm.numTiles + kExtraParts, 32 * W, smemBytes, s>>>(prm);
+    // enough CTAs for kFillWaves full waves of work items; more items than that are taken at a stride
+    uint32_t waves = kFillWaves;
+    if (const char* w = std::getenv("DXRV_WAVES")) waves = (uint32_t)atoi(w);
+    const uint32_t perSm = W == 4 ? 9u : W == 8 ? 4u : 2u;
+    const uint32_t workCtas = std::min<uint32_t>(prm.numTiles + kExtraParts, std::max(1u, waves * perSm * (prm.numWriters / 2u)));
+    k_trace_fill_columns<W, SY, SZ><<<prm.numWriters + workCtas, 32 * W, smemBytes, s>>>(prm);
     if (ev) cudaEventRecord(ev[2], s);
-    static const char* const kRoles[5] = {"surplus", "writer", "heavy part", "light tile", "merged part"};
+    static const char* const kRoles[6] = {"?", "writer", "heavy part", "light tile", "merged part", "surplus"};
     (void)kRoles;
-    DXRV_TL_REPORT(s, prm.numWriters + prm.numTiles + kExtraParts, kRoles, 5);
+    DXRV_TL_REPORT(s, prm.numWriters + workCtas, kRoles, 6);
 }
 }  // namespace
 
@@ -876,13 +992,13 @@ size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
     parityTileCounts(N, z0, z1, numTiles, candCap);
     const size_t tilesPad = (numTiles + 31u) & ~31u;
     const size_t Ps = sharedRowWords((N + 31) / 32), Mw = (Ps + 31) / 32;
-    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw) + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
+    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw) + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
 }
 
 size_t parityScratchZeroWords(uint32_t N)
 {
     const size_t Ps = sharedRowWords((N + 31) / 32), Mw = (Ps + 31) / 32;
-    return 32 + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw);
+    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw);
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
@@ -901,7 +1017,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     const size_t tilesPad = (prm.numTiles + 31u) & ~31u;
     prm.tilesPad = (uint32_t)tilesPad;
     uint32_t* p = walkBuf;
-    prm.bucketCount = p;  p += 32;
+    prm.bucketCount = p;  p += kCounterWords;
     prm.heavyArrive = p;  p += kHeavySlots;
     prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * (prm.Ps + prm.Mw);      // 16-byte aligned: all sizes are multiples of 4 words
     prm.lightTiles = p;   p += kLightClasses * tilesPad;
@@ -911,7 +1027,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.candList = p;
     prm.crossings = dCrossings; prm.err = dErr;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
-    cudaMemsetAsync(prm.bucketCount, 0, 32 * sizeof(uint32_t), s);
+    cudaMemsetAsync(prm.bucketCount, 0, kCounterWords * sizeof(uint32_t), s);
     // warps per CTA by row length (see k_trace_fill_columns); every choice keeps rows-per-warp x groups-per-row
     // a multiple of 32
     if (prm.Ps <= 32) launchVariant<4, 16, 8>(s, prm, ev);
