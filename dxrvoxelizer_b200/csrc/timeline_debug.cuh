@@ -52,12 +52,12 @@ inline void timelineReport(cudaStream_t s, uint32_t numBlocks, const char* const
     }
     std::vector<double> fin(1024, 0.0);
     for (uint32_t b = 0; b < nb; ++b)
-        if (h[4 * b + 2] >= 2 && h[4 * b + 2] <= 4) { double& f = fin[h[4 * b + 3] & 1023]; f = std::max(f, (h[4 * b + 1] - t0) * 1e-3); }
+        if (h[4 * b + 2] >= 1 && h[4 * b + 2] <= 4) { double& f = fin[h[4 * b + 3] & 1023]; f = std::max(f, (h[4 * b + 1] - t0) * 1e-3); }
     std::vector<double> f;
     for (double v : fin) if (v > 0) f.push_back(v);
     std::sort(f.begin(), f.end());
     if (!f.empty())
-        std::printf("  SM finish (roles 2..4): min %.1f p25 %.1f med %.1f p75 %.1f max %.1f us (%zu SMs)\n", f[0], f[f.size() / 4], f[f.size() / 2],
+        std::printf("  SM finish (roles 1..4): min %.1f p25 %.1f med %.1f p75 %.1f max %.1f us (%zu SMs)\n", f[0], f[f.size() / 4], f[f.size() / 2],
                     f[3 * f.size() / 4], f.back(), f.size());
 }
 }  // namespace dxrv

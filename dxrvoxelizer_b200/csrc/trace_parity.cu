@@ -14,15 +14,20 @@
 //                        every ancestor box), pushes inner children and appends leaf children to the
 //                        super-tile's candidate list in HBM.  All walks of a 1024^2-column grid are in
 //                        flight at once, so the kernel takes about one root-to-leaf latency chain.
-//   k_trace_fill_columns HBM-write bound.  One CTA per super-tile: one candidate triangle per thread,
-//                        each covered column gets the exact crossing test and toggles ONE bit (the
-//                        first voxel whose centre is beyond the crossing) in shared-memory bit rows --
-//                        XOR makes the order of crossings irrelevant, so no per-column hit list or sort
-//                        is needed; the toggles become occupancy by an inclusive prefix-XOR along x (in
-//                        registers per 128-bit group, ballot carry across lanes) and every word of the
-//                        slab is written exactly once with coalesced 128-bit stores -- no clear pass,
-//                        no scatter to HBM.  A super-tile whose candidate list overflowed (huge meshes)
-//                        walks the tree itself, CTA-cooperatively, instead of reading a list.
+//   k_trace_fill_columns writes every word of the slab exactly once, no clear pass, no scatter to HBM.
+//                        * Empty super-tiles (most of a real grid) are streamed by one "writer" CTA per SM
+//                          with TMA bulk stores out of a zeroed shared buffer, concurrently with
+//                        * the busy super-tiles, which the other CTAs take in order of decreasing work
+//                          (crowded tiles are split into parts that merge through a scratch buffer).
+//                          Tracing: candidate triangles -> row units (triangle x z row, with a
+//                          conservative y interval) -> (row unit, column) pairs, both flattened over the
+//                          32 lanes of a warp; every pair gets the exact crossing test, and a crossing
+//                          XORs a suffix mask into the column's shared-memory bit row plus one bit into
+//                          the column's word mask -- XOR makes the order of crossings irrelevant, so no
+//                          per-column hit list or sort is needed.  Write-out: the word mask tells which
+//                          whole words to flip; coalesced 128-bit stores.
+//                        A super-tile whose candidate list overflowed (huge meshes) walks the tree itself,
+//                        CTA-cooperatively, instead of reading a list.
 #include <algorithm>
 #include <cstdlib>
 #include "kernels.h"
@@ -127,7 +132,6 @@ struct ParityParams
     uint32_t tilesY;         // super-tiles along y
     uint32_t numTiles;
     uint32_t tilesPad;       // numTiles rounded up to a multiple of 32
-    uint32_t tuneSplit, tunePart, tuneHeavy;
     uint32_t numWriters;     // leading CTAs of the fill kernel that only write the empty super-tiles
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
@@ -194,10 +198,10 @@ __device__ __forceinline__ void fileTiles(const ParityParams& prm, uint32_t firs
     const uint32_t tile = firstTile + lane;
     const bool active = count != 0xffffffffu;
     if (active) prm.candCount[tile] = count;
-    const bool isEmpty = active && count == 0u, isLight = active && count > 0u && count < prm.tuneHeavy;
-    const bool isHeavy = active && count >= prm.tuneHeavy;
+    const bool isEmpty = active && count == 0u, isLight = active && count > 0u && count < kHeavyTile;
+    const bool isHeavy = active && count >= kHeavyTile;
     int cls = -1;
-    if (isLight) cls = count >= prm.tuneHeavy / 2 ? 0 : count >= prm.tuneHeavy / 4 ? 1 : count >= prm.tuneHeavy / 8 ? 2 : 3;
+    if (isLight) cls = count >= kHeavyTile / 2 ? 0 : count >= kHeavyTile / 4 ? 1 : count >= kHeavyTile / 8 ? 2 : 3;
     const uint32_t mE = __ballot_sync(0xffffffffu, isEmpty);
     uint32_t mC[kLightClasses], baseC[kLightClasses], baseE = 0;
 #pragma unroll
@@ -219,9 +223,9 @@ __device__ __forceinline__ void fileTiles(const ParityParams& prm, uint32_t firs
     }
 
     uint32_t parts = isHeavy ? 1u : 0u, slot = 0xffffu;
-    if (isHeavy && count <= prm.candCap && count >= prm.tuneSplit)   // (an overflowed list is not split: that CTA walks itself)
+    if (isHeavy && count <= prm.candCap && count >= kSplitTile)   // (an overflowed list is not split: that CTA walks itself)
     {
-        parts = min((count + prm.tunePart - 1u) / prm.tunePart, kMaxParts);
+        parts = min((count + kPartSize - 1u) / kPartSize, kMaxParts);
         slot = atomicAdd(prm.bucketCount + 3, 1u);
         if (slot >= kHeavySlots || atomicAdd(prm.bucketCount + 4, parts - 1u) + parts - 1u > kExtraParts) { parts = 1u; slot = 0xffffu; }
     }
@@ -243,6 +247,7 @@ template <int SY, int SZ>
 __global__ void __launch_bounds__(32 * kWalkWarps)
 k_walk_columns(const ParityParams prm)
 {
+    DXRV_TL_SCOPE();
     __shared__ uint32_t sStack[kWalkWarps][kWalkStack];
     __shared__ uint32_t sCount[32];
     const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
@@ -306,6 +311,13 @@ k_walk_columns(const ParityParams prm)
     if (lane == 0) sCount[warp] = count;
     __syncthreads();
     if (warp == 0) fileTiles(prm, blockIdx.x * kWalkWarps, sCount[lane]);
+#ifdef DXRV_TIMELINE
+    {
+        uint32_t mx = 0;
+        for (int i = 0; i < kWalkWarps; ++i) if (sCount[i] != 0xffffffffu && sCount[i] > mx) mx = sCount[i];
+        DXRV_TL_ROLE(mx == 0 ? 1 : mx < 192 ? 2 : mx < 768 ? 3 : 4);
+    }
+#endif
 }
 
 // ---- empty super-tiles: nothing to trace, 16 KB of zeros to write.  A few dedicated "writer" CTAs
@@ -954,17 +966,17 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
         attrSet[dev] = true;
     }
     prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 0) ? 2u * (uint32_t)smCount[dev] : 296u;
-    prm.tuneSplit = kSplitTile; prm.tunePart = kPartSize; prm.tuneHeavy = kHeavyTile;
-    if (const char* w = std::getenv("DXRV_SPLIT")) prm.tuneSplit = atoi(w);
-    if (const char* w = std::getenv("DXRV_PART")) prm.tunePart = atoi(w);
-    if (const char* w = std::getenv("DXRV_HEAVY")) prm.tuneHeavy = atoi(w);
-    if (const char* w = std::getenv("DXRV_WRITERS")) prm.numWriters = (uint32_t)atoi(w) > 0 ? (uint32_t)atoi(w) : prm.numWriters;
     if (ev) cudaEventRecord(ev[0], s);
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
     if (ev) cudaEventRecord(ev[1], s);
+#ifdef DXRV_TIMELINE
+    {
+        static const char* const kWalkRoles[5] = {"?", "empty CTA", "light CTA", "heavy CTA", "very heavy CTA"};
+        if (std::getenv("DXRV_DBG_TIMELINE_WALK")) DXRV_TL_REPORT(s, (prm.numTiles + kWalkWarps - 1) / kWalkWarps, kWalkRoles, 5);
+    }
+#endif
     // enough CTAs for kFillWaves full waves of work items; more items than that are taken at a stride
-    uint32_t waves = kFillWaves;
-    if (const char* w = std::getenv("DXRV_WAVES")) waves = (uint32_t)atoi(w);
+    const uint32_t waves = kFillWaves;
     const uint32_t perSm = W == 4 ? 9u : W == 8 ? 4u : 2u;
     const uint32_t workCtas = std::min<uint32_t>(prm.numTiles + kExtraParts, std::max(1u, waves * perSm * (prm.numWriters / 2u)));
     k_trace_fill_columns<W, SY, SZ><<<prm.numWriters + workCtas, 32 * W, smemBytes, s>>>(prm);
