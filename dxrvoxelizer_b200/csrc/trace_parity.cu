@@ -133,6 +133,8 @@ struct ParityParams
     uint32_t numTiles;
     uint32_t tilesPad;       // numTiles rounded up to a multiple of 32
     uint32_t numWriters;     // leading CTAs of the fill kernel that only write the empty super-tiles
+    uint32_t bulkStores;     // 0: the writers use ordinary stores (DXRV_NO_BULK_STORE=1; compute-sanitizer's
+                             // initcheck does not see what cp.async.bulk writes)
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
     uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [5] cursor of the empty-tile writers, [8..11] light tiles per class, [32 + smid] writer claim of an SM
@@ -374,7 +376,7 @@ __device__ __forceinline__ void writeEmptyTiles(const ParityParams& prm, uint32_
 {
     const uint32_t lane = laneId();
     const uint32_t N = prm.N, P = prm.P;
-    const bool bulk = (P & 3u) == 0u;
+    const bool bulk = (P & 3u) == 0u && prm.bulkStores != 0u;
     if (bulk)
     {
         for (uint32_t i = threadIdx.x; i < ((uint32_t)SY * P) >> 2; i += blockDim.x) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0, 0, 0, 0);
@@ -966,6 +968,8 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
         attrSet[dev] = true;
     }
     prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 0) ? 2u * (uint32_t)smCount[dev] : 296u;
+    static const bool noBulk = [] { const char* e = std::getenv("DXRV_NO_BULK_STORE"); return e && e[0] && e[0] != '0'; }();
+    prm.bulkStores = noBulk ? 0u : 1u;
     if (ev) cudaEventRecord(ev[0], s);
     k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
     if (ev) cudaEventRecord(ev[1], s);

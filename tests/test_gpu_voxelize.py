@@ -139,6 +139,30 @@ def test_external_grid_target_and_device_pointer(vox, assets):
     assert np.array_equal(got, full)
 
 
+@pytest.mark.parametrize("N,layers", [(128, 128), (256, 256), (1024, 40), (1280, 24), (2048, 24), (4096, 16)])
+def test_every_word_of_the_slab_is_written(vox, assets, N, layers):
+    """MODE_PARITY promises to write every word of the slab exactly once with no clear pass (empty tiles by
+    the TMA writer CTAs, the rest by the tracing CTAs; 4, 8 or 16 warps per CTA by row length).  Run it
+    into a buffer poisoned with ones and into one poisoned with zeros: a word nobody wrote would differ."""
+    import torch
+    m = assets("dragon.obj")
+    vox.build_bvh(m)
+    P = (N + 31) // 32
+    z0 = (N - layers) // 2
+    words = layers * N * P
+    out = []
+    for poison in (-1, 0):
+        buf = torch.full((words,), poison, dtype=torch.int32, device="cuda:0")
+        torch.cuda.synchronize()
+        vox.set_grid_target(buf.data_ptr(), words * 4)
+        vox.voxelize(N, d.MODE_PARITY, z0, z0 + layers)
+        vox.synchronize()
+        out.append(buf.cpu().numpy().view(np.uint32))
+        vox.set_grid_target(None, 0)
+    assert np.array_equal(out[0], out[1])
+    assert 0 < popcount(out[0]) < words * 32
+
+
 def test_full_size_1024_parity_against_oracle(vox, assets, oracle_mod):
     """C3 at full size: dragon, N = 1024 (128 MiB bit grid).  The accelerated oracle finishes in
     seconds at this size, so the check is still a full bit-exact comparison, plus the size-independent
