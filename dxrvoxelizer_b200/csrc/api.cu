@@ -27,6 +27,7 @@ struct dxrv_ctx
     int device = 0;
     int smCount = 148;
     cudaStream_t ownStream = nullptr;
+    SideStream side{};               // fork/join partner of `stream` inside a build
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -256,7 +257,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
             launchMorton(s, m, ctx->dBound, k0, v0, keyShift, numPasses, hist, ctx->dErr);
             ctx->launches += 1;
             ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, k0, v0, k1, v1, T, numPasses, true, nullptr);
-            ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
+            ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, &ctx->side, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
                                                                 ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr);
         }
     });
@@ -309,6 +310,13 @@ int dxrv_create(dxrv_ctx** out, int cuda_device)
     if (const char* ng = std::getenv("DXRV_NO_GRAPHS")) ctx->useGraphs = !(ng[0] && ng[0] != '0');
     if ((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
     ctx->stream = ctx->ownStream;
+    if (cudaStreamCreateWithFlags(&ctx->side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->side.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->side.join, cudaEventDisableTiming) != cudaSuccess)
+    {
+        cudaGetLastError();
+        ctx->side = SideStream{};   // no side stream: builds run serially
+    }
     if ((e = cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaEventCreate"); }
     const size_t smallBytes = 64 * sizeof(float) + 6 * kBoundsMaxBlocks * sizeof(float);
     if ((e = cudaMalloc(&ctx->dSmall, smallBytes)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaMalloc"); }
@@ -336,6 +344,9 @@ void dxrv_destroy(dxrv_ctx* ctx)
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     for (cudaEvent_t e : ctx->prof) if (e) cudaEventDestroy(e);
+    if (ctx->side.fork) cudaEventDestroy(ctx->side.fork);
+    if (ctx->side.join) cudaEventDestroy(ctx->side.join);
+    if (ctx->side.stream) cudaStreamDestroy(ctx->side.stream);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     cudaGetLastError();
     delete ctx;

@@ -32,7 +32,9 @@ size_t boxPyramidFloat4s(uint32_t numTris);
 // k_hierarchy_boxes + k_refit_atomic (large meshes: bottom-up refit with atomics); returns the number of
 // kernels launched.  refitScratch: 3 * numTris uint32, only touched when useAtomicRefit(numTris).
 bool useAtomicRefit(uint32_t numTris);
-int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
+// side (nullable): a second stream + two events; with it the leaf/pyramid kernels run beside the topology kernel.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
                              const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
                              uint32_t* refitScratch, float* rootBox, uint32_t* dErr);
 

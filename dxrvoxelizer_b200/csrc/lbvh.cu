@@ -364,14 +364,15 @@ __device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int numL
     return x ? __clz(x) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
 }
 
-// kBoxes = true : child boxes by range union from the pyramid (no dependency chain; best for small meshes,
-//                  where everything is latency bound -- 100 k triangles)
-// kBoxes = false: topology + parent references only; k_refit_atomic then fits the boxes bottom-up (O(T) traffic
-//                  instead of O(T log T) pyramid reads; best for millions of triangles, where throughput counts)
-template <bool kBoxes>
+// Topology only (child references + leaf range of every node): it needs nothing but the sorted keys, so it
+// runs concurrently with k_leaf_setup / k_box_level; the child boxes follow in k_node_boxes or k_refit_atomic.
+// kLatency = true : small meshes, where everything is latency bound (100 k triangles): multi-probe searches
+// kLatency = false: millions of nodes, mostly tiny ranges, throughput counts: classic one-probe-per-step searches,
+//                   and parent references for k_refit_atomic (O(T) traffic instead of O(T log T) pyramid reads)
+template <bool kLatency>
 __global__ void __launch_bounds__(128, 8)
-k_hierarchy_boxes(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __restrict__ nodes, Pyramid pyr,
-                  float* __restrict__ rootBox, uint32_t* __restrict__ nodeParent, uint32_t* __restrict__ leafParent)
+k_hierarchy_topology(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __restrict__ nodes,
+                     uint32_t* __restrict__ nodeParent, uint32_t* __restrict__ leafParent)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numLeaves - 1) return;
@@ -387,7 +388,7 @@ k_hierarchy_boxes(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __r
     };
     long long l = 0, s = 0;
     int j, dNode;
-    if (kBoxes)
+    if (kLatency)
     {
         // latency regime (small meshes): several independent probes per round
         long long lMax = 2;
@@ -456,24 +457,94 @@ k_hierarchy_boxes(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* __r
     float4* dst = reinterpret_cast<float4*>(nodes + i);
     // child references + the node's leaf range (debug / tests)
     dst[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float((uint32_t)first), __uint_as_float((uint32_t)last));
-    if (kBoxes)
-    {
-        const RangeBox b0 = rangeQuery(pyr, (uint32_t)first, (uint32_t)gamma);
-        const RangeBox b1 = rangeQuery(pyr, (uint32_t)gamma + 1u, (uint32_t)last);
-        dst[0] = make_float4(b0.ylo, b0.yhi, b0.zlo, b0.zhi);
-        dst[1] = make_float4(b1.ylo, b1.yhi, b1.zlo, b1.zhi);
-        dst[2] = make_float4(b0.xlo, b0.xhi, b1.xlo, b1.xhi);
-        if (i == 0)
-        {
-            rootBox[0] = fminf(b0.xlo, b1.xlo); rootBox[1] = fminf(b0.ylo, b1.ylo); rootBox[2] = fminf(b0.zlo, b1.zlo);
-            rootBox[3] = fmaxf(b0.xhi, b1.xhi); rootBox[4] = fmaxf(b0.yhi, b1.yhi); rootBox[5] = fmaxf(b0.zhi, b1.zhi);
-        }
-    }
-    else
+    if (!kLatency)
     {
         // parent reference: node index | (1u << 31 when the child is the right one)
         if (leftLeaf) leafParent[gamma] = (uint32_t)i; else nodeParent[gamma] = (uint32_t)i;
         if (rightLeaf) leafParent[gamma + 1] = (uint32_t)i | 0x80000000u; else nodeParent[gamma + 1] = (uint32_t)i | 0x80000000u;
+    }
+}
+
+// ---- child boxes by range union from the pyramid (small meshes: no dependency chain between nodes) ------
+// union of the leaf boxes [first, last] by the whole warp: the at most 15 + 15 entries of every pyramid level
+// (64 at the top) are one load per lane, and the loads of ALL levels are in flight together -- for the few
+// nodes near the root, whose ranges touch every level, this replaces ~30 dependent round trips by one.
+__device__ __forceinline__ RangeBox rangeQueryWarp(const Pyramid& pyr, uint32_t first, uint32_t last)
+{
+    const uint32_t lane = laneId();
+    float4 yz[kMaxBoxLevels + 1], xx[kMaxBoxLevels + 1];
+    const float4 none0 = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY), none1 = make_float4(INFINITY, -INFINITY, 0.0f, 0.0f);
+    uint32_t lo = first, hi = last + 1u;  // half open, in units of level-l entries
+    bool done = false;
+    yz[kMaxBoxLevels] = none0; xx[kMaxBoxLevels] = none1;   // second half of a 33..64-entry top-level run
+#pragma unroll
+    for (int l = 0; l < kMaxBoxLevels; ++l)
+    {
+        yz[l] = none0; xx[l] = none1;
+        if (done || l >= pyr.numLevels || lo >= hi) { done = true; continue; }
+        const float4* lev = pyr.level[l];
+        if (l == pyr.numLevels - 1 || hi - lo <= 15u)
+        {
+            // the last run: at most 64 entries (top level), two per lane
+            const uint32_t n = hi - lo;
+            if (lane < n) { yz[l] = __ldg(lev + 2 * (size_t)(lo + lane)); xx[l] = __ldg(lev + 2 * (size_t)(lo + lane) + 1); }
+            if (lane + 32u < n) { yz[kMaxBoxLevels] = __ldg(lev + 2 * (size_t)(lo + 32u + lane)); xx[kMaxBoxLevels] = __ldg(lev + 2 * (size_t)(lo + 32u + lane) + 1); }
+            done = true;
+            continue;
+        }
+        const uint32_t head = (16u - (lo & 15u)) & 15u;   // entries up to the next multiple of 16
+        const uint32_t tail = hi & 15u;                    // entries after the last multiple of 16
+        uint32_t e = 0xffffffffu;
+        if (lane < head) e = lo + lane;
+        else if (lane >= 16u && lane - 16u < tail) e = hi - tail + (lane - 16u);
+        if (e != 0xffffffffu) { yz[l] = __ldg(lev + 2 * (size_t)e); xx[l] = __ldg(lev + 2 * (size_t)e + 1); }
+        lo = (lo + head) >> 4; hi = (hi - tail) >> 4;
+    }
+    RangeBox box;
+    box.clear();
+#pragma unroll
+    for (int l = 0; l <= kMaxBoxLevels; ++l) box.add(yz[l], xx[l]);
+    box.shuffleXor(1); box.shuffleXor(2); box.shuffleXor(4); box.shuffleXor(8); box.shuffleXor(16);
+    return box;
+}
+
+constexpr uint32_t kWarpQueryRange = 48;   // nodes covering more leaves than this get the warp-wide query
+
+__device__ __forceinline__ void storeChildBoxes(BvhNode* node, const RangeBox& b0, const RangeBox& b1, bool isRoot, float* rootBox)
+{
+    float4* dst = reinterpret_cast<float4*>(node);
+    dst[0] = make_float4(b0.ylo, b0.yhi, b0.zlo, b0.zhi);
+    dst[1] = make_float4(b1.ylo, b1.yhi, b1.zlo, b1.zhi);
+    dst[2] = make_float4(b0.xlo, b0.xhi, b1.xlo, b1.xhi);
+    if (isRoot)
+    {
+        rootBox[0] = fminf(b0.xlo, b1.xlo); rootBox[1] = fminf(b0.ylo, b1.ylo); rootBox[2] = fminf(b0.zlo, b1.zlo);
+        rootBox[3] = fmaxf(b0.xhi, b1.xhi); rootBox[4] = fmaxf(b0.yhi, b1.yhi); rootBox[5] = fmaxf(b0.zhi, b1.zhi);
+    }
+}
+
+__global__ void __launch_bounds__(128, 4)
+k_node_boxes(int numLeaves, BvhNode* __restrict__ nodes, const __grid_constant__ Pyramid pyr, float* __restrict__ rootBox)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < numLeaves - 1;
+    uint32_t first = 0, gamma = 0, last = 0;
+    if (valid)
+    {
+        // {c0, c1, first, last} as written by k_hierarchy_topology; c0 = gamma (| leaf flag)
+        const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const float4*>(nodes + i) + 3);
+        gamma = t.x & ~kLeafFlag; first = t.z; last = t.w;
+    }
+    const bool wide = valid && last - first > kWarpQueryRange;
+    if (valid && !wide)
+        storeChildBoxes(nodes + i, rangeQuery(pyr, first, gamma), rangeQuery(pyr, gamma + 1u, last), i == 0, rootBox);
+    for (uint32_t todo = __ballot_sync(0xffffffffu, wide); todo; todo &= todo - 1u)
+    {
+        const int src = __ffs(todo) - 1;
+        const uint32_t f = __shfl_sync(0xffffffffu, first, src), g = __shfl_sync(0xffffffffu, gamma, src), l = __shfl_sync(0xffffffffu, last, src);
+        const RangeBox b0 = rangeQueryWarp(pyr, f, g);
+        const RangeBox b1 = rangeQueryWarp(pyr, g + 1u, l);
+        if ((int)laneId() == src) storeChildBoxes(nodes + i, b0, b1, i == 0, rootBox);
     }
 }
 
@@ -607,7 +678,7 @@ size_t boxPyramidFloat4s(uint32_t numTris)
     return total;
 }
 
-int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
+int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
                              const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
                              uint32_t* refitScratch, float* rootBox, uint32_t* dErr)
 {
@@ -626,33 +697,42 @@ int launchLeavesAndHierarchy(cudaStream_t s, const MeshView& m, const float* dBo
     }
     for (int l = pyr.numLevels; l < kMaxBoxLevels; ++l) { pyr.level[l] = nullptr; pyr.count[l] = 0; }
     int launches = 0;
-    k_leaf_setup<<<(m.numTris + 255) / 256, 256, 0, s>>>(m, dBound, sortedPrims, tris, pyr, rootBox, dErr);
+    // Two independent chains once the keys are sorted: {leaves, triangle records, box pyramid} and {topology}.
+    // With a side stream they run concurrently (also under stream capture: the events become graph edges).
+    const bool forked = side && side->stream && m.numTris > 1;
+    cudaStream_t sb = forked ? side->stream : s;
+    if (forked)
+    {
+        cudaEventRecord(side->fork, s);
+        cudaStreamWaitEvent(sb, side->fork, 0);
+    }
+    k_leaf_setup<<<(m.numTris + 255) / 256, 256, 0, sb>>>(m, dBound, sortedPrims, tris, pyr, rootBox, dErr);
     ++launches;
     for (int l = 3; l < pyr.numLevels; ++l)
     {
-        k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, s>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l]);
+        k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, sb>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l]);
         ++launches;
     }
+    if (forked) cudaEventRecord(side->join, sb);
     if (m.numTris > 1)
     {
         const uint32_t blocks = (m.numTris - 1 + 127) / 128;
-        if (!atomicRefit)
-        {
-            k_hierarchy_boxes<true><<<blocks, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, pyr, rootBox, nullptr, nullptr);
-            ++launches;
-        }
+        // refitScratch = [nodeParent T][leafParent T][flags T]
+        uint32_t* nodeParent = refitScratch;
+        uint32_t* leafParent = refitScratch + m.numTris;
+        uint32_t* flags = refitScratch + 2 * (size_t)m.numTris;
+        if (!atomicRefit) k_hierarchy_topology<true><<<blocks, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, nullptr, nullptr);
         else
         {
-            // refitScratch = [nodeParent T][leafParent T][flags T]
-            uint32_t* nodeParent = refitScratch;
-            uint32_t* leafParent = refitScratch + m.numTris;
-            uint32_t* flags = refitScratch + 2 * (size_t)m.numTris;
             cudaMemsetAsync(flags, 0, sizeof(uint32_t) * m.numTris, s);
-            k_hierarchy_boxes<false><<<blocks, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, pyr, rootBox, nodeParent, leafParent);
+            k_hierarchy_topology<false><<<blocks, 128, 0, s>>>(sortedKeys, (int)m.numTris, nodes, nodeParent, leafParent);
+        }
+        if (forked) cudaStreamWaitEvent(s, side->join, 0);
+        if (!atomicRefit) k_node_boxes<<<blocks, 128, 0, s>>>((int)m.numTris, nodes, pyr, rootBox);
+        else
             k_refit_atomic<<<(m.numTris + 255) / 256, 256, 0, s>>>((int)m.numTris, pyr.level[0], nodes, nodeParent, leafParent, flags,
                                                                    rootBox, dErr);
-            launches += 2;
-        }
+        launches += 2;
     }
     return launches;
 }
