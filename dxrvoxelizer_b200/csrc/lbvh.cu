@@ -5,12 +5,16 @@
 //   k_bounds          min/max of all vertex positions -> {c, w}     (Voxelizer.cpp:52-57)
 //   k_morton          per triangle: scene-space box centre -> Morton key, fused digit histograms
 //   (onesweep.cu)     stable radix sort of (key, triangle)
-//   k_leaf_setup      per sorted leaf: scene-space triangle, its box, 16- and 256-leaf summary boxes
+//   k_leaf_setup      per sorted leaf: scene-space triangle, its box, 16- and 256-leaf summary boxes, and the
+//                     prefix / suffix unions inside every aligned group of 16 (the box pyramid)
 //   k_box_level       coarser summary levels (16:1) for big meshes
-//   k_hierarchy_boxes Karras 2012 radix tree over the sorted keys (index tie-break for duplicates);
-//                     each node's child boxes are the unions of CONTIGUOUS leaf ranges, answered from
-//                     the summary pyramid -- no parent pointers, no atomics, no bottom-up latency chain
-//                     (the classic refit walks leaf-to-root with a fence + atomic per level)
+//   k_hierarchy_topology  Karras 2012 radix tree over the sorted keys (index tie-break for duplicates);
+//                     needs only the keys, so it runs BESIDE the two kernels above (side stream / graph fork)
+//   k_node_boxes      each node's child boxes are the unions of CONTIGUOUS leaf ranges, answered from the
+//                     pyramid with two independent loads per level -- no parent pointers, no atomics, no
+//                     bottom-up latency chain (the classic refit walks leaf-to-root with a fence + atomic
+//                     per level; k_refit_atomic does that for meshes of millions of triangles, where
+//                     throughput counts and not latency)
 #include "kernels.h"
 
 namespace dxrv
@@ -198,11 +202,29 @@ struct RangeBox
         zlo = fminf(zlo, yz.z); zhi = fmaxf(zhi, yz.w);
         xlo = fminf(xlo, x.x);  xhi = fmaxf(xhi, x.y);
     }
-    __device__ __forceinline__ void shuffleXor(int o)
+    __device__ __forceinline__ void unite(const RangeBox& o)
     {
-        ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
-        zlo = fminf(zlo, __shfl_xor_sync(0xffffffffu, zlo, o)); zhi = fmaxf(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
-        xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        ylo = fminf(ylo, o.ylo); yhi = fmaxf(yhi, o.yhi);
+        zlo = fminf(zlo, o.zlo); zhi = fmaxf(zhi, o.zhi);
+        xlo = fminf(xlo, o.xlo); xhi = fmaxf(xhi, o.xhi);
+    }
+    // this box of the lane `delta` lanes below (up = true) / above within its group of 16 lanes
+    __device__ __forceinline__ RangeBox shifted16(bool up, unsigned delta) const
+    {
+        RangeBox r;
+        if (up)
+        {
+            r.ylo = __shfl_up_sync(0xffffffffu, ylo, delta, 16); r.yhi = __shfl_up_sync(0xffffffffu, yhi, delta, 16);
+            r.zlo = __shfl_up_sync(0xffffffffu, zlo, delta, 16); r.zhi = __shfl_up_sync(0xffffffffu, zhi, delta, 16);
+            r.xlo = __shfl_up_sync(0xffffffffu, xlo, delta, 16); r.xhi = __shfl_up_sync(0xffffffffu, xhi, delta, 16);
+        }
+        else
+        {
+            r.ylo = __shfl_down_sync(0xffffffffu, ylo, delta, 16); r.yhi = __shfl_down_sync(0xffffffffu, yhi, delta, 16);
+            r.zlo = __shfl_down_sync(0xffffffffu, zlo, delta, 16); r.zhi = __shfl_down_sync(0xffffffffu, zhi, delta, 16);
+            r.xlo = __shfl_down_sync(0xffffffffu, xlo, delta, 16); r.xhi = __shfl_down_sync(0xffffffffu, xhi, delta, 16);
+        }
+        return r;
     }
     __device__ __forceinline__ void store(float4* dst) const
     {
@@ -211,19 +233,40 @@ struct RangeBox
     }
 };
 
+// Entry i of a level: its box at [stride*i], and (stride == 6) the union of the entries from the start of
+// its aligned group of 16 up to it ("prefix", at +2) and from it to the end of the group ("suffix", at +4).
+// With those, the part of a contiguous range that falls into one group costs ONE entry to read whenever
+// the range enters or leaves the group across its boundary.  The top level (<= 16 entries) has boxes only.
 struct Pyramid
 {
-    float4* level[kMaxBoxLevels];   // level[l][2*i], level[l][2*i+1]
+    float4* level[kMaxBoxLevels];
     uint32_t count[kMaxBoxLevels];  // entries per level
     int numLevels;
+    uint32_t stride;                // float4 per entry: 6, or 2 (boxes only: large meshes, k_refit_atomic)
 };
+
+// inclusive prefix / suffix unions over each group of 16 consecutive lanes
+__device__ __forceinline__ void groupScans16(const RangeBox& box, RangeBox& pre, RangeBox& suf)
+{
+    const uint32_t hl = laneId() & 15u;
+    pre = box; suf = box;
+#pragma unroll
+    for (unsigned o = 1; o < 16u; o <<= 1)
+    {
+        const RangeBox a = pre.shifted16(true, o), b = suf.shifted16(false, o);
+        if (hl >= o) pre.unite(a);
+        if (hl + o < 16u) suf.unite(b);
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_leaf_setup(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __restrict__ sortedPrims,
              Tri48* __restrict__ tris, Pyramid pyr, float* __restrict__ rootBox, uint32_t* __restrict__ err)
 {
-    __shared__ float sBox[8][6];
+    __shared__ float sGroup[16][6];
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t S = pyr.stride;
+    const bool scans = S == 6u;
     RangeBox box;
     box.clear();
     if (j < m.numTris)
@@ -248,70 +291,91 @@ k_leaf_setup(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __r
         box.ylo = fminf(fminf(a.y, b.y), c.y); box.yhi = fmaxf(fmaxf(a.y, b.y), c.y);
         box.zlo = fminf(fminf(a.z, b.z), c.z); box.zhi = fmaxf(fmaxf(a.z, b.z), c.z);
         box.xlo = fminf(fminf(a.x, b.x), c.x); box.xhi = fmaxf(fmaxf(a.x, b.x), c.x);
-        box.store(pyr.level[0] + 2 * (size_t)j);
+        box.store(pyr.level[0] + (size_t)S * j);
         if (m.numTris == 1)
         {
             rootBox[0] = box.xlo; rootBox[1] = box.ylo; rootBox[2] = box.zlo;
             rootBox[3] = box.xhi; rootBox[4] = box.yhi; rootBox[5] = box.zhi;
         }
     }
-    // level 1: 16 consecutive leaves = one half-warp
-    box.shuffleXor(1); box.shuffleXor(2); box.shuffleXor(4); box.shuffleXor(8);
-    if (pyr.numLevels > 1 && (threadIdx.x & 15u) == 0u && j < m.numTris) box.store(pyr.level[1] + 2 * (size_t)(j >> 4));
-    // level 2: the 256 leaves of this block
-    if (pyr.numLevels > 2)
+    if (pyr.numLevels < 2) return;   // (uniform) a single level is read directly
+    // level 0 scans and level 1: 16 consecutive leaves = one half-warp (leaves past the end are neutral boxes)
+    RangeBox pre, suf;
+    groupScans16(box, pre, suf);
+    if (scans && j < m.numTris)
     {
-        box.shuffleXor(16);
-        const int warp = threadIdx.x >> 5;
-        if (laneId() == 0)
+        pre.store(pyr.level[0] + (size_t)S * j + 2);
+        suf.store(pyr.level[0] + (size_t)S * j + 4);
+    }
+    const uint32_t group = threadIdx.x >> 4;   // 16 groups = 16 level-1 entries per block
+    if ((threadIdx.x & 15u) == 15u)
+    {
+        // lane 15's prefix is the union of its group
+        if (16u * blockIdx.x + group < pyr.count[1]) pre.store(pyr.level[1] + (size_t)S * (16u * blockIdx.x + group));
+        sGroup[group][0] = pre.ylo; sGroup[group][1] = pre.yhi; sGroup[group][2] = pre.zlo;
+        sGroup[group][3] = pre.zhi; sGroup[group][4] = pre.xlo; sGroup[group][5] = pre.xhi;
+    }
+    if (pyr.numLevels < 3) return;   // (uniform) level 1 is the top: boxes only
+    __syncthreads();
+    // level 1 scans and level 2: the block's 16 level-1 entries, by its first half-warp
+    if (threadIdx.x < 32)
+    {
+        const uint32_t t = threadIdx.x & 15u;
+        RangeBox g;
+        g.ylo = sGroup[t][0]; g.yhi = sGroup[t][1]; g.zlo = sGroup[t][2]; g.zhi = sGroup[t][3]; g.xlo = sGroup[t][4]; g.xhi = sGroup[t][5];
+        groupScans16(g, pre, suf);
+        const uint32_t e = 16u * blockIdx.x + t;
+        if (scans && threadIdx.x < 16 && e < pyr.count[1])
         {
-            sBox[warp][0] = box.ylo; sBox[warp][1] = box.yhi; sBox[warp][2] = box.zlo;
-            sBox[warp][3] = box.zhi; sBox[warp][4] = box.xlo; sBox[warp][5] = box.xhi;
+            pre.store(pyr.level[1] + (size_t)S * e + 2);
+            suf.store(pyr.level[1] + (size_t)S * e + 4);
         }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            for (int w = 1; w < 8; ++w)
-            {
-                box.ylo = fminf(box.ylo, sBox[w][0]); box.yhi = fmaxf(box.yhi, sBox[w][1]);
-                box.zlo = fminf(box.zlo, sBox[w][2]); box.zhi = fmaxf(box.zhi, sBox[w][3]);
-                box.xlo = fminf(box.xlo, sBox[w][4]); box.xhi = fmaxf(box.xhi, sBox[w][5]);
-            }
-            box.store(pyr.level[2] + 2 * (size_t)blockIdx.x);
-        }
+        if (threadIdx.x == 15) pre.store(pyr.level[2] + (size_t)S * blockIdx.x);
     }
 }
 
-// level l (>= 3) from level l-1: one thread per entry, 16 children each
+// level l (>= 3) from level l-1: one thread per entry, 16 children each; also the children's scans
 __global__ void __launch_bounds__(128)
-k_box_level(const float4* __restrict__ src, uint32_t srcCount, float4* __restrict__ dst, uint32_t dstCount)
+k_box_level(float4* __restrict__ src, uint32_t srcCount, float4* __restrict__ dst, uint32_t dstCount, uint32_t S)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dstCount) return;
-    RangeBox box;
-    box.clear();
     // all 32 loads are issued before the first min/max: one memory round trip, not sixteen
     float4 yz[16], xx[16];
 #pragma unroll
     for (uint32_t q = 0; q < 16u; ++q)
     {
         const uint32_t c = min(16u * i + q, srcCount - 1u);   // clamped duplicates do not change a union
-        yz[q] = __ldg(src + 2 * (size_t)c);
-        xx[q] = __ldg(src + 2 * (size_t)c + 1);
+        yz[q] = __ldg(src + (size_t)S * c);
+        xx[q] = __ldg(src + (size_t)S * c + 1);
     }
+    RangeBox run;
+    run.clear();
 #pragma unroll
-    for (uint32_t q = 0; q < 16u; ++q) box.add(yz[q], xx[q]);
-    box.store(dst + 2 * (size_t)i);
+    for (uint32_t q = 0; q < 16u; ++q)
+    {
+        run.add(yz[q], xx[q]);
+        if (S == 6u && 16u * i + q < srcCount) run.store(src + (size_t)S * (16u * i + q) + 2);
+    }
+    run.store(dst + (size_t)S * i);
+    if (S != 6u) return;
+    run.clear();
+#pragma unroll
+    for (int q = 15; q >= 0; --q)
+    {
+        run.add(yz[q], xx[q]);
+        if (16u * i + (uint32_t)q < srcCount) run.store(src + (size_t)S * (16u * i + (uint32_t)q) + 4);
+    }
 }
 
-// union of `n` consecutive entries starting at `first`; loads are issued in batches of 8 entries
+// union of `n` (<= 16) consecutive entries starting at `first`; loads are issued in batches of 8 entries
 // (16 independent 128-bit loads in flight) instead of one dependent round trip per entry
-__device__ __forceinline__ void addRun(RangeBox& box, const float4* __restrict__ lev, uint32_t first, uint32_t n)
+__device__ __forceinline__ void addRun(RangeBox& box, const float4* __restrict__ lev, uint32_t S, uint32_t first, uint32_t n)
 {
     if (n <= 2u)   // most nodes are tiny: do not pay for a padded batch
     {
-        if (n >= 1u) box.add(__ldg(lev + 2 * (size_t)first), __ldg(lev + 2 * (size_t)first + 1));
-        if (n == 2u) box.add(__ldg(lev + 2 * (size_t)first + 2), __ldg(lev + 2 * (size_t)first + 3));
+        if (n >= 1u) box.add(__ldg(lev + (size_t)S * first), __ldg(lev + (size_t)S * first + 1));
+        if (n == 2u) box.add(__ldg(lev + (size_t)S * (first + 1u)), __ldg(lev + (size_t)S * (first + 1u) + 1));
         return;
     }
 #pragma unroll 1
@@ -322,34 +386,60 @@ __device__ __forceinline__ void addRun(RangeBox& box, const float4* __restrict__
         for (uint32_t q = 0; q < 8u; ++q)
         {
             const uint32_t c = first + min(base + q, n - 1u);   // clamped duplicates do not change a union
-            yz[q] = __ldg(lev + 2 * (size_t)c);
-            xx[q] = __ldg(lev + 2 * (size_t)c + 1);
+            yz[q] = __ldg(lev + (size_t)S * c);
+            xx[q] = __ldg(lev + (size_t)S * c + 1);
         }
 #pragma unroll
         for (uint32_t q = 0; q < 8u; ++q) box.add(yz[q], xx[q]);
     }
 }
 
-// union of the leaf boxes [first, last]: at most 15 + 15 entries per pyramid level (64 at the top)
+// Union of the leaf boxes [first, last].  Per level the range is cut at the multiples of 16: the piece before
+// the first cut is the SUFFIX of entry lo, the piece after the last cut the PREFIX of entry hi-1, the whole
+// groups between are entries of the next level.  Two loads per level, none depending on another (the adds of
+// a level are delayed until the next level's loads are issued), and at most 16 direct entries at the end.
 __device__ __forceinline__ RangeBox rangeQuery(const Pyramid& pyr, uint32_t first, uint32_t last)
 {
     RangeBox box;
     box.clear();
+    const uint32_t S = pyr.stride;
+    const float4 none0 = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY), none1 = make_float4(INFINITY, -INFINITY, 0.0f, 0.0f);
+    float4 pYz0 = none0, pXx0 = none1, pYz1 = none0, pXx1 = none1;   // loads in flight
     uint32_t lo = first, hi = last + 1u;  // half open, in units of level-l entries
     for (int l = 0; l < pyr.numLevels && lo < hi; ++l)
     {
         const float4* lev = pyr.level[l];
-        if (l == pyr.numLevels - 1 || hi - lo <= 15u)
+        const bool top = l == pyr.numLevels - 1;
+        if (top || hi - lo <= 15u)
         {
-            addRun(box, lev, lo, hi - lo);
+            if (!top && S == 6u && (lo >> 4) != ((hi - 1u) >> 4))
+            {
+                // two neighbouring groups: suffix of lo + prefix of hi-1
+                const float4 a0 = __ldg(lev + (size_t)S * lo + 4), a1 = __ldg(lev + (size_t)S * lo + 5);
+                const float4 b0 = __ldg(lev + (size_t)S * (hi - 1u) + 2), b1 = __ldg(lev + (size_t)S * (hi - 1u) + 3);
+                box.add(a0, a1); box.add(b0, b1);
+            }
+            else addRun(box, lev, S, lo, hi - lo);
             break;
         }
         const uint32_t head = (16u - (lo & 15u)) & 15u;   // entries up to the next multiple of 16
         const uint32_t tail = hi & 15u;                    // entries after the last multiple of 16
-        addRun(box, lev, lo, head);
-        addRun(box, lev, hi - tail, tail);
+        float4 nYz0 = none0, nXx0 = none1, nYz1 = none0, nXx1 = none1;
+        if (S == 6u)
+        {
+            if (head) { nYz0 = __ldg(lev + (size_t)S * lo + 4); nXx0 = __ldg(lev + (size_t)S * lo + 5); }
+            if (tail) { nYz1 = __ldg(lev + (size_t)S * (hi - 1u) + 2); nXx1 = __ldg(lev + (size_t)S * (hi - 1u) + 3); }
+        }
+        else
+        {
+            addRun(box, lev, S, lo, head);
+            addRun(box, lev, S, hi - tail, tail);
+        }
+        box.add(pYz0, pXx0); box.add(pYz1, pXx1);
+        pYz0 = nYz0; pXx0 = nXx0; pYz1 = nYz1; pXx1 = nXx1;
         lo = (lo + head) >> 4; hi = (hi - tail) >> 4;
     }
+    box.add(pYz0, pXx0); box.add(pYz1, pXx1);
     return box;
 }
 
@@ -466,50 +556,6 @@ k_hierarchy_topology(const uint32_t* __restrict__ keys, int numLeaves, BvhNode* 
 }
 
 // ---- child boxes by range union from the pyramid (small meshes: no dependency chain between nodes) ------
-// union of the leaf boxes [first, last] by the whole warp: the at most 15 + 15 entries of every pyramid level
-// (64 at the top) are one load per lane, and the loads of ALL levels are in flight together -- for the few
-// nodes near the root, whose ranges touch every level, this replaces ~30 dependent round trips by one.
-__device__ __forceinline__ RangeBox rangeQueryWarp(const Pyramid& pyr, uint32_t first, uint32_t last)
-{
-    const uint32_t lane = laneId();
-    float4 yz[kMaxBoxLevels + 1], xx[kMaxBoxLevels + 1];
-    const float4 none0 = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY), none1 = make_float4(INFINITY, -INFINITY, 0.0f, 0.0f);
-    uint32_t lo = first, hi = last + 1u;  // half open, in units of level-l entries
-    bool done = false;
-    yz[kMaxBoxLevels] = none0; xx[kMaxBoxLevels] = none1;   // second half of a 33..64-entry top-level run
-#pragma unroll
-    for (int l = 0; l < kMaxBoxLevels; ++l)
-    {
-        yz[l] = none0; xx[l] = none1;
-        if (done || l >= pyr.numLevels || lo >= hi) { done = true; continue; }
-        const float4* lev = pyr.level[l];
-        if (l == pyr.numLevels - 1 || hi - lo <= 15u)
-        {
-            // the last run: at most 64 entries (top level), two per lane
-            const uint32_t n = hi - lo;
-            if (lane < n) { yz[l] = __ldg(lev + 2 * (size_t)(lo + lane)); xx[l] = __ldg(lev + 2 * (size_t)(lo + lane) + 1); }
-            if (lane + 32u < n) { yz[kMaxBoxLevels] = __ldg(lev + 2 * (size_t)(lo + 32u + lane)); xx[kMaxBoxLevels] = __ldg(lev + 2 * (size_t)(lo + 32u + lane) + 1); }
-            done = true;
-            continue;
-        }
-        const uint32_t head = (16u - (lo & 15u)) & 15u;   // entries up to the next multiple of 16
-        const uint32_t tail = hi & 15u;                    // entries after the last multiple of 16
-        uint32_t e = 0xffffffffu;
-        if (lane < head) e = lo + lane;
-        else if (lane >= 16u && lane - 16u < tail) e = hi - tail + (lane - 16u);
-        if (e != 0xffffffffu) { yz[l] = __ldg(lev + 2 * (size_t)e); xx[l] = __ldg(lev + 2 * (size_t)e + 1); }
-        lo = (lo + head) >> 4; hi = (hi - tail) >> 4;
-    }
-    RangeBox box;
-    box.clear();
-#pragma unroll
-    for (int l = 0; l <= kMaxBoxLevels; ++l) box.add(yz[l], xx[l]);
-    box.shuffleXor(1); box.shuffleXor(2); box.shuffleXor(4); box.shuffleXor(8); box.shuffleXor(16);
-    return box;
-}
-
-constexpr uint32_t kWarpQueryRange = 48;   // nodes covering more leaves than this get the warp-wide query
-
 __device__ __forceinline__ void storeChildBoxes(BvhNode* node, const RangeBox& b0, const RangeBox& b1, bool isRoot, float* rootBox)
 {
     float4* dst = reinterpret_cast<float4*>(node);
@@ -527,25 +573,11 @@ __global__ void __launch_bounds__(128, 4)
 k_node_boxes(int numLeaves, BvhNode* __restrict__ nodes, const __grid_constant__ Pyramid pyr, float* __restrict__ rootBox)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < numLeaves - 1;
-    uint32_t first = 0, gamma = 0, last = 0;
-    if (valid)
-    {
-        // {c0, c1, first, last} as written by k_hierarchy_topology; c0 = gamma (| leaf flag)
-        const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const float4*>(nodes + i) + 3);
-        gamma = t.x & ~kLeafFlag; first = t.z; last = t.w;
-    }
-    const bool wide = valid && last - first > kWarpQueryRange;
-    if (valid && !wide)
-        storeChildBoxes(nodes + i, rangeQuery(pyr, first, gamma), rangeQuery(pyr, gamma + 1u, last), i == 0, rootBox);
-    for (uint32_t todo = __ballot_sync(0xffffffffu, wide); todo; todo &= todo - 1u)
-    {
-        const int src = __ffs(todo) - 1;
-        const uint32_t f = __shfl_sync(0xffffffffu, first, src), g = __shfl_sync(0xffffffffu, gamma, src), l = __shfl_sync(0xffffffffu, last, src);
-        const RangeBox b0 = rangeQueryWarp(pyr, f, g);
-        const RangeBox b1 = rangeQueryWarp(pyr, g + 1u, l);
-        if ((int)laneId() == src) storeChildBoxes(nodes + i, b0, b1, i == 0, rootBox);
-    }
+    if (i >= numLeaves - 1) return;
+    // {c0, c1, first, last} as written by k_hierarchy_topology; c0 = gamma (| leaf flag)
+    const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const float4*>(nodes + i) + 3);
+    const uint32_t gamma = t.x & ~kLeafFlag, first = t.z, last = t.w;
+    storeChildBoxes(nodes + i, rangeQuery(pyr, first, gamma), rangeQuery(pyr, gamma + 1u, last), i == 0, rootBox);
 }
 
 // ---- bottom-up refit with one atomic per node (large meshes) -----------------------------------------
@@ -671,8 +703,8 @@ size_t boxPyramidFloat4s(uint32_t numTris)
     uint32_t c = numTris ? numTris : 1;
     for (int l = 0; l < kMaxBoxLevels; ++l)
     {
-        total += 2 * (size_t)c + 2;
-        if (c <= 64) break;
+        total += 6 * (size_t)c + 6;
+        if (c <= 16) break;
         c = (c + 15) / 16;
     }
     return total;
@@ -688,11 +720,12 @@ int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshV
     uint32_t c = m.numTris;
     float4* p = pyramidMem;
     pyr.numLevels = 0;
+    pyr.stride = atomicRefit ? 2u : 6u;
     for (int l = 0; l < kMaxBoxLevels; ++l)
     {
         pyr.level[l] = p; pyr.count[l] = c; pyr.numLevels = l + 1;
-        p += 2 * (size_t)c + 2;
-        if (c <= 64 || atomicRefit) break;   // the bottom-up refit only needs the leaf boxes (level 0)
+        p += (size_t)pyr.stride * c + pyr.stride;
+        if (c <= 16 || atomicRefit) break;   // the bottom-up refit only needs the leaf boxes (level 0)
         c = (c + 15) / 16;
     }
     for (int l = pyr.numLevels; l < kMaxBoxLevels; ++l) { pyr.level[l] = nullptr; pyr.count[l] = 0; }
@@ -710,7 +743,7 @@ int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshV
     ++launches;
     for (int l = 3; l < pyr.numLevels; ++l)
     {
-        k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, sb>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l]);
+        k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, sb>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l], pyr.stride);
         ++launches;
     }
     if (forked) cudaEventRecord(side->join, sb);

@@ -111,6 +111,16 @@ def test_lbvh_invariants_on_shipped_meshes(vox, assets, name):
     _check_tree(vox, m)
 
 
+@pytest.mark.parametrize("shape", ["knot600", "knot16384", "ico81920"])
+def test_lbvh_invariants_on_synthetic_meshes(vox, meshes_mod, shape):
+    """Triangle counts that put 33..64 entries on the top level of the box pyramid (600 -> 38, 16384 -> 64: the
+    two-entries-per-lane branch of the warp-wide range query) and one with four levels."""
+    m = {"knot600": lambda: meshes_mod.torus_knot(30, 10, seed=1), "knot16384": lambda: meshes_mod.torus_knot(256, 32, seed=4),
+         "ico81920": lambda: meshes_mod.icosphere(6, seed=2, rotate=True)}[shape]()
+    vox.build_bvh(m)
+    _check_tree(vox, m)
+
+
 @pytest.mark.parametrize("tris", [1, 2, 3, 12])
 def test_lbvh_tiny_meshes(vox, meshes_mod, tris):
     from dxrvoxelizer_b200 import Mesh
