@@ -577,6 +577,35 @@ k_node_boxes(int numLeaves, BvhNode* __restrict__ nodes, const __grid_constant__
     // {c0, c1, first, last} as written by k_hierarchy_topology; c0 = gamma (| leaf flag)
     const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const float4*>(nodes + i) + 3);
     const uint32_t gamma = t.x & ~kLeafFlag, first = t.z, last = t.w;
+    const uint32_t n = last - first + 1u;
+    if (n <= 16u)
+    {
+        // 19 nodes in 20: few leaves -- read them once, in one or two batches, and deal them to the two children
+        const float4* lev = pyr.level[0];
+        const uint32_t S = pyr.stride, n0 = gamma - first + 1u;   // leaves of child 0
+        RangeBox b0, b1;
+        b0.clear(); b1.clear();
+#pragma unroll 1
+        for (uint32_t base = 0; base < n; base += 8u)
+        {
+            float4 yz[8], xx[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8u; ++q)
+            {
+                const uint32_t c = first + min(base + q, n - 1u);   // clamped duplicates do not change a union
+                yz[q] = __ldg(lev + (size_t)S * c);
+                xx[q] = __ldg(lev + (size_t)S * c + 1);
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < 8u; ++q)
+            {
+                if (min(base + q, n - 1u) < n0) b0.add(yz[q], xx[q]);
+                else b1.add(yz[q], xx[q]);
+            }
+        }
+        storeChildBoxes(nodes + i, b0, b1, i == 0, rootBox);
+        return;
+    }
     storeChildBoxes(nodes + i, rangeQuery(pyr, first, gamma), rangeQuery(pyr, gamma + 1u, last), i == 0, rootBox);
 }
 
