@@ -10,6 +10,7 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <algorithm>
 #include <cstdlib>
 
 #include "../../include/dxrv.h"
@@ -162,6 +163,33 @@ int runCaptured(dxrv_ctx* ctx, const std::vector<uint8_t>& key, F&& enqueue)
     {
         enqueue();
         ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr;
+    }
+    // A graph of the same shape with other parameters (the next mesh of a batch: same kernels, other pointers)
+    // is patched into an executable graph we already have -- instantiating costs far more than the kernels
+    // of a small mesh take.  Candidates: same kind of call (first key word), same number of launches.
+    if (ok)
+    {
+        const uint64_t launchesNow = ctx->launches - before;
+        dxrv_ctx::GraphEntry* best = nullptr;
+        for (auto& g : ctx->graphs)
+            if (g.launches == launchesNow && g.key.size() >= 4 && key.size() >= 4 && std::equal(key.begin(), key.begin() + 4, g.key.begin()) &&
+                (!best || g.lastUse > best->lastUse))
+                best = &g;
+        if (best)
+        {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(best->exec, graph, &info) == cudaSuccess)
+            {
+                cudaGraphDestroy(graph);
+                best->key = key; best->lastUse = ctx->graphClock;
+                DXRV_CUDA(cudaGraphLaunch(best->exec, ctx->stream));
+                return DXRV_OK;
+            }
+            cudaGetLastError();
+            // a failed update leaves that executable graph in an unspecified state: drop it
+            cudaGraphExecDestroy(best->exec);
+            ctx->graphs.erase(ctx->graphs.begin() + (best - ctx->graphs.data()));
+        }
     }
     if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
     if (graph) cudaGraphDestroy(graph);
