@@ -246,12 +246,12 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     }
     if (useAtomicRefit(T))
     {
-        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->refitScratch), ctx->refitCap, sizeof(uint32_t) * 3 * (size_t)T);
+        cudaError_t e = ensure(ctx->refitScratch, ctx->refitCap, sizeof(uint32_t) * 3 * (size_t)T);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(refit scratch)");
     }
     {
         size_t need = SortTemp::bytesFor(T);
-        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->sortTemp), ctx->sortTempCap, need);
+        cudaError_t e = ensure(ctx->sortTemp, ctx->sortTempCap, need);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(sort temp)");
     }
 
@@ -420,7 +420,7 @@ int dxrv_build_bvh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts, uint3
     const size_t vBytes = (size_t)numVerts * strideBytes, iBytes = (size_t)numIndices * sizeof(uint32_t);
     cudaError_t e = ensure(ctx->vertsOwned, ctx->vertsCap, vBytes);
     if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(vertices)");
-    e = ensure(reinterpret_cast<uint8_t*&>(ctx->idxOwned), ctx->idxCap, iBytes);
+    e = ensure(ctx->idxOwned, ctx->idxCap, iBytes);
     if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(indices)");
     // upload heaps of Voxelizer::createVB / createIB (Voxelizer.cpp:115-138)
     DXRV_CUDA(cudaMemcpyAsync(ctx->vertsOwned, vertices, vBytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -480,7 +480,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     }
     else
     {
-        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->gridOwned), ctx->gridCap, bytes);
+        cudaError_t e = ensure(ctx->gridOwned, ctx->gridCap, bytes);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(grid)");
         grid = ctx->gridOwned;
     }
@@ -488,7 +488,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     if (wantTexels)
     {
         const size_t tb = (size_t)(slabEnd - slabBegin) * N * N * sizeof(uint32_t);
-        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->texels), ctx->texCap, tb);
+        cudaError_t e = ensure(ctx->texels, ctx->texCap, tb);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(texels)");
         texels = ctx->texels;
     }
@@ -500,7 +500,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         const size_t zeroBytes = sizeof(uint32_t) * parityScratchZeroWords(N);
         // (a re-allocation may hand back the very same address, so compare capacities, not pointers)
         const bool reallocated = !ctx->walkBuf || walkBytes > ctx->walkCap;
-        cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->walkBuf), ctx->walkCap, walkBytes);
+        cudaError_t e = ensure(ctx->walkBuf, ctx->walkCap, walkBytes);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(walk lists)");
         if (reallocated || zeroBytes != ctx->walkZeroed)
         {
@@ -603,7 +603,7 @@ int dxrv_build_mips(dxrv_ctx* ctx, uint32_t* numLevels)
         words += mipWords(ctx->N, layers, levels);
         ++levels;
     }
-    cudaError_t e = ensure(reinterpret_cast<uint8_t*&>(ctx->mips), ctx->mipCap, words * sizeof(uint32_t));
+    cudaError_t e = ensure(ctx->mips, ctx->mipCap, words * sizeof(uint32_t));
     if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(mips)");
     const uint32_t* src = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
     uint32_t* dst = ctx->mips;

@@ -3,6 +3,10 @@
 
 #include "../../include/dxrv.h"
 
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 DXRVoxelizer::DXRVoxelizer() {}
 
 DXRVoxelizer::~DXRVoxelizer()
@@ -75,12 +79,65 @@ bool DXRVoxelizer::BuildAccelerationStructures()
     return true;
 }
 
-// z-slab of GPU g out of k over [begin, end): contiguous, disjoint, sizes differ by at most one layer
-static void slabOf(uint32_t begin, uint32_t end, int g, int k, uint32_t& z0, uint32_t& z1)
+// Cut points of the k z-slabs over [begin, end): contiguous, disjoint, balanced by cost.  Equal slabs are only
+// balanced for a mesh that fills the grid evenly; the cost of layer z is modelled as 1 (its stores) +
+// 1.2 * t(z) / mean(t), t(z) = triangles whose z extent overlaps the layer (the same model, measured on a
+// B200, as dxrvoxelizer_b200/sharding.py balanced_slabs), and the cuts split the cumulative cost evenly.
+void DXRVoxelizer::computeSlabs(uint32_t begin, uint32_t end, int k)
 {
-    const uint32_t layers = end - begin;
-    z0 = begin + static_cast<uint32_t>(static_cast<uint64_t>(layers) * g / k);
-    z1 = begin + static_cast<uint32_t>(static_cast<uint64_t>(layers) * (g + 1) / k);
+    m_cuts.assign(static_cast<size_t>(k) + 1, end);
+    m_cuts[0] = begin;
+    const uint32_t N = m_gridSize, layers = end - begin;
+    if (k <= 1 || layers == 0) return;
+    std::vector<double> cost(layers, 1.0);
+    const uint32_t numTris = m_numIndices / 3;
+    if (numTris && m_vertices && m_stride >= 12)
+    {
+        std::vector<double> diff(static_cast<size_t>(N) + 1, 0.0);
+        const uint8_t* vb = static_cast<const uint8_t*>(m_vertices);
+        for (uint32_t t = 0; t < numTris; ++t)
+        {
+            double zmin = 1e300, zmax = -1e300;
+            for (int c = 0; c < 3; ++c)
+            {
+                const uint32_t vi = m_indices[3 * static_cast<size_t>(t) + c];
+                if (vi >= m_numVerts) continue;
+                float z;
+                std::memcpy(&z, vb + static_cast<size_t>(m_stride) * vi + 8, sizeof z);
+                const double zs = (static_cast<double>(z) - m_bound[2]) / m_bound[3];
+                zmin = std::min(zmin, zs); zmax = std::max(zmax, zs);
+            }
+            if (zmin > zmax) continue;
+            const double lo = std::floor((zmin + 1.0) * 0.5 * N - 0.5), hi = std::ceil((zmax + 1.0) * 0.5 * N - 0.5);
+            const uint32_t l = static_cast<uint32_t>(std::min(std::max(lo, 0.0), N - 1.0)), h = static_cast<uint32_t>(std::min(std::max(hi, 0.0), N - 1.0));
+            diff[l] += 1.0; diff[h + 1] -= 1.0;
+        }
+        std::vector<double> t(N);
+        double run = 0.0, total = 0.0;
+        for (uint32_t z = 0; z < N; ++z) { run += diff[z]; t[z] = run; total += run; }
+        if (total > 0.0)
+            for (uint32_t z = begin; z < end; ++z) cost[z - begin] += 1.2 * t[z] / (total / N);
+    }
+    double sum = 0.0;
+    for (double c : cost) sum += c;
+    double acc = 0.0;
+    uint32_t z = 0;
+    for (int g = 1; g < k; ++g)
+    {
+        const double target = sum * g / k;
+        while (z < layers && acc + cost[z] <= target) acc += cost[z++];
+        uint32_t cut = begin + z;
+        cut = std::max(cut, m_cuts[g - 1] + (layers >= static_cast<uint32_t>(k) ? 1u : 0u));   // every GPU keeps a layer when there are enough
+        cut = std::min(cut, end - std::min<uint32_t>(layers, static_cast<uint32_t>(k - g)));
+        m_cuts[g] = std::max(cut, m_cuts[g - 1]);
+    }
+}
+
+void DXRVoxelizer::slabOf(int g, uint32_t& z0, uint32_t& z1) const
+{
+    if (static_cast<size_t>(g) + 1 >= m_cuts.size()) { z0 = z1 = 0; return; }   // no Voxelize() yet
+    z0 = m_cuts[static_cast<size_t>(g)];
+    z1 = m_cuts[static_cast<size_t>(g) + 1];
 }
 
 bool DXRVoxelizer::Voxelize()
@@ -89,10 +146,11 @@ bool DXRVoxelizer::Voxelize()
     const uint32_t end = m_slabEnd ? m_slabEnd : m_gridSize;
     m_gridFetched = false;
     const int k = 1 + static_cast<int>(m_more.size());
+    computeSlabs(m_slabBegin, end, k);
     for (int g = 0; g < k; ++g)
     {
         uint32_t z0, z1;
-        slabOf(m_slabBegin, end, g, k, z0, z1);
+        slabOf(g, z0, z1);
         if (z0 == z1) continue;
         dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
         if (dxrv_voxelize(c, m_gridSize, m_mode, z0, z1) != DXRV_OK)
@@ -116,13 +174,12 @@ const uint32_t* DXRVoxelizer::Grid()
     if (!m_gridFetched)
     {
         m_grid.resize(GridWords());
-        const uint32_t end = m_slabEnd ? m_slabEnd : m_gridSize;
         const size_t wordsPerLayer = static_cast<size_t>(m_gridSize) * ((m_gridSize + 31) / 32);
         const int k = 1 + static_cast<int>(m_more.size());
         for (int g = 0; g < k; ++g)   // gather: every GPU's slab lands at its offset of the host grid
         {
             uint32_t z0, z1;
-            slabOf(m_slabBegin, end, g, k, z0, z1);
+            slabOf(g, z0, z1);
             if (z0 == z1) continue;
             dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
             if (dxrv_fetch_grid(c, m_grid.data() + (z0 - m_slabBegin) * wordsPerLayer, (z1 - z0) * wordsPerLayer * sizeof(uint32_t),
@@ -141,12 +198,11 @@ bool DXRVoxelizer::CountInside(uint64_t& count)
 {
     if (!m_ctx) { m_error = "Init has not been called"; return false; }
     count = 0;
-    const uint32_t end = m_slabEnd ? m_slabEnd : m_gridSize;
     const int k = 1 + static_cast<int>(m_more.size());
     for (int g = 0; g < k; ++g)
     {
         uint32_t z0, z1;
-        slabOf(m_slabBegin, end, g, k, z0, z1);
+        slabOf(g, z0, z1);
         if (z0 == z1) continue;
         dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
         uint64_t part = 0;

@@ -67,9 +67,12 @@ public:
 
 private:
     bool fail(const char* what);
+    void computeSlabs(uint32_t begin, uint32_t end, int k);   // cost-balanced z-slab cut points of the k GPUs
+    void slabOf(int g, uint32_t& z0, uint32_t& z1) const;
 
     dxrv_ctx* m_ctx = nullptr;            // context of the first GPU
     std::vector<dxrv_ctx*> m_more;        // contexts of GPUs 2..k
+    std::vector<uint32_t> m_cuts;         // k + 1 slab cut points of the last Voxelize()
     int m_gpus = 1;
     dxrv_mesh* m_mesh = nullptr;
     const void* m_vertices = nullptr;

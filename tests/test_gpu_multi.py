@@ -60,3 +60,23 @@ def test_zslab_sharding_two_gpus(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_cli_two_gpus_matches_one(tmp_path):
+    """The C++ host class with SetGpuCount(2): cost-balanced z-slabs on two contexts, gathered on the host --
+    the grid dump must equal the single-GPU one byte for byte (and `-gpus 1` is checked against the oracle
+    in test_gpu_voxelize.py::test_cli_matches_oracle)."""
+    import numpy as np
+    import torch
+    import dxrvoxelizer_b200 as d
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "dxrvoxelizer_b200", "dxrvoxelizer")
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("grid%d.bin" % gpus)
+        r = subprocess.run([exe, "-mesh", d.asset_path("dragon.obj"), "-grid", "256", "-mode", "parity", "-gpus", str(gpus), "-out", str(out)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(np.fromfile(out, np.uint32))
+    assert outs[0].size == 256 * 256 * 8 and np.array_equal(outs[0], outs[1])
