@@ -509,8 +509,16 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
             ctx->walkZeroed = zeroBytes;
         }
     }
+    // fine mesh on a coarse grid: triangle-parallel scatter instead of the tile kernels (DXRV_PARITY_PATH=tiles|scatter forces one)
+    bool scatter = algo == DXRV_MODE_PARITY && useScatterParity(ctx->mesh.numTris, N);
+    if (const char* f = std::getenv("DXRV_PARITY_PATH"))
+    {
+        if (!std::strcmp(f, "tiles")) scatter = false;
+        else if (!std::strcmp(f, "scatter") && algo == DXRV_MODE_PARITY && ctx->mesh.numTris >= 2 && N <= 2048) scatter = true;
+    }
     std::vector<uint8_t> key;
     keyPush(key, (uint32_t)0x70C5u);
+    keyPush(key, (uint32_t)scatter);
     keyPush(key, N); keyPush(key, mode); keyPush(key, slabBegin); keyPush(key, slabEnd);
     keyPush(key, grid); keyPush(key, texels); keyPush(key, ctx->walkBuf);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
@@ -518,8 +526,12 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     const int rc = runCaptured(ctx, key, [&]() {
         if (algo == DXRV_MODE_PARITY)
         {
-            ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
-                                                              ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr);
+            if (scatter)
+                ctx->launches += (uint64_t)launchScatterFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->dCrossings,
+                                                                    ctx->profiling ? ctx->prof : nullptr);
+            else
+                ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
+                                                                  ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr);
             ctx->profValid = ctx->profiling;
         }
         else

@@ -77,6 +77,13 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
                            uint32_t* grid, uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr,
                            cudaEvent_t* ev /* nullable: {before walk, between, after fill} */);
 
+// ---- scatter_parity.cu --------------------------------------------------------------------------
+// MODE_PARITY for meshes that are fine relative to the grid (useScatterParity): triangle-parallel scatter of
+// toggle bits + in-place prefix pass; same result, bit for bit, as launchTraceFillColumns.
+bool useScatterParity(uint32_t numTris, uint32_t N);
+int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
+                             unsigned long long* dCrossings, cudaEvent_t* ev /* nullable, as above */);
+
 // ---- trace_shader.cu ----------------------------------------------------------------------------
 // MODE_SHADER: one radial closest-hit ray per voxel (DXRVoxelizer.hlsl raygenMain/closestHitMain).
 // texels may be null.  verts/indices are the ORIGINAL buffers (normals at byte offset 12).
