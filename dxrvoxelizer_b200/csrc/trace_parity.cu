@@ -112,7 +112,7 @@ constexpr int kLightClasses = 4;        // light tiles are scheduled by halving 
                                         // kernel's tail is made of its smallest work items
 constexpr uint32_t kSplitTile = 512;    // candidates from which a tile is split ...
 constexpr uint32_t kPartSize = 256;     // ... into parts of about this many candidates
-constexpr uint32_t kMaxParts = 12;
+constexpr uint32_t kMaxParts = 64;
 constexpr uint32_t kHeavySlots = 1024;  // tiles that can be split per launch
 constexpr uint32_t kExtraParts = 2048;  // extra CTAs (beyond one per tile) a launch provides
 
@@ -896,7 +896,11 @@ void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, 
 {
     const uint32_t SY = 16, SZ = 8;
     numTiles = ((N + SY - 1) / SY) * ((z1 - z0 + SZ - 1) / SZ);
+    // candidate slots per tile: 2048, more when the tiles are few (a coarse grid puts thousands of triangles of a
+    // surface seen edge-on into one tile; a list that overflows sends its tile to the slow in-kernel walk) --
+    // up to 256 MiB of lists in all
     candCap = 2048;
+    while (candCap < 32768u && (uint64_t)numTiles * candCap * 2u * sizeof(uint32_t) <= (256ull << 20)) candCap *= 2u;
 }
 
 // words of device scratch launchTraceFillColumns needs (see the layout below); the region up to

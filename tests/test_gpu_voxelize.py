@@ -163,6 +163,22 @@ def test_every_word_of_the_slab_is_written(vox, assets, N, layers):
     assert 0 < popcount(out[0]) < words * 32
 
 
+@pytest.mark.parametrize("name,N", [("dragon.obj", 256), ("TuringBowl.obj", 192), ("cube", 100), ("knot", 320)])
+def test_scatter_and_tile_paths_agree(vox, assets, meshes_mod, oracle_mod, monkeypatch, name, N):
+    """MODE_PARITY has two implementations (tile kernels / triangle-parallel scatter, chosen by triangle density):
+    force each on the same input -- fine meshes, a coarse one (12 huge triangles) and a ragged N -- and
+    require identical grids and crossing counts, equal to the oracle's."""
+    m = {"cube": meshes_mod.cube, "knot": lambda: meshes_mod.torus_knot(192, 24, seed=3)}.get(name, lambda: assets(name))()
+    ref = oracle_mod.voxelize(m.vertices, m.indices, N, oracle_mod.MODE_PARITY)
+    for path in ("tiles", "scatter"):
+        monkeypatch.setenv("DXRV_PARITY_PATH", path)
+        got = _run(vox, m, N, d.MODE_PARITY)
+        assert popcount(got ^ ref["bits"]) == 0, path
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], path
+        half = _run(vox, m, N, d.MODE_PARITY, N // 3, N // 3 + 17)        # a slab
+        assert np.array_equal(half, got[N // 3:N // 3 + 17]), path
+
+
 def test_full_size_1024_parity_against_oracle(vox, assets, oracle_mod):
     """C3 at full size: dragon, N = 1024 (128 MiB bit grid).  The accelerated oracle finishes in
     seconds at this size, so the check is still a full bit-exact comparison, plus the size-independent
