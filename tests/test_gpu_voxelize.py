@@ -179,6 +179,29 @@ def test_scatter_and_tile_paths_agree(vox, assets, meshes_mod, oracle_mod, monke
         assert np.array_equal(half, got[N // 3:N // 3 + 17]), path
 
 
+@pytest.mark.parametrize("seed,N", [(1, 37), (2, 64), (3, 160), (4, 256)])
+def test_random_triangle_soup_both_paths(vox, oracle_mod, monkeypatch, seed, N):
+    """Fuzz: an open soup of triangles of every size -- slivers, sub-voxel specks, sheets spanning the grid,
+    axis-aligned ones whose edges run through column centres -- through both MODE_PARITY paths.  Nothing is
+    watertight here, so columns have odd crossing counts; the toggling semantics (Spec H) still define every bit."""
+    from dxrvoxelizer_b200 import Mesh
+    rng = np.random.default_rng(seed)
+    n = 400
+    centre = rng.uniform(-1, 1, size=(n, 1, 3))
+    size = 10.0 ** rng.uniform(-3.5, 0.3, size=(n, 1, 1))
+    tri = centre + size * rng.uniform(-1, 1, size=(n, 3, 3))
+    snap = rng.random(n) < 0.2                                   # some triangles on the voxel lattice: exact ties
+    tri[snap] = np.round(tri[snap] * N / 2) * 2 / N
+    pos = np.concatenate([tri.reshape(-1, 3), [[-1, -1, -1], [1, 1, 1]]]).astype(np.float32)   # pin the bound to the cube
+    m = Mesh.from_arrays(pos, np.arange(3 * n, dtype=np.uint32).reshape(n, 3))
+    ref = oracle_mod.voxelize(m.vertices, m.indices, N, oracle_mod.MODE_PARITY)
+    for path in ("tiles", "scatter"):
+        monkeypatch.setenv("DXRV_PARITY_PATH", path)
+        got = _run(vox, m, N, d.MODE_PARITY)
+        assert popcount(got ^ ref["bits"]) == 0, path
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], path
+
+
 def test_full_size_1024_parity_against_oracle(vox, assets, oracle_mod):
     """C3 at full size: dragon, N = 1024 (128 MiB bit grid).  The accelerated oracle finishes in
     seconds at this size, so the check is still a full bit-exact comparison, plus the size-independent
@@ -297,10 +320,12 @@ def test_cli_matches_oracle(tmp_path, oracle_mod, assets):
     assert popcount(got ^ ref) == 0 and info["inside"] == popcount(ref) and info["triangles"] == m.num_triangles
 
 
-@pytest.mark.parametrize("N", [384, 1280, 1664])
+@pytest.mark.parametrize("N", [384, 1280, 1664, 2048, 4096])
 def test_weak_scaling_grid_sizes_slab(vox, assets, oracle_mod, N):
     """Grids of the multi-GPU bench (N % 128 == 0 but not a power of two: shared row pitch > global pitch,
-    IEEE division in centre()): a few z-slabs against the oracle."""
+    IEEE division in centre()) and the two larger CTA shapes (8 and 16 warps, N = 2048 / 4096 -- also the sizes
+    at which the float index estimates of the conservative culling are least accurate): a few z-slabs
+    against the oracle."""
     m = assets("dragon.obj")
     vox.build_bvh(m)
     for z0 in (N // 2 - 8, N // 2 + 40):
