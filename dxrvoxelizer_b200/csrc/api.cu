@@ -527,7 +527,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         if (algo == DXRV_MODE_PARITY)
         {
             if (scatter)
-                ctx->launches += (uint64_t)launchScatterFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->dCrossings,
+                ctx->launches += (uint64_t)launchScatterFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf, ctx->dCrossings,
                                                                     ctx->profiling ? ctx->prof : nullptr);
             else
                 ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,

@@ -82,7 +82,8 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
 // toggle bits + in-place prefix pass; same result, bit for bit, as launchTraceFillColumns.
 bool useScatterParity(uint32_t numTris, uint32_t N);
 int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
-                             unsigned long long* dCrossings, cudaEvent_t* ev /* nullable, as above */);
+                             uint32_t* walkBuf /* the tile path's scratch, same contract */, unsigned long long* dCrossings,
+                             cudaEvent_t* ev /* nullable, as above */);
 
 // ---- trace_shader.cu ----------------------------------------------------------------------------
 // MODE_SHADER: one radial closest-hit ray per voxel (DXRVoxelizer.hlsl raygenMain/closestHitMain).

@@ -12,10 +12,14 @@
 //                       grid with a global atomicXor -- neighbouring triangles are neighbours in Morton order,
 //                       so the atomics of a warp land in a handful of L2 lines.  Most triangles cross no column
 //                       centre at all and cost one record.
+//   k_scatter_huge      the few triangles that cover thousands of columns (a ground plane under a detailed object)
+//                       would keep one warp busy for milliseconds: k_scatter_crossings only lists them, and this
+//                       kernel deals their ROWS to all the warps of the machine (it exits at once when the list is empty)
 //   k_prefix_rows       occupancy = prefix-XOR of the toggles along x, in place: 128 bits per lane, ballot carry
 //
 // XOR commutes, so the result is bit-identical to the tile path's whatever the order of the atomics.
 // The LBVH is not needed here (its sorted triangle records are); it is still built, the metric counts it.
+#include <algorithm>
 #include "kernels.h"
 #include "parity_common.cuh"
 
@@ -24,6 +28,8 @@ namespace dxrv
 namespace
 {
 constexpr int kScatterWarps = 4;
+constexpr uint32_t kHugePairs = 8192;   // rows x bounding columns from which a triangle goes to k_scatter_huge
+constexpr uint32_t kHugeCap = 4096;     // triangles that list holds (more are handled in line)
 
 struct ScatterParams
 {
@@ -34,6 +40,9 @@ struct ScatterParams
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
     unsigned long long* crossings;
+    uint32_t* hugeCount;     // one word, zero on entry; reset by the prefix kernel
+    uint32_t* hugeList;      // [hugeCap] sorted-triangle slots
+    uint32_t hugeCap;
 };
 
 __global__ void __launch_bounds__(32 * kScatterWarps)
@@ -69,6 +78,14 @@ k_scatter_crossings(const ScatterParams prm)
             const int r0 = min(max((int)ceilf((zlo + 1.0f) * halfN - 0.5f - kIdxSlack) - (int)prm.z0, 0), (int)layers);
             const int r1 = min(max((int)floorf((zhi + 1.0f) * halfN - 0.5f + kIdxSlack) - (int)prm.z0, -1), (int)layers - 1);
             zA = (uint32_t)r0; h = (uint32_t)max(r1 - r0 + 1, 0);
+            // a triangle over thousands of columns is listed for k_scatter_huge instead (when the list has room)
+            const float ylo = fminf(fminf(a.y, b.y), c.y), yhi = fmaxf(fmaxf(a.y, b.y), c.y);
+            const float wEst = fminf((yhi - ylo) * halfN + 2.0f, fN);
+            if (h != 0u && (float)h * wEst > (float)kHugePairs)
+            {
+                const uint32_t at = atomicAdd(prm.hugeCount, 1u);
+                if (at < prm.hugeCap) { prm.hugeList[at] = slot; h = 0; }
+            }
         }
         // records {a.xyz, zA | b.xyz, first row unit | c.xyz, -} of the triangles that have rows; owner lookup
         // by start masks exactly as in k_trace_fill_columns
@@ -156,13 +173,55 @@ k_scatter_crossings(const ScatterParams prm)
     if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
 }
 
+// The listed huge triangles: every warp of the grid takes rows of every one of them at a stride, its lanes the
+// columns of the row's conservative interval.
+__global__ void __launch_bounds__(128)
+k_scatter_huge(const ScatterParams prm)
+{
+    const uint32_t count = min(__ldcg(prm.hugeCount), prm.hugeCap);
+    if (count == 0u) return;
+    const uint32_t lane = laneId();
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), numWarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t N = prm.N, P = prm.P, layers = prm.z1 - prm.z0;
+    const float fN = (float)N, invNPow2 = prm.invNPow2, halfN = 0.5f * fN;
+    uint32_t myCrossings = 0;
+    for (uint32_t b = 0; b < count; ++b)
+    {
+        const float4* t = reinterpret_cast<const float4*>(prm.tris + __ldcg(prm.hugeList + b));
+        const float4 ta = __ldg(t), tb = __ldg(t + 1), tc = __ldg(t + 2);
+        const float zlo = fminf(fminf(ta.z, tb.z), tc.z), zhi = fmaxf(fmaxf(ta.z, tb.z), tc.z);
+        const int r0 = min(max((int)ceilf((zlo + 1.0f) * halfN - 0.5f - kIdxSlack) - (int)prm.z0, 0), (int)layers);
+        const int r1 = min(max((int)floorf((zhi + 1.0f) * halfN - 0.5f + kIdxSlack) - (int)prm.z0, -1), (int)layers - 1);
+        for (int zl = r0 + (int)gwarp; zl <= r1; zl += (int)numWarps)
+        {
+            const float Zc = centreOf(prm.z0 + (uint32_t)zl, fN, invNPow2);
+            float lo, hi;
+            rowIntervalY(ta, tb, tc, Zc, lo, hi);
+            const int ya = min(max((int)ceilf((1.0f - hi) * halfN - 0.5f - kIdxSlack), 0), (int)N);
+            const int yb = min(max((int)floorf((1.0f - lo) * halfN - 0.5f + kIdxSlack), -1), (int)N - 1);
+            for (int y = ya + (int)lane; y <= yb; y += 32)
+            {
+                uint32_t ix;
+                if (columnCrossing(ta, tb, tc, -centreOf((uint32_t)y, fN, invNPow2), Zc, N, fN, invNPow2, ix))
+                {
+                    ++myCrossings;
+                    if (ix < N) atomicXor(prm.grid + ((size_t)zl * N + (uint32_t)y) * P + (ix >> 5), 1u << (ix & 31u));
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) myCrossings += __shfl_xor_sync(0xffffffffu, myCrossings, o);
+    if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
+}
+
 // toggles -> occupancy, in place.  kGroups = 128-bit groups per row (a power of two <= 32): a warp holds
 // 32 / kGroups whole rows, one group per lane, and the carry into a lane is the parity of the lower lanes of its row.
 template <int kGroups>
 __global__ void __launch_bounds__(256)
-k_prefix_rows_vec(uint4* __restrict__ grid, size_t numGroups)
+k_prefix_rows_vec(uint4* __restrict__ grid, size_t numGroups, uint32_t* __restrict__ hugeCount)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) *hugeCount = 0;   // leave the list empty for the next launch
     const uint32_t lane = laneId();
     uint4 t = g < numGroups ? grid[g] : make_uint4(0, 0, 0, 0);
     uint32_t par;
@@ -179,9 +238,10 @@ k_prefix_rows_vec(uint4* __restrict__ grid, size_t numGroups)
 
 // any row length: one thread per row
 __global__ void __launch_bounds__(256)
-k_prefix_rows_any(uint32_t* __restrict__ grid, size_t numRows, uint32_t P, uint32_t tailMask)
+k_prefix_rows_any(uint32_t* __restrict__ grid, size_t numRows, uint32_t P, uint32_t tailMask, uint32_t* __restrict__ hugeCount)
 {
     const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0) *hugeCount = 0;
     if (row >= numRows) return;
     uint32_t* w = grid + row * P;
     uint32_t carry = 0;
@@ -204,7 +264,7 @@ bool useScatterParity(uint32_t numTris, uint32_t N)
 }
 
 int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
-                             unsigned long long* dCrossings, cudaEvent_t* ev)
+                             uint32_t* walkBuf, unsigned long long* dCrossings, cudaEvent_t* ev)
 {
     ScatterParams prm;
     prm.tris = bvh.tris; prm.numTris = bvh.numTris;
@@ -212,6 +272,13 @@ int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uin
     prm.z0 = z0; prm.z1 = z1;
     prm.invNPow2 = ((N & (N - 1)) == 0) ? 1.0f / (float)N : 0.0f;
     prm.grid = grid; prm.crossings = dCrossings;
+    // scratch shared with the tile path (same buffer, never used by both in one call): the list counter is a spare
+    // word of its zero-initialised, self-cleaning head; the list itself lies in the candidate-list area
+    uint32_t numTiles, candCap;
+    parityTileCounts(N, z0, z1, numTiles, candCap);
+    prm.hugeCount = walkBuf + 6;
+    prm.hugeList = walkBuf + (parityScratchWords(N, z0, z1) - (size_t)numTiles * candCap);
+    prm.hugeCap = (uint32_t)std::min<size_t>(kHugeCap, (size_t)numTiles * candCap);
     const size_t numRows = (size_t)(z1 - z0) * N, words = numRows * prm.P;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
     if (ev) cudaEventRecord(ev[0], s);
@@ -221,6 +288,7 @@ int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uin
     uint32_t blocks = (numChunks + kScatterWarps - 1) / kScatterWarps;
     if (blocks > 148u * 16u) blocks = 148u * 16u;
     k_scatter_crossings<<<blocks, 32 * kScatterWarps, smemBytes, s>>>(prm);
+    k_scatter_huge<<<148 * 4, 128, 0, s>>>(prm);
     if (ev) cudaEventRecord(ev[1], s);
     const uint32_t groups = prm.P / 4u;
     const bool vec = (prm.P & 3u) == 0u && (N & 31u) == 0u && groups <= 32u && (groups & (groups - 1u)) == 0u;
@@ -231,20 +299,20 @@ int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uin
         uint4* g4 = reinterpret_cast<uint4*>(grid);
         switch (groups)
         {
-        case 1: k_prefix_rows_vec<1><<<pb, 256, 0, s>>>(g4, numGroups); break;
-        case 2: k_prefix_rows_vec<2><<<pb, 256, 0, s>>>(g4, numGroups); break;
-        case 4: k_prefix_rows_vec<4><<<pb, 256, 0, s>>>(g4, numGroups); break;
-        case 8: k_prefix_rows_vec<8><<<pb, 256, 0, s>>>(g4, numGroups); break;
-        case 16: k_prefix_rows_vec<16><<<pb, 256, 0, s>>>(g4, numGroups); break;
-        default: k_prefix_rows_vec<32><<<pb, 256, 0, s>>>(g4, numGroups); break;
+        case 1: k_prefix_rows_vec<1><<<pb, 256, 0, s>>>(g4, numGroups, prm.hugeCount); break;
+        case 2: k_prefix_rows_vec<2><<<pb, 256, 0, s>>>(g4, numGroups, prm.hugeCount); break;
+        case 4: k_prefix_rows_vec<4><<<pb, 256, 0, s>>>(g4, numGroups, prm.hugeCount); break;
+        case 8: k_prefix_rows_vec<8><<<pb, 256, 0, s>>>(g4, numGroups, prm.hugeCount); break;
+        case 16: k_prefix_rows_vec<16><<<pb, 256, 0, s>>>(g4, numGroups, prm.hugeCount); break;
+        default: k_prefix_rows_vec<32><<<pb, 256, 0, s>>>(g4, numGroups, prm.hugeCount); break;
         }
     }
     else
     {
         const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
-        k_prefix_rows_any<<<(unsigned)((numRows + 255) / 256), 256, 0, s>>>(grid, numRows, prm.P, tailMask);
+        k_prefix_rows_any<<<(unsigned)((numRows + 255) / 256), 256, 0, s>>>(grid, numRows, prm.P, tailMask, prm.hugeCount);
     }
     if (ev) cudaEventRecord(ev[2], s);
-    return 2;
+    return 3;
 }
 }  // namespace dxrv

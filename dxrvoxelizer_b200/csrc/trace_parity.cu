@@ -62,7 +62,7 @@ struct ParityParams
                              // initcheck does not see what cp.async.bulk writes)
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
-    uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [5] cursor of the empty-tile writers, [8..11] light tiles per class, [32 + smid] writer claim of an SM
+    uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [5] cursor of the empty-tile writers, [6] (scatter path) huge-triangle count, [8..11] light tiles per class, [32 + smid] writer claim of an SM
     uint32_t* lightTiles;    // [kLightClasses][tilesPad]  light tiles, classed by candidate count
     uint32_t* emptyTiles;    // [numTiles]
     uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}

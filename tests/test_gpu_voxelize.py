@@ -202,6 +202,30 @@ def test_random_triangle_soup_both_paths(vox, oracle_mod, monkeypatch, seed, N):
         assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], path
 
 
+def test_fine_mesh_with_huge_triangles(vox, assets, oracle_mod, monkeypatch):
+    """A detailed object over a two-triangle ground sheet: the triangle density sends it down the scatter path,
+    where the sheet's triangles cover a quarter of all columns each -- they are listed and rasterised by the whole
+    grid (k_scatter_huge) instead of by one warp.  Same bits as the tile path and the oracle."""
+    from dxrvoxelizer_b200 import Mesh
+    m = assets("bunny.obj")
+    pos = m.vertices[:, :3]
+    lo, hi = pos.min(0), pos.max(0)
+    y = lo[1] - 0.05 * (hi[1] - lo[1])
+    e = 0.5 * (hi - lo).max()
+    c = 0.5 * (lo + hi)
+    sheet = np.array([[c[0] - e, y, c[2] - e], [c[0] + e, y, c[2] - e], [c[0] + e, y + 0.3 * e, c[2] + e], [c[0] - e, y + 0.3 * e, c[2] + e]], np.float32)
+    n0 = pos.shape[0]
+    tris = np.concatenate([m.indices.reshape(-1, 3), [[n0, n0 + 1, n0 + 2], [n0, n0 + 2, n0 + 3]]]).astype(np.uint32)
+    mm = Mesh.from_arrays(np.concatenate([pos, sheet]), tris)
+    N = 192
+    ref = oracle_mod.voxelize(mm.vertices, mm.indices, N, oracle_mod.MODE_PARITY)
+    for path in ("scatter", "tiles", "scatter"):
+        monkeypatch.setenv("DXRV_PARITY_PATH", path)
+        got = _run(vox, mm, N, d.MODE_PARITY)
+        assert popcount(got ^ ref["bits"]) == 0, path
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], path
+
+
 def test_full_size_1024_parity_against_oracle(vox, assets, oracle_mod):
     """C3 at full size: dragon, N = 1024 (128 MiB bit grid).  The accelerated oracle finishes in
     seconds at this size, so the check is still a full bit-exact comparison, plus the size-independent
