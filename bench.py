@@ -338,6 +338,7 @@ def run_ours(args):
             "roofline": {"kernel": "k_trace_fill_columns", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": fill_ms_rank0, "peak_source": peak_src,
+                         "frac_of_nominal_8000_GBps": achieved / 8000.0,
                          "timing": "cudaEventRecord on the launching stream around the kernel, mean of %d launches" % prof_steps},
             "cpu_baseline": cpu,
             "clocks": clocks,
