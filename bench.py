@@ -288,6 +288,20 @@ def run_ours(args):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
+    # where the end-to-end time goes (separate short loop with a synchronisation between compute and read-back)
+    up_ms = down_ms = 0.0
+    if world == 1:
+        reps = min(args.steps, 20)
+        for _ in range(reps):
+            ta = time.perf_counter()
+            vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
+            vox.voxelize(N, d.MODE_PARITY, z0, z1)
+            vox.synchronize()
+            tb = time.perf_counter()
+            vox.fetch_into(h_grid.data_ptr(), slab_bytes)
+            tc = time.perf_counter()
+            up_ms += (tb - ta) * 1e3 / reps
+            down_ms += (tc - tb) * 1e3 / reps
 
     # ---- strong-scaling side number: ONE 1024^3 grid split into `world` slabs ---------------------
     zs_ms = None
@@ -333,7 +347,8 @@ def run_ours(args):
             "ms_per_1024_cubed_grid": step_ms if world == 1 else zs_ms,
             "e2e": {"value": total_voxels / (e2e_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(N * N * ((N + 31) // 32) * 4),
-                    "timing": "wall clock around synchronising C-ABI calls, max over ranks"},
+                    "timing": "wall clock around synchronising C-ABI calls, max over ranks",
+                    "phases_ms": ({"h2d_mesh_build_voxelize": up_ms, "d2h_grid": down_ms} if world == 1 else None)},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_trace_fill_columns", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
