@@ -74,7 +74,7 @@ __device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* 
 
 // ---- one digit pass ----------------------------------------------------------------------------------
 template <int kItems>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, kItems >= 8 ? 4 : 1)
 k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                 uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n, int shift,
                 const uint32_t* __restrict__ digitCount, volatile uint32_t* __restrict__ lookback,
@@ -83,7 +83,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     constexpr int kTile = kSortThreads * kItems;
     // predecessor tiles fetched per round trip of the look-back: the small-tile variant is latency bound
     // (many tiles, few keys), the big-tile variant is register bound
-    constexpr int kLookbackWindow = kItems >= 8 ? 4 : 12;
+    constexpr int kLookbackWindow = kItems >= 8 ? 8 : 12;
     __shared__ uint32_t warpHist[kSortWarps][kRadix];  // 8 KB
     __shared__ uint32_t binStart[kRadix];
     __shared__ uint32_t globalBase[kRadix];
@@ -236,6 +236,17 @@ int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* va
         if (histBlocks > 148 * 4) histBlocks = 148 * 4;
         k_radix_histogram<<<histBlocks, kSortThreads, 0, s>>>(keysA, n, hist);
         ++launches;
+    }
+    {
+        // four 43 KB CTAs per SM need more than the default shared-memory carve-out
+        static bool carveSet[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !carveSet[dev])
+        {
+            cudaFuncSetAttribute(k_onesweep_pass<kBigItems>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveSet[dev] = true;
+        }
     }
     uint32_t *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
     for (int p = 0; p < numPasses; ++p)
