@@ -28,8 +28,8 @@ void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32
 constexpr int kMaxBoxLevels = 8;
 // float4 entries needed for the leaf-box pyramid of numTris leaves
 size_t boxPyramidFloat4s(uint32_t numTris);
-// k_leaf_setup (+ k_box_level) + k_hierarchy_boxes (small meshes: child boxes by range union) or
-// k_hierarchy_boxes + k_refit_atomic (large meshes: bottom-up refit with atomics); returns the number of
+// k_leaf_setup (+ k_box_level) beside k_hierarchy_topology, then k_node_boxes (small meshes: child boxes by range
+// union) or k_refit_atomic (large meshes: bottom-up refit with atomics); returns the number of
 // kernels launched.  refitScratch: 3 * numTris uint32, only touched when useAtomicRefit(numTris).
 bool useAtomicRefit(uint32_t numTris);
 // side (nullable): a second stream + two events; with it the leaf/pyramid kernels run beside the topology kernel.
