@@ -189,8 +189,9 @@ def run_ours(args):
     if world > 1:
         dist.broadcast(meta, 0)
     nv, stride, ni = (int(x) for x in meta.tolist())
-    h_vb = torch.empty(nv * stride, dtype=torch.uint8).pin_memory()
-    h_ib = torch.empty(ni, dtype=torch.int32).pin_memory()
+    with numa_local(local):
+        h_vb = torch.empty(nv * stride, dtype=torch.uint8).pin_memory()
+        h_ib = torch.empty(ni, dtype=torch.int32).pin_memory()
     if rank == 0:
         h_vb.copy_(torch.from_numpy(mesh.vertex_bytes))
         h_ib.copy_(torch.from_numpy(mesh.indices.view(np.int32)))
@@ -212,7 +213,9 @@ def run_ours(args):
     z0, z1 = balanced_slabs(host_mesh, N, world)[rank]
 
     slab_bytes = (z1 - z0) * N * ((N + 31) // 32) * 4
-    h_grid = torch.empty(slab_bytes, dtype=torch.uint8).pin_memory()
+    with numa_local(local):
+        h_grid = torch.empty(slab_bytes, dtype=torch.uint8).pin_memory()
+        h_grid.zero_()   # touch the pages while the thread still sits next to the GPU
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step_resident():
@@ -366,6 +369,36 @@ def run_ours(args):
     vox.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+class numa_local:
+    """Allocate pinned host buffers on the NUMA node next to GPU `index`: the thread is moved onto the CPUs NVML
+    reports for that GPU while the pages are allocated and touched, then gets its original affinity back (the CPU
+    baseline must see every core).  A D2H copy into far memory crosses the socket interconnect and loses bandwidth;
+    with 8 ranks reading back at once it is the difference between the PCIe links and one saturated socket link.
+    Best effort: without NVML (or on a single-node box) it does nothing."""
+    def __init__(self, index):
+        self.index, self.saved = index, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
 
 
 def ncu_traffic():
