@@ -15,7 +15,7 @@ MODE_SHADER, MODE_PARITY, EMIT_TEXELS = 0, 1, 0x100
 FORMAT_BITS, FORMAT_U8, FORMAT_R10G10B10A2 = 0, 1, 2
 INFO_NUM_TRIANGLES, INFO_NUM_NODES, INFO_KERNEL_LAUNCHES, INFO_CROSSINGS, INFO_SM_COUNT = 0, 1, 2, 3, 4
 INFO_LAST_WALK_NS, INFO_LAST_FILL_NS = 5, 6
-DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_ROOT_BOX = 0, 1, 2, 3, 5
+DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_ROOT_BOX, DBG_BINS_STATE = 0, 1, 2, 3, 5, 6
 
 _c = ctypes
 _vp, _u32, _u64, _sz, _int = _c.c_void_p, _c.c_uint32, _c.c_uint64, _c.c_size_t, _c.c_int

@@ -65,6 +65,9 @@ struct dxrv_ctx
     uint32_t* mips = nullptr; size_t mipCap = 0;      // occupancy pyramid levels 1.. (concatenated)
     uint32_t mipLevels = 0;                            // levels incl. level 0; 0 = not built for the current grid
     uint32_t* walkBuf = nullptr; size_t walkCap = 0, walkZeroed = 0;  // MODE_PARITY candidate lists + split-tile scratch
+    uint8_t* binsBuf = nullptr; size_t binsCap = 0;                   // MODE_SHADER direction bins (shader_bins.cu)
+    ShaderBinsSizes binsSizes{};
+    bool binsValid = false;                                            // built for the current acceleration structure
     uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
     bool haveGrid = false, haveTexels = false;
 
@@ -229,6 +232,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     const uint32_t T = m.numTris;
     ctx->haveBvh = false;
     ctx->haveGrid = false;
+    ctx->binsValid = false;
     if (T > ctx->capTris || !ctx->nodes)
     {
         const size_t cap = T + T / 8 + 16;
@@ -367,7 +371,8 @@ void dxrv_destroy(dxrv_ctx* ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
-                    ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips};
+                    ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips,
+                    ctx->binsBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -509,6 +514,20 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
             ctx->walkZeroed = zeroBytes;
         }
     }
+    bool buildBins = false, forceBvh = false;
+    if (algo == DXRV_MODE_SHADER)
+    {
+        // direction bins of the current acceleration structure (built by the first MODE_SHADER voxelize after a build)
+        if (const char* f = std::getenv("DXRV_SHADER_PATH")) forceBvh = !std::strcmp(f, "bvh");
+        const ShaderBinsSizes sz = forceBvh ? shaderBinsSizes(0) : shaderBinsSizes(ctx->mesh.numTris);
+        if (!ctx->binsValid || sz.R != ctx->binsSizes.R || sz.cap != ctx->binsSizes.cap || !ctx->binsBuf)
+        {
+            cudaError_t e = ensure(ctx->binsBuf, ctx->binsCap, sz.bytes);
+            if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(direction bins)");
+            ctx->binsSizes = sz;
+            buildBins = true;
+        }
+    }
     // fine mesh on a coarse grid: triangle-parallel scatter instead of the tile kernels (DXRV_PARITY_PATH=tiles|scatter forces one)
     bool scatter = algo == DXRV_MODE_PARITY && useScatterParity(ctx->mesh.numTris, N);
     if (const char* f = std::getenv("DXRV_PARITY_PATH"))
@@ -521,6 +540,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     keyPush(key, (uint32_t)scatter);
     keyPush(key, N); keyPush(key, mode); keyPush(key, slabBegin); keyPush(key, slabEnd);
     keyPush(key, grid); keyPush(key, texels); keyPush(key, ctx->walkBuf);
+    keyPush(key, ctx->binsBuf); keyPush(key, (uint32_t)buildBins); keyPush(key, (uint32_t)forceBvh); keyPush(key, ctx->binsSizes.R);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
     keyPush(key, ctx->mesh.verts); keyPush(key, ctx->mesh.numVerts); keyPush(key, ctx->mesh.stride); keyPush(key, ctx->mesh.indices); keyPush(key, ctx->mesh.numTris);
     const int rc = runCaptured(ctx, key, [&]() {
@@ -536,14 +556,19 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         }
         else
         {
-            launchTraceShader(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr);
-            ctx->launches += 1;
+            if (buildBins) ctx->launches += (uint64_t)launchShaderBinsBuild(ctx->stream, bvh, ctx->binsBuf, ctx->binsSizes, forceBvh);
+            // exactly one of the two does the work (device-side overflow flag of the bins)
+            launchTraceShaderBins(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr, ctx->binsBuf, ctx->binsSizes);
+            launchTraceShaderBvh(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr,
+                                 shaderBinsView(ctx->binsBuf, ctx->binsSizes).state);
+            ctx->launches += 2;
         }
     });
     if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
+    if (algo == DXRV_MODE_SHADER) ctx->binsValid = true;
     return DXRV_OK;
 }
 
@@ -722,6 +747,16 @@ int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes)
     DeviceGuard g(ctx->device);
     const size_t T = ctx->mesh.numTris;
     const void* src = nullptr; size_t need = 0;
+    if (what == DXRV_DBG_BINS_STATE)
+    {
+        if (!ctx->binsValid || !ctx->binsBuf) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_debug_read: no MODE_SHADER voxelize since the last build");
+        if (bytes != 16) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: size mismatch");
+        uint32_t* out = static_cast<uint32_t*>(hostDst);
+        DXRV_CUDA(cudaMemcpyAsync(out, shaderBinsView(ctx->binsBuf, ctx->binsSizes).state, 12, cudaMemcpyDeviceToHost, ctx->stream));
+        DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+        out[3] = ctx->binsSizes.R;
+        return DXRV_OK;
+    }
     switch (what)
     {
     case DXRV_DBG_MORTON_SORTED: src = ctx->keysA; need = T * 4; break;

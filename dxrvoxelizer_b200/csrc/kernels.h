@@ -85,11 +85,36 @@ int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uin
                              uint32_t* walkBuf /* the tile path's scratch, same contract */, unsigned long long* dCrossings,
                              cudaEvent_t* ev /* nullable, as above */);
 
-// ---- trace_shader.cu ----------------------------------------------------------------------------
+// ---- shader_bins.cu / trace_shader.cu ---------------------------------------------------------------
 // MODE_SHADER: one radial closest-hit ray per voxel (DXRVoxelizer.hlsl raygenMain/closestHitMain).
+// Default path: direction bins (shader_bins.cu) built once per acceleration structure; the LBVH walk
+// (trace_shader.cu) runs when the bins' device-side overflow flag is up.  Both launches are always enqueued;
+// exactly one of the two kernels does the work (the other returns at once), so no host round trip is needed.
+struct ShaderBinsView
+{
+    uint4* cells;         // [6 R^2] {first entry, count | unsorted flag, bits(max rmax), 0}
+    uint4* entries;       // [cap]   {bits(rmin), bits(rmax), triangle slot, 0}
+    uint32_t* cursors;    // [6 R^2] counts -> local exclusive offsets -> local end offsets
+    uint32_t* blockSums;  // [numBlocks] exclusive base of every 2048-cell tile
+    uint32_t* nearList;   // [nearCap] slots of the triangles closer than 1e-3 to the grid centre
+    uint32_t* state;      // [0] total entries, [1] overflow flag, [2] near count
+    uint32_t R, cap, nearCap;
+};
+struct ShaderBinsSizes
+{
+    uint32_t R, cap, nearCap, numBlocks;
+    size_t offCells, offEntries, offCursors, offBlockSums, offNear, offState, bytes;
+};
+uint32_t shaderBinsResolution(uint32_t numTris);
+ShaderBinsSizes shaderBinsSizes(uint32_t numTris);
+ShaderBinsView shaderBinsView(void* base, const ShaderBinsSizes& s);
+// returns the number of kernels launched; forceOverflow: build nothing, raise the flag (LBVH walk only)
+int launchShaderBinsBuild(cudaStream_t s, const BvhView& bvh, void* base, const ShaderBinsSizes& sz, bool forceOverflow);
 // texels may be null.  verts/indices are the ORIGINAL buffers (normals at byte offset 12).
-void launchTraceShader(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0,
-                       uint32_t z1, uint32_t* grid, uint32_t* texels, uint32_t* dErr);
+void launchTraceShaderBins(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
+                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, void* base, const ShaderBinsSizes& sz);
+void launchTraceShaderBvh(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
+                          uint32_t* grid, uint32_t* texels, uint32_t* dErr, const uint32_t* binsState /* nullable: always run */);
 
 // ---- view.cu (headless port of the reference's viewer pass, PSRayCast.hlsl) -----------------------------
 void launchRaycastView(cudaStream_t s, const uint32_t* grid, uint32_t N, uint32_t width, uint32_t height,

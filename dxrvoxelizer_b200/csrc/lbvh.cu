@@ -640,6 +640,7 @@ k_refit_atomic(int numLeaves, const float4* __restrict__ leafBoxes, BvhNode* __r
         *(reinterpret_cast<float2*>(&n->x01) + slot) = make_float2(xx.x, xx.y);
         __threadfence();  // release: the box must be visible before the arrival counter moves
         if (atomicAdd(flags + pi, 1u) == 0u) return;  // first child to arrive: the sibling will carry on
+        __threadfence();  // acquire: order the loads below after the arrival counter (PTX memory model)
         // second arrival: the sibling's box was released before its increment; read it past L1
         const float4 syz = __ldcg(slot ? &n->yz0 : &n->yz1);
         const float2 sxx = __ldcg(reinterpret_cast<const float2*>(&n->x01) + (1u - slot));

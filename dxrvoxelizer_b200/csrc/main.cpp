@@ -3,7 +3,8 @@
 // (reference DXRVoxelizer.cpp:363-408): '-' or '/' prefixes, case-insensitive names, a value may
 // start with '-' only when a digit or '.' follows; defaults Assets/bunny.obj and posScale (0,0,0,1)
 // (DXRVoxelizer.cpp:36-37).  -warp / -uma select D3D adapters in the reference and are accepted and
-// ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity, -device k,
+// ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity (default shader = the
+// reference's function; parity = the column-parity fast path), -device k,
 // -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words),
 // -view file.ppm (the reference's viewer pass, 1280 x 720).
 #include <algorithm>
@@ -57,7 +58,7 @@ int main(int argc, char** argv)
     float posScale[4] = {0.0f, 0.0f, 0.0f, 1.0f};
     uint32_t grid = 64, slab0 = 0, slab1 = 0;
     int device = 0, frames = 1, gpus = 1;
-    DXRVoxelizer::Mode mode = DXRVoxelizer::MODE_PARITY;
+    DXRVoxelizer::Mode mode = DXRVoxelizer::MODE_SHADER;   // Dragon.sh / TuringBowl.sh reproduce the reference's grid
 
     Args a{argc, argv};
     for (int i = 1; i < argc; ++i)

@@ -9,9 +9,12 @@
 // watertight test, hit distance clamped into the triangle's own slab interval, closest hit = the
 // lexicographic minimum of (tc, primitive index) -- so the result does not depend on the hierarchy.
 //
-// One warp produces one 32-voxel word of the bit grid (lane = x & 31): per-lane stack traversal of the
-// LBVH with near-child-first ordering, one __ballot_sync, one store.
+// This file is the GENERAL closest-hit kernel: per-lane stack traversal of the LBVH with near-child-first
+// ordering (one warp = one 32-voxel word, one __ballot_sync, one store).  Since round 2 the default MODE_SHADER
+// path is shader_bins.cu (direction bins: an exact accelerator for this radial ray family); this kernel runs
+// when the bins' entry budget overflows (device-side flag, no host round trip) or when DXRV_SHADER_PATH=bvh.
 #include "kernels.h"
+#include "shader_common.cuh"
 
 namespace dxrv
 {
@@ -20,212 +23,94 @@ namespace
 constexpr int kShaderThreads = 128;
 constexpr int kLocalStack = 64;  // LBVH depth <= 62 (30 key bits + 32 index bits)
 
-__device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
-
-struct RaySetup
-{
-    float Ox, Oy, Oz, Dx, Dy, Dz, ix, iy, iz;
-    float Sx, Sy, Sz;
-    int kx, ky, kz;
-};
-
-struct BestHit
-{
-    float tc;
-    uint32_t prim;
-    float bx, by;
-};
-
-__device__ __forceinline__ bool slabTest(const RaySetup& r, float lox, float loy, float loz, float hix, float hiy,
-                                         float hiz, float& tin, float& tout)
-{
-    tin = 0.0f; tout = kTMax;
-    float t0 = __fmul_rn(__fsub_rn(lox, r.Ox), r.ix), t1 = __fmul_rn(__fsub_rn(hix, r.Ox), r.ix);
-    tin = fmaxsel(fminsel(t0, t1), tin); tout = fminsel(fmaxsel(t0, t1), tout);
-    t0 = __fmul_rn(__fsub_rn(loy, r.Oy), r.iy); t1 = __fmul_rn(__fsub_rn(hiy, r.Oy), r.iy);
-    tin = fmaxsel(fminsel(t0, t1), tin); tout = fminsel(fmaxsel(t0, t1), tout);
-    t0 = __fmul_rn(__fsub_rn(loz, r.Oz), r.iz); t1 = __fmul_rn(__fsub_rn(hiz, r.Oz), r.iz);
-    tin = fmaxsel(fminsel(t0, t1), tin); tout = fminsel(fmaxsel(t0, t1), tout);
-    return tin <= tout;
-}
-
-// Spec H steps 1-4 for one (ray, triangle) pair
-__device__ __forceinline__ void testTriangle(const RaySetup& r, const Tri48* __restrict__ tris, uint32_t slot, BestHit& best)
-{
-    const float4* t = reinterpret_cast<const float4*>(tris + slot);
-    const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
-    const uint32_t prim = __float_as_uint(a.w);
-    float tin, tout;
-    if (!slabTest(r, fminsel(fminsel(a.x, b.x), c.x), fminsel(fminsel(a.y, b.y), c.y), fminsel(fminsel(a.z, b.z), c.z),
-                  fmaxsel(fmaxsel(a.x, b.x), c.x), fmaxsel(fmaxsel(a.y, b.y), c.y), fmaxsel(fmaxsel(a.z, b.z), c.z), tin, tout))
-        return;
-    const float Ax3 = __fsub_rn(a.x, r.Ox), Ay3 = __fsub_rn(a.y, r.Oy), Az3 = __fsub_rn(a.z, r.Oz);
-    const float Bx3 = __fsub_rn(b.x, r.Ox), By3 = __fsub_rn(b.y, r.Oy), Bz3 = __fsub_rn(b.z, r.Oz);
-    const float Cx3 = __fsub_rn(c.x, r.Ox), Cy3 = __fsub_rn(c.y, r.Oy), Cz3 = __fsub_rn(c.z, r.Oz);
-    const float Akz = pick(Ax3, Ay3, Az3, r.kz), Bkz = pick(Bx3, By3, Bz3, r.kz), Ckz = pick(Cx3, Cy3, Cz3, r.kz);
-    const float Ax = __fsub_rn(pick(Ax3, Ay3, Az3, r.kx), __fmul_rn(r.Sx, Akz));
-    const float Ay = __fsub_rn(pick(Ax3, Ay3, Az3, r.ky), __fmul_rn(r.Sy, Akz));
-    const float Bx = __fsub_rn(pick(Bx3, By3, Bz3, r.kx), __fmul_rn(r.Sx, Bkz));
-    const float By = __fsub_rn(pick(Bx3, By3, Bz3, r.ky), __fmul_rn(r.Sy, Bkz));
-    const float Cx = __fsub_rn(pick(Cx3, Cy3, Cz3, r.kx), __fmul_rn(r.Sx, Ckz));
-    const float Cy = __fsub_rn(pick(Cx3, Cy3, Cz3, r.ky), __fmul_rn(r.Sy, Ckz));
-    float U, V, W;
-    edgeValues(Ax, Ay, Bx, By, Cx, Cy, U, V, W);
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
-    const float det = __fadd_rn(__fadd_rn(U, V), W);
-    if (det == 0.0f) return;
-    const float tt = __fdiv_rn(weighted3(U, __fmul_rn(r.Sz, Akz), V, __fmul_rn(r.Sz, Bkz), W, __fmul_rn(r.Sz, Ckz)), det);
-    const float tc = fminsel(fmaxsel(tt, tin), tout);
-    if (!(tc > 0.0f && tc < kTMax)) return;
-    if (tc < best.tc || (tc == best.tc && prim < best.prim))
-    {
-        best.tc = tc; best.prim = prim;
-        best.bx = __fdiv_rn(V, det); best.by = __fdiv_rn(W, det);
-    }
-}
-
-__device__ __forceinline__ uint32_t unorm10(float v)
-{
-    if (!(v > 0.0f)) return 0u;
-    if (v > 1.0f) v = 1.0f;
-    return (uint32_t)__fadd_rn(__fmul_rn(v, 1023.0f), 0.5f);
-}
-
-struct ShaderParams
-{
-    const BvhNode* nodes;
-    const Tri48* tris;
-    uint32_t numTris;
-    const uint8_t* verts;
-    uint32_t stride;
-    const uint32_t* indices;
-    uint32_t N, P, z0;
-    uint64_t numWords;
-    uint32_t* grid;
-    uint32_t* texels;
-    uint32_t* err;
-};
-
 __global__ void __launch_bounds__(kShaderThreads)
 k_trace_shader(const ShaderParams prm)
 {
+    // runs only when the direction bins are not usable (shader_bins.cu): forced, or their entry budget overflowed
+    if (prm.binsState && __ldg(prm.binsState + 1) == 0u) return;
     const uint32_t lane = laneId();
-    const uint64_t word = (uint64_t)blockIdx.x * (kShaderThreads / 32) + (threadIdx.x >> 5);
-    if (word >= prm.numWords) return;
     const uint32_t N = prm.N, P = prm.P;
     const float fN = (float)N;
-    const uint64_t row = word / P;
-    const uint32_t x = (uint32_t)(word - row * P) * 32u + lane;
-    const uint32_t y = (uint32_t)(row % N), z = prm.z0 + (uint32_t)(row / N);
-
-    bool inside = false;
-    uint32_t texel = 0;
-    RaySetup r;
-    r.Ox = voxelCentre(x, fN);
-    r.Oy = -voxelCentre(y, fN);
-    r.Oz = voxelCentre(z, fN);
-    const bool live = x < N && !(r.Ox == 0.0f && r.Oy == 0.0f && r.Oz == 0.0f) && prm.numTris > 0;
-    if (live)
+    for (uint64_t word = (uint64_t)blockIdx.x * (kShaderThreads / 32) + (threadIdx.x >> 5); word < prm.numWords;
+         word += (uint64_t)gridDim.x * (kShaderThreads / 32))
     {
-        const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.Ox, r.Ox), __fmul_rn(r.Oy, r.Oy)), __fmul_rn(r.Oz, r.Oz)));
-        r.Dx = __fdiv_rn(r.Ox, len); r.Dy = __fdiv_rn(r.Oy, len); r.Dz = __fdiv_rn(r.Oz, len);
-        r.ix = __fdiv_rn(1.0f, r.Dx); r.iy = __fdiv_rn(1.0f, r.Dy); r.iz = __fdiv_rn(1.0f, r.Dz);
-        if (r.ix > kFltMax) r.ix = kFltMax; if (r.ix < -kFltMax) r.ix = -kFltMax;
-        if (r.iy > kFltMax) r.iy = kFltMax; if (r.iy < -kFltMax) r.iy = -kFltMax;
-        if (r.iz > kFltMax) r.iz = kFltMax; if (r.iz < -kFltMax) r.iz = -kFltMax;
-        int kz = 0; float m = fabsf(r.Dx);
-        if (fabsf(r.Dy) > m) { kz = 1; m = fabsf(r.Dy); }
-        if (fabsf(r.Dz) > m) { kz = 2; }
-        int kx = (kz + 1) % 3, ky = (kx + 1) % 3;
-        const float dz = pick(r.Dx, r.Dy, r.Dz, kz);
-        if (dz < 0.0f) { const int t = kx; kx = ky; ky = t; }
-        r.kx = kx; r.ky = ky; r.kz = kz;
-        r.Sx = __fdiv_rn(pick(r.Dx, r.Dy, r.Dz, kx), dz);
-        r.Sy = __fdiv_rn(pick(r.Dx, r.Dy, r.Dz, ky), dz);
-        r.Sz = __fdiv_rn(1.0f, dz);
+        const uint64_t row = word / P;
+        const uint32_t x = (uint32_t)(word - row * P) * 32u + lane;
+        const uint32_t y = (uint32_t)(row % N), z = prm.z0 + (uint32_t)(row / N);
 
-        BestHit best;
-        best.tc = INFINITY; best.prim = 0xffffffffu; best.bx = 0.0f; best.by = 0.0f;
-
-        if (prm.numTris == 1) testTriangle(r, prm.tris, 0, best);
-        else
+        bool inside = false;
+        uint32_t texel = 0;
+        RaySetup r;
+        r.Ox = voxelCentre(x, fN);
+        r.Oy = -voxelCentre(y, fN);
+        r.Oz = voxelCentre(z, fN);
+        const bool live = x < N && !(r.Ox == 0.0f && r.Oy == 0.0f && r.Oz == 0.0f) && prm.numTris > 0;
+        if (live)
         {
-            uint32_t stack[kLocalStack];
-            int sp = 0;
-            uint32_t node = 0;
-            uint32_t guard = 0;
-            while (true)
+            raySetup(r, rayLength(r.Ox, r.Oy, r.Oz));
+            BestHit best;
+            best.tc = INFINITY; best.prim = 0xffffffffu; best.bx = 0.0f; best.by = 0.0f;
+
+            if (prm.numTris == 1) testTriangle(r, prm.tris, 0, best);
+            else
             {
-                const float4* q = reinterpret_cast<const float4*>(prm.nodes + node);
-                const float4 yz0 = __ldg(q), yz1 = __ldg(q + 1), x01 = __ldg(q + 2);
-                const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
-                float tin0, tout0, tin1, tout1;
-                bool h0 = slabTest(r, x01.x, yz0.x, yz0.z, x01.y, yz0.y, yz0.w, tin0, tout0) && !(tin0 > best.tc);
-                bool h1 = slabTest(r, x01.z, yz1.x, yz1.z, x01.w, yz1.y, yz1.w, tin1, tout1) && !(tin1 > best.tc);
-                if (h0 && (q3.x & kLeafFlag)) { testTriangle(r, prm.tris, q3.x & ~kLeafFlag, best); h0 = false; }
-                if (h1 && (q3.y & kLeafFlag))
+                uint32_t stack[kLocalStack];
+                int sp = 0;
+                uint32_t node = 0;
+                uint32_t guard = 0;
+                while (true)
                 {
-                    if (!(tin1 > best.tc)) testTriangle(r, prm.tris, q3.y & ~kLeafFlag, best);
-                    h1 = false;
+                    const float4* q = reinterpret_cast<const float4*>(prm.nodes + node);
+                    const float4 yz0 = __ldg(q), yz1 = __ldg(q + 1), x01 = __ldg(q + 2);
+                    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(q + 3));
+                    float tin0, tout0, tin1, tout1;
+                    bool h0 = slabTest(r, x01.x, yz0.x, yz0.z, x01.y, yz0.y, yz0.w, tin0, tout0) && !(tin0 > best.tc);
+                    bool h1 = slabTest(r, x01.z, yz1.x, yz1.z, x01.w, yz1.y, yz1.w, tin1, tout1) && !(tin1 > best.tc);
+                    if (h0 && (q3.x & kLeafFlag)) { testTriangle(r, prm.tris, q3.x & ~kLeafFlag, best); h0 = false; }
+                    if (h1 && (q3.y & kLeafFlag))
+                    {
+                        if (!(tin1 > best.tc)) testTriangle(r, prm.tris, q3.y & ~kLeafFlag, best);
+                        h1 = false;
+                    }
+                    if (h0 && h1)
+                    {
+                        const bool firstIs1 = tin1 < tin0;
+                        if (sp >= kLocalStack || ++guard > 4u * prm.numTris + 64u) { atomicMax(prm.err, (uint32_t)kErrStackOverflow); break; }
+                        stack[sp++] = firstIs1 ? q3.x : q3.y;
+                        node = firstIs1 ? q3.y : q3.x;
+                    }
+                    else if (h0) node = q3.x;
+                    else if (h1) node = q3.y;
+                    else
+                    {
+                        if (sp == 0) break;
+                        node = stack[--sp];
+                    }
+                    if (++guard > 8u * prm.numTris + 64u) { atomicMax(prm.err, (uint32_t)kErrStackOverflow); break; }
                 }
-                if (h0 && h1)
-                {
-                    const bool firstIs1 = tin1 < tin0;
-                    if (sp >= kLocalStack || ++guard > 4u * prm.numTris + 64u) { atomicMax(prm.err, (uint32_t)kErrStackOverflow); break; }
-                    stack[sp++] = firstIs1 ? q3.x : q3.y;
-                    node = firstIs1 ? q3.y : q3.x;
-                }
-                else if (h0) node = q3.x;
-                else if (h1) node = q3.y;
-                else
-                {
-                    if (sp == 0) break;
-                    node = stack[--sp];
-                }
-                if (++guard > 8u * prm.numTris + 64u) { atomicMax(prm.err, (uint32_t)kErrStackOverflow); break; }
             }
+            if (best.prim != 0xffffffffu) inside = shadeHit(prm, r, best, texel);
         }
 
-        if (best.prim != 0xffffffffu)
-        {
-            // closestHitMain: interpolate the (object-space) vertex normals with the barycentrics of
-            // vertices 1 and 2, normalise, compare against the ray direction
-            const uint32_t i0 = __ldg(prm.indices + 3 * (size_t)best.prim), i1 = __ldg(prm.indices + 3 * (size_t)best.prim + 1),
-                           i2 = __ldg(prm.indices + 3 * (size_t)best.prim + 2);
-            const float* n0 = reinterpret_cast<const float*>(prm.verts + (size_t)prm.stride * i0 + 12);
-            const float* n1 = reinterpret_cast<const float*>(prm.verts + (size_t)prm.stride * i1 + 12);
-            const float* n2 = reinterpret_cast<const float*>(prm.verts + (size_t)prm.stride * i2 + 12);
-            float nrm[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-            {
-                const float v0 = __ldg(n0 + q), v1 = __ldg(n1 + q), v2 = __ldg(n2 + q);
-                nrm[q] = __fadd_rn(__fadd_rn(v0, __fmul_rn(best.bx, __fsub_rn(v1, v0))), __fmul_rn(best.by, __fsub_rn(v2, v0)));
-            }
-            const float nl = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nrm[0], nrm[0]), __fmul_rn(nrm[1], nrm[1])), __fmul_rn(nrm[2], nrm[2])));
-            const float nx = __fdiv_rn(nrm[0], nl), ny = __fdiv_rn(nrm[1], nl), nz = __fdiv_rn(nrm[2], nl);
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(nx, r.Dx), __fmul_rn(ny, r.Dy)), __fmul_rn(nz, r.Dz));
-            inside = d > kThreshold;
-            if (inside) texel = unorm10(nx) | (unorm10(ny) << 10) | (unorm10(nz) << 20) | (3u << 30);
-        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, inside);
+        if (lane == 0) prm.grid[word] = bits;
+        if (prm.texels && x < N) prm.texels[row * N + x] = texel;
     }
-
-    const uint32_t bits = __ballot_sync(0xffffffffu, inside);
-    if (lane == 0) prm.grid[word] = bits;
-    if (prm.texels && x < N) prm.texels[row * N + x] = texel;
 }
 }  // namespace
 
-void launchTraceShader(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
-                       uint32_t* grid, uint32_t* texels, uint32_t* dErr)
+void launchTraceShaderBvh(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
+                          uint32_t* grid, uint32_t* texels, uint32_t* dErr, const uint32_t* binsState)
 {
     ShaderParams prm;
     prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
     prm.verts = m.verts; prm.stride = m.stride; prm.indices = m.indices;
     prm.N = N; prm.P = (N + 31) / 32; prm.z0 = z0;
     prm.numWords = (uint64_t)(z1 - z0) * N * prm.P;
-    prm.grid = grid; prm.texels = texels; prm.err = dErr;
-    const uint64_t blocks = (prm.numWords + (kShaderThreads / 32) - 1) / (kShaderThreads / 32);
-    k_trace_shader<<<(unsigned)blocks, kShaderThreads, 0, s>>>(prm);
+    prm.grid = grid; prm.texels = texels; prm.err = dErr; prm.binsState = binsState;
+    // grid-stride over the words: any slab of any N <= 8192 fits (a one-shot grid overflowed 2^31-1 blocks from N ~ 6500)
+    const uint64_t want = (prm.numWords + (kShaderThreads / 32) - 1) / (kShaderThreads / 32);
+    const uint64_t cap = 148ull * 16ull * 64ull;
+    k_trace_shader<<<(unsigned)(want < cap ? want : cap), kShaderThreads, 0, s>>>(prm);
 }
 }  // namespace dxrv

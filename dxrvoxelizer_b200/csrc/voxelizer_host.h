@@ -35,6 +35,8 @@ public:
     // Shard the grid into z-slabs over `count` GPUs (devices m_device .. m_device+count-1), one context
     // each, mesh/BVH replicated.  Call before Init.  (New: the reference is single-GPU.)
     void SetGpuCount(int count) { m_gpus = count < 1 ? 1 : count; }
+    // Default MODE_SHADER: what the reference's DispatchRays computes.  MODE_PARITY (column parity, a different
+    // function: 17-69 voxels of 262 144 differ on the shipped meshes at 64^3) is an explicit opt-in.
     void SetMode(Mode mode) { m_mode = mode; }
     // z-slab [begin, end) computed by Voxelize(); end = 0 means the whole grid.
     void SetSlab(uint32_t begin, uint32_t end) { m_slabBegin = begin; m_slabEnd = end; }
@@ -79,7 +81,7 @@ private:
     const uint32_t* m_indices = nullptr;
     uint32_t m_numVerts = 0, m_stride = 0, m_numIndices = 0;
     int m_device = 0;
-    Mode m_mode = MODE_PARITY;
+    Mode m_mode = MODE_SHADER;   // the reference's function (DXRVoxelizer.hlsl:58-85,132-140); MODE_PARITY is the opt-in fast path
     uint32_t m_gridSize = 64;  // GRID_SIZE, Voxelizer.cpp:8
     uint32_t m_slabBegin = 0, m_slabEnd = 0;
     float m_bound[4] = {0, 0, 0, 1};

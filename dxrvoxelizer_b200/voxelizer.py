@@ -139,7 +139,8 @@ class Voxelizer:
         return out
 
     # -- Voxelizer::voxelize ------------------------------------------------------------------------
-    def voxelize(self, N, mode=L.MODE_PARITY, z0=0, z1=None, texels=False):
+    def voxelize(self, N, mode=L.MODE_SHADER, z0=0, z1=None, texels=False):
+        """mode defaults to MODE_SHADER, the reference's function; MODE_PARITY is the opt-in fast path."""
         z1 = N if z1 is None else z1
         self._check(self._lib.dxrv_voxelize(self._h, N, mode | (L.EMIT_TEXELS if texels else 0), z0, z1))
         self._shape = (z1 - z0, N, (N + 31) // 32)

@@ -174,7 +174,9 @@ enum dxrv_debug_buffer
     DXRV_DBG_PRIM_SORTED = 1,   /* uint32[T]   original triangle index per sorted slot      */
     DXRV_DBG_NODES = 2,         /* 64 B * (T-1) internal nodes, see csrc/common.cuh           */
     DXRV_DBG_TRIS = 3,          /* 48 B * T    normalised triangles in sorted order         */
-    DXRV_DBG_ROOT_BOX = 5       /* float[6]    lo.xyz hi.xyz of the root                    */
+    DXRV_DBG_ROOT_BOX = 5,      /* float[6]    lo.xyz hi.xyz of the root                    */
+    DXRV_DBG_BINS_STATE = 6     /* uint32[4]   MODE_SHADER direction bins of the last voxelize: entries, overflow
+                                   flag (1 = the LBVH walk produced the grid), near-list length, cells per face edge */
 };
 DXRV_API int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes);
 /* Standalone key/value radix sort on the device (the LBVH's onesweep), for tests/bench:
