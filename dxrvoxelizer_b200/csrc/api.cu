@@ -51,6 +51,7 @@ struct dxrv_ctx
     float* dBound = nullptr;
     float* dRootBox = nullptr;
     float* dPartials = nullptr;
+    float* dCentres = nullptr;          // voxel-centre table of the current N (MODE_SHADER)
     uint32_t* dCounter = nullptr;
     uint32_t* dErr = nullptr;
     unsigned long long* dCrossings = nullptr;
@@ -350,7 +351,7 @@ int dxrv_create(dxrv_ctx** out, int cuda_device)
         ctx->side = SideStream{};   // no side stream: builds run serially
     }
     if ((e = cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaEventCreate"); }
-    const size_t smallBytes = 64 * sizeof(float) + 6 * kBoundsMaxBlocks * sizeof(float);
+    const size_t smallBytes = 64 * sizeof(float) + 6 * kBoundsMaxBlocks * sizeof(float) + 8192 * sizeof(float);
     if ((e = cudaMalloc(&ctx->dSmall, smallBytes)) != cudaSuccess) { cudaStreamDestroy(ctx->ownStream); delete ctx; return cudaFail(nullptr, e, "cudaMalloc"); }
     cudaMemset(ctx->dSmall, 0, smallBytes);
     float* f = static_cast<float*>(ctx->dSmall);
@@ -361,6 +362,7 @@ int dxrv_create(dxrv_ctx** out, int cuda_device)
     ctx->dCrossings = reinterpret_cast<unsigned long long*>(f + 16);   // 8-byte aligned
     ctx->dCount = reinterpret_cast<unsigned long long*>(f + 18);
     ctx->dPartials = f + 64;
+    ctx->dCentres = f + 64 + 6 * kBoundsMaxBlocks;
     *out = ctx;
     return DXRV_OK;
 }
@@ -514,17 +516,25 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
             ctx->walkZeroed = zeroBytes;
         }
     }
-    bool buildBins = false, forceBvh = false;
+    bool buildBins = false, useBins = false;
     if (algo == DXRV_MODE_SHADER)
     {
-        // direction bins of the current acceleration structure (built by the first MODE_SHADER voxelize after a build)
-        if (const char* f = std::getenv("DXRV_SHADER_PATH")) forceBvh = !std::strcmp(f, "bvh");
-        const ShaderBinsSizes sz = forceBvh ? shaderBinsSizes(0) : shaderBinsSizes(ctx->mesh.numTris);
-        if (!ctx->binsValid || sz.R != ctx->binsSizes.R || sz.cap != ctx->binsSizes.cap || !ctx->binsBuf)
+        // Direction bins of the current acceleration structure: built by the first MODE_SHADER voxelize that is large
+        // enough to pay for them (the build costs about as much as 100^3 rays through the LBVH), then reused by
+        // every later voxelize until the next build.  DXRV_SHADER_PATH=bins|bvh forces one kernel.
+        useBins = N >= 160u || ctx->binsValid;
+        if (const char* f = std::getenv("DXRV_SHADER_PATH"))
+        {
+            if (!std::strcmp(f, "bvh")) useBins = false;
+            else if (!std::strcmp(f, "bins")) useBins = true;
+        }
+        const ShaderBinsSizes sz = shaderBinsSizes(ctx->mesh.numTris);
+        if (useBins && (!ctx->binsValid || sz.R != ctx->binsSizes.R || sz.cap != ctx->binsSizes.cap || !ctx->binsBuf))
         {
             cudaError_t e = ensure(ctx->binsBuf, ctx->binsCap, sz.bytes);
             if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(direction bins)");
             ctx->binsSizes = sz;
+            ctx->binsValid = false;
             buildBins = true;
         }
     }
@@ -540,7 +550,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     keyPush(key, (uint32_t)scatter);
     keyPush(key, N); keyPush(key, mode); keyPush(key, slabBegin); keyPush(key, slabEnd);
     keyPush(key, grid); keyPush(key, texels); keyPush(key, ctx->walkBuf);
-    keyPush(key, ctx->binsBuf); keyPush(key, (uint32_t)buildBins); keyPush(key, (uint32_t)forceBvh); keyPush(key, ctx->binsSizes.R);
+    keyPush(key, ctx->binsBuf); keyPush(key, (uint32_t)buildBins); keyPush(key, (uint32_t)useBins); keyPush(key, ctx->binsSizes.R);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
     keyPush(key, ctx->mesh.verts); keyPush(key, ctx->mesh.numVerts); keyPush(key, ctx->mesh.stride); keyPush(key, ctx->mesh.indices); keyPush(key, ctx->mesh.numTris);
     const int rc = runCaptured(ctx, key, [&]() {
@@ -556,19 +566,24 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         }
         else
         {
-            if (buildBins) ctx->launches += (uint64_t)launchShaderBinsBuild(ctx->stream, bvh, ctx->binsBuf, ctx->binsSizes, forceBvh);
-            // exactly one of the two does the work (device-side overflow flag of the bins)
-            launchTraceShaderBins(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr, ctx->binsBuf, ctx->binsSizes);
-            launchTraceShaderBvh(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr,
-                                 shaderBinsView(ctx->binsBuf, ctx->binsSizes).state);
-            ctx->launches += 2;
+            if (useBins)
+            {
+                if (buildBins) ctx->launches += (uint64_t)launchShaderBinsBuild(ctx->stream, bvh, ctx->binsBuf, ctx->binsSizes, false);
+                // exactly one of the two does the work (device-side overflow flag of the bins)
+                launchTraceShaderBins(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr, ctx->binsBuf, ctx->binsSizes, ctx->dCentres);
+                launchTraceShaderBvh(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr,
+                                     shaderBinsView(ctx->binsBuf, ctx->binsSizes).state);
+                ctx->launches += 2;
+            }
+            else launchTraceShaderBvh(ctx->stream, bvh, ctx->mesh, N, slabBegin, slabEnd, grid, texels, ctx->dErr, nullptr);
+            ctx->launches += 1;
         }
     });
     if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
-    if (algo == DXRV_MODE_SHADER) ctx->binsValid = true;
+    if (algo == DXRV_MODE_SHADER && useBins) ctx->binsValid = true;
     return DXRV_OK;
 }
 
@@ -749,9 +764,9 @@ int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes)
     const void* src = nullptr; size_t need = 0;
     if (what == DXRV_DBG_BINS_STATE)
     {
-        if (!ctx->binsValid || !ctx->binsBuf) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_debug_read: no MODE_SHADER voxelize since the last build");
         if (bytes != 16) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_debug_read: size mismatch");
         uint32_t* out = static_cast<uint32_t*>(hostDst);
+        if (!ctx->binsValid || !ctx->binsBuf) { out[0] = 0; out[1] = 1; out[2] = 0; out[3] = 0; return DXRV_OK; }   // LBVH walk only
         DXRV_CUDA(cudaMemcpyAsync(out, shaderBinsView(ctx->binsBuf, ctx->binsSizes).state, 12, cudaMemcpyDeviceToHost, ctx->stream));
         DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
         out[3] = ctx->binsSizes.R;

@@ -92,18 +92,20 @@ int launchScatterFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uin
 // exactly one of the two kernels does the work (the other returns at once), so no host round trip is needed.
 struct ShaderBinsView
 {
-    uint4* cells;         // [6 R^2] {first entry, count | unsorted flag, bits(max rmax), 0}
-    uint4* entries;       // [cap]   {bits(rmin), bits(rmax), triangle slot, 0}
+    uint4* cells;         // [6 R^2] {first entry, count | unsorted flag, bits(max rmax), bits((max rmax)^2)}
+    uint4* entries;       // [cap]   {bits(rmin), bits(rmax), triangle slot, bits(min rmin of this and all later entries)}
     uint32_t* cursors;    // [6 R^2] counts -> local exclusive offsets -> local end offsets
     uint32_t* blockSums;  // [numBlocks] exclusive base of every 2048-cell tile
     uint32_t* nearList;   // [nearCap] slots of the triangles closer than 1e-3 to the grid centre
-    uint32_t* state;      // [0] total entries, [1] overflow flag, [2] near count
-    uint32_t R, cap, nearCap;
+    uint4* bigRects;      // [2 * bigCap] rectangles of more than 64 cells: {slot, face, iu0, nu}, {iv0, cells, bits(rmin), bits(rmax)}
+    uint32_t* bigCells;   // [bigCap] cells whose lists are sorted by a whole warp
+    uint32_t* state;      // [0] total entries, [1] overflow flag, [2] near count, [3] big rectangles, [4] big cells
+    uint32_t R, cap, nearCap, bigCap;
 };
 struct ShaderBinsSizes
 {
-    uint32_t R, cap, nearCap, numBlocks;
-    size_t offCells, offEntries, offCursors, offBlockSums, offNear, offState, bytes;
+    uint32_t R, cap, nearCap, bigCap, numBlocks;
+    size_t offCells, offEntries, offCursors, offBlockSums, offNear, offBigRects, offBigCells, offState, bytes;
 };
 uint32_t shaderBinsResolution(uint32_t numTris);
 ShaderBinsSizes shaderBinsSizes(uint32_t numTris);
@@ -112,7 +114,8 @@ ShaderBinsView shaderBinsView(void* base, const ShaderBinsSizes& s);
 int launchShaderBinsBuild(cudaStream_t s, const BvhView& bvh, void* base, const ShaderBinsSizes& sz, bool forceOverflow);
 // texels may be null.  verts/indices are the ORIGINAL buffers (normals at byte offset 12).
 void launchTraceShaderBins(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
-                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, void* base, const ShaderBinsSizes& sz);
+                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, void* base, const ShaderBinsSizes& sz,
+                           float* centres /* device scratch, >= N floats: the voxel-centre table */);
 void launchTraceShaderBvh(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, const uint32_t* binsState /* nullable: always run */);
 

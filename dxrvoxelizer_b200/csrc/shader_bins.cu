@@ -157,7 +157,12 @@ __device__ __forceinline__ void emit(const ShaderBinsView& bins, uint32_t cell, 
     }
 }
 
-// One thread per triangle (sorted slot); rectangles of more than 32 cells are walked by the whole warp.
+// One warp = 32 consecutive sorted triangles (neighbours in Morton order: their rectangles overlap heavily).
+// Per cube-map face the warp rasterises the UNION of its rectangles with one lane per CELL: the lane counts the
+// warp's triangles covering its cell and issues ONE atomic for all of them (14x fewer atomics than one per
+// (triangle, cell), and 32 of them in flight at once instead of a dependent chain per triangle).  Warps whose
+// union is large (triangles far apart, scene-sized triangles) fall back to one lane per triangle, rectangles of
+// more than 32 cells walked by the whole warp.
 template <bool kFill>
 __global__ void __launch_bounds__(256)
 k_bins_scatter(const Tri48* __restrict__ tris, uint32_t numTris, const ShaderBinsView bins)
@@ -165,7 +170,9 @@ k_bins_scatter(const Tri48* __restrict__ tris, uint32_t numTris, const ShaderBin
     if (kFill && bins.state[1] != 0u) return;   // over budget: the LBVH walk takes over
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = laneId();
+    const uint32_t warpBase = j - lane;
     TriGeo g;
+    g.rminS = g.rmaxS = 0.0f;
     bool ok = j < numTris && triGeometry(tris, j, g);
     if (ok && !(g.rlo >= kNearRadius))
     {
@@ -182,23 +189,84 @@ k_bins_scatter(const Tri48* __restrict__ tris, uint32_t numTris, const ShaderBin
     {
         int iu0 = 0, iu1 = -1, iv0 = 0, iv1 = -1;
         const bool v = ok && faceRect(g, f, bins.R, iu0, iu1, iv0, iv1);
+        if (!__any_sync(0xffffffffu, v)) continue;
+        const int U0 = __reduce_min_sync(0xffffffffu, v ? iu0 : 0x7fffffff), U1 = __reduce_max_sync(0xffffffffu, v ? iu1 : -1);
+        const int V0 = __reduce_min_sync(0xffffffffu, v ? iv0 : 0x7fffffff), V1 = __reduce_max_sync(0xffffffffu, v ? iv1 : -1);
+        const uint32_t W = (uint32_t)(U1 - U0 + 1), H = (uint32_t)(V1 - V0 + 1), area = W * H;
+        if (W <= 255u && H <= 255u && area <= 512u)
+        {
+            // own rectangle relative to the union's origin, 8 bits per bound; an invalid lane covers nothing (lo > hi)
+            const uint32_t packed = v ? ((uint32_t)(iu0 - U0) | ((uint32_t)(iu1 - U0) << 8) | ((uint32_t)(iv0 - V0) << 16) | ((uint32_t)(iv1 - V0) << 24))
+                                      : 0x000000ffu;
+            for (uint32_t c0 = 0; c0 < area; c0 += 32u)
+            {
+                const uint32_t c = c0 + lane;
+                const uint32_t cu = c % W, cv = c / W;
+                const bool inb = c < area;
+                uint32_t k = 0;
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t)
+                {
+                    const uint32_t p = __shfl_sync(0xffffffffu, packed, t);
+                    k += (inb && cu >= (p & 255u) && cu <= ((p >> 8) & 255u) && cv >= ((p >> 16) & 255u) && cv <= (p >> 24)) ? 1u : 0u;
+                }
+                const uint32_t cell = (uint32_t)f * RR + (uint32_t)(V0 + (int)cv) * bins.R + (uint32_t)(U0 + (int)cu);
+                if (!kFill)
+                {
+                    if (k) atomicAdd(bins.cursors + cell, k);
+                }
+                else
+                {
+                    uint32_t idx = 0;
+                    if (k) idx = __ldg(bins.blockSums + (cell / kScanTile)) + atomicAdd(bins.cursors + cell, k);
+                    if (__any_sync(0xffffffffu, k != 0u))
+                    {
+#pragma unroll 4
+                        for (int t = 0; t < 32; ++t)
+                        {
+                            const uint32_t p = __shfl_sync(0xffffffffu, packed, t);
+                            const float rm = __shfl_sync(0xffffffffu, g.rminS, t), rx = __shfl_sync(0xffffffffu, g.rmaxS, t);
+                            if (inb && cu >= (p & 255u) && cu <= ((p >> 8) & 255u) && cv >= ((p >> 16) & 255u) && cv <= (p >> 24))
+                                bins.entries[idx++] = make_uint4(__float_as_uint(rm), __float_as_uint(rx), warpBase + (uint32_t)t, 0u);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
         const uint32_t nu = v ? (uint32_t)(iu1 - iu0 + 1) : 0u, nv = v ? (uint32_t)(iv1 - iv0 + 1) : 0u;
         const uint32_t n = nu * nv;
-        if (n > 0u && n <= 32u)
+        if (n > 0u && n <= 64u)
             for (uint32_t c = 0; c < n; ++c)
                 emit<kFill>(bins, (uint32_t)f * RR + (uint32_t)(iv0 + (int)(c / nu)) * bins.R + (uint32_t)(iu0 + (int)(c % nu)), j, g.rminS, g.rmaxS);
-        uint32_t big = __ballot_sync(0xffffffffu, n > 32u);
-        while (big)
+        if (n > 64u && !kFill)
         {
-            const int L = __ffs(big) - 1;
-            big &= big - 1u;
-            const uint32_t bn = __shfl_sync(0xffffffffu, n, L), bnu = __shfl_sync(0xffffffffu, nu, L);
-            const int bu0 = __shfl_sync(0xffffffffu, iu0, L), bv0 = __shfl_sync(0xffffffffu, iv0, L);
-            const uint32_t bj = __shfl_sync(0xffffffffu, j, L);
-            const float bmin = __shfl_sync(0xffffffffu, g.rminS, L), bmax = __shfl_sync(0xffffffffu, g.rmaxS, L);
-            for (uint32_t c = lane; c < bn; c += 32u)
-                emit<kFill>(bins, (uint32_t)f * RR + (uint32_t)(bv0 + (int)(c / bnu)) * bins.R + (uint32_t)(bu0 + (int)(c % bnu)), bj, bmin, bmax);
+            // large rectangle (a triangle near the grid centre, or a scene-sized one): listed once by the counting pass
+            // and rasterised by the whole grid in k_bins_big, in both passes
+            const uint32_t idx = atomicAdd(bins.state + 3, 1u);
+            if (idx < bins.bigCap)
+            {
+                bins.bigRects[2 * idx] = make_uint4(j, (uint32_t)f, (uint32_t)iu0, nu);
+                bins.bigRects[2 * idx + 1] = make_uint4((uint32_t)iv0, n, __float_as_uint(g.rminS), __float_as_uint(g.rmaxS));
+            }
+            else bins.state[1] = 1u;
         }
+    }
+}
+
+// The listed large rectangles: one CTA per rectangle (grid-stride), one thread per cell.
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+k_bins_big(const ShaderBinsView bins)
+{
+    if (bins.state[1] != 0u) return;
+    const uint32_t count = min(bins.state[3], bins.bigCap);
+    const uint32_t RR = bins.R * bins.R;
+    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x)
+    {
+        const uint4 a = __ldg(bins.bigRects + 2 * item), b = __ldg(bins.bigRects + 2 * item + 1);
+        for (uint32_t c = threadIdx.x; c < b.y; c += blockDim.x)
+            emit<kFill>(bins, a.y * RR + (b.x + c / a.w) * bins.R + (a.z + c % a.w), a.x, __uint_as_float(b.z), __uint_as_float(b.w));
     }
 }
 
@@ -272,9 +340,47 @@ k_bins_scan_sums(uint32_t* __restrict__ blockSums, uint32_t numBlocks, uint32_t*
     }
 }
 
-// ---- per cell: sort by (rmin, slot), header ----------------------------------------------------------------------
-__device__ __forceinline__ bool entryLess(const uint4& a, const uint4& b) { return a.x < b.x || (a.x == b.x && a.z < b.z); }
+// ---- per cell: sort by (rmax, slot), suffix minima of rmin, header -----------------------------------------------
+// Order by rmax: the entries behind a ray's origin (rmax < rho) are a PREFIX of the list, found by bisection; the
+// walk may stop at entry i when the smallest rmin of entries i.. (stored in .w) exceeds rho + best tc.
+__device__ __forceinline__ bool entryLess(const uint4& a, const uint4& b) { return a.y < b.y || (a.y == b.y && a.z < b.z); }
 
+// Insertion sort of one list by its own thread, then the suffix minima; returns the largest rmax.
+__device__ __forceinline__ float sortOwnList(uint4* e, uint32_t n)
+{
+    for (uint32_t i = 1; i < n; ++i)
+    {
+        const uint4 x = e[i];
+        uint32_t k = i;
+        while (k > 0u)
+        {
+            const uint4 p = e[k - 1];
+            if (!entryLess(x, p)) break;
+            e[k] = p;
+            --k;
+        }
+        e[k] = x;
+    }
+    uint32_t run = 0x7f800000u;   // +inf; non-negative floats order like their bit patterns
+    for (uint32_t i = n; i-- > 0u;)
+    {
+        run = min(run, e[i].x);
+        e[i].w = run;
+    }
+    return n ? __uint_as_float(e[n - 1].y) : 0.0f;
+}
+
+__device__ __forceinline__ uint4 cellHeader(uint32_t first, uint32_t n, uint32_t flags, float rmaxAll)
+{
+    // {first entry, count | flags, max rmax, (max rmax)^2 rounded up: lets the tracer reject a voxel on rho^2}
+    return make_uint4(first, n | flags, __float_as_uint(rmaxAll), __float_as_uint(__fmul_ru(rmaxAll, rmaxAll) * 1.000001f));
+}
+
+constexpr uint32_t kOwnSortMax = 48;      // longest list sorted by its own thread
+
+// One thread per cell, one warp per 32 consecutive cells -- whose lists are one contiguous piece of the entry
+// array: it is staged in shared memory (coalesced), every lane sorts its own list there, and it goes back coalesced.
+// Longer lists are listed for k_bins_finish_big (one warp each, spread over the whole grid).
 __global__ void __launch_bounds__(kFinishThreads)
 k_bins_finish(const ShaderBinsView bins, uint32_t numCells)
 {
@@ -289,45 +395,69 @@ k_bins_finish(const ShaderBinsView bins, uint32_t numCells)
         first = base + ((c % kScanTile) ? bins.cursors[c - 1] : 0u);
         n = base + bins.cursors[c] - first;
     }
-    uint32_t flags = 0;
     float rmaxAll = 0.0f;
-    if (n > 0u && n <= 16u)
+    const bool own = n <= kOwnSortMax;
+    // The warp's lists are one contiguous piece of the entry array.  It is staged through shared memory in batches of
+    // consecutive cells (as many as fit kSortCap entries): coalesced in, every lane sorts its own list, coalesced out.
+    const uint32_t endMine = first + n;
+    uint32_t startLane = 0;
+    while (startLane < 32u)
     {
-        // insertion sort in place (the list is this thread's own)
-        uint4* e = bins.entries + first;
-        for (uint32_t i = 0; i < n; ++i)
+        const uint32_t bFirst = __shfl_sync(0xffffffffu, first, startLane);
+        const uint32_t fits = __ballot_sync(0xffffffffu, lane >= startLane && endMine - bFirst <= (uint32_t)kSortCap);
+        // first + n is monotone over the lanes, so the fitting lanes are a run starting at startLane
+        const uint32_t run = (uint32_t)__popc(fits);
+        if (run == 0u) { ++startLane; continue; }        // a single list longer than the staging buffer: not sorted here
+        const uint32_t bEnd = __shfl_sync(0xffffffffu, endMine, startLane + run - 1u);
+        const uint32_t total = bEnd - bFirst;
+        const bool mine = lane >= startLane && lane < startLane + run;
+        if (total > 0u)
         {
-            const uint4 x = e[i];
-            rmaxAll = fmaxf(rmaxAll, __uint_as_float(x.y));
-            uint32_t k = i;
-            while (k > 0u)
-            {
-                const uint4 p = e[k - 1];
-                if (!entryLess(x, p)) break;
-                e[k] = p;
-                --k;
-            }
-            e[k] = x;
+            for (uint32_t i = lane; i < total; i += 32u) sh[warp][i] = bins.entries[bFirst + i];
+            __syncwarp();
+            if (mine && own) rmaxAll = sortOwnList(&sh[warp][first - bFirst], n);
+            __syncwarp();
+            for (uint32_t i = lane; i < total; i += 32u) bins.entries[bFirst + i] = sh[warp][i];
+            __syncwarp();
+        }
+        startLane += run;
+    }
+    if (c < numCells)
+    {
+        if (own) bins.cells[c] = cellHeader(first, n, 0u, rmaxAll);
+        else
+        {
+            const uint32_t idx = atomicAdd(bins.state + 4, 1u);
+            if (idx < bins.bigCap) bins.bigCells[idx] = c;
+            // (more long lists than the table holds: the rest stay unsorted, which is slower but still exact)
+            uint32_t mx = 0u;
+            if (idx >= bins.bigCap)
+                for (uint32_t i = 0; i < n; ++i) mx = max(mx, bins.entries[first + i].y);
+            bins.cells[c] = cellHeader(first, n, kBinsUnsorted, __uint_as_float(mx));
         }
     }
-    uint32_t big = __ballot_sync(0xffffffffu, n > 16u);
-    while (big)
+}
+
+// One warp per listed cell: bitonic sort in shared memory (lists up to kSortCap entries), suffix minima, header.
+__global__ void __launch_bounds__(kFinishThreads)
+k_bins_finish_big(const ShaderBinsView bins)
+{
+    __shared__ uint4 sh[kFinishThreads / 32][kSortCap];
+    if (bins.state[1] != 0u) return;
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    const uint32_t count = min(bins.state[4], bins.bigCap);
+    for (uint32_t item = blockIdx.x * (kFinishThreads / 32) + warp; item < count; item += gridDim.x * (kFinishThreads / 32))
     {
-        const int L = __ffs(big) - 1;
-        big &= big - 1u;
-        const uint32_t bf = __shfl_sync(0xffffffffu, first, L), bn = __shfl_sync(0xffffffffu, n, L);
-        uint4* e = bins.entries + bf;
-        float mx = 0.0f;
-        if (bn <= (uint32_t)kSortCap)
+        const uint32_t c = __ldg(bins.bigCells + item);
+        const uint4 hdr = bins.cells[c];
+        const uint32_t n = hdr.y & ~kBinsUnsorted;
+        uint4* e = bins.entries + hdr.x;
+        uint32_t mx = 0u;
+        if (n <= (uint32_t)kSortCap)
         {
             uint32_t M = 32;
-            while (M < bn) M <<= 1;
-            for (uint32_t i = lane; i < M; i += 32u)
-            {
-                const uint4 x = i < bn ? e[i] : make_uint4(0xffffffffu, 0u, 0xffffffffu, 0u);
-                if (i < bn) mx = fmaxf(mx, __uint_as_float(x.y));
-                sh[warp][i] = x;
-            }
+            while (M < n) M <<= 1;
+            for (uint32_t i = lane; i < M; i += 32u) sh[warp][i] = i < n ? e[i] : make_uint4(0u, 0xffffffffu, 0xffffffffu, 0u);
             __syncwarp();
             for (uint32_t k = 2; k <= M; k <<= 1)
                 for (uint32_t jj = k >> 1; jj > 0u; jj >>= 1)
@@ -344,95 +474,264 @@ k_bins_finish(const ShaderBinsView bins, uint32_t numCells)
                     }
                     __syncwarp();
                 }
-            for (uint32_t i = lane; i < bn; i += 32u) e[i] = sh[warp][i];
+            // suffix minima of rmin: every lane scans its own contiguous chunk backwards, then the chunks are chained
+            const uint32_t chunk = (n + 31u) / 32u;
+            const uint32_t lo = min(lane * chunk, n), hi = min(lo + chunk, n);
+            uint32_t run = 0x7f800000u;
+            for (uint32_t i = hi; i-- > lo;) run = min(run, sh[warp][i].x);
+            // exclusive suffix over lanes: min of the chunk minima of all higher lanes
+            uint32_t suf = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + (uint32_t)o < 32u) suf = min(suf, t);
+            }
+            uint32_t after = __shfl_down_sync(0xffffffffu, suf, 1);
+            if (lane == 31u) after = 0x7f800000u;
+            run = after;
+            for (uint32_t i = hi; i-- > lo;)
+            {
+                run = min(run, sh[warp][i].x);
+                sh[warp][i].w = run;
+            }
             __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32u) e[i] = sh[warp][i];
+            mx = n ? sh[warp][n - 1].y : 0u;
+            __syncwarp();
+            if (lane == 0u) bins.cells[c] = cellHeader(hdr.x, n, 0u, __uint_as_float(mx));
         }
         else
         {
-            for (uint32_t i = lane; i < bn; i += 32u) mx = fmaxf(mx, __uint_as_float(e[i].y));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((int)lane == L)
-        {
-            rmaxAll = mx;
-            if (bn > (uint32_t)kSortCap) flags = kBinsUnsorted;
+            for (uint32_t i = lane; i < n; i += 32u) mx = max(mx, e[i].y);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0u) bins.cells[c] = cellHeader(hdr.x, n, kBinsUnsorted, __uint_as_float(mx));
         }
     }
-    if (c < numCells) bins.cells[c] = make_uint4(first, n | flags, __float_as_uint(rmaxAll), 0u);
 }
 
 // ---- trace --------------------------------------------------------------------------------------------------------
+// One warp = a sub-brick of 8 (x) x 2 (y) x 2 (z) voxels: neighbouring rays share cube-map cells and radii, so the
+// lanes' list walks have similar lengths and read the same entries / triangles (a 32 x 1 x 1 row spans up to 15 cells).
+// The warp's 32 result bits are four bytes of four different grid words; each is stored as one byte (every byte of
+// the slab is written exactly once, by exactly one warp -- no barrier, no atomics, no clear).
 constexpr int kTraceThreads = 128;
 
+struct RayK
+{
+    float Ox, Oy, Oz, Dx, Dy, Dz;
+    float S1, S2, Sz;       // D[K1]/D[KZ], D[K2]/D[KZ], 1/D[KZ] with K1 = (KZ+1)%3, K2 = (KZ+2)%3
+};
+
+template <int K> __device__ __forceinline__ float comp(float x, float y, float z) { return K == 0 ? x : (K == 1 ? y : z); }
+
+// Spec H steps 1-4 for one pair, specialised for the ray's dominant axis KZ (no per-pair selects).  Two identities
+// keep this bit-identical to shader_common.cuh::testTriangle: (i) a pair is a hit iff slab test AND watertight test
+// pass, so the (cheaper to fail) watertight test runs first; (ii) Spec H swaps kx and ky when D[kz] < 0, which
+// negates U, V, W and det exactly (fl(a - b) = -fl(b - a)) and leaves the sign test, t = T/det and the
+// barycentrics unchanged -- so the natural order (K1, K2) serves both signs.
+template <int KZ>
+__device__ __forceinline__ void testTriangleK(const RayK& r, const Tri48* __restrict__ tris, uint32_t slot, BestHit& best)
+{
+    constexpr int K1 = (KZ + 1) % 3, K2 = (KZ + 2) % 3;
+    const float4* t = reinterpret_cast<const float4*>(tris + slot);
+    const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+    const float Ax3 = __fsub_rn(a.x, r.Ox), Ay3 = __fsub_rn(a.y, r.Oy), Az3 = __fsub_rn(a.z, r.Oz);
+    const float Bx3 = __fsub_rn(b.x, r.Ox), By3 = __fsub_rn(b.y, r.Oy), Bz3 = __fsub_rn(b.z, r.Oz);
+    const float Cx3 = __fsub_rn(c.x, r.Ox), Cy3 = __fsub_rn(c.y, r.Oy), Cz3 = __fsub_rn(c.z, r.Oz);
+    const float Akz = comp<KZ>(Ax3, Ay3, Az3), Bkz = comp<KZ>(Bx3, By3, Bz3), Ckz = comp<KZ>(Cx3, Cy3, Cz3);
+    const float Ax = __fsub_rn(comp<K1>(Ax3, Ay3, Az3), __fmul_rn(r.S1, Akz));
+    const float Ay = __fsub_rn(comp<K2>(Ax3, Ay3, Az3), __fmul_rn(r.S2, Akz));
+    const float Bx = __fsub_rn(comp<K1>(Bx3, By3, Bz3), __fmul_rn(r.S1, Bkz));
+    const float By = __fsub_rn(comp<K2>(Bx3, By3, Bz3), __fmul_rn(r.S2, Bkz));
+    const float Cx = __fsub_rn(comp<K1>(Cx3, Cy3, Cz3), __fmul_rn(r.S1, Ckz));
+    const float Cy = __fsub_rn(comp<K2>(Cx3, Cy3, Cz3), __fmul_rn(r.S2, Ckz));
+    float U, V, W;
+    edgeValues(Ax, Ay, Bx, By, Cx, Cy, U, V, W);
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    if (det == 0.0f) return;
+    // the pair passed the watertight test (rare): only now the slab interval, with the reciprocals Spec H prescribes
+    float ix = __fdiv_rn(1.0f, r.Dx), iy = __fdiv_rn(1.0f, r.Dy), iz = __fdiv_rn(1.0f, r.Dz);
+    if (ix > kFltMax) ix = kFltMax; if (ix < -kFltMax) ix = -kFltMax;
+    if (iy > kFltMax) iy = kFltMax; if (iy < -kFltMax) iy = -kFltMax;
+    if (iz > kFltMax) iz = kFltMax; if (iz < -kFltMax) iz = -kFltMax;
+    float tin = 0.0f, tout = kTMax;
+    {
+        float t0 = __fmul_rn(__fsub_rn(fminsel(fminsel(a.x, b.x), c.x), r.Ox), ix), t1 = __fmul_rn(__fsub_rn(fmaxsel(fmaxsel(a.x, b.x), c.x), r.Ox), ix);
+        tin = fmaxsel(fminsel(t0, t1), tin); tout = fminsel(fmaxsel(t0, t1), tout);
+        t0 = __fmul_rn(__fsub_rn(fminsel(fminsel(a.y, b.y), c.y), r.Oy), iy); t1 = __fmul_rn(__fsub_rn(fmaxsel(fmaxsel(a.y, b.y), c.y), r.Oy), iy);
+        tin = fmaxsel(fminsel(t0, t1), tin); tout = fminsel(fmaxsel(t0, t1), tout);
+        t0 = __fmul_rn(__fsub_rn(fminsel(fminsel(a.z, b.z), c.z), r.Oz), iz); t1 = __fmul_rn(__fsub_rn(fmaxsel(fmaxsel(a.z, b.z), c.z), r.Oz), iz);
+        tin = fmaxsel(fminsel(t0, t1), tin); tout = fminsel(fmaxsel(t0, t1), tout);
+    }
+    if (!(tin <= tout)) return;
+    const float tt = __fdiv_rn(weighted3(U, __fmul_rn(r.Sz, Akz), V, __fmul_rn(r.Sz, Bkz), W, __fmul_rn(r.Sz, Ckz)), det);
+    const float tc = fminsel(fmaxsel(tt, tin), tout);
+    if (!(tc > 0.0f && tc < kTMax)) return;
+    const uint32_t prim = __float_as_uint(a.w);
+    if (tc < best.tc || (tc == best.tc && prim < best.prim))
+    {
+        best.tc = tc; best.prim = prim;
+        best.bx = __fdiv_rn(V, det); best.by = __fdiv_rn(W, det);
+    }
+}
+
+struct TraceGeom
+{
+    uint32_t unitsX, unitsY, unitsZ;   // sub-bricks per axis: 4 P, ceil(N / 2), ceil(layers / 2)
+    uint32_t strideX, strideY, strideZ;  // total warps of the grid, decomposed in the same mixed radix
+    uint32_t layers;
+};
+
 __global__ void __launch_bounds__(kTraceThreads)
-k_trace_shader_bins(const ShaderParams prm, const ShaderBinsView bins)
+k_trace_shader_bins(const ShaderParams prm, const ShaderBinsView bins, const float* __restrict__ centres, const TraceGeom g)
 {
     if (__ldg(bins.state + 1) != 0u) return;   // over budget: k_trace_shader (LBVH walk) produces the grid
     const uint32_t lane = laneId();
     const uint32_t N = prm.N, P = prm.P, R = bins.R;
-    const float fN = (float)N, halfR = 0.5f * (float)R;
+    const float halfR = 0.5f * (float)R;
     const uint32_t nearCount = min(__ldg(bins.state + 2), bins.nearCap);
-    for (uint64_t word = (uint64_t)blockIdx.x * (kTraceThreads / 32) + (threadIdx.x >> 5); word < prm.numWords;
-         word += (uint64_t)gridDim.x * (kTraceThreads / 32))
+    const uint32_t lx = lane & 7u, ly = (lane >> 3) & 1u, lz = lane >> 4;
+    uint8_t* gridBytes = reinterpret_cast<uint8_t*>(prm.grid);
+    // first sub-brick of this warp, then mixed-radix increments by the total number of warps
+    uint32_t ux, uy, uz;
     {
-        const uint64_t row = word / P;
-        const uint32_t x = (uint32_t)(word - row * P) * 32u + lane;
-        const uint32_t y = (uint32_t)(row % N), z = prm.z0 + (uint32_t)(row / N);
-
-        bool inside = false;
-        uint32_t texel = 0;
-        RaySetup r;
-        r.Ox = voxelCentre(x, fN);
-        r.Oy = -voxelCentre(y, fN);
-        r.Oz = voxelCentre(z, fN);
-        const bool live = x < N && !(r.Ox == 0.0f && r.Oy == 0.0f && r.Oz == 0.0f) && prm.numTris > 0;
-        if (live)
+        const uint64_t w0 = (uint64_t)blockIdx.x * (kTraceThreads / 32) + (threadIdx.x >> 5);
+        ux = (uint32_t)(w0 % g.unitsX);
+        const uint64_t t = w0 / g.unitsX;
+        uy = (uint32_t)(t % g.unitsY);
+        uz = (uint32_t)(t / g.unitsY);
+    }
+    while (uz < g.unitsZ)
+    {
+        const uint32_t x = ux * 8u + lx, y = uy * 2u + ly, zl = uz * 2u + lz;
+        const bool valid = x < N && y < N && zl < g.layers;
+        bool inside = false, active = false, sorted = true;
+        uint32_t texel = 0, n = 0;
+        int kz = 0;
+        float rho = 0.0f;
+        const uint4* e = bins.entries;
+        RayK r;
+        r.Ox = r.Oy = r.Oz = r.Dx = r.Dy = r.Dz = r.S1 = r.S2 = r.Sz = 0.0f;
+        if (valid)
         {
-            // cube-map cell of the direction (first largest |component| wins ties, any consistent rule will do:
-            // the rectangles are dilated and clamped onto the closed face)
-            const float ax = fabsf(r.Ox), ay = fabsf(r.Oy), az = fabsf(r.Oz);
-            int m = 0; float pm = ax;
-            if (ay > pm) { m = 1; pm = ay; }
-            if (az > pm) { m = 2; pm = az; }
-            const float inv = 1.0f / pm;
-            const float u = pick(r.Oy, r.Oz, r.Ox, m) * inv, v = pick(r.Oz, r.Ox, r.Oy, m) * inv;
-            const int last = (int)R - 1;
-            const int iu = max(0, min(last, (int)((u + 1.0f) * halfR))), iv = max(0, min(last, (int)((v + 1.0f) * halfR)));
-            const uint32_t face = 2u * (uint32_t)m + (pick(r.Ox, r.Oy, r.Oz, m) < 0.0f ? 1u : 0u);
-            const uint4 hdr = __ldg(bins.cells + ((size_t)face * R + (uint32_t)iv) * R + (uint32_t)iu);
-            const uint32_t n = hdr.y & ~kBinsUnsorted;
-            const float rho = rayLength(r.Ox, r.Oy, r.Oz);
-            const bool any = n > 0u && !(__uint_as_float(hdr.z) < rho);
-            if (any || nearCount)
+            r.Ox = __ldg(centres + x);
+            r.Oy = -__ldg(centres + y);
+            r.Oz = __ldg(centres + prm.z0 + zl);
+            if (!(r.Ox == 0.0f && r.Oy == 0.0f && r.Oz == 0.0f) && prm.numTris > 0)
             {
-                raySetup(r, rho);
-                BestHit best;
-                best.tc = INFINITY; best.prim = 0xffffffffu; best.bx = 0.0f; best.by = 0.0f;
-                for (uint32_t k = 0; k < nearCount; ++k) testTriangle(r, prm.tris, __ldg(bins.nearList + k), best);
-                if (any)
+                // cube-map cell of the direction (first largest |component| wins ties; any consistent rule will do:
+                // the rectangles are dilated and clamped onto the closed face)
+                const float ax = fabsf(r.Ox), ay = fabsf(r.Oy), az = fabsf(r.Oz);
+                int m = 0; float pm = ax;
+                if (ay > pm) { m = 1; pm = ay; }
+                if (az > pm) { m = 2; pm = az; }
+                const float inv = __fdividef(1.0f, pm);
+                const float u = pick(r.Oy, r.Oz, r.Ox, m) * inv, v = pick(r.Oz, r.Ox, r.Oy, m) * inv;
+                const int last = (int)R - 1;
+                const int iu = max(0, min(last, (int)((u + 1.0f) * halfR))), iv = max(0, min(last, (int)((v + 1.0f) * halfR)));
+                const uint32_t face = 2u * (uint32_t)m + (pick(r.Ox, r.Oy, r.Oz, m) < 0.0f ? 1u : 0u);
+                const uint4 hdr = __ldg(bins.cells + ((size_t)face * R + (uint32_t)iv) * R + (uint32_t)iu);
+                // rho^2 against the cell's (max rmax)^2: most voxels lie outside every surface layer of their direction
+                const float rho2 = __fadd_rn(__fadd_rn(__fmul_rn(r.Ox, r.Ox), __fmul_rn(r.Oy, r.Oy)), __fmul_rn(r.Oz, r.Oz));
+                n = hdr.y & ~kBinsUnsorted;
+                if (n > 0u && !(__uint_as_float(hdr.w) < rho2)) { e = bins.entries + hdr.x; sorted = (hdr.y & kBinsUnsorted) == 0u; }
+                else n = 0u;
+                if (n > 0u || nearCount)
                 {
-                    const bool sorted = (hdr.y & kBinsUnsorted) == 0u;
-                    const uint4* e = bins.entries + hdr.x;
-                    for (uint32_t i = 0; i < n; ++i)
-                    {
-                        const uint4 en = __ldg(e + i);
-                        if (__uint_as_float(en.y) < rho) continue;                       // behind the origin
-                        if (__uint_as_float(en.x) > __fadd_rn(rho, best.tc))             // cannot beat the best hit
-                        {
-                            if (sorted) break;
-                            continue;
-                        }
-                        testTriangle(r, prm.tris, en.z, best);
-                    }
+                    rho = __fsqrt_rn(rho2);   // = rayLength(): Spec H's |O|
+                    r.Dx = __fdiv_rn(r.Ox, rho); r.Dy = __fdiv_rn(r.Oy, rho); r.Dz = __fdiv_rn(r.Oz, rho);
+                    // Spec H: kz = axis of the largest |D| (first wins ties); chosen on D itself (two different |O|
+                    // components may round to the same |D|)
+                    float md = fabsf(r.Dx);
+                    if (fabsf(r.Dy) > md) { kz = 1; md = fabsf(r.Dy); }
+                    if (fabsf(r.Dz) > md) { kz = 2; }
+                    const float dk = pick(r.Dx, r.Dy, r.Dz, kz);
+                    r.S1 = __fdiv_rn(pick(r.Dy, r.Dz, r.Dx, kz), dk);
+                    r.S2 = __fdiv_rn(pick(r.Dz, r.Dx, r.Dy, kz), dk);
+                    r.Sz = __fdiv_rn(1.0f, dk);
+                    active = true;
                 }
-                if (best.prim != 0xffffffffu) inside = shadeHit(prm, r, best, texel);
             }
         }
+        BestHit best;
+        best.tc = INFINITY; best.prim = 0xffffffffu; best.bx = 0.0f; best.by = 0.0f;
+        for (uint32_t k = 0; k < nearCount; ++k)
+            if (active)
+            {
+                const uint32_t slot = __ldg(bins.nearList + k);
+                if (kz == 0) testTriangleK<0>(r, prm.tris, slot, best);
+                else if (kz == 1) testTriangleK<1>(r, prm.tris, slot, best);
+                else testTriangleK<2>(r, prm.tris, slot, best);
+            }
+        // "while-while": every lane first runs ahead to its next candidate (a cheap scan of 16-byte entries), then the
+        // lanes that found one test together -- the exact tests are the expensive part and must not run at a few
+        // lanes per instruction.
+        bool walking = active && n > 0u;
+        uint32_t i = 0;
+        if (walking && sorted && n > 8u)
+        {
+            // entries behind the origin (rmax < rho) are a prefix of the list (sorted by rmax): bisect over it
+            uint32_t lo = 0, hi = n;
+            while (lo < hi)
+            {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__uint_as_float(__ldg(&e[mid].y)) < rho) lo = mid + 1u; else hi = mid;
+            }
+            i = lo;
+        }
+        while (__any_sync(0xffffffffu, walking))
+        {
+            uint32_t slot = 0xffffffffu;
+            if (walking)
+            {
+                while (i < n)
+                {
+                    const uint4 en = __ldg(e + i);
+                    ++i;
+                    if (__uint_as_float(en.y) < rho) continue;                 // behind the origin
+                    const float reach = __fadd_rn(rho, best.tc);
+                    if (sorted && __uint_as_float(en.w) > reach) { i = n; break; }   // nothing from here on can beat the best hit
+                    if (__uint_as_float(en.x) > reach) continue;               // this one cannot
+                    slot = en.z;
+                    break;
+                }
+                walking = slot != 0xffffffffu;
+            }
+            __syncwarp();
+            if (walking)
+            {
+                if (kz == 0) testTriangleK<0>(r, prm.tris, slot, best);
+                else if (kz == 1) testTriangleK<1>(r, prm.tris, slot, best);
+                else testTriangleK<2>(r, prm.tris, slot, best);
+            }
+        }
+        if (best.prim != 0xffffffffu)
+        {
+            RaySetup rs;
+            rs.Dx = r.Dx; rs.Dy = r.Dy; rs.Dz = r.Dz;
+            inside = shadeHit(prm, rs, best, texel);
+        }
         const uint32_t bits = __ballot_sync(0xffffffffu, inside);
-        if (lane == 0) prm.grid[word] = bits;
-        if (prm.texels && x < N) prm.texels[row * N + x] = texel;
+        if (lane < 4u)
+        {
+            // row `lane` of the sub-brick = (ly, lz) = (lane & 1, lane >> 1): its 8 voxels are lanes 8*lane .. 8*lane+7
+            const uint32_t yy = uy * 2u + (lane & 1u), zz = uz * 2u + (lane >> 1);
+            if (yy < N && zz < g.layers && ux * 8u < P * 32u)
+                gridBytes[(((size_t)zz * N + yy) * P) * 4u + ux] = (uint8_t)((bits >> (8u * lane)) & 0xffu);
+        }
+        if (prm.texels && valid) prm.texels[((size_t)zl * N + y) * N + x] = texel;
+        ux += g.strideX; if (ux >= g.unitsX) { ux -= g.unitsX; ++uy; }
+        uy += g.strideY; if (uy >= g.unitsY) { uy -= g.unitsY; ++uz; }
+        uz += g.strideZ;
     }
+}
+
+__global__ void k_voxel_centres(float* __restrict__ centres, uint32_t N)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) centres[i] = voxelCentre(i, (float)N);
 }
 }  // namespace
 
@@ -460,6 +759,7 @@ ShaderBinsSizes shaderBinsSizes(uint32_t numTris)
     if (cap > (1u << 27)) cap = 1u << 27;
     s.cap = (uint32_t)cap;
     s.nearCap = 4096;
+    s.bigCap = 1u << 16;
     s.numBlocks = (uint32_t)((cells + kScanTile - 1) / kScanTile);
     auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
     s.offCells = 0;
@@ -467,7 +767,9 @@ ShaderBinsSizes shaderBinsSizes(uint32_t numTris)
     s.offCursors = s.offEntries + align(cap * sizeof(uint4));
     s.offBlockSums = s.offCursors + align((cells + 8) * sizeof(uint32_t));
     s.offNear = s.offBlockSums + align((s.numBlocks + 1) * sizeof(uint32_t));
-    s.offState = s.offNear + align(s.nearCap * sizeof(uint32_t));
+    s.offBigRects = s.offNear + align(s.nearCap * sizeof(uint32_t));
+    s.offBigCells = s.offBigRects + align(2 * (size_t)s.bigCap * sizeof(uint4));
+    s.offState = s.offBigCells + align((size_t)s.bigCap * sizeof(uint32_t));
     s.bytes = s.offState + 256;
     return s;
 }
@@ -482,7 +784,9 @@ ShaderBinsView shaderBinsView(void* base, const ShaderBinsSizes& s)
     v.blockSums = reinterpret_cast<uint32_t*>(p + s.offBlockSums);
     v.nearList = reinterpret_cast<uint32_t*>(p + s.offNear);
     v.state = reinterpret_cast<uint32_t*>(p + s.offState);
-    v.R = s.R; v.cap = s.cap; v.nearCap = s.nearCap;
+    v.bigRects = reinterpret_cast<uint4*>(p + s.offBigRects);
+    v.bigCells = reinterpret_cast<uint32_t*>(p + s.offBigCells);
+    v.R = s.R; v.cap = s.cap; v.nearCap = s.nearCap; v.bigCap = s.bigCap;
     return v;
 }
 
@@ -490,7 +794,7 @@ int launchShaderBinsBuild(cudaStream_t s, const BvhView& bvh, void* base, const 
 {
     const ShaderBinsView v = shaderBinsView(base, sz);
     const uint32_t cells = 6u * sz.R * sz.R;
-    cudaMemsetAsync(v.state, 0, 16, s);
+    cudaMemsetAsync(v.state, 0, 32, s);
     if (forceOverflow)
     {
         // DXRV_SHADER_PATH=bvh: raise the flag, build nothing
@@ -500,16 +804,25 @@ int launchShaderBinsBuild(cudaStream_t s, const BvhView& bvh, void* base, const 
     cudaMemsetAsync(v.cursors, 0, sizeof(uint32_t) * ((size_t)cells + 8), s);
     const uint32_t T = bvh.numTris;
     const uint32_t tb = (T + 255) / 256;
-    if (T) k_bins_scatter<false><<<tb, 256, 0, s>>>(bvh.tris, T, v);
+    if (T)
+    {
+        k_bins_scatter<false><<<tb, 256, 0, s>>>(bvh.tris, T, v);
+        k_bins_big<false><<<148 * 4, 256, 0, s>>>(v);
+    }
     k_bins_scan_local<<<sz.numBlocks, 256, 0, s>>>(v.cursors, cells, v.blockSums);
     k_bins_scan_sums<<<1, 1024, 0, s>>>(v.blockSums, sz.numBlocks, v.state, sz.cap);
-    if (T) k_bins_scatter<true><<<tb, 256, 0, s>>>(bvh.tris, T, v);
+    if (T)
+    {
+        k_bins_scatter<true><<<tb, 256, 0, s>>>(bvh.tris, T, v);
+        k_bins_big<true><<<148 * 4, 256, 0, s>>>(v);
+    }
     k_bins_finish<<<(cells + kFinishThreads - 1) / kFinishThreads, kFinishThreads, 0, s>>>(v, cells);
-    return T ? 5 : 3;
+    k_bins_finish_big<<<148 * 4, kFinishThreads, 0, s>>>(v);
+    return T ? 8 : 4;
 }
 
 void launchTraceShaderBins(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
-                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, void* base, const ShaderBinsSizes& sz)
+                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, void* base, const ShaderBinsSizes& sz, float* centres)
 {
     const ShaderBinsView v = shaderBinsView(base, sz);
     ShaderParams prm;
@@ -518,8 +831,18 @@ void launchTraceShaderBins(cudaStream_t s, const BvhView& bvh, const MeshView& m
     prm.N = N; prm.P = (N + 31) / 32; prm.z0 = z0;
     prm.numWords = (uint64_t)(z1 - z0) * N * prm.P;
     prm.grid = grid; prm.texels = texels; prm.err = dErr; prm.binsState = v.state;
-    const uint64_t want = (prm.numWords + (kTraceThreads / 32) - 1) / (kTraceThreads / 32);
-    const uint64_t cap = 148ull * 16ull * 8ull;
-    k_trace_shader_bins<<<(unsigned)(want < cap ? want : cap), kTraceThreads, 0, s>>>(prm, v);
+    k_voxel_centres<<<(N + 255) / 256, 256, 0, s>>>(centres, N);
+    TraceGeom g;
+    g.layers = z1 - z0;
+    g.unitsX = prm.P * 4u; g.unitsY = (N + 1u) / 2u; g.unitsZ = (g.layers + 1u) / 2u;
+    const uint64_t units = (uint64_t)g.unitsX * g.unitsY * g.unitsZ;
+    const uint64_t wantBlocks = (units + (kTraceThreads / 32) - 1) / (kTraceThreads / 32);
+    const uint64_t capBlocks = 148ull * 16ull * 8ull;
+    const uint32_t blocks = (uint32_t)(wantBlocks < capBlocks ? wantBlocks : capBlocks);
+    uint64_t stride = (uint64_t)blocks * (kTraceThreads / 32);
+    g.strideX = (uint32_t)(stride % g.unitsX); stride /= g.unitsX;
+    g.strideY = (uint32_t)(stride % g.unitsY); stride /= g.unitsY;
+    g.strideZ = (uint32_t)stride;
+    k_trace_shader_bins<<<blocks, kTraceThreads, 0, s>>>(prm, v, centres, g);
 }
 }  // namespace dxrv

@@ -110,7 +110,7 @@ void launchTraceShaderBvh(cudaStream_t s, const BvhView& bvh, const MeshView& m,
     prm.grid = grid; prm.texels = texels; prm.err = dErr; prm.binsState = binsState;
     // grid-stride over the words: any slab of any N <= 8192 fits (a one-shot grid overflowed 2^31-1 blocks from N ~ 6500)
     const uint64_t want = (prm.numWords + (kShaderThreads / 32) - 1) / (kShaderThreads / 32);
-    const uint64_t cap = 148ull * 16ull * 64ull;
+    const uint64_t cap = 148ull * 16ull;
     k_trace_shader<<<(unsigned)(want < cap ? want : cap), kShaderThreads, 0, s>>>(prm);
 }
 }  // namespace dxrv

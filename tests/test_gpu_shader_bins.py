@@ -43,6 +43,7 @@ def test_any_bin_resolution_gives_the_same_grid(vox, assets, oracle_mod, monkeyp
     m = assets("bunny.obj")
     ref = oracle_mod.voxelize(m.vertices, m.indices, 64, oracle_mod.MODE_SHADER, texels=True)
     monkeypatch.setenv("DXRV_SHADER_BINS_R", str(R))
+    monkeypatch.setenv("DXRV_SHADER_PATH", "bins")               # (N < 160 would take the LBVH walk by default)
     bits, tex = _shader(vox, m, 64)
     assert popcount(bits ^ ref["bits"]) == 0 and np.array_equal(tex, ref["texels"])
 
@@ -81,9 +82,11 @@ def test_soup_against_brute_force_oracle(vox, oracle_mod, monkeypatch):
     _both_paths(vox, monkeypatch, m, 40, ref)
 
 
-def test_near_list_overflow_falls_back_on_the_device(vox, meshes_mod, oracle_mod):
+def test_near_list_overflow_falls_back_on_the_device(vox, meshes_mod, oracle_mod, monkeypatch):
     """More than 4096 triangles within 1e-3 of the grid centre: the near list overflows, the bins raise their
     device flag and the LBVH walk produces the grid (no host round trip) -- still the oracle's bits."""
+    from dxrvoxelizer_b200 import _lib as L
+    monkeypatch.setenv("DXRV_SHADER_PATH", "bins")
     ball = meshes_mod.icosphere(4, seed=2)                       # 5120 triangles
     v = ball.vertices.copy()
     v[:, :3] *= 4e-4
@@ -92,14 +95,19 @@ def test_near_list_overflow_falls_back_on_the_device(vox, meshes_mod, oracle_mod
     verts = np.concatenate([v, far.vertices])
     idx = np.concatenate([ball.indices.reshape(-1, 3), far.indices.reshape(-1, 3) + nv]).astype(np.uint32)
     m = d.Mesh(verts, idx, ball.stride)
-    ref = oracle_mod.voxelize(m.vertices, m.indices, 64, oracle_mod.MODE_SHADER, texels=True)
-    bits, tex = _shader(vox, m, 64)
+    bound = [0.0, 0.0, 0.0, 1.25]                                # pin the grid centre onto the small ball
+    ref = oracle_mod.voxelize(m.vertices, m.indices, 64, oracle_mod.MODE_SHADER, texels=True, bound=bound)
+    bits, tex = _shader(vox, m, 64, bound=bound)
     assert popcount(bits ^ ref["bits"]) == 0 and np.array_equal(tex, ref["texels"])
+    st = vox.debug_read(L.DBG_BINS_STATE, np.uint32, 4)
+    assert st[1] == 1 and st[2] > 4096                           # overflow flag up, near list over its capacity
 
 
-def test_entry_budget_overflow_falls_back_on_the_device(vox, oracle_mod):
+def test_entry_budget_overflow_falls_back_on_the_device(vox, oracle_mod, monkeypatch):
     """Thousands of scene-sized triangles: every one covers a large part of every cube-map face, the lists would
     need far more than the entry budget -> flag -> LBVH walk."""
+    from dxrvoxelizer_b200 import _lib as L
+    monkeypatch.setenv("DXRV_SHADER_PATH", "bins")
     rng = np.random.default_rng(11)
     n = 3000
     tri = rng.uniform(-1, 1, size=(n, 3, 3))
@@ -109,6 +117,8 @@ def test_entry_budget_overflow_falls_back_on_the_device(vox, oracle_mod):
     ref = oracle_mod.voxelize(m.vertices, m.indices, 32, oracle_mod.MODE_SHADER, texels=True)
     bits, tex = _shader(vox, m, 32)
     assert popcount(bits ^ ref["bits"]) == 0 and np.array_equal(tex, ref["texels"])
+    st = vox.debug_read(L.DBG_BINS_STATE, np.uint32, 4)
+    assert st[1] == 1 and st[0] > (1 << 20)                      # more entries than the budget
 
 
 @pytest.mark.parametrize("name,N,slabs", [("dragon.obj", 256, (100, 127, 128, 200)), ("dragon.obj", 1024, (511, 600)),
@@ -123,11 +133,31 @@ def test_slabs_at_larger_grids(vox, assets, oracle_mod, name, N, slabs):
         assert popcount(vox.fetch_bits() ^ ref["bits"]) == 0, z0
 
 
-def test_bins_are_rebuilt_for_every_acceleration_structure(vox, assets, meshes_mod, oracle_mod):
+def test_bins_are_rebuilt_for_every_acceleration_structure(vox, assets, meshes_mod, oracle_mod, monkeypatch):
     """The bins are cached per build: a new mesh (even of the same size) must not see the old lists."""
+    monkeypatch.setenv("DXRV_SHADER_PATH", "bins")
     a, b = meshes_mod.icosphere(4, seed=1), meshes_mod.icosphere(4, seed=2, rotate=True)
     for m in (a, b, a):
         bits, _ = _shader(vox, m, 64, texels=False)
         assert popcount(bits ^ oracle_mod.voxelize(m.vertices, m.indices, 64, oracle_mod.MODE_SHADER)["bits"]) == 0
         vox.voxelize(64, d.MODE_SHADER, 10, 20)                  # second voxelize on the same build: cached bins
         assert np.array_equal(vox.fetch_bits(), bits[10:20])
+
+
+def test_default_path_by_grid_size(vox, assets, oracle_mod):
+    """Small grids take the LBVH walk (the bins would cost more to build than 64^3 rays cost to trace), large ones
+    build the bins, and later small voxelizes on the same acceleration structure reuse them."""
+    from dxrvoxelizer_b200 import _lib as L
+    m = assets("bunny.obj")
+    ref64 = oracle_mod.voxelize(m.vertices, m.indices, 64, oracle_mod.MODE_SHADER)["bits"]
+    vox.build_bvh(m)
+    vox.voxelize(64, d.MODE_SHADER)
+    assert vox.debug_read(L.DBG_BINS_STATE, np.uint32, 4)[3] == 0            # no bins built
+    assert popcount(vox.fetch_bits() ^ ref64) == 0
+    vox.voxelize(192, d.MODE_SHADER, 90, 92)
+    st = vox.debug_read(L.DBG_BINS_STATE, np.uint32, 4)
+    assert st[3] >= 8 and st[1] == 0 and st[0] > 0                           # bins built, no overflow
+    ref = oracle_mod.voxelize(m.vertices, m.indices, 192, oracle_mod.MODE_SHADER, z0=90, z1=92)["bits"]
+    assert popcount(vox.fetch_bits() ^ ref) == 0
+    vox.voxelize(64, d.MODE_SHADER)                                          # reuses the bins
+    assert popcount(vox.fetch_bits() ^ ref64) == 0
