@@ -1,27 +1,36 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the voxelization hot path (BASELINE.json: "Gvoxels/s end-to-end
-incl. BVH build at 1/2/4/8 B200; ms per 1024^3 grid").
+"""bench.py -- benchmark of the voxelization hot path (BASELINE.json: "Gvoxels/s end-to-end incl. BVH build at
+1/2/4/8 B200; ms per 1024^3 grid").
 
-A step = one pass of the hot path over one mesh: LBVH build (bounds, Morton, onesweep sort, Karras
-hierarchy, refit) + MODE_PARITY trace/fill of the bit-packed grid.  Workload: the reference's
-Stanford dragon (Bin/Assets/dragon.obj via Dragon.bat) at 1024^3 voxels PER GPU:
-  N=1      1024^3 grid, one GPU does all of it (BASELINE configs[2] at one GPU).
-  N=2,4,8  z-slab sharding, weak scaling: the grid grows to 1280^3 / 1664^3 / 2048^3 so every rank
-           still fills ~1024^3 voxels (its own z-slab); the mesh/BVH is replicated, no data-path
-           collective in the timed region.  ("zslab_1024" in the JSON additionally reports the
-           strong-scaling number: ONE 1024^3 grid split into N slabs.)
+Default workload (--config c3, BASELINE.json configs[2]): the reference's Stanford dragon (Bin/Assets/dragon.obj via
+Dragon.bat) at ONE 1024^3 bit-packed grid, MODE_PARITY, the LBVH rebuilt every step.
+  N=1      one GPU fills the whole grid.
+  N=2,4,8  STRONG scaling: the same 1024^3 grid split into N cost-balanced z-slabs, one per rank; the mesh is
+           replicated (NCCL broadcast), every rank builds the identical LBVH, no collective in the timed region.
+           (`weak_scaling` in the JSON is a side number: the grid grown to 1280^3/1664^3/2048^3.)
+A step = LBVH build (bounds, Morton, onesweep sort, Karras hierarchy, boxes) + trace/fill of the rank's slab.
+
+`mismatched_voxels`  correctness GATE, run before anything is timed: every rank fetches its slab and XORs it against
+             the CPU oracle's grid of the same layers; the sum over ranks must be 0 or the bench exits non-zero.
+             (`shader_mismatched_voxels`: the same for MODE_SHADER on a few layers of the slab.)
 `value`      inputs (vertex/index buffers) resident in HBM; CUDA-event time, max over ranks.
-`e2e`        same metric through the C ABI with HOST buffers: H2D of the mesh, build, voxelize and
-             D2H of the rank's slab inside the timed region (wall clock around synchronising calls).
-`roofline`   dominant kernel (k_trace_fill_columns): algorithmic bytes / its CUDA-event time.
-`cpu_baseline` the CPU oracle (a port: the reference itself is DXR/Windows-only) on the host cores.
-`--impl reference` times that same oracle as the reference arm.
+`e2e`        same metric through the C ABI with HOST buffers: H2D of the mesh, build, voxelize and D2H of the
+             rank's slab inside the timed region (wall clock around synchronising calls, max over ranks).
+`roofline`   dominant kernel (k_trace_fill_columns) on rank 0: algorithmic bytes / its CUDA-event time.
+`phases_ms.shader_1024`  MODE_SHADER (the reference's own function: radial closest-hit rays) on the same slab,
+             direction bins rebuilt every step.
+`cpu_baseline` (N=1) the CPU oracle (a port: the reference itself is DXR/Windows-only) on all host cores.
+`--impl reference` times that same oracle as the reference arm; it never imports the product package.
+`--config c4` (synthetic 16.8 M-triangle torus knot at 512^3, build-dominated) and `--config c5` (256 distinct
+meshes, OBJ text -> grid, at 256^3, mesh-parallel) are BASELINE.json configs[3] and [4].
 """
 import argparse
 import json
+import lzma
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -33,20 +42,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "gvoxels_per_s_incl_bvh_build"
 UNIT = "Gvoxel/s"
-GRID_FOR_GPUS = {1: 1024, 2: 1280, 4: 1664, 8: 2048}   # ~1024^3 voxels per GPU
-
-
-def grid_for(n_gpus):
-    if n_gpus in GRID_FOR_GPUS:
-        return GRID_FOR_GPUS[n_gpus]
-    n = int(round(1024 * n_gpus ** (1.0 / 3.0) / 32.0)) * 32
-    while n % n_gpus:
-        n += 32
-    return n
-
-
-def slab_of(rank, world, N):
-    return N * rank // world, N * (rank + 1) // world
+GRID = 1024
+WEAK_GRID = {2: 1280, 4: 1664, 8: 2048}   # ~1024^3 voxels per GPU (side number only)
 
 
 def measured_peak():
@@ -106,159 +103,256 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def load_workload():
-    import dxrvoxelizer_b200 as d
-    return d.load_obj(d.asset_path("dragon.obj"))
+def popcount(a):
+    return int(np.unpackbits(np.ascontiguousarray(a).reshape(-1).view(np.uint8)).sum())
 
 
-# ---------------------------------------------------------------------------------------------------
+# ---- mesh loading without the product (reference arm) ---------------------------------------------------------
+def unpack_asset(name):
+    """assets/<name>.xz -> a temp file (the product's dxrvoxelizer_b200.assets does the same; the reference arm
+    must not import the product package)."""
+    out = os.path.join(tempfile.gettempdir(), "dxrv_bench_%d_%s" % (os.getuid(), name))
+    if not os.path.exists(out):
+        with open(os.path.join(ROOT, "assets", name + ".xz"), "rb") as f:
+            raw = lzma.decompress(f.read())
+        tmp = out + ".tmp%d" % os.getpid()
+        with open(tmp, "wb") as f:
+            f.write(raw)
+        os.replace(tmp, out)
+    return out
+
+
+def load_mesh_without_product(name):
+    """(vertices float32 [nv, stride/4], indices uint32) through the REFERENCE's own ObjLoader compiled into
+    oracle/_ref (XUSG/Optional/XUSGObjLoader.cpp, unmodified); positions-only numpy parse when that is absent."""
+    import oracle
+    path = unpack_asset(name)
+    if oracle.ref_loader_available():
+        vb, ib, stride, _ = oracle.ref_load_obj(path)
+        return vb.view(np.float32).reshape(-1, stride // 4), ib, "oracle/_ref ObjLoader (the reference's own loader)"
+    pos, tri = [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("v "):
+                x, y, z = line.split()[1:4]
+                pos.append((float(x), float(y), -float(z)))          # z flip, XUSGObjLoader.cpp:198
+            elif line.startswith("f "):
+                c = [int(t.split("/")[0]) - 1 for t in line.split()[1:]]
+                for k in range(1, len(c) - 1):
+                    tri.append((c[0], c[k], c[k + 1]))               # fan, XUSGObjLoader.cpp:263-297
+    idx = np.asarray(tri, np.uint32).reshape(-1)[::-1].copy()         # whole index array reversed, :227
+    return np.asarray(pos, np.float32), idx, "numpy positions-only parse (oracle/_ref absent)"
+
+
+# ---- reference arm ----------------------------------------------------------------------------------------------
 def run_reference(args):
-    """Reference arm: the reference's own implementation cannot run here (Windows + D3D12/DXR +
-    binary-only XUSG), so this times the CPU oracle port of its algorithm with all host threads on
-    the same workload.  Rank 0 only."""
+    """The reference's own implementation cannot run here (Windows + D3D12/DXR + binary-only XUSG), so this times
+    the CPU oracle port of the path with all host threads on the same workload: the WHOLE 1024^3 dragon grid per
+    step at any N (strong scaling: the job does not grow with N).  The algorithm timed is MODE_PARITY, the same one
+    the GPU arm's headline uses (the oracle's MODE_SHADER rate is reported beside it).  Rank 0 only; the product
+    package is never imported here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
-    mesh = load_workload()
+    verts, idx, how = load_mesh_without_product("dragon.obj")
     world = args.gpus
-    N = grid_for(world)
     threads = host_threads()
-    # bounded sample: the central z-slab one GPU owns (N/world layers ~ 1024^3 voxels; the whole grid
-    # at N=1), ~0.5 s per step on 8 cores
-    layers = max(1, N // world)
-    z0 = (N - layers) // 2
-    for _ in range(args.warmup):
-        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
+    N = GRID
+    for _ in range(max(1, args.warmup)):
+        oracle.voxelize(verts, idx, N, oracle.MODE_PARITY, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
+        oracle.voxelize(verts, idx, N, oracle.MODE_PARITY, threads=threads)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
-    value = layers * N * N / dt * 1e-9
-    sample = "central z-slab of %d layers of the %d^3 dragon grid per step (MODE_PARITY, own yz-bin build included)" % (layers, N)
+    value = float(N) ** 3 / dt * 1e-9
+    # the reference's actual function (radial closest hit): a bounded sample of 4 central layers
+    shader_rate = float("nan")
+    if verts.shape[1] >= 6:                                      # (needs vertex normals)
+        t1 = time.perf_counter()
+        oracle.voxelize(verts, idx, N, oracle.MODE_SHADER, z0=N // 2 - 2, z1=N // 2 + 2, threads=threads)
+        shader_rate = 4.0 * N * N / (time.perf_counter() - t1) * 1e-9
+    sample = "the whole %d^3 dragon grid per step, MODE_PARITY (column-parity algorithm), own yz-bin build included" % N
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(1, args.warmup), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "reference asset dragon.obj (Stanford dragon, 100k triangles)",
-        "config": workload_config(N, world, mesh),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(N, world, idx.size // 3, verts.shape[0]),
+        "mesh_loader": how,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "algorithm": "MODE_PARITY (column parity); the reference's shader algorithm (MODE_SHADER) runs at "
+                                      "%.3f Gvoxel/s on the same cores (4 central layers sampled)" % shader_rate,
+                         "shader_gvoxels_per_s": shader_rate},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(N, world, mesh):
-    return {"workload": "dragon.obj %d^3 MODE_PARITY, LBVH rebuilt every step, z-slab per GPU" % N,
-            "grid": N, "voxels_per_gpu_mean": N * N * N // world, "slabs": "one z-slab per GPU, cut points balance stores + triangles per layer",
-            "triangles": mesh.num_triangles,
-            "vertices": mesh.num_vertices, "mode": "parity", "parallelism": "zslab%d" % world,
+def workload_config(N, world, tris, verts):
+    return {"workload": "dragon.obj %d^3 MODE_PARITY, LBVH rebuilt every step, one grid split into %d z-slab(s)" % (N, world),
+            "grid": N, "voxels_total": N * N * N, "slabs": "one z-slab per GPU, cut points balance stores + triangles per layer",
+            "triangles": int(tris), "vertices": int(verts), "mode": "parity", "parallelism": "zslab%d" % world,
             "l2": "flushed between timed steps (256 MiB device write, untimed)"}
 
 
-# ---------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# ---- our arm -----------------------------------------------------------------------------------------------------
+class Rig:
+    """Process-group, device and context plumbing shared by the configs."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import dxrvoxelizer_b200 as d
+        self.torch, self.dist, self.d = torch, dist, d
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, self.world))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream()
+        self.vox = d.Voxelizer(self.local)
+        self.vox.set_stream(self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce_max(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def reduce_sum(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def flush_l2(self, i=0):
+        with self.torch.cuda.stream(self.stream):
+            self.flush.fill_(i & 0xff)
+
+    def replicate_mesh(self, mesh):
+        """rank 0's mesh -> pinned host + device copies on every rank (NCCL broadcast over NVLink)."""
+        torch, dist = self.torch, self.dist
+        if self.rank == 0:
+            meta = torch.tensor([mesh.num_vertices, mesh.stride, mesh.indices.size], dtype=torch.int64, device="cuda")
+        else:
+            meta = torch.zeros(3, dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            dist.broadcast(meta, 0)
+        nv, stride, ni = (int(x) for x in meta.tolist())
+        with numa_local(self.local):
+            h_vb = torch.empty(nv * stride, dtype=torch.uint8).pin_memory()
+            h_ib = torch.empty(ni, dtype=torch.int32).pin_memory()
+        if self.rank == 0:
+            h_vb.copy_(torch.from_numpy(mesh.vertex_bytes))
+            h_ib.copy_(torch.from_numpy(mesh.indices.view(np.int32)))
+        d_vb, d_ib = h_vb.cuda(), h_ib.cuda()
+        if self.world > 1:
+            dist.broadcast(d_vb, 0)
+            dist.broadcast(d_ib, 0)
+            h_vb.copy_(d_vb)
+            h_ib.copy_(d_ib)
+        torch.cuda.synchronize()
+        host_mesh = self.d.Mesh(h_vb.numpy(), h_ib.numpy().view(np.uint32), stride)
+        return host_mesh, (h_vb, h_ib, d_vb, d_ib, nv, stride, ni)
+
+    def close(self):
+        self.vox.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def gate_slab(rig, host_mesh, N, mode, z0, z1, layers=None):
+    """XOR-popcount of this rank's slab against the CPU oracle (the checker; nothing here is timed).
+    layers: None = every layer of the slab, else an iterable of single layers (MODE_SHADER: the oracle needs
+    ~0.1 s per 1024^2 layer)."""
+    import oracle
+    threads = max(1, host_threads() // rig.world)
+    rig.vox.voxelize(N, mode, z0, z1)
+    got = rig.vox.fetch_bits()
+    mism = 0
+    if layers is None:
+        ref = oracle.voxelize(host_mesh.vertices, host_mesh.indices, N, mode, z0=z0, z1=z1, threads=threads)["bits"]
+        mism = popcount(got ^ ref)
+        checked = z1 - z0
+    else:
+        checked = 0
+        for z in layers:
+            ref = oracle.voxelize(host_mesh.vertices, host_mesh.indices, N, mode, z0=z, z1=z + 1, threads=threads)["bits"]
+            mism += popcount(got[z - z0:z - z0 + 1] ^ ref)
+            checked += 1
+    return mism, checked
+
+
+def run_c3(args):
     import dxrvoxelizer_b200 as d
     from dxrvoxelizer_b200 import _lib as L
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    N = grid_for(world)
-    stream = torch.cuda.Stream()
-    vox = d.Voxelizer(local)
-    vox.set_stream(stream.cuda_stream)
-
-    # ---- inputs: rank 0 loads the OBJ; the mesh is replicated by NCCL broadcast over NVLink ----
-    if rank == 0:
-        mesh = load_workload()
-        meta = torch.tensor([mesh.num_vertices, mesh.stride, mesh.indices.size], dtype=torch.int64, device="cuda")
-    else:
-        mesh, meta = None, torch.zeros(3, dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.broadcast(meta, 0)
-    nv, stride, ni = (int(x) for x in meta.tolist())
-    with numa_local(local):
-        h_vb = torch.empty(nv * stride, dtype=torch.uint8).pin_memory()
-        h_ib = torch.empty(ni, dtype=torch.int32).pin_memory()
-    if rank == 0:
-        h_vb.copy_(torch.from_numpy(mesh.vertex_bytes))
-        h_ib.copy_(torch.from_numpy(mesh.indices.view(np.int32)))
-    d_vb = h_vb.cuda()
-    d_ib = h_ib.cuda()
-    if world > 1:
-        dist.broadcast(d_vb, 0)
-        dist.broadcast(d_ib, 0)
-        h_vb.copy_(d_vb)
-        h_ib.copy_(d_ib)
-    torch.cuda.synchronize()
-    T = ni // 3
-    # z-slab of this rank.  Equal slabs are badly balanced for a real mesh (the dragon is thin along z: the ranks
-    # owning its layers would do all the crossing tests), so the cut points balance a cost model instead:
-    # stores + triangles overlapping the layer (dxrvoxelizer_b200.sharding.balanced_slabs, host-side, untimed,
-    # identical on every rank because the mesh is replicated).
     from dxrvoxelizer_b200.sharding import balanced_slabs
-    host_mesh = d.Mesh(h_vb.numpy(), h_ib.numpy().view(np.uint32), stride)
+    rig = Rig(args)
+    torch, vox, stream, rank, world = rig.torch, rig.vox, rig.stream, rig.rank, rig.world
+    N = GRID
+    mesh = d.load_obj(d.asset_path("dragon.obj")) if rank == 0 else None
+    host_mesh, (h_vb, h_ib, d_vb, d_ib, nv, stride, ni) = rig.replicate_mesh(mesh)
+    T = ni // 3
+    # z-slab of this rank.  Equal slabs are badly balanced for a real mesh (the dragon is thin along z), so the cut
+    # points balance a cost model instead (dxrvoxelizer_b200.sharding.balanced_slabs: host-side, untimed, identical
+    # on every rank because the mesh is replicated).
     z0, z1 = balanced_slabs(host_mesh, N, world)[rank]
-
-    slab_bytes = (z1 - z0) * N * ((N + 31) // 32) * 4
-    with numa_local(local):
+    P = (N + 31) // 32
+    slab_bytes = (z1 - z0) * N * P * 4
+    with numa_local(rig.local):
         h_grid = torch.empty(slab_bytes, dtype=torch.uint8).pin_memory()
-        h_grid.zero_()   # touch the pages while the thread still sits next to the GPU
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        h_grid.zero_()
 
-    def step_resident():
+    def build():
         vox.build_bvh_device(d_vb.data_ptr(), nv, stride, d_ib.data_ptr(), ni)
-        vox.voxelize(N, d.MODE_PARITY, z0, z1)
 
-    def step_e2e():
-        if world > 1:
-            # replicate the host mesh of rank 0: H2D on rank 0, NCCL broadcast, build from device memory
-            with torch.cuda.stream(stream):
-                if rank == 0:
-                    d_vb.copy_(h_vb, non_blocking=True)
-                    d_ib.copy_(h_ib, non_blocking=True)
-                dist.broadcast(d_vb, 0)
-                dist.broadcast(d_ib, 0)
-            vox.build_bvh_device(d_vb.data_ptr(), nv, stride, d_ib.data_ptr(), ni)
-        else:
-            vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
-        vox.voxelize(N, d.MODE_PARITY, z0, z1)
-        vox.fetch_into(h_grid.data_ptr(), slab_bytes)
+    # ---- correctness gate (before any timing) ---------------------------------------------------------------
+    build()
+    mism, checked = gate_slab(rig, host_mesh, N, d.MODE_PARITY, z0, z1)
+    mid = (z0 + z1) // 2
+    shader_layers = sorted({z0, mid, min(mid + 1, z1 - 1), z1 - 1})
+    smism, schecked = gate_slab(rig, host_mesh, N, d.MODE_SHADER, z0, z1, layers=shader_layers)
+    mism_total, smism_total, checked_total, schecked_total = rig.reduce_sum([mism, smism, checked, schecked])
+    if mism_total != 0 or smism_total != 0:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "error": "GPU grid differs from the CPU oracle", "n_gpus": world,
+                              "mismatched_voxels": int(mism_total), "shader_mismatched_voxels": int(smism_total)}))
+        rig.close()
+        raise SystemExit(3)
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(rig.local)
     if rank == 0:
         sampler.start()
 
-    # ---- device-resident arm --------------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
+    # ---- device-resident arm --------------------------------------------------------------------------------
+    def step_resident():
+        build()
+        vox.voxelize(N, d.MODE_PARITY, z0, z1)
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step_resident()
     vox.synchronize()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = vox.info(L.INFO_KERNEL_LAUNCHES)
-    barrier()
+    rig.barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.fill_(i & 0xff)                      # evict L2 (untimed)
+        rig.flush_l2(i)                                # evict L2 (untimed)
         ev[i][0].record(stream)
-        vox.build_bvh_device(d_vb.data_ptr(), nv, stride, d_ib.data_ptr(), ni)
+        build()
         ev[i][1].record(stream)
         vox.voxelize(N, d.MODE_PARITY, z0, z1)
         ev[i][2].record(stream)
-    barrier()
-    t_wall1 = time.time()
+    rig.barrier()
     launches = vox.info(L.INFO_KERNEL_LAUNCHES) - launches0
     vox.synchronize()
     build_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
@@ -266,117 +360,149 @@ def run_ours(args):
     step_ms = sum(e[0].elapsed_time(e[2]) for e in ev) / args.steps
     crossings = vox.info(L.INFO_CROSSINGS)
 
-    # ---- the dominant kernel on its own: CUDA events recorded by the library on the launching stream
-    # right around k_walk_columns / k_trace_fill_columns, same step sequence and L2 flush as above ----
+    # ---- the dominant kernel on its own: CUDA events recorded by the library on the launching stream right
+    # around k_walk_columns / k_trace_fill_columns, same step sequence and L2 flush as above -------------------
     vox.set_profiling(True)
     walk_ns = fill_ns = 0
     prof_steps = min(args.steps, 50)
     for i in range(prof_steps):
-        with torch.cuda.stream(stream):
-            flush.fill_(i & 0xff)
-        vox.build_bvh_device(d_vb.data_ptr(), nv, stride, d_ib.data_ptr(), ni)
-        vox.voxelize(N, d.MODE_PARITY, z0, z1)
+        rig.flush_l2(i)
+        step_resident()
         walk_ns += vox.info(L.INFO_LAST_WALK_NS)
         fill_ns += vox.info(L.INFO_LAST_FILL_NS)
     vox.set_profiling(False)
     walk_ms, fill_ms = walk_ns / prof_steps * 1e-6, fill_ns / prof_steps * 1e-6
 
-    # ---- end-to-end arm (host buffers through the C ABI) ----------------------------------------
+    # ---- MODE_SHADER on the same slab (the reference's own function), bins rebuilt every step ------------------
+    shader_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        build(); vox.voxelize(N, d.MODE_SHADER, z0, z1)
+    rig.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(shader_steps):
+        build(); vox.voxelize(N, d.MODE_SHADER, z0, z1)
+    s1.record(stream)
+    rig.barrier()
+    shader_ms = s0.elapsed_time(s1) / shader_steps
+
+    # ---- end-to-end arm (host buffers through the C ABI) ------------------------------------------------------
+    def step_e2e():
+        if world > 1:
+            # replicate the host mesh of rank 0: H2D on rank 0, NCCL broadcast, build from device memory
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    d_vb.copy_(h_vb, non_blocking=True)
+                    d_ib.copy_(h_ib, non_blocking=True)
+                rig.dist.broadcast(d_vb, 0)
+                rig.dist.broadcast(d_ib, 0)
+            build()
+        else:
+            vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
+        vox.voxelize(N, d.MODE_PARITY, z0, z1)
+        vox.fetch_into(h_grid.data_ptr(), slab_bytes)
+
     for _ in range(3):
         step_e2e()
-    barrier()
+    rig.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
-    barrier()
+    rig.barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     # where the end-to-end time goes (separate short loop with a synchronisation between compute and read-back)
+    reps = min(args.steps, 20)
     up_ms = down_ms = 0.0
-    if world == 1:
-        reps = min(args.steps, 20)
-        for _ in range(reps):
-            ta = time.perf_counter()
+    for _ in range(reps):
+        ta = time.perf_counter()
+        if world == 1:
             vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
-            vox.voxelize(N, d.MODE_PARITY, z0, z1)
-            vox.synchronize()
-            tb = time.perf_counter()
-            vox.fetch_into(h_grid.data_ptr(), slab_bytes)
-            tc = time.perf_counter()
-            up_ms += (tb - ta) * 1e3 / reps
-            down_ms += (tc - tb) * 1e3 / reps
+        else:
+            build()
+        vox.voxelize(N, d.MODE_PARITY, z0, z1)
+        vox.synchronize()
+        tb = time.perf_counter()
+        vox.fetch_into(h_grid.data_ptr(), slab_bytes)
+        tc = time.perf_counter()
+        up_ms += (tb - ta) * 1e3 / reps
+        down_ms += (tc - tb) * 1e3 / reps
+    d2h_gbs = slab_bytes / (down_ms * 1e-3) * 1e-9 if down_ms > 0 else 0.0
 
-    # ---- strong-scaling side number: ONE 1024^3 grid split into `world` slabs ---------------------
-    zs_ms = None
-    if world > 1:
-        a, b = balanced_slabs(host_mesh, 1024, world)[rank]
-        def step_1024():
-            vox.build_bvh_device(d_vb.data_ptr(), nv, stride, d_ib.data_ptr(), ni)
-            vox.voxelize(1024, d.MODE_PARITY, a, b)
+    # ---- weak-scaling side number: the grid grown so that every rank still fills ~1024^3 voxels -----------------
+    weak = None
+    if world in WEAK_GRID:
+        Nw = WEAK_GRID[world]
+        a, b = balanced_slabs(host_mesh, Nw, world)[rank]
         for _ in range(3):
-            step_1024()
-        barrier()
+            build(); vox.voxelize(Nw, d.MODE_PARITY, a, b)
+        rig.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            step_1024()
+            build(); vox.voxelize(Nw, d.MODE_PARITY, a, b)
         e1.record(stream)
-        barrier()
-        zs_ms = e0.elapsed_time(e1) / args.steps
+        rig.barrier()
+        weak = (Nw, e0.elapsed_time(e1) / args.steps)
 
-    # ---- max over ranks ---------------------------------------------------------------------------
+    # ---- max over ranks ---------------------------------------------------------------------------------------
     fill_ms_rank0 = fill_ms   # the roofline of the kernel is a per-GPU figure: rank 0's launches against rank 0's bytes
-    times = torch.tensor([step_ms, build_ms, trace_ms, e2e_ms, zs_ms or 0.0, walk_ms, fill_ms], dtype=torch.float64, device="cuda")
+    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms = rig.reduce_max(
+        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0])
+    per_rank = None
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    step_ms, build_ms, trace_ms, e2e_ms, zs_ms, walk_ms, fill_ms = times.tolist()
+        gathered = [None] * world
+        rig.dist.all_gather_object(gathered, {"rank": rank, "slab": [z0, z1], "d2h_gbs": round(d2h_gbs, 2), "d2h_ms": round(down_ms, 4),
+                                              "fill_kernel_ms": round(fill_ms_rank0, 5)})
+        per_rank = gathered
 
     if rank == 0:
         total_voxels = float(N) ** 3
         peak, peak_src = measured_peak()
-        # algorithmic bytes of one k_trace_fill_columns launch on one GPU: the slab
-        # of the bit grid written once + every scene-space triangle (48 B) read once.  (The BVH nodes
-        # are read by k_walk_columns, which is latency bound and reported under phases_ms.)
+        # algorithmic bytes of one k_trace_fill_columns launch on one GPU: the slab of the bit
+        # grid written once + every scene-space triangle (48 B) read once.
         alg_bytes = slab_bytes + 48 * T
         achieved = alg_bytes / (fill_ms_rank0 * 1e-3) * 1e-9
-        cpu = cpu_baseline(mesh, N, world)
         out = {
             "metric": METRIC, "value": total_voxels / (step_ms * 1e-3) * 1e-9, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "steps": args.steps, "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "reference asset dragon.obj (Stanford dragon, 100k triangles); no synthetic substitution needed",
-            "config": workload_config(N, world, mesh),
-            "phases_ms": {"bvh_build": build_ms, "voxelize": trace_ms, "k_walk_columns": walk_ms, "k_trace_fill_columns": fill_ms},
-            "ms_per_1024_cubed_grid": step_ms if world == 1 else zs_ms,
+            "config": workload_config(N, world, T, nv),
+            "mismatched_voxels": int(mism_total), "gate": {"parity_layers_checked": int(checked_total), "shader_layers_checked": int(schecked_total),
+                                                            "shader_mismatched_voxels": int(smism_total),
+                                                            "how": "XOR-popcount of every rank's fetched slab against the CPU oracle before timing"},
+            "phases_ms": {"bvh_build": build_ms, "voxelize": trace_ms, "k_walk_columns": walk_ms, "k_trace_fill_columns": fill_ms,
+                          "shader_1024": shader_ms},
+            "shader": {"ms_per_1024_cubed_grid_incl_build_and_bins": shader_ms, "grays_per_s": total_voxels / (shader_ms * 1e-3) * 1e-9,
+                       "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), same slabs, LBVH + direction bins rebuilt every step"},
+            "ms_per_1024_cubed_grid": step_ms,
             "e2e": {"value": total_voxels / (e2e_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(N * N * ((N + 31) // 32) * 4),
+                    "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(N * N * P * 4),
                     "timing": "wall clock around synchronising C-ABI calls, max over ranks",
-                    "phases_ms": ({"h2d_mesh_build_voxelize": up_ms, "d2h_grid": down_ms} if world == 1 else None)},
+                    "phases_ms": {"h2d_mesh_build_voxelize": up_ms, "d2h_grid": down_ms}, "d2h_gbs_rank0": d2h_gbs,
+                    "per_rank": per_rank},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_trace_fill_columns", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(world),
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": fill_ms_rank0, "peak_source": peak_src,
                          "frac_of_nominal_8000_GBps": achieved / 8000.0,
                          "timing": "cudaEventRecord on the launching stream around the kernel, mean of %d launches" % prof_steps},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu_baseline(host_mesh, N) if world == 1 else None,
             "clocks": clocks,
             "crossings": int(crossings),
         }
-        if world > 1:
-            out["zslab_1024"] = {"ms_per_1024_cubed_grid": zs_ms, "gvoxels_per_s": 1024.0 ** 3 / (zs_ms * 1e-3) * 1e-9,
-                                 "scaling": "strong"}
+        if weak:
+            out["weak_scaling"] = {"grid": weak[0], "ms_per_step": weak_ms, "gvoxels_per_s": float(weak[0]) ** 3 / (weak_ms * 1e-3) * 1e-9,
+                                   "scaling": "weak", "note": "side number: ~1024^3 voxels per GPU; not the BASELINE.json config"}
         print(json.dumps(out))
-    vox.close()
-    if world > 1:
-        dist.destroy_process_group()
+    rig.close()
 
 
 class numa_local:
     """Allocate pinned host buffers on the NUMA node next to GPU `index`: the thread is moved onto the CPUs NVML
     reports for that GPU while the pages are allocated and touched, then gets its original affinity back (the CPU
-    baseline must see every core).  A D2H copy into far memory crosses the socket interconnect and loses bandwidth;
-    with 8 ranks reading back at once it is the difference between the PCIe links and one saturated socket link.
-    Best effort: without NVML (or on a single-node box) it does nothing."""
+    baseline must see every core).  Best effort: without NVML (or on a single-node box) it does nothing."""
     def __init__(self, index):
         self.index, self.saved = index, None
 
@@ -401,9 +527,12 @@ class numa_local:
         return False
 
 
-def ncu_traffic():
+def ncu_traffic(world):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    ncu --set full capture (profiles/), or null when no capture is recorded."""
+    ncu --set full capture of THIS configuration (profiles/roofline_traffic.json: dragon 1024^3, one GPU);
+    null at N > 1, where the slab differs and no capture exists."""
+    if world != 1:
+        return None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             return json.load(f).get("k_trace_fill_columns_dram_bytes_per_launch")
@@ -411,23 +540,27 @@ def ncu_traffic():
         return None
 
 
-def cpu_baseline(mesh, N, world):
-    """The CPU oracle (a port of the reference's algorithm) on the box's host cores, bounded sample."""
+def cpu_baseline(mesh, N):
+    """The CPU oracle (a port of the path) on the box's host cores: the whole grid, best of 3."""
     import oracle
     threads = host_threads()
-    layers = max(1, N // world)
-    z0 = (N - layers) // 2
-    oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
+    oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, threads=threads)
     best = 1e30
     t_all = time.perf_counter()
     for _ in range(3):
         t = time.perf_counter()
-        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, z0=z0, z1=z0 + layers, threads=threads)
+        oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_PARITY, threads=threads)
         best = min(best, time.perf_counter() - t)
         if time.perf_counter() - t_all > 25:
             break
-    return {"value": layers * N * N / best * 1e-9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "central z-slab of %d layers of the %d^3 dragon grid, MODE_PARITY, own acceleration build included, best of 3" % (layers, N)}
+    t = time.perf_counter()
+    oracle.voxelize(mesh.vertices, mesh.indices, N, oracle.MODE_SHADER, z0=N // 2 - 2, z1=N // 2 + 2, threads=threads)
+    shader_rate = 4.0 * N * N / (time.perf_counter() - t) * 1e-9
+    return {"value": float(N) ** 3 / best * 1e-9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "the whole %d^3 dragon grid, MODE_PARITY (the column-parity algorithm the GPU headline uses), own acceleration build "
+                      "included, best of 3" % N,
+            "shader_gvoxels_per_s": shader_rate,
+            "shader_sample": "MODE_SHADER (the reference's radial closest-hit algorithm), 4 central layers of the same grid"}
 
 
 def main():
@@ -436,11 +569,15 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c3":
+        run_c3(args)
     else:
-        run_ours(args)
+        import bench_configs
+        (bench_configs.run_c4 if args.config == "c4" else bench_configs.run_c5)(args, Rig, ClockSampler, measured_peak, host_threads, popcount)
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_NO_BVH, ERR_NO_GRID, ERR_IO, ERR_OOM, ERR_UNSUPPO
 MODE_SHADER, MODE_PARITY, EMIT_TEXELS = 0, 1, 0x100
 FORMAT_BITS, FORMAT_U8, FORMAT_R10G10B10A2 = 0, 1, 2
 INFO_NUM_TRIANGLES, INFO_NUM_NODES, INFO_KERNEL_LAUNCHES, INFO_CROSSINGS, INFO_SM_COUNT = 0, 1, 2, 3, 4
-INFO_LAST_WALK_NS, INFO_LAST_FILL_NS = 5, 6
+INFO_LAST_WALK_NS, INFO_LAST_FILL_NS, INFO_LAST_BUILD_NS, INFO_LAST_SORT_NS = 5, 6, 7, 8
 DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_ROOT_BOX, DBG_BINS_STATE = 0, 1, 2, 3, 5, 6
 
 _c = ctypes
@@ -57,6 +57,19 @@ SIGNATURES = {
     "dxrv_ipc_export_grid": (_int, [_vp, _sz, _vp, _c.POINTER(_vp)]),
     "dxrv_ipc_open": (_int, [_vp, _vp, _c.POINTER(_vp)]),
     "dxrv_ipc_close": (_int, [_vp, _vp]),
+    "dxrv_comm_get_unique_id": (_int, [_vp]),
+    "dxrv_comm_init": (_int, [_vp, _vp, _int, _int]),
+    "dxrv_comm_init_all": (_int, [_c.POINTER(_vp), _int]),
+    "dxrv_comm_destroy": (_int, [_vp]),
+    "dxrv_group_begin": (_int, []),
+    "dxrv_group_end": (_int, []),
+    "dxrv_bcast_u32": (_int, [_vp, _vp, _u32, _int]),
+    "dxrv_bcast_mesh": (_int, [_vp, _vp, _u32, _u32, _vp, _u32, _int]),
+    "dxrv_build_bvh_replicated": (_int, [_vp, _vp]),
+    "dxrv_gather_grid": (_int, [_vp, _int]),
+    "dxrv_full_grid_device": (_int, [_vp, _c.POINTER(_vp), _c.POINTER(_sz)]),
+    "dxrv_fetch_full_grid": (_int, [_vp, _vp, _sz]),
+    "dxrv_share_grid_target": (_int, [_vp, _vp, _u32, _u32, _u32]),
 }
 
 _lib = None

@@ -13,120 +13,10 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "../../include/dxrv.h"
-#include "kernels.h"
-
-namespace dxrv
-{
-std::string& globalError();  // obj_capi.cpp
-}
-
-using namespace dxrv;
-
-struct dxrv_ctx
-{
-    int device = 0;
-    int smCount = 148;
-    cudaStream_t ownStream = nullptr;
-    SideStream side{};               // fork/join partner of `stream` inside a build
-    cudaStream_t stream = nullptr;
-    std::string err;
-
-    // mesh (either borrowed device pointers or owned staging copies)
-    uint8_t* vertsOwned = nullptr; size_t vertsCap = 0;
-    uint32_t* idxOwned = nullptr;  size_t idxCap = 0;
-    MeshView mesh{};
-    bool haveBvh = false;
-
-    // LBVH
-    uint32_t *keysA = nullptr, *keysB = nullptr, *valsA = nullptr, *valsB = nullptr;
-    BvhNode* nodes = nullptr;
-    Tri48* tris = nullptr;
-    float4* pyramid = nullptr;          // leaf boxes + 16:1 summary levels
-    uint32_t* refitScratch = nullptr; size_t refitCap = 0;   // parents + arrival flags (large meshes only)
-    void* sortTemp = nullptr; size_t sortTempCap = 0;
-    size_t capTris = 0;
-
-    // small device scalars: [0..3] bound, [4..9] root box, then counters
-    float* dBound = nullptr;
-    float* dRootBox = nullptr;
-    float* dPartials = nullptr;
-    float* dCentres = nullptr;          // voxel-centre table of the current N (MODE_SHADER)
-    uint32_t* dCounter = nullptr;
-    uint32_t* dErr = nullptr;
-    unsigned long long* dCrossings = nullptr;
-    unsigned long long* dCount = nullptr;
-    void* dSmall = nullptr;
-
-    // grid
-    uint32_t* gridOwned = nullptr; size_t gridCap = 0;
-    uint32_t* gridTarget = nullptr; size_t gridTargetBytes = 0;
-    uint32_t* texels = nullptr; size_t texCap = 0;
-    uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
-    uint32_t* mips = nullptr; size_t mipCap = 0;      // occupancy pyramid levels 1.. (concatenated)
-    uint32_t mipLevels = 0;                            // levels incl. level 0; 0 = not built for the current grid
-    uint32_t* walkBuf = nullptr; size_t walkCap = 0, walkZeroed = 0;  // MODE_PARITY candidate lists + split-tile scratch
-    uint8_t* binsBuf = nullptr; size_t binsCap = 0;                   // MODE_SHADER direction bins (shader_bins.cu)
-    ShaderBinsSizes binsSizes{};
-    bool binsValid = false;                                            // built for the current acceleration structure
-    uint32_t N = 0, z0 = 0, z1 = 0, mode = 0;
-    bool haveGrid = false, haveTexels = false;
-
-    // CUDA graphs: the kernel sequence of a build / voxelize call is captured once per distinct
-    // parameter set and replayed afterwards (the per-launch gaps matter at 100 k triangles)
-    struct GraphEntry { std::vector<uint8_t> key; cudaGraphExec_t exec = nullptr; uint64_t launches = 0, lastUse = 0; };
-    std::vector<GraphEntry> graphs;
-    uint64_t graphClock = 0;
-    bool useGraphs = true;
-
-    cudaEvent_t copyDone = nullptr;
-    cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};  // MODE_PARITY kernel timing (dxrv_set_profiling)
-    bool profiling = false, profValid = false;
-    uint64_t launches = 0;
-};
+#include "ctx.h"
 
 namespace
 {
-int fail(dxrv_ctx* c, int code, const std::string& msg)
-{
-    if (c) c->err = msg; else globalError() = msg;
-    return code;
-}
-
-int cudaFail(dxrv_ctx* c, cudaError_t e, const char* what)
-{
-    char buf[256];
-    std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
-    cudaGetLastError();  // clear the non-sticky error state
-    return fail(c, e == cudaErrorMemoryAllocation ? DXRV_ERR_OOM : DXRV_ERR_CUDA, buf);
-}
-
-#define DXRV_CUDA(call)                                                   \
-    do {                                                                  \
-        cudaError_t e_ = (call);                                          \
-        if (e_ != cudaSuccess) return cudaFail(ctx, e_, #call);           \
-    } while (0)
-
-struct DeviceGuard
-{
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-template <typename T>
-cudaError_t ensure(T*& p, size_t& cap, size_t need)
-{
-    if (need <= cap && p) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    const size_t grow = need + need / 8;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), grow ? grow : 16);
-    if (e == cudaSuccess) cap = grow ? grow : 16;
-    return e;
-}
-
-size_t slabWords(uint32_t N, uint32_t z0, uint32_t z1) { return (size_t)(z1 - z0) * N * ((N + 31) / 32); }
-
 int checkDeviceError(dxrv_ctx* ctx)
 {
     uint32_t e = 0;
@@ -281,6 +171,8 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     keyPush(key, ctx->keysA); keyPush(key, ctx->keysB); keyPush(key, ctx->valsA); keyPush(key, ctx->valsB);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp); keyPush(key, ctx->refitScratch);
     const int rc = runCaptured(ctx, key, [&]() {
+        const bool prof = ctx->profiling;   // (runCaptured launches directly, without a graph, while profiling)
+        if (prof) cudaEventRecord(ctx->profBuild[0], s);
         if (haveBound) { launchSetBound(s, bnd[0], bnd[1], bnd[2], bnd[3], ctx->dBound); }
         else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
         ctx->launches += 1;
@@ -289,10 +181,13 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
             uint32_t* hist = sortClearTemp(s, ctx->sortTemp, T);
             launchMorton(s, m, ctx->dBound, k0, v0, keyShift, numPasses, hist, ctx->dErr);
             ctx->launches += 1;
+            if (prof) cudaEventRecord(ctx->profBuild[1], s);
             ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, k0, v0, k1, v1, T, numPasses, true, nullptr);
+            if (prof) cudaEventRecord(ctx->profBuild[2], s);
             ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, &ctx->side, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
                                                                 ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr);
         }
+        if (prof) { cudaEventRecord(ctx->profBuild[3], s); ctx->profBuildValid = T > 0; }
     });
     if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
@@ -312,6 +207,11 @@ int validateMeshArgs(dxrv_ctx* ctx, const void* v, uint32_t numVerts, uint32_t s
     return DXRV_OK;
 }
 }  // namespace
+
+namespace dxrv
+{
+int buildContextMesh(dxrv_ctx* ctx, const float bound[4]) { return buildOnDevice(ctx, bound); }
+}  // namespace dxrv
 
 extern "C" {
 
@@ -372,13 +272,15 @@ void dxrv_destroy(dxrv_ctx* ctx)
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
+    commRelease(ctx);
+    void* ptrs[] = {ctx->gridFull, ctx->dSlabs, ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
                     ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips,
                     ctx->binsBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     for (cudaEvent_t e : ctx->prof) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->profBuild) if (e) cudaEventDestroy(e);
     if (ctx->side.fork) cudaEventDestroy(ctx->side.fork);
     if (ctx->side.join) cudaEventDestroy(ctx->side.join);
     if (ctx->side.stream) cudaStreamDestroy(ctx->side.stream);
@@ -403,10 +305,15 @@ int dxrv_set_profiling(dxrv_ctx* ctx, int enable)
     if (!ctx) return DXRV_ERR_INVALID_ARG;
     DeviceGuard g(ctx->device);
     if (enable)
+    {
         for (cudaEvent_t& e : ctx->prof)
             if (!e) DXRV_CUDA(cudaEventCreate(&e));
+        for (cudaEvent_t& e : ctx->profBuild)
+            if (!e) DXRV_CUDA(cudaEventCreate(&e));
+    }
     ctx->profiling = enable != 0;
     ctx->profValid = false;
+    ctx->profBuildValid = false;
     return DXRV_OK;
 }
 
@@ -473,7 +380,14 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     if (mode & ~(uint32_t)(DXRV_MODE_MASK | DXRV_EMIT_TEXELS)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: unknown mode flags");
     if (wantTexels && algo != DXRV_MODE_SHADER) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: DXRV_EMIT_TEXELS needs DXRV_MODE_SHADER");
     if (N == 0 || N > 8192) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: N must be in [1, 8192]");
-    if (slabBegin >= slabEnd || slabEnd > N) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: need 0 <= slabBegin < slabEnd <= N");
+    if (slabBegin > slabEnd || slabEnd > N) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: need 0 <= slabBegin <= slabEnd <= N");
+    if (slabBegin == slabEnd)
+    {
+        // an empty slab (more GPUs than layers): nothing to compute, but the context takes part in a later gather
+        ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
+        ctx->haveGrid = true; ctx->haveTexels = false; ctx->mipLevels = 0;
+        return DXRV_OK;
+    }
     if (algo == DXRV_MODE_SHADER && ctx->mesh.stride < 24)
         return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: MODE_SHADER needs vertex normals (strideBytes >= 24)");
     DeviceGuard g(ctx->device);
@@ -740,6 +654,17 @@ int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value)
         float ms = 0.0f;
         const int a = what == DXRV_INFO_LAST_WALK_NS ? 0 : 1;
         DXRV_CUDA(cudaEventElapsedTime(&ms, ctx->prof[a], ctx->prof[a + 1]));
+        *value = (uint64_t)(ms * 1e6f + 0.5f);
+        return DXRV_OK;
+    }
+    case DXRV_INFO_LAST_BUILD_NS:
+    case DXRV_INFO_LAST_SORT_NS:
+    {
+        if (!ctx->profBuildValid) return fail(ctx, DXRV_ERR_NO_BVH, "dxrv_get_info: enable dxrv_set_profiling and build first");
+        DXRV_CUDA(cudaEventSynchronize(ctx->profBuild[3]));
+        float ms = 0.0f;
+        if (what == DXRV_INFO_LAST_BUILD_NS) DXRV_CUDA(cudaEventElapsedTime(&ms, ctx->profBuild[0], ctx->profBuild[3]));
+        else DXRV_CUDA(cudaEventElapsedTime(&ms, ctx->profBuild[1], ctx->profBuild[2]));
         *value = (uint64_t)(ms * 1e6f + 0.5f);
         return DXRV_OK;
     }

@@ -65,16 +65,35 @@ bool DXRVoxelizer::BuildAccelerationStructures()
 {
     if (!m_ctx || !m_vertices) { m_error = "Init has not been called"; return false; }
     // bound = NULL: extracted on the device as Voxelizer.cpp:52-57 does on the host
-    if (dxrv_build_bvh(m_ctx, m_vertices, m_numVerts, m_stride, m_indices, m_numIndices, nullptr) != DXRV_OK)
-        return fail("dxrv_build_bvh");
-    // every further GPU builds the identical tree from the same host arrays (calls are asynchronous:
-    // the builds run concurrently)
-    for (dxrv_ctx* c : m_more)
-        if (dxrv_build_bvh(c, m_vertices, m_numVerts, m_stride, m_indices, m_numIndices, nullptr) != DXRV_OK)
+    if (m_more.empty())
+    {
+        if (dxrv_build_bvh(m_ctx, m_vertices, m_numVerts, m_stride, m_indices, m_numIndices, nullptr) != DXRV_OK)
+            return fail("dxrv_build_bvh");
+    }
+    else
+    {
+        // One upload to the first GPU, NCCL broadcast to the others over NVLink (one group: this thread drives all
+        // communicators), then every GPU builds the identical tree -- the builds are asynchronous and run concurrently.
+        if (!m_commReady)
         {
-            m_error = std::string("dxrv_build_bvh: ") + dxrv_last_error(c);
-            return false;
+            std::vector<dxrv_ctx*> all{m_ctx};
+            all.insert(all.end(), m_more.begin(), m_more.end());
+            if (dxrv_comm_init_all(all.data(), static_cast<int>(all.size())) != DXRV_OK) return fail("dxrv_comm_init_all");
+            m_commReady = true;
         }
+        if (dxrv_group_begin() != DXRV_OK) return fail("dxrv_group_begin");
+        bool ok = dxrv_bcast_mesh(m_ctx, m_vertices, m_numVerts, m_stride, m_indices, m_numIndices, 0) == DXRV_OK;
+        for (dxrv_ctx* c : m_more)
+            ok = ok && dxrv_bcast_mesh(c, nullptr, m_numVerts, m_stride, nullptr, m_numIndices, 0) == DXRV_OK;
+        if (dxrv_group_end() != DXRV_OK || !ok) return fail("dxrv_bcast_mesh");
+        if (dxrv_build_bvh_replicated(m_ctx, nullptr) != DXRV_OK) return fail("dxrv_build_bvh_replicated");
+        for (dxrv_ctx* c : m_more)
+            if (dxrv_build_bvh_replicated(c, nullptr) != DXRV_OK)
+            {
+                m_error = std::string("dxrv_build_bvh_replicated: ") + dxrv_last_error(c);
+                return false;
+            }
+    }
     if (dxrv_get_bound(m_ctx, m_bound) != DXRV_OK) return fail("dxrv_get_bound");
     return true;
 }
@@ -147,12 +166,28 @@ bool DXRVoxelizer::Voxelize()
     m_gridFetched = false;
     const int k = 1 + static_cast<int>(m_more.size());
     computeSlabs(m_slabBegin, end, k);
+    // several GPUs, whole grid: every GPU's fill kernel stores its slab straight into the first GPU's full grid
+    // (peer access over NVLink), so Grid() is ONE device-to-host copy; slab offsets must be 16-byte aligned
+    m_fused = k > 1 && m_slabBegin == 0 && end == m_gridSize;
+    const size_t layerBytes = static_cast<size_t>(m_gridSize) * ((m_gridSize + 31) / 32) * sizeof(uint32_t);
+    for (int g = 0; g < k && m_fused; ++g)
+    {
+        uint32_t z0, z1;
+        slabOf(g, z0, z1);
+        if (z1 > z0 && (layerBytes * z0) % 16) m_fused = false;
+    }
     for (int g = 0; g < k; ++g)
     {
         uint32_t z0, z1;
         slabOf(g, z0, z1);
         if (z0 == z1) continue;
         dxrv_ctx* c = g ? m_more[g - 1] : m_ctx;
+        if (m_fused && dxrv_share_grid_target(c, m_ctx, m_gridSize, z0, z1) != DXRV_OK)
+        {
+            m_error = std::string("dxrv_share_grid_target: ") + dxrv_last_error(c);
+            return false;
+        }
+        if (!m_fused && k > 1) dxrv_set_grid_target(c, nullptr, 0);
         if (dxrv_voxelize(c, m_gridSize, m_mode, z0, z1) != DXRV_OK)
         {
             m_error = std::string("dxrv_voxelize: ") + dxrv_last_error(c);
@@ -176,6 +211,15 @@ const uint32_t* DXRVoxelizer::Grid()
         m_grid.resize(GridWords());
         const size_t wordsPerLayer = static_cast<size_t>(m_gridSize) * ((m_gridSize + 31) / 32);
         const int k = 1 + static_cast<int>(m_more.size());
+        if (m_fused)
+        {
+            for (dxrv_ctx* c : m_more)
+                if (dxrv_synchronize(c) != DXRV_OK) { m_error = std::string("dxrv_synchronize: ") + dxrv_last_error(c); return nullptr; }
+            if (dxrv_synchronize(m_ctx) != DXRV_OK) { fail("dxrv_synchronize"); return nullptr; }
+            if (dxrv_fetch_full_grid(m_ctx, m_grid.data(), m_grid.size() * sizeof(uint32_t)) != DXRV_OK) { fail("dxrv_fetch_full_grid"); return nullptr; }
+            m_gridFetched = true;
+            return m_grid.data();
+        }
         for (int g = 0; g < k; ++g)   // gather: every GPU's slab lands at its offset of the host grid
         {
             uint32_t z0, z1;

@@ -88,5 +88,7 @@ private:
     float m_posScale[4] = {0, 0, 0, 1};  // DXRVoxelizer.cpp:37
     std::vector<uint32_t> m_grid;
     bool m_gridFetched = false;
+    bool m_commReady = false;   // NCCL communicators of the k contexts exist (dxrv_comm_init_all)
+    bool m_fused = false;       // the last Voxelize() stored every slab into the first GPU's full grid
     std::string m_error;
 };

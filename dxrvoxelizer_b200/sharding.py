@@ -5,7 +5,7 @@ The voxelization path shards without any collective in the data path (SURVEY.md 
 run along x, a z-slab owns whole rays and its output is one contiguous byte range of the grid.  The
 mesh (a few MB) is replicated once; every rank builds the identical LBVH (the radix sort is stable
 and deterministic) and fills its own slab.  Slabs are gathered only when a full grid is requested:
-  * gather="nccl"  all_gather_into_tensor of the device slabs (equal slabs) / all_gather (ragged);
+  * gather()       dxrv_gather_grid inside the library: ncclSend/Recv to a root, or one ncclBroadcast per slab;
   * gather="peer"  the owner exports its full-size grid through CUDA IPC, every rank's fill kernel
                    then stores straight into the owner's memory over NVLink (the gather is fused
                    into the 128-bit stores of k_trace_fill_columns; no collective at all).
@@ -38,6 +38,9 @@ def balanced_slabs(mesh, N, world, bound=None, compute_weight=1.2):
         raise ValueError("bad world/N")
     if world == 1:
         return [(0, N)]
+    if N <= world:
+        # more ranks than layers: one layer each, the rest get empty slabs (dxrv_voxelize accepts them)
+        return [(min(r, N), min(r + 1, N)) for r in range(world)]
     pos = mesh.vertices[:, :3].astype(np.float64)
     if bound is None:
         mn, mx = pos.min(0), pos.max(0)
@@ -109,7 +112,10 @@ def gather_slabs(local_slab, N, world, group=None):
 
 
 class ShardedVoxelizer:
-    """One rank's share of a z-slab sharded voxelization (GPU path; needs NCCL + CUDA)."""
+    """One rank's share of a z-slab sharded voxelization: one process per GPU.  Everything on the data path goes
+    through the C ABI (dxrv_comm_init / dxrv_bcast_mesh / dxrv_build_bvh_replicated / dxrv_voxelize /
+    dxrv_gather_grid): NCCL lives inside libdxrv.so.  torch.distributed is used once, to ship the 128-byte NCCL
+    unique id (any out-of-band channel would do), and by nothing else here."""
 
     def __init__(self, local_device, group=None):
         import torch
@@ -121,7 +127,11 @@ class ShardedVoxelizer:
         self.vox = Voxelizer(local_device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.vox.set_stream(self.stream.cuda_stream)
+        uid = [Voxelizer.comm_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, group=group)
+        self.vox.comm_init(uid[0], self.rank, self.world)
         self._peer = None
+        self.slabs = None
 
     def close(self):
         if self._peer is not None and self._peer[0] is not None and self.rank != self._peer[2]:
@@ -129,44 +139,69 @@ class ShardedVoxelizer:
         self.vox.close()
 
     def replicate_and_build(self, mesh, src=0, bound=None):
-        """Broadcast the mesh over NCCL and build the LBVH from the device-resident copy."""
-        m, vb, ib = broadcast_mesh(mesh, src, self.device, self.group)
-        self.torch.cuda.synchronize(self.device)
-        self._vb, self._ib, self.mesh = vb, ib, m
-        self.vox.build_bvh_device(vb.data_ptr(), m.num_vertices, m.stride, ib.data_ptr(), m.indices.size, bound)
-        return m
+        """Broadcast rank src's host mesh over NCCL (inside the library) and build the LBVH on every rank.
+        Returns (num_vertices, stride, num_indices)."""
+        hdr = np.zeros(3, np.uint32)
+        if self.rank == src:
+            hdr[:] = (mesh.num_vertices, mesh.stride, mesh.indices.size)
+        hdr = self.vox.bcast_u32(hdr, src)
+        self.vox.bcast_mesh(mesh if self.rank == src else None, int(hdr[0]), int(hdr[1]), int(hdr[2]), src)
+        self.vox.build_bvh_replicated(bound)
+        self.mesh = mesh if self.rank == src else None
+        self._src = src
+        return tuple(int(x) for x in hdr)
 
-    def voxelize(self, N, mode=L.MODE_PARITY):
-        z0, z1 = slab_range(self.rank, self.world, N)
-        self.N, self.z0, self.z1 = N, z0, z1
-        self.vox.voxelize(N, mode, z0, z1)
+    def plan_slabs(self, N, balanced=True):
+        """[(z0, z1)] * world, identical on every rank: cost-balanced cuts computed by the rank that holds the host
+        mesh and broadcast as world + 1 words (equal slabs when balanced=False or no host mesh exists)."""
+        cuts = np.zeros(self.world + 1, np.uint32)
+        if self.rank == getattr(self, "_src", 0):
+            if balanced and getattr(self, "mesh", None) is not None:
+                sl = balanced_slabs(self.mesh, N, self.world)
+            else:
+                sl = [slab_range(r, self.world, N) for r in range(self.world)]
+            cuts[:] = [sl[0][0]] + [b for _, b in sl]
+        cuts = self.vox.bcast_u32(cuts, getattr(self, "_src", 0))
+        self.slabs = [(int(cuts[r]), int(cuts[r + 1])) for r in range(self.world)]
+        return self.slabs
+
+    def voxelize(self, N, mode=L.MODE_PARITY, balanced=False):
+        if self.slabs is None or getattr(self, "N", None) != N or getattr(self, "_balanced", None) != balanced:
+            self.plan_slabs(N, balanced)
+            self._balanced = balanced
+        self.N = N
+        self.z0, self.z1 = self.slabs[self.rank]
+        self.vox.voxelize(N, mode, self.z0, self.z1)     # (an empty slab -- more ranks than layers -- computes nothing)
 
     def local_slab(self):
         return self.vox.fetch_bits()
 
+    def gather(self, root=-1):
+        """dxrv_gather_grid: the full grid on `root` (ncclSend/Recv) or on every rank (root < 0); returns it as a
+        numpy array on the ranks that hold it, None elsewhere."""
+        self.vox.gather_grid(root)
+        if root < 0 or root == self.rank:
+            return self.vox.fetch_full_grid(self.N)
+        return None
+
     def gather_nccl(self):
         """Full grid on every rank as a device tensor (int32 view of the uint32 words)."""
-        torch, dist = self.torch, self.dist
-        N, P = self.N, (self.N + 31) // 32
+        self.vox.gather_grid(-1)
+        ptr, nbytes = self.vox.full_grid_device()
         self.vox.synchronize()
-        ptr, nbytes = self.vox.grid_device()
-        sizes = [slab_words(N, *slab_range(r, self.world, N)) for r in range(self.world)]
-        biggest = max(sizes)
-        mine = torch.zeros(biggest, dtype=torch.int32, device=self.device)
-        # wrap the context's grid without a copy through the CUDA array interface
-        view = torch.as_tensor(_DevicePtr(ptr, sizes[self.rank]), device=self.device)
-        mine[: sizes[self.rank]].copy_(view)
-        gathered = torch.empty(biggest * self.world, dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        if len(set(sizes)) == 1:
-            full = gathered
-        else:  # ragged slabs were padded to the largest one
-            full = torch.cat([gathered[r * biggest: r * biggest + sizes[r]] for r in range(self.world)])
-        return full.view(N, N, P)
+        t = self.torch.as_tensor(_DevicePtr(ptr, nbytes // 4), device=self.device)
+        return t.view(self.N, self.N, (self.N + 31) // 32)
 
     def setup_peer_gather(self, N, owner=0):
-        """Fused gather: rank `owner` exports its full-size grid (CUDA IPC); every rank aims its fill
-        kernel at its slab inside that allocation.  Call once per (N, owner); then voxelize()."""
+        """Fused gather across processes: rank `owner` exports its full-size grid (CUDA IPC); every rank aims its fill
+        kernel at its slab inside that allocation (the 128-bit stores go over NVLink).  Returns False -- and changes
+        nothing -- when some slab's byte offset is not 16-byte aligned (odd N with an odd cut: N = 33, 63, ...): use
+        gather() then."""
+        self.plan_slabs(N, balanced=False)
+        self._balanced = False
+        self.N = N
+        if any((slab_words(N, 0, a) * 4) % 16 for a, b in self.slabs if b > a):
+            return False
         full_bytes = slab_words(N, 0, N) * 4
         handle = [None]
         if self.rank == owner:
@@ -177,11 +212,11 @@ class ShardedVoxelizer:
         self.dist.broadcast_object_list(handle, src=owner, group=self.group)
         if self.rank != owner:
             base = self.vox.ipc_open(handle[0])
-        z0, z1 = slab_range(self.rank, self.world, N)
-        off = slab_words(N, 0, z0) * 4
-        self.vox.set_grid_target(base + off, slab_words(N, z0, z1) * 4)
+        z0, z1 = self.slabs[self.rank]
+        if z1 > z0:
+            self.vox.set_grid_target(base + slab_words(N, 0, z0) * 4, slab_words(N, z0, z1) * 4)
         self._peer = (base if self.rank != owner else None, full_bytes, owner, base)
-        return base
+        return True
 
 
 class _DevicePtr:

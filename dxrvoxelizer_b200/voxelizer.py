@@ -226,6 +226,54 @@ class Voxelizer:
         self._check(self._lib.dxrv_debug_sort_pairs(self._h, k.ctypes.data, v.ctypes.data, k.size))
         return k, v
 
+    # -- multi-GPU (include/dxrv.h "multi-GPU" section; NCCL inside the library) -----------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = (ctypes.c_ubyte * 128)()
+        rc = L.lib().dxrv_comm_get_unique_id(buf)
+        if rc != L.OK:
+            raise L.DxrvError(rc, L.lib().dxrv_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.dxrv_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._check(self._lib.dxrv_comm_destroy(self._h))
+
+    def bcast_u32(self, values, root=0):
+        a = np.ascontiguousarray(values, dtype=np.uint32).copy()
+        self._check(self._lib.dxrv_bcast_u32(self._h, a.ctypes.data, a.size, root))
+        return a
+
+    def bcast_mesh(self, mesh, num_verts, stride, num_indices, root=0):
+        """mesh: the host Mesh on the root, None elsewhere; the three sizes on every rank."""
+        v = mesh.vertex_bytes.ctypes.data if mesh is not None else None
+        i = mesh.indices.ctypes.data if mesh is not None else None
+        self._mesh = mesh
+        self._check(self._lib.dxrv_bcast_mesh(self._h, v, num_verts, stride, i, num_indices, root))
+
+    def build_bvh_replicated(self, bound=None):
+        b = None if bound is None else np.ascontiguousarray(bound, dtype=np.float32)
+        self._check(self._lib.dxrv_build_bvh_replicated(self._h, None if b is None else b.ctypes.data))
+
+    def gather_grid(self, root=-1):
+        self._check(self._lib.dxrv_gather_grid(self._h, root))
+
+    def full_grid_device(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self._lib.dxrv_full_grid_device(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def fetch_full_grid(self, N):
+        out = np.empty((N, N, (N + 31) // 32), np.uint32)
+        self._check(self._lib.dxrv_fetch_full_grid(self._h, out.ctypes.data, out.nbytes))
+        return out
+
+    def share_grid_target(self, owner, N, z0, z1):
+        self._check(self._lib.dxrv_share_grid_target(self._h, owner._h, N, z0, z1))
+
     def ipc_export_grid(self, full_bytes):
         handle = (ctypes.c_ubyte * 64)()
         p = ctypes.c_void_p()

@@ -113,8 +113,9 @@ DXRV_API int dxrv_get_bound(dxrv_ctx* ctx, float bound[4]);
 /* ---- voxelization ----------------------------------------------------------------------
  * Replaces Voxelizer::voxelize (Content/Voxelizer.cpp:351-369): DispatchRays(N, N*N, 1) of
  * raygenMain/closestHitMain/missMain.  N replaces the GRID_SIZE macro (Voxelizer.cpp:8).
- * Computes grid layers z in [slabBegin, slabEnd) (0 <= slabBegin < slabEnd <= N).  Every
- * word of the slab is written exactly once; no clear is needed. */
+ * Computes grid layers z in [slabBegin, slabEnd) (0 <= slabBegin <= slabEnd <= N; an empty slab
+ * computes nothing and only lets the context take part in dxrv_gather_grid).  Every word of the
+ * slab is written exactly once; no clear is needed. */
 DXRV_API int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin,
                            uint32_t slabEnd);
 /* Copy the slab computed by the last dxrv_voxelize to host memory (synchronises).
@@ -161,10 +162,13 @@ enum dxrv_info
     DXRV_INFO_CROSSINGS = 3,       /* MODE_PARITY: surface crossings found by the last voxelize */
     DXRV_INFO_SM_COUNT = 4,
     DXRV_INFO_LAST_WALK_NS = 5,    /* device time of the last k_walk_columns (needs dxrv_set_profiling) */
-    DXRV_INFO_LAST_FILL_NS = 6     /* device time of the last k_trace_fill_columns                       */
+    DXRV_INFO_LAST_FILL_NS = 6,    /* device time of the last k_trace_fill_columns                       */
+    DXRV_INFO_LAST_BUILD_NS = 7,   /* device time of the last acceleration-structure build (needs dxrv_set_profiling) */
+    DXRV_INFO_LAST_SORT_NS = 8     /* ... of its onesweep radix-sort passes alone                        */
 };
 DXRV_API int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value);
-/* Record CUDA events around the MODE_PARITY kernels of every dxrv_voxelize (for roofline reporting). */
+/* Record CUDA events around the MODE_PARITY kernels of every dxrv_voxelize and around the phases of every build
+ * (for roofline reporting; builds then run outside their CUDA graph). */
 DXRV_API int dxrv_set_profiling(dxrv_ctx* ctx, int enable);
 
 /* Read back an internal device buffer for tests (synchronises).  `what`: */
@@ -212,6 +216,43 @@ DXRV_API void dxrv_host_free(void* p);
 DXRV_API int dxrv_ipc_export_grid(dxrv_ctx* ctx, size_t fullBytes, void* handle64, void** d_ptr);
 DXRV_API int dxrv_ipc_open(dxrv_ctx* ctx, const void* handle64, void** d_ptr);
 DXRV_API int dxrv_ipc_close(dxrv_ctx* ctx, void* d_ptr);
+
+/* ---- multi-GPU: z-slab sharding over the GPUs of one box -----------------------------------------------------
+ * New relative to the reference, which is single-GPU (XUSG/RayTracing/XUSGRayTracing.h:386 SetNodeMask is never
+ * called); it replaces nothing there and extends the lower surface XUSGRayTracing.h:170-180,212-230,325-330
+ * (BottomLevelAS::Build / TopLevelAS::Build / DispatchRays) to several devices: the mesh is replicated by NCCL
+ * broadcast over NVLink, every GPU builds the identical LBVH (the sort is stable, the boxes are exact unions) and
+ * fills its own z-slab (dxrv_voxelize slab arguments); slabs are gathered only when a full grid is requested.
+ * NCCL is loaded with dlopen("libnccl.so.2") by the first call below; DXRV_ERR_UNSUPPORTED if it is not installed.
+ * One process per GPU: rank 0 calls dxrv_comm_get_unique_id and ships the 128 bytes to the other ranks (any
+ * out-of-band channel), every rank calls dxrv_comm_init.  One process, several GPUs: dxrv_comm_init_all, and
+ * collective calls of several contexts from one thread go between dxrv_group_begin / dxrv_group_end. */
+#define DXRV_COMM_ID_BYTES 128
+DXRV_API int dxrv_comm_get_unique_id(void* id128);
+DXRV_API int dxrv_comm_init(dxrv_ctx* ctx, const void* id128, int rank, int world);
+DXRV_API int dxrv_comm_init_all(dxrv_ctx** ctxs, int count);
+DXRV_API int dxrv_comm_destroy(dxrv_ctx* ctx);
+DXRV_API int dxrv_group_begin(void);
+DXRV_API int dxrv_group_end(void);
+/* Broadcast count (<= 64) words from root's host array into every rank's (blocking; carries the mesh sizes). */
+DXRV_API int dxrv_bcast_u32(dxrv_ctx* ctx, uint32_t* values, uint32_t count, int root);
+/* Replicate root's mesh into context-owned device buffers of every rank: H2D on the root (host arrays borrowed
+ * for the call), ncclBroadcast of vertices and indices.  numVerts / strideBytes / numIndices must be passed by
+ * every rank; vertices / indices are read on the root only.  Collective, stream-ordered. */
+DXRV_API int dxrv_bcast_mesh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts, uint32_t strideBytes,
+                             const uint32_t* indices, uint32_t numIndices, int root);
+/* dxrv_build_bvh on the mesh the last dxrv_bcast_mesh left in the context (Voxelizer.cpp:264-326 on every GPU). */
+DXRV_API int dxrv_build_bvh_replicated(dxrv_ctx* ctx, const float bound[4]);
+/* Gather the z-slabs of every rank's last dxrv_voxelize (same N, disjoint slabs) into the full N^3 BITS grid, in
+ * device memory owned by the context, on `root` (ncclSend/ncclRecv) or on every rank when root < 0 (one
+ * ncclBroadcast per slab).  Layers no rank computed are zero.  Collective; synchronises once (slab table). */
+DXRV_API int dxrv_gather_grid(dxrv_ctx* ctx, int root);
+DXRV_API int dxrv_full_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);
+DXRV_API int dxrv_fetch_full_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes);
+/* Fused gather for contexts of ONE process: make ctx's next dxrv_voxelize(N, mode, slabBegin, slabEnd) store its
+ * slab straight into `owner`'s full grid (peer access over NVLink is enabled; owner may be ctx itself), so the
+ * full grid is complete on the owner when every context's stream has drained -- no collective, one D2H. */
+DXRV_API int dxrv_share_grid_target(dxrv_ctx* ctx, dxrv_ctx* owner, uint32_t N, uint32_t slabBegin, uint32_t slabEnd);
 
 #ifdef __cplusplus
 }

@@ -19,30 +19,47 @@ import oracle
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-sv = ShardedVoxelizer(rank)
+sv = ShardedVoxelizer(rank)                      # dxrv_comm_init inside
 mesh = d.load_obj(d.asset_path("bunny.obj")) if rank == 0 else None
-m = sv.replicate_and_build(mesh)
+nv, stride, ni = sv.replicate_and_build(mesh)    # dxrv_bcast_u32 + dxrv_bcast_mesh + dxrv_build_bvh_replicated
+ref_mesh = d.load_obj(d.asset_path("bunny.obj"))
+assert (nv, stride, ni) == (ref_mesh.num_vertices, ref_mesh.stride, ref_mesh.indices.size)
+for N, mode, balanced in ((96, d.MODE_PARITY, False), (96, d.MODE_PARITY, True), (100, d.MODE_SHADER, True), (33, d.MODE_PARITY, False)):
+    want = oracle.voxelize(ref_mesh.vertices, ref_mesh.indices, N, mode)["bits"]
+    sv.voxelize(N, mode, balanced=balanced)
+    full = sv.gather(-1)                         # dxrv_gather_grid: every rank gets the grid (one ncclBroadcast per slab)
+    assert np.array_equal(full, want), ("all-gather", N, mode, balanced)
+    sv.voxelize(N, mode, balanced=balanced)
+    full = sv.gather(world - 1)                  # ncclSend / ncclRecv to the last rank
+    assert (full is None) == (rank != world - 1)
+    if full is not None:
+        assert np.array_equal(full, want), ("gather to root", N, mode, balanced)
+    t = sv.gather_nccl()
+    assert np.array_equal(t.cpu().numpy().view(np.uint32), want), ("device view", N)
+# more ranks than layers: ranks beyond N get empty slabs and still take part in the gather
+want = oracle.voxelize(ref_mesh.vertices, ref_mesh.indices, 1, 1)["bits"]
+sv.slabs = None
+sv.voxelize(1, d.MODE_PARITY, balanced=True)
+assert np.array_equal(sv.gather(-1), want)
+# fused gather across processes: every rank's fill kernel stores straight into rank 0's grid over NVLink
 N = 96
-want = oracle.voxelize(m.vertices, m.indices, N, 1)["bits"]
-sv.voxelize(N)
-full = sv.gather_nccl().cpu().numpy().view(np.uint32)
-assert np.array_equal(full, want), "nccl gather"
-# fused gather: every rank's fill kernel stores straight into rank 0's grid over NVLink
-sv.setup_peer_gather(N, owner=0)
+want = oracle.voxelize(ref_mesh.vertices, ref_mesh.indices, N, 1)["bits"]
+assert sv.setup_peer_gather(N, owner=0)
 dist.barrier()
-sv.voxelize(N)
+sv.vox.voxelize(N, d.MODE_PARITY, *sv.slabs[rank])
 sv.vox.synchronize()
 dist.barrier()
 if rank == 0:
-    sv.vox._shape = (N, N, (N + 31) // 32)
-    got = np.empty(sv.vox._shape, np.uint32)
-    import ctypes
     torch.cuda.synchronize()
     base = sv._peer[3]
     t = torch.as_tensor(d.sharding._DevicePtr(base, N * N * ((N + 31) // 32)), device="cuda:0")
     got = t.cpu().numpy().view(np.uint32).reshape(N, N, -1)
     assert np.array_equal(got, want), "peer gather"
 dist.barrier()
+sv2 = ShardedVoxelizer(rank)
+sv2.replicate_and_build(mesh)
+assert sv2.setup_peer_gather(33, owner=0) is False      # odd pitch + odd cut: unaligned slab offset -> caller falls back to gather()
+sv2.close()
 sv.close()
 dist.destroy_process_group()
 print("rank", rank, "ok")
@@ -80,3 +97,40 @@ def test_cli_two_gpus_matches_one(tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(np.fromfile(out, np.uint32))
     assert outs[0].size == 256 * 256 * 8 and np.array_equal(outs[0], outs[1])
+
+
+def test_c_abi_one_process_two_gpus(oracle_mod=None):
+    """The multi-GPU entry points for ONE process driving several GPUs, through ctypes: dxrv_comm_init_all, grouped
+    dxrv_bcast_mesh, dxrv_build_bvh_replicated, slabs, grouped dxrv_gather_grid; then the fused form
+    (dxrv_share_grid_target: the second GPU's fill kernel stores into the first GPU's grid over NVLink)."""
+    import ctypes
+    import numpy as np
+    import torch
+    import dxrvoxelizer_b200 as d
+    from dxrvoxelizer_b200 import _lib as L
+    import oracle
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    lib = L.lib()
+    a, b = d.Voxelizer(0), d.Voxelizer(1)
+    arr = (ctypes.c_void_p * 2)(a._h, b._h)
+    assert lib.dxrv_comm_init_all(arr, 2) == 0, lib.dxrv_last_error(a._h)
+    m = d.load_obj(d.asset_path("dragon.obj"))
+    assert lib.dxrv_group_begin() == 0
+    a.bcast_mesh(m, m.num_vertices, m.stride, m.indices.size, 0)
+    b.bcast_mesh(None, m.num_vertices, m.stride, m.indices.size, 0)
+    assert lib.dxrv_group_end() == 0
+    a.build_bvh_replicated(); b.build_bvh_replicated()
+    N = 128
+    want = oracle.voxelize(m.vertices, m.indices, N, 1)["bits"]
+    a.voxelize(N, d.MODE_PARITY, 0, 70); b.voxelize(N, d.MODE_PARITY, 70, N)
+    assert lib.dxrv_group_begin() == 0
+    a.gather_grid(0); b.gather_grid(0)
+    assert lib.dxrv_group_end() == 0
+    assert np.array_equal(a.fetch_full_grid(N), want)
+    # fused: both slabs land in a's full grid, no collective
+    a.share_grid_target(a, N, 0, 64); b.share_grid_target(a, N, 64, N)
+    a.voxelize(N, d.MODE_PARITY, 0, 64); b.voxelize(N, d.MODE_PARITY, 64, N)
+    b.synchronize(); a.synchronize()
+    assert np.array_equal(a.fetch_full_grid(N), want)
+    b.close(); a.close()

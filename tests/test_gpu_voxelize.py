@@ -111,7 +111,7 @@ def test_error_behaviour(vox, meshes_mod):
     with pytest.raises(d.DxrvError) as e:
         fresh.fetch_bits(np.empty((1, 1, 1), np.uint32))
     assert e.value.code == L.ERR_NO_GRID
-    for bad in ((0, 1, 0, 0), (64, 9, 0, 64), (64, 1, 10, 10), (64, 1, 0, 65), (64, L.MODE_PARITY | L.EMIT_TEXELS, 0, 64)):
+    for bad in ((0, 1, 0, 0), (64, 9, 0, 64), (64, 1, 11, 10), (64, 1, 0, 65), (64, L.MODE_PARITY | L.EMIT_TEXELS, 0, 64)):
         with pytest.raises(d.DxrvError) as e:
             fresh._check(fresh._lib.dxrv_voxelize(fresh._h, *bad))
         assert e.value.code == L.ERR_INVALID_ARG

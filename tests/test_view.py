@@ -72,3 +72,54 @@ def test_gpu_view_matches_oracle(vox, assets, oracle_mod, name, N):
     with pytest.raises(d.DxrvError):
         vox.voxelize(N, d.MODE_PARITY, 0, N // 2)
         vox.render_view(320, 180, s2l, eye, light)                 # needs the full grid
+
+
+# ---- the one artefact of the voxel stage the reference tree holds: its README screenshot -------------------------
+def _silhouette(rgb):
+    clear = np.array([0, 51, 102], np.float32)                    # CLEAR_COLOR (SharedConst.h:8) as UNORM8
+    return np.abs(rgb[..., :3].astype(np.float32) - clear).sum(-1) > 60
+
+
+def _iou(a, b):
+    return float((a & b).sum()) / float(max(1, (a | b).sum()))
+
+
+def _screenshot_ious(render, bound):
+    """IoU of the rendered silhouette with the reference screenshot (tests/golden/make_reference_screenshot.py),
+    under the reference's DEFAULT camera (DXRVoxelizer.cpp:222-234), for the grid as the current sources define it
+    and for its reflection in local x (same camera: reflecting the object = reflecting eye, light and ray origins)."""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_screenshot_bunny64.npz"))["rgb"]
+    want = _silhouette(ref)
+    s2l, eye, light = d.default_view(bound, 480, 270)
+    mirror = np.diag([-1.0, 1.0, 1.0, 1.0]).astype(np.float32)
+    flip = np.array([-1.0, 1.0, 1.0], np.float32)
+    as_is = _iou(_silhouette(render(s2l, eye, light)), want)
+    mirrored = _iou(_silhouette(render(s2l @ mirror, eye * flip, light * flip)), want)
+    return as_is, mirrored, float(want.mean())
+
+
+def test_oracle_grid_against_the_reference_screenshot(assets, oracle_mod):
+    """bunny, GRID_SIZE 64, MODE_SHADER (what the reference's window shows) through the oracle's viewer pass against
+    Doc/Images/SolidVoxelization.jpg.  Finding: the screenshot matches the silhouette to
+    IoU 0.99 -- volume, proportions, camera and viewer constants all agree -- but with the OBJECT REFLECTED IN LOCAL X
+    under the unchanged default camera; as the current sources define the grid (z flip in the loader,
+    XUSGObjLoader.cpp:198,227; x = launch index, hlsl:46-49; tex = (0.5,-0.5,0.5)*pos+0.5, PSRayCast.hlsl:137) the IoU
+    is 0.55.  The screenshot therefore predates the shipped loader/shader conventions (or was taken with another
+    asset orientation); it pins the shape, not the handedness."""
+    m = assets("bunny.obj")
+    bits = oracle_mod.voxelize(m.vertices, m.indices, 64, oracle_mod.MODE_SHADER)["bits"]
+    as_is, mirrored, cover = _screenshot_ious(lambda s, e, l: oracle_mod.render_view(bits, 64, 480, 270, s, e, l), oracle_mod.bound(m.vertices))
+    assert 0.15 < cover < 0.21                                     # the bunny covers ~18 % of the reference's frame
+    assert mirrored > 0.97, (as_is, mirrored)
+    assert as_is < mirrored
+
+
+@pytest.mark.gpu
+def test_gpu_grid_against_the_reference_screenshot(vox, assets):
+    """Same pin for the product path: dxrv_voxelize (MODE_SHADER, 64^3) + dxrv_render_view on the GPU."""
+    m = assets("bunny.obj")
+    vox.build_bvh(m)
+    vox.voxelize(64, d.MODE_SHADER)
+    as_is, mirrored, _ = _screenshot_ious(lambda s, e, l: vox.render_view(480, 270, s, e, l), vox.bound())
+    assert mirrored > 0.97, (as_is, mirrored)
