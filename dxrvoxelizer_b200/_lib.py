@@ -67,6 +67,7 @@ SIGNATURES = {
     "dxrv_bcast_mesh": (_int, [_vp, _vp, _u32, _u32, _vp, _u32, _int]),
     "dxrv_build_bvh_replicated": (_int, [_vp, _vp]),
     "dxrv_gather_grid": (_int, [_vp, _int]),
+    "dxrv_gather_grid_slabs": (_int, [_vp, _int, _vp]),
     "dxrv_full_grid_device": (_int, [_vp, _c.POINTER(_vp), _c.POINTER(_sz)]),
     "dxrv_fetch_full_grid": (_int, [_vp, _vp, _sz]),
     "dxrv_share_grid_target": (_int, [_vp, _vp, _u32, _u32, _u32]),

@@ -246,31 +246,17 @@ static int ensureFullGrid(dxrv_ctx* ctx, size_t bytes)
     return DXRV_OK;
 }
 
-int dxrv_gather_grid(dxrv_ctx* ctx, int root)
+static int gatherWithTable(dxrv_ctx* ctx, int root, const uint32_t* all /* {z0, z1} per rank */)
 {
-    int rc = needComm(ctx, "dxrv_gather_grid");
-    if (rc) return rc;
-    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_gather_grid: call dxrv_voxelize first");
     const int world = ctx->commWorld, me = ctx->commRank;
-    if (root >= world) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: bad root");
-    DeviceGuard g(ctx->device);
     ncclComm_t comm = static_cast<ncclComm_t>(ctx->comm);
-    if (!ctx->dSlabs) DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->dSlabs), sizeof(uint32_t) * 2 * 1024));
-    if (world > 340) return fail(ctx, DXRV_ERR_UNSUPPORTED, "dxrv_gather_grid: too many ranks");
-    // every rank learns every slab range {z0, z1, N}
-    uint32_t mine[3] = {ctx->z0, ctx->z1, ctx->N};
-    std::vector<uint32_t> all((size_t)3 * world);
-    DXRV_CUDA(cudaMemcpyAsync(ctx->dSlabs + 3 * me, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-    DXRV_NCCL(nccl().AllGather(ctx->dSlabs + 3 * me, ctx->dSlabs, 3, ncclUint32, comm, ctx->stream));
-    DXRV_CUDA(cudaMemcpyAsync(all.data(), ctx->dSlabs, sizeof(uint32_t) * 3 * world, cudaMemcpyDeviceToHost, ctx->stream));
-    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
     const uint32_t N = ctx->N;
+    if (all[2 * me] != ctx->z0 || all[2 * me + 1] != ctx->z1) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: the slab table disagrees with this rank's last dxrv_voxelize");
     std::vector<char> covered(N, 0);
     for (int r = 0; r < world; ++r)
     {
-        if (all[3 * r + 2] != N || all[3 * r] > all[3 * r + 1] || all[3 * r + 1] > N)
-            return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: the ranks voxelized different grids");
-        for (uint32_t z = all[3 * r]; z < all[3 * r + 1]; ++z)
+        if (all[2 * r] > all[2 * r + 1] || all[2 * r + 1] > N) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: bad slab table");
+        for (uint32_t z = all[2 * r]; z < all[2 * r + 1]; ++z)
         {
             if (covered[z]) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: overlapping slabs");
             covered[z] = 1;
@@ -280,7 +266,7 @@ int dxrv_gather_grid(dxrv_ctx* ctx, int root)
     const size_t layerWords = (size_t)N * ((N + 31) / 32);
     if (receive)
     {
-        rc = ensureFullGrid(ctx, layerWords * N * sizeof(uint32_t));
+        const int rc = ensureFullGrid(ctx, layerWords * N * sizeof(uint32_t));
         if (rc) return rc;
         // layers nobody computed stay zero (a partial job: some ranks idle)
         bool holes = false;
@@ -293,7 +279,7 @@ int dxrv_gather_grid(dxrv_ctx* ctx, int root)
     ncclResult_t r = ncclSuccess;
     for (int p = 0; p < world && r == ncclSuccess; ++p)
     {
-        const size_t off = layerWords * all[3 * p], cnt = layerWords * (all[3 * p + 1] - all[3 * p]);
+        const size_t off = layerWords * all[2 * p], cnt = layerWords * (all[2 * p + 1] - all[2 * p]);
         if (cnt == 0) continue;   // empty slab: every rank skips it
         if (root < 0) r = nccl().Broadcast(p == me ? slab : ctx->gridFull + off, ctx->gridFull + off, cnt, ncclUint32, p, comm, ctx->stream);
         else if (p == me) { if (me != root) r = nccl().Send(slab, cnt, ncclUint32, root, comm, ctx->stream); }
@@ -308,6 +294,43 @@ int dxrv_gather_grid(dxrv_ctx* ctx, int root)
     ctx->haveFull = receive;
     ctx->fullN = N;
     return DXRV_OK;
+}
+
+int dxrv_gather_grid(dxrv_ctx* ctx, int root)
+{
+    int rc = needComm(ctx, "dxrv_gather_grid");
+    if (rc) return rc;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_gather_grid: call dxrv_voxelize first");
+    const int world = ctx->commWorld, me = ctx->commRank;
+    if (root >= world) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: bad root");
+    if (world > 340) return fail(ctx, DXRV_ERR_UNSUPPORTED, "dxrv_gather_grid: too many ranks");
+    DeviceGuard g(ctx->device);
+    ncclComm_t comm = static_cast<ncclComm_t>(ctx->comm);
+    if (!ctx->dSlabs) DXRV_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->dSlabs), sizeof(uint32_t) * 2 * 1024));
+    // every rank learns every slab range {z0, z1, N}
+    uint32_t mine[3] = {ctx->z0, ctx->z1, ctx->N};
+    std::vector<uint32_t> all((size_t)3 * world), table((size_t)2 * world);
+    DXRV_CUDA(cudaMemcpyAsync(ctx->dSlabs + 3 * me, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    DXRV_NCCL(nccl().AllGather(ctx->dSlabs + 3 * me, ctx->dSlabs, 3, ncclUint32, comm, ctx->stream));
+    DXRV_CUDA(cudaMemcpyAsync(all.data(), ctx->dSlabs, sizeof(uint32_t) * 3 * world, cudaMemcpyDeviceToHost, ctx->stream));
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < world; ++r)
+    {
+        if (all[3 * r + 2] != ctx->N) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid: the ranks voxelized different grids");
+        table[2 * r] = all[3 * r]; table[2 * r + 1] = all[3 * r + 1];
+    }
+    return gatherWithTable(ctx, root, table.data());
+}
+
+int dxrv_gather_grid_slabs(dxrv_ctx* ctx, int root, const uint32_t* slabs)
+{
+    int rc = needComm(ctx, "dxrv_gather_grid_slabs");
+    if (rc) return rc;
+    if (!slabs) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid_slabs: null slab table");
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_gather_grid_slabs: call dxrv_voxelize first");
+    if (root >= ctx->commWorld) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_gather_grid_slabs: bad root");
+    DeviceGuard g(ctx->device);
+    return gatherWithTable(ctx, root, slabs);
 }
 
 int dxrv_full_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes)

@@ -258,8 +258,13 @@ class Voxelizer:
         b = None if bound is None else np.ascontiguousarray(bound, dtype=np.float32)
         self._check(self._lib.dxrv_build_bvh_replicated(self._h, None if b is None else b.ctypes.data))
 
-    def gather_grid(self, root=-1):
-        self._check(self._lib.dxrv_gather_grid(self._h, root))
+    def gather_grid(self, root=-1, slabs=None):
+        """slabs: [(z0, z1)] of every rank when the caller knows them (no internal exchange: usable inside a group)."""
+        if slabs is None:
+            self._check(self._lib.dxrv_gather_grid(self._h, root))
+        else:
+            t = np.ascontiguousarray(slabs, dtype=np.uint32).reshape(-1)
+            self._check(self._lib.dxrv_gather_grid_slabs(self._h, root, t.ctypes.data))
 
     def full_grid_device(self):
         p, n = ctypes.c_void_p(), ctypes.c_size_t()

@@ -247,6 +247,9 @@ DXRV_API int dxrv_build_bvh_replicated(dxrv_ctx* ctx, const float bound[4]);
  * device memory owned by the context, on `root` (ncclSend/ncclRecv) or on every rank when root < 0 (one
  * ncclBroadcast per slab).  Layers no rank computed are zero.  Collective; synchronises once (slab table). */
 DXRV_API int dxrv_gather_grid(dxrv_ctx* ctx, int root);
+/* Same with the slab table {z0, z1} of every rank supplied by the caller: no internal exchange and no host
+ * synchronisation, so it may be called for several contexts inside one dxrv_group_begin / dxrv_group_end. */
+DXRV_API int dxrv_gather_grid_slabs(dxrv_ctx* ctx, int root, const uint32_t* slabs);
 DXRV_API int dxrv_full_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);
 DXRV_API int dxrv_fetch_full_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes);
 /* Fused gather for contexts of ONE process: make ctx's next dxrv_voxelize(N, mode, slabBegin, slabEnd) store its

@@ -58,7 +58,7 @@ if rank == 0:
 dist.barrier()
 sv2 = ShardedVoxelizer(rank)
 sv2.replicate_and_build(mesh)
-assert sv2.setup_peer_gather(33, owner=0) is False      # odd pitch + odd cut: unaligned slab offset -> caller falls back to gather()
+assert sv2.setup_peer_gather(35, owner=0) is False      # 280-byte layers, cut at z = 17: unaligned slab offset -> caller falls back to gather()
 sv2.close()
 sv.close()
 dist.destroy_process_group()
@@ -125,7 +125,7 @@ def test_c_abi_one_process_two_gpus(oracle_mod=None):
     want = oracle.voxelize(m.vertices, m.indices, N, 1)["bits"]
     a.voxelize(N, d.MODE_PARITY, 0, 70); b.voxelize(N, d.MODE_PARITY, 70, N)
     assert lib.dxrv_group_begin() == 0
-    a.gather_grid(0); b.gather_grid(0)
+    a.gather_grid(0, [(0, 70), (70, N)]); b.gather_grid(0, [(0, 70), (70, N)])
     assert lib.dxrv_group_end() == 0
     assert np.array_equal(a.fetch_full_grid(N), want)
     # fused: both slabs land in a's full grid, no collective
