@@ -167,7 +167,8 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     std::vector<uint8_t> key;
     keyPush(key, (uint32_t)0xB01Du);
     keyPush(key, m.verts); keyPush(key, m.numVerts); keyPush(key, m.stride); keyPush(key, m.indices); keyPush(key, m.numTris);
-    keyPush(key, (uint32_t)haveBound); keyPush(key, bnd);
+    const bool withTree = ctx->treeWanted;
+    keyPush(key, (uint32_t)haveBound); keyPush(key, bnd); keyPush(key, (uint32_t)withTree);
     keyPush(key, ctx->keysA); keyPush(key, ctx->keysB); keyPush(key, ctx->valsA); keyPush(key, ctx->valsB);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp); keyPush(key, ctx->refitScratch);
     const int rc = runCaptured(ctx, key, [&]() {
@@ -185,14 +186,25 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
             ctx->launches += (uint64_t)radixSortPairs(s, ctx->sortTemp, k0, v0, k1, v1, T, numPasses, true, nullptr);
             if (prof) cudaEventRecord(ctx->profBuild[2], s);
             ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, &ctx->side, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
-                                                                ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr);
+                                                                ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr,
+                                                                withTree ? (kBuildLeaves | kBuildTree) : kBuildLeaves);
         }
         if (prof) { cudaEventRecord(ctx->profBuild[3], s); ctx->profBuildValid = T > 0; }
     });
     if (rc) return rc;
     DXRV_CUDA(cudaGetLastError());
     ctx->haveBvh = true;
+    ctx->treeBuilt = withTree || T < 2;
     return DXRV_OK;
+}
+
+// Enqueue the hierarchy of the current build if no consumer has needed it yet (called inside a voxelize's launch
+// sequence, so it is captured into the same CUDA graph).
+void enqueueTree(dxrv_ctx* ctx)
+{
+    if (ctx->treeBuilt) return;
+    ctx->launches += (uint64_t)launchLeavesAndHierarchy(ctx->stream, nullptr, ctx->mesh, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
+                                                        ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr, kBuildTree);
 }
 
 int validateMeshArgs(dxrv_ctx* ctx, const void* v, uint32_t numVerts, uint32_t stride, const uint32_t* idx, uint32_t numIndices,
@@ -464,10 +476,13 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     keyPush(key, (uint32_t)scatter);
     keyPush(key, N); keyPush(key, mode); keyPush(key, slabBegin); keyPush(key, slabEnd);
     keyPush(key, grid); keyPush(key, texels); keyPush(key, ctx->walkBuf);
+    const bool needTree = (algo == DXRV_MODE_SHADER || !scatter) && !ctx->treeBuilt;
+    keyPush(key, (uint32_t)needTree);
     keyPush(key, ctx->binsBuf); keyPush(key, (uint32_t)buildBins); keyPush(key, (uint32_t)useBins); keyPush(key, ctx->binsSizes.R);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
     keyPush(key, ctx->mesh.verts); keyPush(key, ctx->mesh.numVerts); keyPush(key, ctx->mesh.stride); keyPush(key, ctx->mesh.indices); keyPush(key, ctx->mesh.numTris);
     const int rc = runCaptured(ctx, key, [&]() {
+        if (needTree) enqueueTree(ctx);
         if (algo == DXRV_MODE_PARITY)
         {
             if (scatter)
@@ -497,6 +512,8 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
+    if (needTree) ctx->treeBuilt = true;
+    ctx->treeWanted = algo == DXRV_MODE_SHADER || !scatter;   // the next build includes the hierarchy iff this consumer traversed it
     if (algo == DXRV_MODE_SHADER && useBins) ctx->binsValid = true;
     return DXRV_OK;
 }
@@ -696,6 +713,12 @@ int dxrv_debug_read(dxrv_ctx* ctx, uint32_t what, void* hostDst, size_t bytes)
         DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
         out[3] = ctx->binsSizes.R;
         return DXRV_OK;
+    }
+    if ((what == DXRV_DBG_NODES || what == DXRV_DBG_ROOT_BOX) && !ctx->treeBuilt)
+    {
+        enqueueTree(ctx);
+        DXRV_CUDA(cudaGetLastError());
+        ctx->treeBuilt = true;
     }
     switch (what)
     {

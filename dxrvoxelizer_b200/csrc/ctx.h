@@ -31,6 +31,9 @@ struct dxrv_ctx
     uint32_t* idxOwned = nullptr;  size_t idxCap = 0;
     MeshView mesh{};
     bool haveBvh = false;
+    // The hierarchy (topology + child boxes) is built with the rest when the previous consumer traversed it, else on
+    // demand by the first dxrv_voxelize that does (include/dxrv.h, dxrv_build_bvh).
+    bool treeBuilt = false, treeWanted = false;
 
     // LBVH
     uint32_t *keysA = nullptr, *keysB = nullptr, *valsA = nullptr, *valsB = nullptr;

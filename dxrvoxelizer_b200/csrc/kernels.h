@@ -34,9 +34,13 @@ size_t boxPyramidFloat4s(uint32_t numTris);
 bool useAtomicRefit(uint32_t numTris);
 // side (nullable): a second stream + two events; with it the leaf/pyramid kernels run beside the topology kernel.
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+// parts: kBuildLeaves = sorted triangle records + leaf boxes + box pyramid; kBuildTree = topology + child boxes (needs the
+// leaves).  Both together run the two chains concurrently (fork/join).  The tree is only needed by consumers that
+// TRAVERSE it (tile-path MODE_PARITY, MODE_SHADER); the scatter path reads the sorted triangle records alone.
+constexpr int kBuildLeaves = 1, kBuildTree = 2;
 int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
                              const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
-                             uint32_t* refitScratch, float* rootBox, uint32_t* dErr);
+                             uint32_t* refitScratch, float* rootBox, uint32_t* dErr, int parts);
 
 // ---- onesweep.cu --------------------------------------------------------------------------------
 struct SortTemp

@@ -158,6 +158,9 @@ k_morton(MeshView m, const float* __restrict__ boundPtr, uint32_t* __restrict__ 
     // grid-stride: a bounded number of CTAs, each flushing its histograms once (one CTA per 256 triangles meant 65 k
     // global atomics on each of the 1024 counters at 16.8 M triangles -- two thirds of the kernel's time)
     const float4 bound = make_float4(__ldg(boundPtr), __ldg(boundPtr + 1), __ldg(boundPtr + 2), __ldg(boundPtr + 3));
+    // The key only ORDERS the triangles (any order gives the same grids): one reciprocal and three multiply-adds
+    // instead of the nine IEEE divisions of the exact scene transform, which k_leaf_setup applies to the records.
+    const float invW = 1.0f / bound.w;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < m.numTris; k += gridDim.x * blockDim.x)
     {
         uint32_t i0 = __ldg(m.indices + 3 * (size_t)k), i1 = __ldg(m.indices + 3 * (size_t)k + 1),
@@ -167,21 +170,26 @@ k_morton(MeshView m, const float* __restrict__ boundPtr, uint32_t* __restrict__ 
             atomicMax(err, (uint32_t)kErrBadIndex);
             i0 = i1 = i2 = 0;
         }
-        const float3 a = scenePos(m.verts, m.stride, i0, bound);
-        const float3 b = scenePos(m.verts, m.stride, i1, bound);
-        const float3 c = scenePos(m.verts, m.stride, i2, bound);
-        const float cx = 0.5f * (fminf(fminf(a.x, b.x), c.x) + fmaxf(fmaxf(a.x, b.x), c.x));
-        const float cy = 0.5f * (fminf(fminf(a.y, b.y), c.y) + fmaxf(fmaxf(a.y, b.y), c.y));
-        const float cz = 0.5f * (fminf(fminf(a.z, b.z), c.z) + fmaxf(fmaxf(a.z, b.z), c.z));
+        const float3 a = loadPos(m.verts, m.stride, i0), b = loadPos(m.verts, m.stride, i1), c = loadPos(m.verts, m.stride, i2);
+        const float cx = (0.5f * (fminf(fminf(a.x, b.x), c.x) + fmaxf(fmaxf(a.x, b.x), c.x)) - bound.x) * invW;
+        const float cy = (0.5f * (fminf(fminf(a.y, b.y), c.y) + fmaxf(fmaxf(a.y, b.y), c.y)) - bound.y) * invW;
+        const float cz = (0.5f * (fminf(fminf(a.z, b.z), c.z) + fmaxf(fmaxf(a.z, b.z), c.z)) - bound.z) * invW;
         const uint32_t key = ((expandBits10(quantize10(cx)) << 2) | (expandBits10(quantize10(cy)) << 1) |
                               expandBits10(quantize10(cz))) >> keyShift;
         keys[k] = key;
         vals[k] = k;
         // neighbouring triangles share their leading digits: one shared-memory atomic per distinct digit of the warp
         const uint32_t active = __activemask();
+        const uint32_t first = (uint32_t)__ffs(active) - 1u;
         for (int p = 0; p < numPasses; ++p)
         {
             const uint32_t dgt = (key >> (8 * p)) & 255u;
+            // the upper digits of 32 neighbouring triangles usually agree: one vote instead of a match
+            if (__all_sync(active, dgt == __shfl_sync(active, dgt, (int)first)))
+            {
+                if (laneId() == first) atomicAdd(&sh[p][dgt], (uint32_t)__popc(active));
+                continue;
+            }
             const uint32_t peers = __match_any_sync(active, dgt);
             if ((uint32_t)(__ffs(peers) - 1) == laneId()) atomicAdd(&sh[p][dgt], (uint32_t)__popc(peers));
         }
@@ -300,7 +308,7 @@ k_leaf_setup(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __r
         box.ylo = fminf(fminf(a.y, b.y), c.y); box.yhi = fmaxf(fmaxf(a.y, b.y), c.y);
         box.zlo = fminf(fminf(a.z, b.z), c.z); box.zhi = fmaxf(fmaxf(a.z, b.z), c.z);
         box.xlo = fminf(fminf(a.x, b.x), c.x); box.xhi = fmaxf(fmaxf(a.x, b.x), c.x);
-        box.store(pyr.level[0] + (size_t)S * j);
+        if (S == 6u) box.store(pyr.level[0] + (size_t)S * j);   // (large meshes: k_refit_atomic derives the leaf box from the record)
         if (m.numTris == 1)
         {
             rootBox[0] = box.xlo; rootBox[1] = box.ylo; rootBox[2] = box.zlo;
@@ -622,14 +630,16 @@ k_node_boxes(int numLeaves, BvhNode* __restrict__ nodes, const __grid_constant__
 // Every leaf starts with its box (pyramid level 0), stores it into its parent's slot, and the SECOND child
 // to arrive at a node (atomic arrival counter, zeroed per build) unions both boxes and carries on upwards.
 __global__ void __launch_bounds__(256)
-k_refit_atomic(int numLeaves, const float4* __restrict__ leafBoxes, BvhNode* __restrict__ nodes,
+k_refit_atomic(int numLeaves, const Tri48* __restrict__ tris, BvhNode* __restrict__ nodes,
                const uint32_t* __restrict__ nodeParent, const uint32_t* __restrict__ leafParent, uint32_t* __restrict__ flags,
                float* __restrict__ rootBox, uint32_t* __restrict__ err)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= numLeaves) return;
-    float4 yz = __ldg(leafBoxes + 2 * (size_t)j);
-    float4 xx = __ldg(leafBoxes + 2 * (size_t)j + 1);
+    const float4* t = reinterpret_cast<const float4*>(tris + j);
+    const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+    float4 yz = make_float4(fminf(fminf(a.y, b.y), c.y), fmaxf(fmaxf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z), fmaxf(fmaxf(a.z, b.z), c.z));
+    float4 xx = make_float4(fminf(fminf(a.x, b.x), c.x), fmaxf(fmaxf(a.x, b.x), c.x), 0.0f, 0.0f);
     uint32_t p = __ldg(leafParent + j);
     for (int level = 0; level < 128; ++level)  // depth <= 62; the bound only guards against a corrupt tree
     {
@@ -752,9 +762,10 @@ size_t boxPyramidFloat4s(uint32_t numTris)
 
 int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshView& m, const float* dBound, const uint32_t* sortedKeys,
                              const uint32_t* sortedPrims, BvhNode* nodes, Tri48* tris, float4* pyramidMem,
-                             uint32_t* refitScratch, float* rootBox, uint32_t* dErr)
+                             uint32_t* refitScratch, float* rootBox, uint32_t* dErr, int parts)
 {
     if (!m.numTris) return 0;
+    const bool doLeaves = (parts & kBuildLeaves) != 0, doTree = (parts & kBuildTree) != 0;
     const bool atomicRefit = useAtomicRefit(m.numTris);
     Pyramid pyr;
     uint32_t c = m.numTris;
@@ -772,22 +783,25 @@ int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshV
     int launches = 0;
     // Two independent chains once the keys are sorted: {leaves, triangle records, box pyramid} and {topology}.
     // With a side stream they run concurrently (also under stream capture: the events become graph edges).
-    const bool forked = side && side->stream && m.numTris > 1;
+    const bool forked = side && side->stream && m.numTris > 1 && doLeaves && doTree;
     cudaStream_t sb = forked ? side->stream : s;
     if (forked)
     {
         cudaEventRecord(side->fork, s);
         cudaStreamWaitEvent(sb, side->fork, 0);
     }
-    k_leaf_setup<<<(m.numTris + 255) / 256, 256, 0, sb>>>(m, dBound, sortedPrims, tris, pyr, rootBox, dErr);
-    ++launches;
-    for (int l = 3; l < pyr.numLevels; ++l)
+    if (doLeaves)
     {
-        k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, sb>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l], pyr.stride);
+        k_leaf_setup<<<(m.numTris + 255) / 256, 256, 0, sb>>>(m, dBound, sortedPrims, tris, pyr, rootBox, dErr);
         ++launches;
+        for (int l = 3; l < pyr.numLevels; ++l)
+        {
+            k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, sb>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l], pyr.stride);
+            ++launches;
+        }
     }
     if (forked) cudaEventRecord(side->join, sb);
-    if (m.numTris > 1)
+    if (m.numTris > 1 && doTree)
     {
         const uint32_t blocks = (m.numTris - 1 + 127) / 128;
         // refitScratch = [nodeParent T][leafParent T][flags T]
@@ -803,7 +817,7 @@ int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshV
         if (forked) cudaStreamWaitEvent(s, side->join, 0);
         if (!atomicRefit) k_node_boxes<<<blocks, 128, 0, s>>>((int)m.numTris, nodes, pyr, rootBox);
         else
-            k_refit_atomic<<<(m.numTris + 255) / 256, 256, 0, s>>>((int)m.numTris, pyr.level[0], nodes, nodeParent, leafParent, flags,
+            k_refit_atomic<<<(m.numTris + 255) / 256, 256, 0, s>>>((int)m.numTris, tris, nodes, nodeParent, leafParent, flags,
                                                                    rootBox, dErr);
         launches += 2;
     }

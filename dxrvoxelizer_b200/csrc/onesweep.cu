@@ -144,14 +144,31 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
         count += c;
     }
 
+    // The tile's digit counts are published at once; the look-back itself is delayed until the pairs sit in shared
+    // memory in sorted order (that scatter needs only tile-local offsets): the predecessors, which started at about
+    // the same time, have published by then, and the look-back rarely spins.
+    volatile uint32_t* lb = lookback + (size_t)tile * kRadix;
+    lb[tid] = (tile == 0 ? kFlagInclusive : kFlagAggregate) | count;
+
+    const uint32_t start = blockExclusiveScan256(count, warpSums);
+    binStart[tid] = start;
+    __syncthreads();
+
+    // ---- scatter into shared memory in sorted order ----
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t pos = binStart[d] + warpHist[warp][d] + rank[i];
+        sKeys[pos] = key[i];
+        sVals[pos] = val[i];
+    }
+
     // ---- decoupled look-back: exclusive count of digit `tid` over all previous tiles.  A window of
     // predecessors is fetched at once, so the latency chain is 1/window of the tile distance. ----
-    volatile uint32_t* lb = lookback + (size_t)tile * kRadix;
     uint32_t prev = 0;
-    if (tile == 0) lb[tid] = kFlagInclusive | count;
-    else
+    if (tile != 0)
     {
-        lb[tid] = kFlagAggregate | count;
         int j = (int)tile - 1;
         bool done = false;
         while (!done)
@@ -172,21 +189,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
         }
         lb[tid] = kFlagInclusive | (prev + count);
     }
-
-    const uint32_t start = blockExclusiveScan256(count, warpSums);
-    binStart[tid] = start;
     globalBase[tid] = digitBase + prev - start;
-    __syncthreads();
-
-    // ---- scatter into shared memory in sorted order ----
-#pragma unroll
-    for (int i = 0; i < kItems; ++i)
-    {
-        const uint32_t d = (key[i] >> shift) & 255u;
-        const uint32_t pos = binStart[d] + warpHist[warp][d] + rank[i];
-        sKeys[pos] = key[i];
-        sVals[pos] = val[i];
-    }
     __syncthreads();
 
     // ---- coalesced write-out (padding keys sort to the end of the tile: positions >= valid) ----

@@ -97,8 +97,14 @@ DXRV_API int dxrv_synchronize(dxrv_ctx* ctx);
  * inverse(Scale(w) * Translate(c)) (Voxelizer.cpp:304-310) is applied as p' = (p - c) / w.
  * bound = {cx, cy, cz, w}; NULL => computed on the device exactly as Voxelizer.cpp:52-57
  * does from ObjLoader::computeAABB (min/max over ALL vertices).
- * The build is an LBVH: bounds -> 30-bit Morton keys -> onesweep radix sort -> Karras
- * hierarchy -> atomic bottom-up refit.  The host variant copies the arrays to the device. */
+ * The build is an LBVH: bounds -> 30-bit Morton keys -> onesweep radix sort -> sorted triangle
+ * records and leaf boxes -> Karras hierarchy -> child boxes (range unions; atomic bottom-up refit
+ * above 2^19 triangles).  RULE for the last two steps: they run inside this call when the previous
+ * dxrv_voxelize of the context traversed the hierarchy (MODE_SHADER, tile-path MODE_PARITY), and
+ * otherwise are deferred to the first dxrv_voxelize that does -- the triangle-parallel scatter path
+ * (fine meshes on coarse grids: 4 T >= N^2) reads the Morton-sorted triangle records only and never
+ * pays for a tree it would not walk.  Results are identical either way.
+ * The host variant copies the arrays to the device. */
 DXRV_API int dxrv_build_bvh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts,
                             uint32_t strideBytes, const uint32_t* indices, uint32_t numIndices,
                             const float bound[4]);
