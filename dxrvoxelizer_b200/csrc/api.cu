@@ -96,7 +96,7 @@ int runCaptured(dxrv_ctx* ctx, const std::vector<uint8_t>& key, F&& enqueue)
         enqueue();
         return DXRV_OK;
     }
-    if (ctx->graphs.size() >= 8)
+    if (ctx->graphs.size() >= 32)
     {
         size_t victim = 0;
         for (size_t i = 1; i < ctx->graphs.size(); ++i) if (ctx->graphs[i].lastUse < ctx->graphs[victim].lastUse) victim = i;
@@ -291,6 +291,8 @@ void dxrv_destroy(dxrv_ctx* ctx)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
+    for (cudaEvent_t e : ctx->chunkDone) if (e) cudaEventDestroy(e);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     for (cudaEvent_t e : ctx->prof) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->profBuild) if (e) cudaEventDestroy(e);
     if (ctx->side.fork) cudaEventDestroy(ctx->side.fork);
@@ -545,6 +547,54 @@ int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format)
     else return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid: unknown format");
     if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid: bytes does not match the slab size in this format");
     DXRV_CUDA(cudaMemcpyAsync(hostDst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    return checkDeviceError(ctx);
+}
+
+int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd, void* hostDst, size_t bytes,
+                          uint32_t chunks)
+{
+    if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
+    if (slabBegin >= slabEnd || slabEnd > N || N == 0 || N > 8192) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: need 0 <= slabBegin < slabEnd <= N <= 8192");
+    if (mode & DXRV_EMIT_TEXELS) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bit grid only");
+    const size_t layerBytes = (size_t)N * ((N + 31) / 32) * sizeof(uint32_t);
+    const uint32_t layers = slabEnd - slabBegin;
+    if (bytes != layerBytes * layers) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bytes does not match the slab size");
+    if (ctx->gridTarget) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: not with an external grid target");
+    DeviceGuard g(ctx->device);
+    if (chunks < 1) chunks = 1;
+    if (chunks > layers) chunks = layers;
+    if (layerBytes % 16) chunks = 1;   // sub-slab offsets must keep the 128-bit store alignment
+    if (!ctx->copyStream)
+    {
+        DXRV_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : ctx->chunkDone) DXRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaError_t e = ensure(ctx->gridOwned, ctx->gridCap, bytes);
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(grid)");
+    uint32_t* base = ctx->gridOwned;
+    int rc = DXRV_OK;
+    // chunk k is computed on the context's stream into its place of the slab; its copy waits for it on the copy stream
+    // while chunk k + 1 is computed
+    for (uint32_t k = 0; k < chunks && rc == DXRV_OK; ++k)
+    {
+        const uint32_t a = slabBegin + (uint32_t)((uint64_t)layers * k / chunks), b = slabBegin + (uint32_t)((uint64_t)layers * (k + 1) / chunks);
+        const size_t off = layerBytes * (a - slabBegin), len = layerBytes * (b - a);
+        ctx->gridTarget = base + off / sizeof(uint32_t);
+        ctx->gridTargetBytes = len;
+        rc = dxrv_voxelize(ctx, N, mode, a, b);
+        if (rc != DXRV_OK) break;
+        cudaEvent_t ev = ctx->chunkDone[k % 2];
+        DXRV_CUDA(cudaEventRecord(ev, ctx->stream));
+        DXRV_CUDA(cudaStreamWaitEvent(ctx->copyStream, ev, 0));
+        DXRV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(hostDst) + off, reinterpret_cast<uint8_t*>(base) + off, len, cudaMemcpyDeviceToHost, ctx->copyStream));
+    }
+    ctx->gridTarget = nullptr;
+    ctx->gridTargetBytes = 0;
+    if (rc != DXRV_OK) { cudaStreamSynchronize(ctx->copyStream); return rc; }
+    DXRV_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    // the context now describes the whole slab, resident in its own grid
+    ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
+    ctx->haveGrid = true; ctx->haveTexels = false; ctx->mipLevels = 0;
     return checkDeviceError(ctx);
 }
 

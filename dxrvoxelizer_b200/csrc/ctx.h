@@ -77,6 +77,8 @@ struct dxrv_ctx
     bool useGraphs = true;
 
     cudaEvent_t copyDone = nullptr;
+    cudaStream_t copyStream = nullptr;                   // dxrv_voxelize_to_host: D2H of chunk k beside the fill of chunk k+1
+    cudaEvent_t chunkDone[2] = {nullptr, nullptr};
     cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};  // MODE_PARITY kernel timing (dxrv_set_profiling)
     cudaEvent_t profBuild[4] = {nullptr, nullptr, nullptr, nullptr};  // build start, keys ready, sorted, done
     bool profiling = false, profValid = false, profBuildValid = false;

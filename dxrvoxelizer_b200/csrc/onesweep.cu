@@ -22,7 +22,16 @@ constexpr int kMaxPasses = 4;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr uint32_t kSmallSort = 1u << 19;  // below this many pairs use the 1024-pair tile
-constexpr int kBigItems = 16;              // items per thread of the bandwidth-bound variant
+#ifndef SORT_ITEMS
+#define SORT_ITEMS 16
+#endif
+#ifndef SORT_MINBLOCKS
+#define SORT_MINBLOCKS 4
+#endif
+#ifndef SORT_LB_WINDOW
+#define SORT_LB_WINDOW 8
+#endif
+constexpr int kBigItems = SORT_ITEMS;      // items per thread of the bandwidth-bound variant
 
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagInclusive = 2u << 30;
@@ -74,7 +83,7 @@ __device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* 
 
 // ---- one digit pass ----------------------------------------------------------------------------------
 template <int kItems>
-__global__ void __launch_bounds__(kSortThreads, kItems >= 8 ? 4 : 1)
+__global__ void __launch_bounds__(kSortThreads, kItems >= 8 ? SORT_MINBLOCKS : 1)
 k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                 uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n, int shift,
                 const uint32_t* __restrict__ digitCount, volatile uint32_t* __restrict__ lookback,
@@ -83,7 +92,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     constexpr int kTile = kSortThreads * kItems;
     // predecessor tiles fetched per round trip of the look-back: the small-tile variant is latency bound
     // (many tiles, few keys), the big-tile variant is register bound
-    constexpr int kLookbackWindow = kItems >= 8 ? 8 : 12;
+    constexpr int kLookbackWindow = kItems >= 8 ? SORT_LB_WINDOW : 12;
     __shared__ uint32_t warpHist[kSortWarps][kRadix];  // 8 KB
     __shared__ uint32_t binStart[kRadix];
     __shared__ uint32_t globalBase[kRadix];
@@ -202,16 +211,175 @@ k_onesweep_pass(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
     }
 }
 
-uint32_t tileSizeFor(uint32_t n) { return n < kSmallSort ? kSortThreads * 4u : kSortThreads * (uint32_t)kBigItems; }
+// ---- one digit pass, bandwidth-bound sizes: 512 threads x 16 pairs = 8192 pairs per tile ---------------------------
+// Same algorithm as k_onesweep_pass.  The decoupled look-back was a third of all instructions of the 4096-pair tile at
+// 16.8 M pairs (all resident tiles start together, so the nearest INCLUSIVE prefix is about a wave of tiles back and
+// every digit thread walks that distance); twice the tile halves the tiles in flight and the look-backs per pair.
+// Measured: 103.6 -> 101.8 us per pass -- the pass stays latency bound.  Shared memory is dynamic (82 KB).
+constexpr int kBigThreads = 512;
+constexpr int kBigWarps = kBigThreads / 32;
+constexpr int kBigTile = kBigThreads * kBigItems;
+constexpr size_t kBigSmemBytes = sizeof(uint32_t) * ((size_t)kBigWarps * kRadix + 2 * kRadix + 2 * (size_t)kBigTile + kBigWarps + 4);
+
+__global__ void __launch_bounds__(kBigThreads, 2)
+k_onesweep_pass_big(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                    uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n, int shift,
+                    const uint32_t* __restrict__ digitCount, volatile uint32_t* __restrict__ lookback,
+                    uint32_t* __restrict__ tileCounter)
+{
+    constexpr int kItems = kBigItems;
+    constexpr int kLookbackWindow = 8;
+    extern __shared__ __align__(16) uint32_t smemBig[];
+    uint32_t (*warpHist)[kRadix] = reinterpret_cast<uint32_t (*)[kRadix]>(smemBig);   // [kBigWarps][256]
+    uint32_t* binStart = smemBig + kBigWarps * kRadix;
+    uint32_t* globalBase = binStart + kRadix;
+    uint32_t* sKeys = globalBase + kRadix;
+    uint32_t* sVals = sKeys + kBigTile;
+    uint32_t* warpSums = sVals + kBigTile;       // [kBigWarps]
+    uint32_t* sTile = warpSums + kBigWarps;
+
+    const uint32_t tid = threadIdx.x, lane = laneId(), warp = tid >> 5;
+    const bool digitThread = tid < (uint32_t)kRadix;
+    if (tid == 0) *sTile = atomicAdd(tileCounter, 1u);
+    for (int i = tid; i < kBigWarps * kRadix; i += kBigThreads) (&warpHist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = *sTile;
+    const uint32_t base = tile * (uint32_t)kBigTile;
+    const uint32_t valid = min((uint32_t)kBigTile, n - base);
+
+    // block-wide exclusive scan of one value per DIGIT thread (threads >= 256 pass 0 and ignore the result)
+    auto scanDigits = [&](uint32_t v) -> uint32_t {
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        if (lane == 31) warpSums[warp] = inc;
+        __syncthreads();
+        uint32_t b = 0;
+#pragma unroll
+        for (int w = 0; w < kRadix / 32; ++w)
+            if ((uint32_t)w < warp) b += warpSums[w];
+        __syncthreads();
+        return b + inc - v;
+    };
+    const uint32_t digitBase = scanDigits(digitThread ? __ldg(digitCount + tid) : 0u);
+
+    // ---- load (warp-striped) ----
+    uint32_t key[kItems], val[kItems], rank[kItems];
+    const uint32_t warpBase = warp * (32u * kItems);
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t local = warpBase + i * 32u + lane;
+        const bool ok = local < valid;
+        key[i] = ok ? __ldg(keysIn + base + local) : 0xffffffffu;
+        val[i] = ok ? __ldg(valsIn + base + local) : 0u;
+    }
+
+    // ---- rank within the warp (stable) ----
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if ((int)lane == leader)
+        {
+            old = warpHist[warp][d];
+            warpHist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = old + __popc(peers & laneMaskLt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: prefix over warps, tile count; published at once ----
+    uint32_t count = 0;
+    if (digitThread)
+    {
+#pragma unroll
+        for (int w = 0; w < kBigWarps; ++w)
+        {
+            const uint32_t c = warpHist[w][tid];
+            warpHist[w][tid] = count;
+            count += c;
+        }
+        lookback[(size_t)tile * kRadix + tid] = (tile == 0 ? kFlagInclusive : kFlagAggregate) | count;
+    }
+    const uint32_t start = scanDigits(count);
+    if (digitThread) binStart[tid] = start;
+    __syncthreads();
+
+    // ---- scatter into shared memory in sorted order ----
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+    {
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t pos = binStart[d] + warpHist[warp][d] + rank[i];
+        sKeys[pos] = key[i];
+        sVals[pos] = val[i];
+    }
+
+    // ---- decoupled look-back (digit threads), delayed behind the scatter ----
+    // (Tried and dropped, measured at 16.8 M pairs: a two-level look-back -- blocks of 32 tiles publishing block
+    // aggregates -- was SLOWER, 127 vs 102 us per pass: the block words add a second spin chain.  The pass is bound by
+    // the latency of this walk)
+    if (digitThread)
+    {
+        uint32_t prev = 0;
+        if (tile != 0)
+        {
+            int j = (int)tile - 1;
+            bool done = false;
+            while (!done)
+            {
+                uint32_t v[kLookbackWindow];
+#pragma unroll
+                for (int q = 0; q < kLookbackWindow; ++q) v[q] = (j - q >= 0) ? lookback[(size_t)(j - q) * kRadix + tid] : 0u;
+#pragma unroll
+                for (int q = 0; q < kLookbackWindow; ++q)
+                {
+                    if (done || j - q < 0) break;
+                    uint32_t x = v[q];
+                    while ((x & ~kValueMask) == 0u) x = lookback[(size_t)(j - q) * kRadix + tid];  // not published yet
+                    prev += x & kValueMask;
+                    if ((x & ~kValueMask) == kFlagInclusive) done = true;
+                }
+                j -= kLookbackWindow;
+            }
+            lookback[(size_t)tile * kRadix + tid] = kFlagInclusive | (prev + count);
+        }
+        globalBase[tid] = digitBase + prev - start;
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out ----
+    for (uint32_t p = tid; p < valid; p += kBigThreads)
+    {
+        const uint32_t k = sKeys[p];
+        const uint32_t dst = globalBase[(k >> shift) & 255u] + p;
+        keysOut[dst] = k;
+        valsOut[dst] = sVals[p];
+    }
+}
+
+uint32_t tileSizeFor(uint32_t n) { return n < kSmallSort ? kSortThreads * 4u : (uint32_t)kBigTile; }
 }  // namespace
+
+static size_t passWords(size_t tiles) { return tiles * kRadix; }
 
 uint32_t SortTemp::tilesFor(uint32_t n) { const uint32_t t = tileSizeFor(n); return (n + t - 1) / t; }
 
 size_t SortTemp::bytesFor(uint32_t n)
 {
     const size_t tiles = tilesFor(n) ? tilesFor(n) : 1;
-    // [hist 4*256][tileCounter 4 (padded to 64)][lookback 4*tiles*256]
-    return sizeof(uint32_t) * (kMaxPasses * kRadix + 64 + (size_t)kMaxPasses * tiles * kRadix);
+    // [hist 4*256][tileCounter 4 (padded to 64)][per pass: look-back words tiles*256]
+    return sizeof(uint32_t) * (kMaxPasses * kRadix + 64 + (size_t)kMaxPasses * passWords(tiles));
 }
 
 uint32_t* sortClearTemp(cudaStream_t s, void* tempBase, uint32_t n)
@@ -241,13 +409,14 @@ int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* va
         ++launches;
     }
     {
-        // four 43 KB CTAs per SM need more than the default shared-memory carve-out
+        // two 82 KB CTAs per SM: dynamic shared memory above 48 KB is opt-in
         static bool carveSet[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev >= 0 && dev < 64 && !carveSet[dev])
         {
-            cudaFuncSetAttribute(k_onesweep_pass<kBigItems>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_onesweep_pass_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmemBytes);
+            cudaFuncSetAttribute(k_onesweep_pass_big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carveSet[dev] = true;
         }
     }
@@ -256,10 +425,10 @@ int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* va
     {
         if (n < kSmallSort)
             k_onesweep_pass<4><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
-                                                              lookback + (size_t)p * tiles * kRadix, tileCounter + p);
+                                                              lookback + (size_t)p * passWords(tiles), tileCounter + p);
         else
-            k_onesweep_pass<kBigItems><<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
-                                                               lookback + (size_t)p * tiles * kRadix, tileCounter + p);
+            k_onesweep_pass_big<<<tiles, kBigThreads, kBigSmemBytes, s>>>(kin, vin, kout, vout, n, p * kRadixBits, hist + p * kRadix,
+                                                                         lookback + (size_t)p * passWords(tiles), tileCounter + p);
         ++launches;
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;

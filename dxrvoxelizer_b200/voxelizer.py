@@ -146,6 +146,12 @@ class Voxelizer:
         self._shape = (z1 - z0, N, (N + 31) // 32)
         self._N = N
 
+    def voxelize_to_host(self, N, mode, z0, z1, ptr, nbytes, chunks=8):
+        """dxrv_voxelize_to_host: voxelize + read-back pipelined in z sub-slabs (ptr: host memory, ideally pinned)."""
+        self._check(self._lib.dxrv_voxelize_to_host(self._h, N, mode, z0, z1, ptr, nbytes, chunks))
+        self._shape = (z1 - z0, N, (N + 31) // 32)
+        self._N = N
+
     def fetch_bits(self, out=None):
         """uint32[(z1-z0), N, P] in the DXRV_FORMAT_BITS layout."""
         if out is None:

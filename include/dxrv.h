@@ -128,6 +128,12 @@ DXRV_API int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sl
  * bytes must equal the slab size in `format`.  The reference has no read-back of the grid
  * (only of the back buffer, DXRVoxelizer.cpp:436,476); this is the headless replacement. */
 DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format);
+/* dxrv_voxelize + dxrv_fetch_grid(DXRV_FORMAT_BITS) as one pipelined call: the slab is computed in `chunks` z sub-slabs
+ * (0 or 1 = no pipelining), and each is copied to hostDst (pinned memory: dxrv_host_alloc) on a second stream while the
+ * next one is computed.  Returns when hostDst holds the whole slab; the context then describes that slab exactly as
+ * after dxrv_voxelize.  bytes must equal the slab size.  Not available with an external grid target. */
+DXRV_API int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd,
+                                   void* hostDst, size_t bytes, uint32_t chunks);
 /* Device pointer / byte size of the slab's DXRV_FORMAT_BITS grid (valid until the next
  * voxelize with a different size, or destroy). */
 DXRV_API int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);

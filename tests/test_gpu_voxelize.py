@@ -396,3 +396,21 @@ def test_million_triangle_mesh_uses_atomic_refit(vox, meshes_mod, oracle_mod):
     assert np.array_equal(root[:3], scene.min(0)) and np.array_equal(root[3:], scene.max(0))
     keys = vox.debug_read(L.DBG_MORTON_SORTED, np.uint32, m.num_triangles)
     assert (np.diff(keys.astype(np.int64)) >= 0).all()
+
+
+@pytest.mark.parametrize("N,z0,z1,chunks", [(256, 0, 256, 8), (256, 40, 200, 3), (128, 0, 128, 1), (100, 10, 90, 4), (33, 0, 33, 8), (64, 5, 8, 16)])
+def test_pipelined_voxelize_to_host(vox, assets, N, z0, z1, chunks):
+    """dxrv_voxelize_to_host: the slab computed and read back in z sub-slabs equals voxelize + fetch, and leaves the
+    context describing the whole slab (N = 100: 16-byte-aligned layers; N = 33: unaligned -> a single chunk)."""
+    import torch
+    m = assets("bunny.obj")
+    vox.build_bvh(m)
+    for mode in (d.MODE_PARITY, d.MODE_SHADER):
+        vox.voxelize(N, mode, z0, z1)
+        want = vox.fetch_bits()
+        host = torch.empty(want.nbytes, dtype=torch.uint8).pin_memory()
+        host.fill_(0xA5)
+        vox.voxelize_to_host(N, mode, z0, z1, host.data_ptr(), want.nbytes, chunks)
+        assert np.array_equal(host.numpy().view(np.uint32).reshape(want.shape), want)
+        assert np.array_equal(vox.fetch_bits(), want)              # the context holds the whole slab afterwards
+        assert vox.count_inside() == popcount(want)
