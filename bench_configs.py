@@ -188,21 +188,26 @@ def run_c5(args, Rig, ClockSampler, measured_peak, host_threads, popcount):
     P = (N + 31) // 32
     grid_bytes = N * N * P * 4
     h_grids = torch.empty((len(mine), grid_bytes), dtype=torch.uint8).pin_memory()
-    loaders = ThreadPoolExecutor(max_workers=max(2, min(8, host_threads() // world)))
+    loaders = ThreadPoolExecutor(max_workers=max(2, host_threads() // world))
 
     def run_share(fetch):
         """parse (thread pool) -> build + voxelize on stream k -> optional D2H; returns the loaded meshes"""
         futures = [loaders.submit(d.load_obj, paths[i]) for i in mine]
         loaded = []
+        in_flight = [None] * n_streams                     # mesh whose grid is still on stream s
         for k, fut in enumerate(futures):
             m = fut.result()
-            c = ctxs[k % n_streams]
+            s = k % n_streams
+            c = ctxs[s]
+            if fetch and in_flight[s] is not None:         # read back the previous grid of THIS stream only: the other
+                c.fetch_into(h_grids[in_flight[s]].data_ptr(), grid_bytes)   # streams keep the GPU busy meanwhile
             c.build_bvh(m)
             c.voxelize(N, d.MODE_PARITY)
-            if fetch:
-                c.fetch_into(h_grids[k].data_ptr(), grid_bytes)
+            in_flight[s] = k
             loaded.append(m)
-        for c in ctxs:
+        for s, c in enumerate(ctxs):
+            if fetch and in_flight[s] is not None:
+                c.fetch_into(h_grids[in_flight[s]].data_ptr(), grid_bytes)
             c.synchronize()
         return loaded
 

@@ -203,7 +203,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
 void enqueueTree(dxrv_ctx* ctx)
 {
     if (ctx->treeBuilt) return;
-    ctx->launches += (uint64_t)launchLeavesAndHierarchy(ctx->stream, nullptr, ctx->mesh, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
+    ctx->launches += (uint64_t)launchLeavesAndHierarchy(ctx->stream, &ctx->side, ctx->mesh, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
                                                         ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr, kBuildTree);
 }
 
@@ -428,7 +428,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         texels = ctx->texels;
     }
 
-    BvhView bvh{ctx->nodes, ctx->tris, ctx->dRootBox, ctx->mesh.numTris};
+    BvhView bvh{ctx->nodes, ctx->tris, ctx->dRootBox, ctx->mesh.numTris};   // (nodes dropped below when the consumer does not walk)
     if (algo == DXRV_MODE_PARITY)
     {
         const size_t walkBytes = sizeof(uint32_t) * parityScratchWords(N, slabBegin, slabEnd);
@@ -478,8 +478,13 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     keyPush(key, (uint32_t)scatter);
     keyPush(key, N); keyPush(key, mode); keyPush(key, slabBegin); keyPush(key, slabEnd);
     keyPush(key, grid); keyPush(key, texels); keyPush(key, ctx->walkBuf);
-    const bool needTree = (algo == DXRV_MODE_SHADER || !scatter) && !ctx->treeBuilt;
-    keyPush(key, (uint32_t)needTree);
+    // MODE_PARITY tile path: candidates by triangle-parallel binning (default) or by the LBVH walk (DXRV_PARITY_CANDIDATES=walk)
+    bool walkTree = false;
+    if (const char* f = std::getenv("DXRV_PARITY_CANDIDATES")) walkTree = !std::strcmp(f, "walk");
+    const bool usesTree = algo == DXRV_MODE_SHADER || (!scatter && walkTree);
+    const bool needTree = usesTree && !ctx->treeBuilt;
+    if (algo == DXRV_MODE_PARITY && !(walkTree && !scatter)) bvh.nodes = nullptr;
+    keyPush(key, (uint32_t)needTree); keyPush(key, (uint32_t)walkTree);
     keyPush(key, ctx->binsBuf); keyPush(key, (uint32_t)buildBins); keyPush(key, (uint32_t)useBins); keyPush(key, ctx->binsSizes.R);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
     keyPush(key, ctx->mesh.verts); keyPush(key, ctx->mesh.numVerts); keyPush(key, ctx->mesh.stride); keyPush(key, ctx->mesh.indices); keyPush(key, ctx->mesh.numTris);
@@ -515,7 +520,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
     if (needTree) ctx->treeBuilt = true;
-    ctx->treeWanted = algo == DXRV_MODE_SHADER || !scatter;   // the next build includes the hierarchy iff this consumer traversed it
+    ctx->treeWanted = usesTree;   // the next build includes the hierarchy iff this consumer traversed it
     if (algo == DXRV_MODE_SHADER && useBins) ctx->binsValid = true;
     return DXRV_OK;
 }

@@ -65,7 +65,7 @@ int radixSortPairs(cudaStream_t s, void* tempBase, uint32_t* keysA, uint32_t* va
 // ---- trace_parity.cu ----------------------------------------------------------------------------
 struct BvhView
 {
-    const BvhNode* nodes;
+    const BvhNode* nodes;   // null: no hierarchy (MODE_PARITY then bins its candidates instead of walking)
     const Tri48* tris;
     const float* rootBox;   // lo.xyz hi.xyz
     uint32_t numTris;

@@ -783,7 +783,7 @@ int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshV
     int launches = 0;
     // Two independent chains once the keys are sorted: {leaves, triangle records, box pyramid} and {topology}.
     // With a side stream they run concurrently (also under stream capture: the events become graph edges).
-    const bool forked = side && side->stream && m.numTris > 1 && doLeaves && doTree;
+    const bool forked = side && side->stream && m.numTris > 1 && doTree && (doLeaves || pyr.numLevels > 3);
     cudaStream_t sb = forked ? side->stream : s;
     if (forked)
     {
@@ -794,12 +794,13 @@ int launchLeavesAndHierarchy(cudaStream_t s, const SideStream* side, const MeshV
     {
         k_leaf_setup<<<(m.numTris + 255) / 256, 256, 0, sb>>>(m, dBound, sortedPrims, tris, pyr, rootBox, dErr);
         ++launches;
+    }
+    if (doTree)   // the coarser pyramid levels serve k_node_boxes only
         for (int l = 3; l < pyr.numLevels; ++l)
         {
             k_box_level<<<(pyr.count[l] + 127) / 128, 128, 0, sb>>>(pyr.level[l - 1], pyr.count[l - 1], pyr.level[l], pyr.count[l], pyr.stride);
             ++launches;
         }
-    }
     if (forked) cudaEventRecord(side->join, sb);
     if (m.numTris > 1 && doTree)
     {

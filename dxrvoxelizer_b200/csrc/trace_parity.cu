@@ -247,6 +247,95 @@ k_walk_columns(const ParityParams prm)
 #endif
 }
 
+// ---- kernel A', the default: the candidate lists WITHOUT a tree walk -----------------------------------------------
+// What the walk computes is, per super-tile, the set of triangles whose (y,z) box meets the tile's rectangle of
+// column centres.  That is a 2-D binning problem, and the parallelism is in the TRIANGLES: one thread per sorted
+// triangle turns its box into a (conservative, then exactly tested) range of tiles and appends its slot to their
+// lists with one atomic each -- a few microseconds for 100 k triangles, no dependent chain of node fetches (the walk
+// is bound by the depth of the LBVH: 28 levels x one L2 round trip), and no hierarchy to build first.  The candidate
+// SET of a tile is the same as the walk's (same boxes, same exact compares), only its order differs, and XOR makes
+// the order irrelevant.  Rectangles of many tiles (scene-sized triangles) are walked by the whole warp.
+// k_file_columns then files every tile as heavy / light / empty exactly as k_walk_columns does.
+template <int SY, int SZ>
+__global__ void __launch_bounds__(256)
+k_bin_columns(const ParityParams prm)
+{
+    extern __shared__ float sRect[];   // exact rectangles of the tiles: yMin/yMax per tile column, zMin/zMax per tile row
+    const uint32_t tilesY = prm.tilesY, tilesZ = (prm.z1 - prm.z0 + SZ - 1) / SZ;
+    float* yMin = sRect; float* yMax = yMin + tilesY; float* zMin = yMax + tilesY; float* zMax = zMin + tilesZ;
+    const float fN = (float)prm.N, halfN = 0.5f * fN;
+    for (uint32_t i = threadIdx.x; i < tilesY; i += blockDim.x)
+    {
+        const uint32_t sy0 = i * SY, yLast = min(sy0 + SY - 1, prm.N - 1);
+        yMax[i] = -centreOf(sy0, fN, prm.invNPow2);   // scene Y decreases with y
+        yMin[i] = -centreOf(yLast, fN, prm.invNPow2);
+    }
+    for (uint32_t i = threadIdx.x; i < tilesZ; i += blockDim.x)
+    {
+        const uint32_t sz0 = prm.z0 + i * SZ, zLast = min(sz0 + SZ - 1, prm.z1 - 1);
+        zMin[i] = centreOf(sz0, fN, prm.invNPow2);
+        zMax[i] = centreOf(zLast, fN, prm.invNPow2);
+    }
+    __syncthreads();
+    const uint32_t lane = laneId();
+    const int layers = (int)(prm.z1 - prm.z0);
+    const uint32_t rounded = (prm.numTris + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < rounded; j += gridDim.x * blockDim.x)
+    {
+        int ty0 = 0, ty1 = -1, tz0 = 0, tz1 = -1;
+        float ylo = 0, yhi = 0, zlo = 0, zhi = 0;
+        if (j < prm.numTris)
+        {
+            const float4* t = reinterpret_cast<const float4*>(prm.tris + j);
+            const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+            ylo = fminf(fminf(a.y, b.y), c.y); yhi = fmaxf(fmaxf(a.y, b.y), c.y);
+            zlo = fminf(fminf(a.z, b.z), c.z); zhi = fmaxf(fmaxf(a.z, b.z), c.z);
+            // conservative index range (one voxel of slack; the exact compares below decide), then tiles
+            const float yA = (1.0f - yhi) * halfN - 1.5f, yB = (1.0f - ylo) * halfN + 0.5f;
+            const float zA = (zlo + 1.0f) * halfN - 1.5f - (float)prm.z0, zB = (zhi + 1.0f) * halfN + 0.5f - (float)prm.z0;
+            if (yB >= 0.0f && yA <= fN - 1.0f && zB >= 0.0f && zA <= (float)(layers - 1))   // (false for NaN boxes)
+            {
+                ty0 = max((int)floorf(yA), 0) / SY; ty1 = min((int)ceilf(yB), (int)prm.N - 1) / SY;
+                tz0 = max((int)floorf(zA), 0) / SZ; tz1 = min((int)ceilf(zB), layers - 1) / SZ;
+            }
+        }
+        const uint32_t nu = (uint32_t)max(ty1 - ty0 + 1, 0), nv = (uint32_t)max(tz1 - tz0 + 1, 0), n = nu * nv;
+        auto emitTile = [&](uint32_t slot, int ty, int tz, float bylo, float byhi, float bzlo, float bzhi) {
+            if (bylo <= yMax[ty] && byhi >= yMin[ty] && bzlo <= zMax[tz] && bzhi >= zMin[tz])
+            {
+                const uint32_t tile = (uint32_t)tz * tilesY + (uint32_t)ty;
+                const uint32_t at = atomicAdd(prm.candCount + tile, 1u);
+                if (at < prm.candCap) prm.candList[(size_t)tile * prm.candCap + at] = slot;
+            }
+        };
+        if (n > 0u && n <= 16u)
+            for (uint32_t q = 0; q < n; ++q) emitTile(j, ty0 + (int)(q % nu), tz0 + (int)(q / nu), ylo, yhi, zlo, zhi);
+        uint32_t big = __ballot_sync(0xffffffffu, n > 16u);
+        while (big)
+        {
+            const int L = __ffs(big) - 1;
+            big &= big - 1u;
+            const uint32_t bn = __shfl_sync(0xffffffffu, n, L), bnu = __shfl_sync(0xffffffffu, nu, L);
+            const int by0 = __shfl_sync(0xffffffffu, ty0, L), bz0 = __shfl_sync(0xffffffffu, tz0, L);
+            const uint32_t bj = __shfl_sync(0xffffffffu, j, L);
+            const float b0 = __shfl_sync(0xffffffffu, ylo, L), b1 = __shfl_sync(0xffffffffu, yhi, L);
+            const float b2 = __shfl_sync(0xffffffffu, zlo, L), b3 = __shfl_sync(0xffffffffu, zhi, L);
+            for (uint32_t q = lane; q < bn; q += 32u) emitTile(bj, by0 + (int)(q % bnu), bz0 + (int)(q / bnu), b0, b1, b2, b3);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * kWalkWarps)
+k_file_columns(const ParityParams prm)
+{
+    const uint32_t firstTile = (blockIdx.x * kWalkWarps + (threadIdx.x >> 5)) * 32u;
+    if (firstTile >= prm.numTiles) return;
+    const uint32_t tile = firstTile + laneId();
+    uint32_t count = 0xffffffffu;
+    if (tile < prm.numTiles) count = min(prm.candCount[tile], prm.candCap + 1u);   // > candCap: the fill kernel scans every triangle
+    fileTiles(prm, firstTile, count);
+}
+
 // ---- empty super-tiles: nothing to trace, 16 KB of zeros to write.  A few dedicated "writer" CTAs
 // (the first blocks of the fill kernel) stream them with fire-and-forget 128-bit stores while the
 // other CTAs of the same SMs rasterise: the write stream of the ~80 % of a real grid that is empty
@@ -622,6 +711,45 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
                 processWarpChunkStaged(has, has ? __ldg(list + first + lane) : 0u);
             }
         }
+        else if (prm.nodes == nullptr)
+        {
+            // ---- overflowed list of a BINNED tile (no hierarchy was built): scan every triangle's box; the ones
+            // that meet the tile go through the same ring of queued candidates as the walk below ----
+            float rYmin, rYmax, rZmin, rZmax;
+            tileRect<SY, SZ>(prm, sy0, sz0, rYmin, rYmax, rZmin, rZmax);
+            uint32_t consumed = 0;
+            const uint32_t lt = laneMaskLt();
+            for (uint32_t base = 0; base < prm.numTris; base += (uint32_t)kThreads)
+            {
+                const uint32_t j = base + tid;
+                bool ov = false;
+                if (j < prm.numTris)
+                {
+                    const float4* t = reinterpret_cast<const float4*>(prm.tris + j);
+                    const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+                    ov = fminf(fminf(a.y, b.y), c.y) <= rYmax && fmaxf(fmaxf(a.y, b.y), c.y) >= rYmin &&
+                         fminf(fminf(a.z, b.z), c.z) <= rZmax && fmaxf(fmaxf(a.z, b.z), c.z) >= rZmin;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, ov);
+                uint32_t off = 0;
+                if (lane == 0 && m) off = atomicAdd(&sCand, (uint32_t)__popc(m));
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (ov) cand[(off + __popc(m & lt)) % kCandCap] = j;
+                __syncthreads();
+                const uint32_t produced = sCand;
+                while (produced - consumed >= (uint32_t)kThreads)
+                {
+                    processWarpChunk(true, cand[(consumed + tid) % kCandCap], 32u);
+                    consumed += kThreads;
+                }
+                __syncthreads();   // the drained ring entries may be overwritten by the next round
+            }
+            for (uint32_t produced = sCand, i0 = consumed + warp * 32u; i0 < produced; i0 += kThreads)
+            {
+                const bool has = i0 + lane < produced;
+                processWarpChunk(has, has ? cand[(i0 + lane) % kCandCap] : 0u, 32u);
+            }
+        }
         else
         {
             // ---- fallback: CTA-cooperative walk (every thread pops a different node) ----
@@ -870,7 +998,17 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
     static const bool noBulk = [] { const char* e = std::getenv("DXRV_NO_BULK_STORE"); return e && e[0] && e[0] != '0'; }();
     prm.bulkStores = noBulk ? 0u : 1u;
     if (ev) cudaEventRecord(ev[0], s);
-    k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
+    if (prm.nodes)
+        k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
+    else
+    {
+        // candidates by triangle-parallel binning (the default): no hierarchy needed
+        const uint32_t tilesZ = (prm.z1 - prm.z0 + SZ - 1) / SZ;
+        const uint32_t binBlocks = std::max(1u, std::min<uint32_t>((prm.numTris + 255u) / 256u, 148u * 8u));
+        k_bin_columns<SY, SZ><<<binBlocks, 256, sizeof(float) * 2 * (prm.tilesY + tilesZ), s>>>(prm);
+        const uint32_t groups = (prm.numTiles + 31u) / 32u;
+        k_file_columns<<<(groups + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
+    }
     if (ev) cudaEventRecord(ev[1], s);
 #ifdef DXRV_TIMELINE
     {
@@ -947,11 +1085,12 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.crossings = dCrossings; prm.err = dErr;
     cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
     cudaMemsetAsync(prm.bucketCount, 0, kCounterWords * sizeof(uint32_t), s);
+    if (!prm.nodes) cudaMemsetAsync(prm.candCount, 0, tilesPad * sizeof(uint32_t), s);   // the binning kernel counts with atomics
     // warps per CTA by row length (see k_trace_fill_columns); every choice keeps rows-per-warp x groups-per-row
     // a multiple of 32
     if (prm.Ps <= 32) launchVariant<4, 16, 8>(s, prm, ev);
     else if (prm.Ps <= 64) launchVariant<8, 16, 8>(s, prm, ev);
     else launchVariant<16, 16, 8>(s, prm, ev);
-    return 2;
+    return prm.nodes ? 2 : 3;
 }
 }  // namespace dxrv

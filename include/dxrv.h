@@ -99,11 +99,13 @@ DXRV_API int dxrv_synchronize(dxrv_ctx* ctx);
  * does from ObjLoader::computeAABB (min/max over ALL vertices).
  * The build is an LBVH: bounds -> 30-bit Morton keys -> onesweep radix sort -> sorted triangle
  * records and leaf boxes -> Karras hierarchy -> child boxes (range unions; atomic bottom-up refit
- * above 2^19 triangles).  RULE for the last two steps: they run inside this call when the previous
- * dxrv_voxelize of the context traversed the hierarchy (MODE_SHADER, tile-path MODE_PARITY), and
- * otherwise are deferred to the first dxrv_voxelize that does -- the triangle-parallel scatter path
- * (fine meshes on coarse grids: 4 T >= N^2) reads the Morton-sorted triangle records only and never
- * pays for a tree it would not walk.  Results are identical either way.
+ * above 2^19 triangles).  RULE for the last two steps (the hierarchy): they run inside this call when
+ * the previous dxrv_voxelize of the context traversed the hierarchy, and otherwise are deferred to the
+ * first dxrv_voxelize that does.  MODE_SHADER traverses it (LBVH walk on small grids, and as the
+ * overflow path of the direction bins).  MODE_PARITY does not by default: its candidates come from
+ * triangle-parallel passes over the Morton-sorted triangle records (2-D binning into column tiles, or
+ * the scatter path for fine meshes on coarse grids); DXRV_PARITY_CANDIDATES=walk selects the LBVH walk
+ * (k_walk_columns) instead.  Grids are identical bit for bit whichever way the candidates are found.
  * The host variant copies the arrays to the device. */
 DXRV_API int dxrv_build_bvh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts,
                             uint32_t strideBytes, const uint32_t* indices, uint32_t numIndices,

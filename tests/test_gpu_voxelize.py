@@ -414,3 +414,32 @@ def test_pipelined_voxelize_to_host(vox, assets, N, z0, z1, chunks):
         assert np.array_equal(host.numpy().view(np.uint32).reshape(want.shape), want)
         assert np.array_equal(vox.fetch_bits(), want)              # the context holds the whole slab afterwards
         assert vox.count_inside() == popcount(want)
+
+
+@pytest.mark.parametrize("name,N,slab", [("dragon.obj", 512, None), ("TuringBowl.obj", 384, (100, 180)), ("cube", 200, None), ("bunny.obj", 1024, (500, 540))])
+def test_walked_and_binned_candidates_agree(vox, assets, meshes_mod, oracle_mod, monkeypatch, name, N, slab):
+    """The tile path of MODE_PARITY finds its candidates by triangle-parallel binning (default, no hierarchy) or by the
+    LBVH walk (DXRV_PARITY_CANDIDATES=walk): same candidate sets, so identical grids and crossing counts, equal to the
+    oracle's; 12 scene-sized triangles (cube) exercise the warp-cooperative rectangles."""
+    m = meshes_mod.cube() if name == "cube" else assets(name)
+    z0, z1 = slab if slab else (0, N)
+    ref = oracle_mod.voxelize(m.vertices, m.indices, N, oracle_mod.MODE_PARITY, z0=z0, z1=z1)
+    monkeypatch.setenv("DXRV_PARITY_PATH", "tiles")
+    for how in ("bins", "walk", "bins"):
+        monkeypatch.setenv("DXRV_PARITY_CANDIDATES", how)
+        got = _run(vox, m, N, d.MODE_PARITY, z0, z1)
+        assert popcount(got ^ ref["bits"]) == 0, how
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], how
+
+
+def test_binned_candidates_overflow_scans_all_triangles(vox, meshes_mod, oracle_mod, monkeypatch):
+    """327 k triangles forced through the tile path at 64^3: 32 tiles, far more candidates per tile than a list holds
+    -> the fill kernel's tree-free fallback (every CTA scans all triangle boxes) -- still the oracle's bits."""
+    m = meshes_mod.icosphere(7, seed=3, normals=False)
+    monkeypatch.setenv("DXRV_PARITY_PATH", "tiles")
+    for how in ("bins", "walk"):
+        monkeypatch.setenv("DXRV_PARITY_CANDIDATES", how)
+        got = _run(vox, m, 64, d.MODE_PARITY)
+        ref = oracle_mod.voxelize(m.vertices, m.indices, 64, 1)
+        assert popcount(got ^ ref["bits"]) == 0, how
+        assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], how
