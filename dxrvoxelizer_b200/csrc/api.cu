@@ -152,8 +152,16 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
 
     cudaStream_t s = ctx->stream;
     // small meshes: 8 bits per axis (24-bit keys, three radix passes); large: all 30 bits
-    const uint32_t keyShift = (T <= (1u << 18)) ? 6u : 0u;
-    const int numPasses = (T <= (1u << 18)) ? 3 : 4;
+    // Key width.  With the hierarchy (a consumer traverses it): 8 bits per axis for small meshes (three radix passes),
+    // all 30 bits for large ones -- the tree's quality depends on it.  Without (MODE_PARITY: the sorted order only
+    // gives neighbouring records neighbouring slots; triangles of one cell keep their mesh order, the sort is
+    // stable): two passes less -- 16-bit keys for small meshes, 24-bit for large ones (the top bits of the
+    // 30-bit code: 5-6 / 8 bits per axis).  A hierarchy built later over such keys is valid (ties are broken by
+    // index) but coarser; the next build widens the keys again.
+    const bool withTree = ctx->treeWanted;
+    const bool small = T <= (1u << 18);
+    const uint32_t keyShift = withTree ? (small ? 6u : 0u) : (small ? 14u : 6u);
+    const int numPasses = withTree ? (small ? 3 : 4) : (small ? 2 : 3);
     // with an odd number of passes start in the B buffers, so that the sorted result is always in A
     // (a single triangle is not sorted at all: it stays where the Morton kernel wrote it)
     const bool startInB = (numPasses & 1) && T >= 2;
@@ -167,7 +175,6 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     std::vector<uint8_t> key;
     keyPush(key, (uint32_t)0xB01Du);
     keyPush(key, m.verts); keyPush(key, m.numVerts); keyPush(key, m.stride); keyPush(key, m.indices); keyPush(key, m.numTris);
-    const bool withTree = ctx->treeWanted;
     keyPush(key, (uint32_t)haveBound); keyPush(key, bnd); keyPush(key, (uint32_t)withTree);
     keyPush(key, ctx->keysA); keyPush(key, ctx->keysB); keyPush(key, ctx->valsA); keyPush(key, ctx->valsB);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp); keyPush(key, ctx->refitScratch);

@@ -489,6 +489,10 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
 
 bool parseObjFast(const char* text, size_t size, ObjMesh& m, std::string& err, unsigned threads)
 {
+    // DXRV_OBJ_THREADS: threads per FILE (default: up to 16).  A batch loader that parses many files at once (C5:
+    // 256 meshes) sets it to 1 and parallelises over the files instead.
+    if (threads == 0)
+        if (const char* e = std::getenv("DXRV_OBJ_THREADS")) threads = (unsigned)std::max(0, std::atoi(e));
     if (threads == 0) threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     const size_t minChunk = 1u << 16;
     size_t numChunks = std::max<size_t>(1, std::min<size_t>(threads, size / minChunk));

@@ -308,8 +308,46 @@ k_bin_columns(const ParityParams prm)
                 if (at < prm.candCap) prm.candList[(size_t)tile * prm.candCap + at] = slot;
             }
         };
-        if (n > 0u && n <= 16u)
-            for (uint32_t q = 0; q < n; ++q) emitTile(j, ty0 + (int)(q % nu), tz0 + (int)(q / nu), ylo, yhi, zlo, zhi);
+        // Small rectangles, all lanes in step: neighbours in Morton order mostly hit the SAME tile, so the lanes of a warp
+        // that do are served by one atomic (a crowded tile otherwise takes thousands of serialised same-address atomics).
+        const uint32_t nSmall = n <= 16u ? n : 0u;
+        const uint32_t rounds = __reduce_max_sync(0xffffffffu, nSmall);
+        // four rounds per batch: their atomics are all issued before the first result is consumed (one L2 round trip
+        // per batch instead of one per round -- the kernel is a latency chain, not a throughput problem)
+        for (uint32_t q0 = 0; q0 < rounds; q0 += 4u)
+        {
+            uint32_t tileK[4], peersK[4], atK[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k)
+            {
+                const uint32_t q = q0 + k;
+                bool has = false;
+                tileK[k] = 0; peersK[k] = 0; atK[k] = 0;
+                if (q < nSmall)
+                {
+                    const int ty = ty0 + (int)(q % nu), tz = tz0 + (int)(q / nu);
+                    has = ylo <= yMax[ty] && yhi >= yMin[ty] && zlo <= zMax[tz] && zhi >= zMin[tz];
+                    tileK[k] = (uint32_t)tz * tilesY + (uint32_t)ty;
+                }
+                const uint32_t act = __ballot_sync(0xffffffffu, has);
+                if (has)
+                {
+                    peersK[k] = __match_any_sync(act, tileK[k]);
+                    if ((int)lane == __ffs(peersK[k]) - 1) atK[k] = atomicAdd(prm.candCount + tileK[k], (uint32_t)__popc(peersK[k]));
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k)
+            {
+                const uint32_t act = __ballot_sync(0xffffffffu, peersK[k] != 0u);
+                if (peersK[k] != 0u)
+                {
+                    (void)act;
+                    const uint32_t at = __shfl_sync(peersK[k], atK[k], __ffs(peersK[k]) - 1) + (uint32_t)__popc(peersK[k] & laneMaskLt());
+                    if (at < prm.candCap) prm.candList[(size_t)tileK[k] * prm.candCap + at] = j;
+                }
+            }
+        }
         uint32_t big = __ballot_sync(0xffffffffu, n > 16u);
         while (big)
         {
