@@ -119,6 +119,7 @@ void keyPush(std::vector<uint8_t>& k, const T& v)
 
 int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
 {
+    NvtxRange range("dxrv build (bounds, Morton, onesweep, leaves[, hierarchy])");
     const MeshView& m = ctx->mesh;
     const uint32_t T = m.numTris;
     ctx->haveBvh = false;
@@ -396,6 +397,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     if (!ctx) return DXRV_ERR_INVALID_ARG;
     if (!ctx->haveBvh) return fail(ctx, DXRV_ERR_NO_BVH, "dxrv_voxelize: call dxrv_build_bvh first");
     const uint32_t algo = mode & DXRV_MODE_MASK;
+    NvtxRange range(algo == DXRV_MODE_PARITY ? "dxrv voxelize MODE_PARITY" : "dxrv voxelize MODE_SHADER");
     const bool wantTexels = (mode & DXRV_EMIT_TEXELS) != 0;
     if (algo != DXRV_MODE_SHADER && algo != DXRV_MODE_PARITY) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: unknown mode");
     if (mode & ~(uint32_t)(DXRV_MODE_MASK | DXRV_EMIT_TEXELS)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize: unknown mode flags");
@@ -536,6 +538,7 @@ int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format)
 {
     if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
     if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_fetch_grid: call dxrv_voxelize first");
+    NvtxRange range("dxrv fetch grid (D2H)");
     DeviceGuard g(ctx->device);
     const uint32_t* grid = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
     const uint32_t layers = ctx->z1 - ctx->z0;

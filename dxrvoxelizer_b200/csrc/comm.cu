@@ -198,6 +198,7 @@ int dxrv_bcast_mesh(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts, uint
     if (root < 0 || root >= ctx->commWorld) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_bcast_mesh: bad root");
     if (numVerts == 0 || strideBytes < 12 || (strideBytes & 3u) || numIndices % 3u)
         return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_bcast_mesh: numVerts / strideBytes / numIndices must be valid on EVERY rank (dxrv_bcast_u32 carries them)");
+    NvtxRange range("dxrv broadcast mesh (NCCL)");
     const bool isRoot = ctx->commRank == root;
     if (isRoot && (!vertices || (numIndices && !indices))) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_bcast_mesh: the root needs the host arrays");
     DeviceGuard g(ctx->device);
@@ -248,6 +249,7 @@ static int ensureFullGrid(dxrv_ctx* ctx, size_t bytes)
 
 static int gatherWithTable(dxrv_ctx* ctx, int root, const uint32_t* all /* {z0, z1} per rank */)
 {
+    NvtxRange range("dxrv gather slabs (NCCL)");
     const int world = ctx->commWorld, me = ctx->commRank;
     ncclComm_t comm = static_cast<ncclComm_t>(ctx->comm);
     const uint32_t N = ctx->N;

@@ -2,6 +2,7 @@
 // Internal to libdxrv.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler injects itself
 
 #include <cstdio>
 #include <string>
@@ -117,6 +118,13 @@ inline int cudaFail(dxrv_ctx* c, cudaError_t e, const char* what)
         cudaError_t e_ = (call);                                          \
         if (e_ != cudaSuccess) return cudaFail(ctx, e_, #call);           \
     } while (0)
+
+// NVTX range per API phase (the reference ships WinPixEventRuntime markers it never calls)
+struct NvtxRange
+{
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard
 {

@@ -47,6 +47,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace dxrv
 {
@@ -511,11 +512,18 @@ k_bins_finish_big(const ShaderBinsView bins)
 }
 
 // ---- trace --------------------------------------------------------------------------------------------------------
+// (Tried and dropped, measured on dragon / bowl / bunny at 512^3: a RAY POOL -- classify 128 voxels cheaply, queue the
+// ones with candidates in shared memory, run the queue on 32 lanes that refill individually or in batches.  It was
+// 10-40 % SLOWER than this kernel at every refill threshold: the compaction destroys the coherence of the sub-brick
+// (neighbouring rays read the same entries and triangles) and the queue management costs more than the idle lanes.)
 // One warp = a sub-brick of 8 (x) x 2 (y) x 2 (z) voxels: neighbouring rays share cube-map cells and radii, so the
 // lanes' list walks have similar lengths and read the same entries / triangles (a 32 x 1 x 1 row spans up to 15 cells).
 // The warp's 32 result bits are four bytes of four different grid words; each is stored as one byte (every byte of
 // the slab is written exactly once, by exactly one warp -- no barrier, no atomics, no clear).
 constexpr int kTraceThreads = 128;
+#ifndef TRACE_MINBLOCKS
+#define TRACE_MINBLOCKS 9   // 56 registers, 36 warps / SM: measured best of 7..10 (8-10 % over 72 registers)
+#endif
 
 struct RayK
 {
@@ -584,7 +592,7 @@ struct TraceGeom
     uint32_t layers;
 };
 
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, TRACE_MINBLOCKS)
 k_trace_shader_bins(const ShaderParams prm, const ShaderBinsView bins, const float* __restrict__ centres, const TraceGeom g)
 {
     if (__ldg(bins.state + 1) != 0u) return;   // over budget: k_trace_shader (LBVH walk) produces the grid
