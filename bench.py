@@ -319,9 +319,12 @@ def run_c3(args):
     build()
     mism, checked = gate_slab(rig, host_mesh, N, d.MODE_PARITY, z0, z1)
     gate_ref = GATE_REF[d.MODE_PARITY]                           # the oracle's slab: also checks the e2e arm's host buffer
-    mid = (z0 + z1) // 2
-    shader_layers = sorted({z0, mid, min(mid + 1, z1 - 1), z1 - 1})
-    smism, schecked = gate_slab(rig, host_mesh, N, d.MODE_SHADER, z0, z1, layers=shader_layers)
+    # MODE_SHADER casts a ray from EVERY voxel, so its slabs are cut evenly (the parity cuts follow the triangles)
+    from dxrvoxelizer_b200.sharding import slab_range as _equal
+    sz0, sz1 = _equal(rank, world, N) if world > 1 else (z0, z1)
+    mid = (sz0 + sz1) // 2
+    shader_layers = sorted({sz0, mid, min(mid + 1, sz1 - 1), sz1 - 1})
+    smism, schecked = gate_slab(rig, host_mesh, N, d.MODE_SHADER, sz0, sz1, layers=shader_layers)
     mism_total, smism_total, checked_total, schecked_total = rig.reduce_sum([mism, smism, checked, schecked])
     if mism_total != 0 or smism_total != 0:
         if rank == 0:
@@ -378,12 +381,12 @@ def run_c3(args):
     # ---- MODE_SHADER on the same slab (the reference's own function), bins rebuilt every step ------------------
     shader_steps = max(2, min(args.steps, 5))
     for _ in range(2):
-        build(); vox.voxelize(N, d.MODE_SHADER, z0, z1)
+        build(); vox.voxelize(N, d.MODE_SHADER, sz0, sz1)
     rig.barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record(stream)
     for _ in range(shader_steps):
-        build(); vox.voxelize(N, d.MODE_SHADER, z0, z1)
+        build(); vox.voxelize(N, d.MODE_SHADER, sz0, sz1)
     s1.record(stream)
     rig.barrier()
     shader_ms = s0.elapsed_time(s1) / shader_steps
@@ -501,7 +504,7 @@ def run_c3(args):
             "phases_ms": {"bvh_build": build_ms, "voxelize": trace_ms, "k_walk_columns": walk_ms, "k_trace_fill_columns": fill_ms,
                           "shader_1024": shader_ms},
             "shader": {"ms_per_1024_cubed_grid_incl_build_and_bins": shader_ms, "grays_per_s": total_voxels / (shader_ms * 1e-3) * 1e-9,
-                       "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), same slabs, LBVH + direction bins rebuilt every step"},
+                       "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), equal z-slabs, LBVH + direction bins rebuilt every step"},
             "ms_per_1024_cubed_grid": step_ms,
             "e2e": {"value": total_voxels / (e2e_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(N * N * P * 4),
