@@ -439,6 +439,33 @@ def run_c3(args):
         step_e2e()
     rig.barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    # ---- the same end-to-end step with the compact read-back format (DXRV_FORMAT_SPARSE_BRICKS, lossless): side number
+    with numa_local(rig.local):
+        h_sparse = torch.empty(e_bytes + e_bytes // 64 + (1 << 16), dtype=torch.uint8).pin_memory()
+
+    def step_e2e_sparse():
+        if world > 1:
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    d_vb.copy_(h_vb, non_blocking=True)
+                    d_ib.copy_(h_ib, non_blocking=True)
+                rig.dist.broadcast(d_vb, 0)
+                rig.dist.broadcast(d_ib, 0)
+            build()
+        else:
+            vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
+        vox.voxelize(N, d.MODE_PARITY, ez0, ez1)
+        return vox.fetch_sparse_into(h_sparse.data_ptr(), h_sparse.numel())
+
+    for _ in range(3):
+        sparse_bytes = step_e2e_sparse()
+    sparse_mism = popcount(d.sparse_decode(h_sparse.numpy()[:sparse_bytes]) ^ e_ref)
+    rig.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_sparse()
+    rig.barrier()
+    sparse_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     # where the end-to-end time goes (separate short loop with a synchronisation between compute and read-back)
     reps = min(args.steps, 20)
@@ -476,8 +503,9 @@ def run_c3(args):
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
     fill_ms_rank0 = fill_ms   # the roofline of the kernel is a per-GPU figure: rank 0's launches against rank 0's bytes
-    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms = rig.reduce_max(
-        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0])
+    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms, sparse_ms = rig.reduce_max(
+        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0, sparse_ms])
+    sparse_bytes_total, sparse_mism_total = rig.reduce_sum([sparse_bytes, sparse_mism])
     per_rank = None
     if world > 1:
         gathered = [None] * world
@@ -513,6 +541,11 @@ def run_c3(args):
                            "the 128 MiB dense bit grid over PCIe is the floor (d2h_grid below, measured unpipelined); N > 1: equal slabs "
                            "(bytes, not compute, bound the read-back), every rank's host buffer checked against the oracle",
                     "mismatched_voxels": int(e2e_mism_total),
+                    "sparse_bricks": {"value": total_voxels / (sparse_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": sparse_ms,
+                                      "d2h_bytes_per_step": int(sparse_bytes_total), "mismatched_voxels_after_decode": int(sparse_mism_total),
+                                      "what": "same step, read-back as DXRV_FORMAT_SPARSE_BRICKS (lossless: header + 2-bit brick states + the "
+                                              "mixed 32x4x4 bricks; dxrv_fetch_grid_sparse / dxrv_sparse_decode) -- a side number for consumers "
+                                              "that can take the compact form; `e2e.value` above is the dense grid, which is at the PCIe roofline"},
                     "phases_ms": {"h2d_mesh_build_voxelize": up_ms, "d2h_grid": down_ms}, "d2h_gbs_rank0": d2h_gbs,
                     "per_rank": per_rank},
             "gpu_launches": int(launches),

@@ -32,6 +32,8 @@ SIGNATURES = {
     "dxrv_get_bound": (_int, [_vp, _vp]),
     "dxrv_voxelize": (_int, [_vp, _u32, _u32, _u32, _u32]),
     "dxrv_fetch_grid": (_int, [_vp, _vp, _sz, _u32]),
+    "dxrv_fetch_grid_sparse": (_int, [_vp, _vp, _sz, _c.POINTER(_sz)]),
+    "dxrv_sparse_decode": (_int, [_vp, _sz, _vp, _sz]),
     "dxrv_voxelize_to_host": (_int, [_vp, _u32, _u32, _u32, _u32, _vp, _sz, _u32]),
     "dxrv_grid_device": (_int, [_vp, _c.POINTER(_vp), _c.POINTER(_sz)]),
     "dxrv_set_grid_target": (_int, [_vp, _vp, _sz]),

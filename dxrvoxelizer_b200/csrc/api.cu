@@ -294,7 +294,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     commRelease(ctx);
     void* ptrs[] = {ctx->gridFull, ctx->dSlabs, ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
-                    ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips,
+                    ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips, ctx->sparseBuf,
                     ctx->binsBuf};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -611,6 +611,69 @@ int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sla
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = false; ctx->mipLevels = 0;
     return checkDeviceError(ctx);
+}
+
+int dxrv_fetch_grid_sparse(dxrv_ctx* ctx, void* hostDst, size_t capacity, size_t* bytesWritten)
+{
+    if (!ctx || !hostDst || !bytesWritten) return DXRV_ERR_INVALID_ARG;
+    *bytesWritten = 0;
+    if (!ctx->haveGrid) return fail(ctx, DXRV_ERR_NO_GRID, "dxrv_fetch_grid_sparse: call dxrv_voxelize first");
+    if (ctx->z1 == ctx->z0) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid_sparse: empty slab");
+    NvtxRange range("dxrv fetch grid (sparse bricks, D2H)");
+    DeviceGuard g(ctx->device);
+    const SparseLayout L = sparseLayout(ctx->N, ctx->z1 - ctx->z0);
+    const size_t countsOff = (L.maxBytes + 255) & ~(size_t)255;
+    cudaError_t e = ensure(ctx->sparseBuf, ctx->sparseCap, countsOff + (size_t)L.numBlocks * sizeof(uint32_t));
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(sparse bricks)");
+    const uint32_t* grid = ctx->gridTarget ? ctx->gridTarget : ctx->gridOwned;
+    ctx->launches += (uint64_t)launchSparseEncode(ctx->stream, grid, ctx->N, ctx->z0, ctx->z1, ctx->sparseBuf,
+                                                  reinterpret_cast<uint32_t*>(ctx->sparseBuf + countsOff));
+    DXRV_CUDA(cudaGetLastError());
+    // the header (with the number of mixed bricks) first, then exactly the bytes that exist
+    if (capacity < 64) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid_sparse: capacity below the header size");
+    DXRV_CUDA(cudaMemcpyAsync(hostDst, ctx->sparseBuf, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    DXRV_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t numMixed = static_cast<const uint32_t*>(hostDst)[9];
+    const size_t total = L.offPayload + (size_t)numMixed * 64;
+    *bytesWritten = total;
+    if (capacity < total) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid_sparse: capacity too small (needed size returned in *bytesWritten)");
+    DXRV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(hostDst) + 64, ctx->sparseBuf + 64, total - 64, cudaMemcpyDeviceToHost, ctx->stream));
+    return checkDeviceError(ctx);
+}
+
+int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_t denseBytes)
+{
+    // pure host code: the inverse of the encoding in sparse.cu
+    if (!blob || !denseDst || blobBytes < 64) return DXRV_ERR_INVALID_ARG;
+    const uint32_t* h = static_cast<const uint32_t*>(blob);
+    if (h[0] != 0x42525844u || h[1] != 1u || h[12] != 32u || h[13] != 4u || h[14] != 4u) return DXRV_ERR_INVALID_ARG;
+    const uint32_t N = h[2], z0 = h[3], z1 = h[4], P = h[5], BY = h[6], BZ = h[7], numBricks = h[8], numMixed = h[9];
+    if (z1 <= z0 || P != (N + 31) / 32 || BY != (N + 3) / 4 || BZ != (z1 - z0 + 3) / 4 || (uint64_t)numBricks != (uint64_t)P * BY * BZ) return DXRV_ERR_INVALID_ARG;
+    const size_t offStates = h[10], offPayload = h[11];
+    if (blobBytes < offPayload + (size_t)numMixed * 64 || offPayload < offStates + (size_t)((numBricks + 15) / 16) * 4) return DXRV_ERR_INVALID_ARG;
+    const uint32_t layers = z1 - z0;
+    if (denseBytes != (size_t)layers * N * P * 4) return DXRV_ERR_INVALID_ARG;
+    const uint32_t* states = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(blob) + offStates);
+    const uint32_t* payload = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(blob) + offPayload);
+    uint32_t* out = static_cast<uint32_t*>(denseDst);
+    const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
+    size_t rank = 0;
+    for (uint32_t b = 0; b < numBricks; ++b)
+    {
+        const uint32_t st = (states[b >> 4] >> (2u * (b & 15u))) & 3u;
+        const uint32_t bx = b % P, t = b / P, by = t % BY, bz = t / BY;
+        const uint32_t fullWord = (bx == P - 1u) ? tailMask : 0xffffffffu;
+        if (st == 2u && rank >= numMixed) return DXRV_ERR_INVALID_ARG;
+        for (uint32_t k = 0; k < 4u; ++k)
+            for (uint32_t j = 0; j < 4u; ++j)
+            {
+                const uint32_t y = 4u * by + j, z = 4u * bz + k;
+                if (y >= N || z >= layers) continue;
+                out[((size_t)z * N + y) * P + bx] = st == 0u ? 0u : (st == 1u ? fullWord : payload[rank * 16 + 4u * k + j]);
+            }
+        if (st == 2u) ++rank;
+    }
+    return rank == numMixed ? DXRV_OK : DXRV_ERR_INVALID_ARG;
 }
 
 int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes)

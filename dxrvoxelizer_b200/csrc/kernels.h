@@ -123,6 +123,17 @@ void launchTraceShaderBins(cudaStream_t s, const BvhView& bvh, const MeshView& m
 void launchTraceShaderBvh(cudaStream_t s, const BvhView& bvh, const MeshView& m, uint32_t N, uint32_t z0, uint32_t z1,
                           uint32_t* grid, uint32_t* texels, uint32_t* dErr, const uint32_t* binsState /* nullable: always run */);
 
+// ---- sparse.cu ------------------------------------------------------------------------------------------
+// DXRV_FORMAT_SPARSE_BRICKS (include/dxrv.h): header | 2-bit brick states | 64-byte payload of the mixed bricks
+struct SparseLayout
+{
+    uint32_t P, BY, BZ, numBricks, stateWords, numBlocks;
+    size_t offStates, offPayload, maxBytes;
+};
+SparseLayout sparseLayout(uint32_t N, uint32_t layers);
+// blob: device memory of sparseLayout().maxBytes; blockCounts: numBlocks words of scratch.  Returns kernels launched.
+int launchSparseEncode(cudaStream_t s, const uint32_t* grid, uint32_t N, uint32_t z0, uint32_t z1, uint8_t* blob, uint32_t* blockCounts);
+
 // ---- view.cu (headless port of the reference's viewer pass, PSRayCast.hlsl) -----------------------------
 void launchRaycastView(cudaStream_t s, const uint32_t* grid, uint32_t N, uint32_t width, uint32_t height,
                        const float screenToLocal[16], const float eye[3], const float light[3], uint32_t* image);

@@ -159,6 +159,18 @@ class Voxelizer:
         self._check(self._lib.dxrv_fetch_grid(self._h, out.ctypes.data, out.nbytes, L.FORMAT_BITS))
         return out
 
+    def fetch_sparse_into(self, ptr, capacity):
+        """dxrv_fetch_grid_sparse into host memory at ptr; returns the bytes written."""
+        n = ctypes.c_size_t()
+        self._check(self._lib.dxrv_fetch_grid_sparse(self._h, ptr, capacity, ctypes.byref(n)))
+        return int(n.value)
+
+    def fetch_sparse(self):
+        """The slab as a DXRV_FORMAT_SPARSE_BRICKS blob (numpy uint8)."""
+        cap = 64 + self._shape[0] * self._shape[1] * self._shape[2] * 4 + (1 << 20) + self._shape[0] * self._shape[1] * self._shape[2] // 16
+        buf = np.empty(cap, np.uint8)
+        return buf[: self.fetch_sparse_into(buf.ctypes.data, cap)].copy()
+
     def fetch_into(self, ptr, nbytes, fmt=L.FORMAT_BITS):
         self._check(self._lib.dxrv_fetch_grid(self._h, ptr, nbytes, fmt))
 
@@ -299,6 +311,18 @@ class Voxelizer:
 
     def ipc_close(self, d_ptr):
         self._check(self._lib.dxrv_ipc_close(self._h, d_ptr))
+
+
+def sparse_decode(blob):
+    """DXRV_FORMAT_SPARSE_BRICKS blob -> dense uint32[(z1-z0), N, P] (dxrv_sparse_decode, host code)."""
+    b = np.ascontiguousarray(blob, dtype=np.uint8)
+    h = b[:64].view(np.uint32)
+    N, z0, z1, P = int(h[2]), int(h[3]), int(h[4]), int(h[5])
+    out = np.empty((z1 - z0, N, P), np.uint32)
+    rc = L.lib().dxrv_sparse_decode(b.ctypes.data, b.size, out.ctypes.data, out.nbytes)
+    if rc != L.OK:
+        raise L.DxrvError(rc, "dxrv_sparse_decode: malformed blob")
+    return out
 
 
 def unpack_bits(bits, N):

@@ -136,6 +136,18 @@ DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_
  * after dxrv_voxelize.  bytes must equal the slab size.  Not available with an external grid target. */
 DXRV_API int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd,
                                    void* hostDst, size_t bytes, uint32_t chunks);
+/* DXRV_FORMAT_SPARSE_BRICKS: a lossless compact form of the slab's BITS grid for consumers that can take it (a solid
+ * voxelization is almost all empty space and solid interior; the dense grid is already at the PCIe roofline).  Bricks
+ * of 32 (x) x 4 (y) x 4 (z) voxels = 16 words of the dense grid; brick b = (bz * BY + by) * P + bx.  Blob:
+ *   header  16 uint32: "DXRB", version 1, N, slabBegin, slabEnd, P, BY, BZ, bricks, mixed bricks, byte offset of the
+ *           states, byte offset of the payload, brick dims 32, 4, 4, 0
+ *   states  2 bits per brick, 16 per uint32 (brick b: bits 2 (b & 15) of word b >> 4): 0 empty, 1 full, 2 mixed
+ *   payload 16 words per mixed brick {z = 4 bz + k {y = 4 by + j}}, in brick order
+ * dxrv_fetch_grid_sparse encodes the slab of the last voxelize on the device and copies exactly the bytes that exist;
+ * *bytesWritten receives their number (also when `capacity` is too small: DXRV_ERR_INVALID_ARG, nothing but the header
+ * copied).  dxrv_sparse_decode (pure host code) expands a blob into the dense BITS layout. */
+DXRV_API int dxrv_fetch_grid_sparse(dxrv_ctx* ctx, void* hostDst, size_t capacity, size_t* bytesWritten);
+DXRV_API int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_t denseBytes);
 /* Device pointer / byte size of the slab's DXRV_FORMAT_BITS grid (valid until the next
  * voxelize with a different size, or destroy). */
 DXRV_API int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);

@@ -1,0 +1,87 @@
+"""DXRV_FORMAT_SPARSE_BRICKS (include/dxrv.h): lossless compact read-back format.  The decoder is host code and is
+checked here against an independent numpy ENCODER written from the format description; the GPU encoder is checked
+against the decoder and against that numpy encoder (byte-identical blobs)."""
+import numpy as np
+import pytest
+
+import dxrvoxelizer_b200 as d
+from conftest import popcount
+
+
+def numpy_encode(bits, N, z0):
+    """uint32[(layers, N, P)] -> blob, straight from the description in dxrv.h."""
+    layers, _, P = bits.shape
+    BY, BZ = (N + 3) // 4, (layers + 3) // 4
+    pad = np.zeros((BZ * 4, BY * 4, P), np.uint32)
+    pad[:layers, :N] = bits
+    exists = np.zeros((BZ * 4, BY * 4), bool)
+    exists[:layers, :N] = True
+    bricks = pad.reshape(BZ, 4, BY, 4, P).transpose(0, 2, 4, 1, 3).reshape(-1, 16)        # [b][4k + j]
+    ex = np.broadcast_to(exists.reshape(BZ, 4, BY, 4)[:, :, :, :, None], (BZ, 4, BY, 4, P)).transpose(0, 2, 4, 1, 3).reshape(-1, 16)
+    tail = np.uint32((1 << (N & 31)) - 1) if N & 31 else np.uint32(0xffffffff)
+    full_word = np.where(np.arange(bricks.shape[0]) % P == P - 1, tail, np.uint32(0xffffffff)).astype(np.uint32)
+    any_ = bricks.any(axis=1)
+    full = ((bricks == full_word[:, None]) | ~ex).all(axis=1) & any_
+    state = np.where(~any_, 0, np.where(full, 1, 2)).astype(np.uint32)
+    nb = bricks.shape[0]
+    sw = np.zeros((nb + 15) // 16, np.uint32)
+    np.bitwise_or.at(sw, np.arange(nb) >> 4, state << (2 * (np.arange(nb) & 15)).astype(np.uint32))
+    payload = bricks[state == 2].reshape(-1)
+    off_states = 64
+    off_payload = (off_states + sw.size * 4 + 63) & ~63
+    header = np.array([0x42525844, 1, N, z0, z0 + layers, P, BY, BZ, nb, int((state == 2).sum()), off_states, off_payload, 32, 4, 4, 0], np.uint32)
+    blob = np.zeros(off_payload + payload.size * 4, np.uint8)
+    blob[:64] = header.view(np.uint8)
+    blob[off_states:off_states + sw.size * 4] = sw.view(np.uint8)
+    blob[off_payload:] = payload.view(np.uint8)
+    return blob
+
+
+@pytest.mark.parametrize("N,layers,seed", [(64, 64, 1), (100, 37, 2), (33, 5, 3), (128, 2, 4), (31, 31, 5)])
+def test_decoder_against_a_numpy_encoder(N, layers, seed):
+    rng = np.random.default_rng(seed)
+    P = (N + 31) // 32
+    occ = np.zeros((layers, N, N), bool)
+    zz, yy, xx = np.meshgrid(np.arange(layers), np.arange(N), np.arange(N), indexing="ij")
+    occ |= (xx - N / 2) ** 2 + (yy - N / 2) ** 2 + (zz - layers / 2) ** 2 < (0.4 * N) ** 2          # a solid ball: empty, full, mixed bricks
+    occ ^= rng.random(occ.shape) < 0.001                                                          # speckle
+    bits = np.packbits(np.pad(occ, ((0, 0), (0, 0), (0, P * 32 - N))), axis=-1, bitorder="little").view(np.uint32).reshape(layers, N, P)
+    blob = numpy_encode(bits, N, 7)
+    assert np.array_equal(d.sparse_decode(blob), bits)
+    bad = blob.copy(); bad[0] ^= 1
+    with pytest.raises(d.DxrvError):
+        d.sparse_decode(bad)
+    with pytest.raises(d.DxrvError):
+        d.sparse_decode(blob[:-8] if blob.size > 72 and blob[:64].view(np.uint32)[9] else blob[:60])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,N,z0,z1,mode", [("dragon.obj", 256, 0, 256, 1), ("bunny.obj", 100, 10, 47, 1), ("TuringBowl.obj", 192, 0, 192, 0),
+                                               ("dragon.obj", 1024, 300, 560, 1), ("bunny.obj", 33, 0, 33, 1)])
+def test_gpu_encoder_round_trip(vox, assets, name, N, z0, z1, mode):
+    m = assets(name)
+    vox.build_bvh(m)
+    vox.voxelize(N, mode, z0, z1)
+    dense = vox.fetch_bits()
+    blob = vox.fetch_sparse()
+    assert np.array_equal(d.sparse_decode(blob), dense)
+    assert np.array_equal(blob, numpy_encode(dense, N, z0))                 # byte-identical to the format description
+    h = blob[:64].view(np.uint32)
+    assert h[9] > 0 and blob.size < dense.nbytes                            # a solid object: far smaller than the dense grid
+    small = np.empty(128, np.uint8)
+    with pytest.raises(d.DxrvError):
+        vox.fetch_sparse_into(small.ctypes.data, small.size)               # capacity too small
+
+
+@pytest.mark.gpu
+def test_empty_and_full_grids(vox, meshes_mod):
+    c = meshes_mod.cube()
+    vox.build_bvh(d.Mesh(c.vertex_bytes, np.zeros(0, np.uint32), c.stride))
+    vox.voxelize(64, d.MODE_PARITY)
+    blob = vox.fetch_sparse()
+    assert blob[:64].view(np.uint32)[9] == 0 and popcount(d.sparse_decode(blob)) == 0
+    vox.build_bvh(meshes_mod.cube(2.0), bound=[0, 0, 0, 1])                 # the cube contains the whole grid
+    vox.voxelize(64, d.MODE_PARITY)
+    dense = vox.fetch_bits()
+    blob = vox.fetch_sparse()
+    assert np.array_equal(d.sparse_decode(blob), dense)
