@@ -319,9 +319,9 @@ def run_c3(args):
     build()
     mism, checked = gate_slab(rig, host_mesh, N, d.MODE_PARITY, z0, z1)
     gate_ref = GATE_REF[d.MODE_PARITY]                           # the oracle's slab: also checks the e2e arm's host buffer
-    # MODE_SHADER casts a ray from EVERY voxel, so its slabs are cut evenly (the parity cuts follow the triangles)
-    from dxrvoxelizer_b200.sharding import slab_range as _equal
-    sz0, sz1 = _equal(rank, world, N) if world > 1 else (z0, z1)
+    # MODE_SHADER runs on the same cost-balanced slabs (measured on 8 GPUs: 2.7 ms against 4.5 ms with equal slabs --
+    # the layers through the mesh are the expensive ones for the radial rays too)
+    sz0, sz1 = z0, z1
     mid = (sz0 + sz1) // 2
     shader_layers = sorted({sz0, mid, min(mid + 1, sz1 - 1), sz1 - 1})
     smism, schecked = gate_slab(rig, host_mesh, N, d.MODE_SHADER, sz0, sz1, layers=shader_layers)
@@ -396,13 +396,36 @@ def run_c3(args):
     # and 2.4 us to copy (128 KiB over PCIe), so equal slabs minimise the longest read-back (the compute-balanced
     # cuts of the device-resident arm give the sparse ends of the dragon a quarter of the grid each).
     if world > 1:
-        from dxrvoxelizer_b200.sharding import slab_range
+        from dxrvoxelizer_b200.sharding import proportional_slabs
         import oracle
-        ez0, ez1 = slab_range(rank, world, N)
+        # The GPUs of one box do not all see the same host link: measured on this pool's 8-GPU boxes, GPU 0 reads back at
+        # 53 GB/s while GPUs 1-3 get 13-17 GB/s and GPUs 4-7 ~25 GB/s when all eight copy at once.  Untimed calibration
+        # under the real pattern: equal slabs, every rank voxelizes, all ranks start their read-back together, best of 5;
+        # the slabs are then cut in proportion to the measured rates.
+        from dxrvoxelizer_b200.sharding import slab_range
+        c0, c1 = slab_range(rank, world, N)
+        cal_bytes = (c1 - c0) * N * P * 4
+        with numa_local(rig.local):
+            cal_h = torch.empty(cal_bytes, dtype=torch.uint8).pin_memory()
+            cal_h.zero_()
+        build()
+        best = 1e30
+        for _ in range(5):
+            vox.voxelize(N, d.MODE_PARITY, c0, c1)
+            vox.synchronize()
+            rig.barrier()
+            tcal = time.perf_counter()
+            vox.fetch_into(cal_h.data_ptr(), cal_bytes)
+            best = min(best, time.perf_counter() - tcal)
+        rates = [None] * world
+        rig.dist.all_gather_object(rates, cal_bytes / best * 1e-9)
+        ez0, ez1 = proportional_slabs(N, rates)[rank]
+        cal_rates = [round(float(r), 2) for r in rates]
+        del cal_h
         e_ref = oracle.voxelize(host_mesh.vertices, host_mesh.indices, N, oracle.MODE_PARITY, z0=ez0, z1=ez1,
                                 threads=max(1, host_threads() // world))["bits"]
     else:
-        ez0, ez1, e_ref = z0, z1, gate_ref
+        ez0, ez1, e_ref, cal_rates = z0, z1, gate_ref, None
     e_bytes = (ez1 - ez0) * N * P * 4
     with numa_local(rig.local):
         h_grid = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
@@ -532,15 +555,16 @@ def run_c3(args):
             "phases_ms": {"bvh_build": build_ms, "voxelize": trace_ms, "k_walk_columns": walk_ms, "k_trace_fill_columns": fill_ms,
                           "shader_1024": shader_ms},
             "shader": {"ms_per_1024_cubed_grid_incl_build_and_bins": shader_ms, "grays_per_s": total_voxels / (shader_ms * 1e-3) * 1e-9,
-                       "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), equal z-slabs, LBVH + direction bins rebuilt every step"},
+                       "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), same z-slabs, LBVH + direction bins rebuilt every step"},
             "ms_per_1024_cubed_grid": step_ms,
             "e2e": {"value": total_voxels / (e2e_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(N * N * P * 4),
                     "timing": "wall clock around synchronising C-ABI calls, max over ranks",
                     "how": "dxrv_build_bvh (host arrays) + dxrv_voxelize_to_host (8 z sub-slabs: D2H of chunk k beside the fill of chunk k+1); "
-                           "the 128 MiB dense bit grid over PCIe is the floor (d2h_grid below, measured unpipelined); N > 1: equal slabs "
-                           "(bytes, not compute, bound the read-back), every rank's host buffer checked against the oracle",
-                    "mismatched_voxels": int(e2e_mism_total),
+                           "the 128 MiB dense bit grid over PCIe is the floor (d2h_grid below, measured unpipelined); N > 1: slabs cut in "
+                           "proportion to every rank's measured read-back rate (bytes, not compute, bound the step; the GPUs of a box share "
+                           "host links unevenly), every rank's host buffer checked against the oracle",
+                    "mismatched_voxels": int(e2e_mism_total), "readback_calibration_gbs": cal_rates,
                     "sparse_bricks": {"value": total_voxels / (sparse_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": sparse_ms,
                                       "d2h_bytes_per_step": int(sparse_bytes_total), "mismatched_voxels_after_decode": int(sparse_mism_total),
                                       "what": "same step, read-back as DXRV_FORMAT_SPARSE_BRICKS (lossless: header + 2-bit brick states + the "

@@ -64,11 +64,18 @@ int runCaptured(dxrv_ctx* ctx, const std::vector<uint8_t>& key, F&& enqueue)
     if (ok)
     {
         const uint64_t launchesNow = ctx->launches - before;
+        // ... but only once a dozen graphs of that kind exist: a call sequence that CYCLES through a few parameter sets
+        // (the z sub-slabs of dxrv_voxelize_to_host, the slabs of a multi-GPU host) gets one executable graph each
+        // and replays them, instead of patching one graph back and forth (capture + update cost ~0.1 ms of CPU time).
         dxrv_ctx::GraphEntry* best = nullptr;
+        size_t sameKind = 0;
         for (auto& g : ctx->graphs)
-            if (g.launches == launchesNow && g.key.size() >= 4 && key.size() >= 4 && std::equal(key.begin(), key.begin() + 4, g.key.begin()) &&
-                (!best || g.lastUse > best->lastUse))
-                best = &g;
+            if (g.launches == launchesNow && g.key.size() >= 4 && key.size() >= 4 && std::equal(key.begin(), key.begin() + 4, g.key.begin()))
+            {
+                ++sameKind;
+                if (!best || g.lastUse < best->lastUse) best = &g;   // least recently used of its kind
+            }
+        if (sameKind < 12) best = nullptr;
         if (best)
         {
             cudaGraphExecUpdateResultInfo info;

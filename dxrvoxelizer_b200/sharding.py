@@ -65,6 +65,20 @@ def balanced_slabs(mesh, N, world, bound=None, compute_weight=1.2):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def proportional_slabs(N, weights):
+    """[(z0, z1)] * len(weights): contiguous slabs covering [0, N) with layer counts proportional to `weights` (e.g. every
+    rank's measured read-back bandwidth, when the slabs go back to the host and bytes bound the step).  Deterministic."""
+    w = np.maximum(np.asarray(weights, np.float64), 0.0)
+    if w.size < 1 or N < 1:
+        raise ValueError("bad weights/N")
+    if w.sum() <= 0:
+        w = np.ones_like(w)
+    cuts = np.floor(np.concatenate([[0.0], np.cumsum(w)]) / w.sum() * N + 0.5).astype(np.int64)
+    cuts[0], cuts[-1] = 0, N
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, N))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(w.size)]
+
+
 def slab_words(N, z0, z1):
     return (z1 - z0) * N * ((N + 31) // 32)
 

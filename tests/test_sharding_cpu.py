@@ -90,3 +90,12 @@ def test_balanced_slabs_cover_grid_and_balance_the_dragon(world, assets):
         equal = [slab_range(r, world, N) for r in range(world)]
         assert worst(slabs) <= worst(equal) * (1.05 if world == 2 else 0.8)
         assert worst(slabs) <= 1.35 * cost.sum() / world
+
+
+def test_proportional_slabs_cover_the_grid():
+    from dxrvoxelizer_b200.sharding import proportional_slabs
+    for N, w in ((1024, [53, 16.7, 16.7, 16.7, 25, 25, 25, 25]), (33, [1, 1]), (5, [1, 0, 3]), (1, [2, 2, 2, 2]), (64, [0, 0])):
+        sl = proportional_slabs(N, w)
+        assert sl[0][0] == 0 and sl[-1][1] == N and all(a[1] == b[0] for a, b in zip(sl, sl[1:])) and all(a <= b for a, b in sl)
+    sl = proportional_slabs(1024, [53, 16.7, 16.7, 16.7, 25, 25, 25, 25])
+    assert sl[0][1] - sl[0][0] > 2.5 * (sl[1][1] - sl[1][0])
