@@ -115,7 +115,7 @@ def run_c4(args, Rig, ClockSampler, measured_peak, host_threads, popcount):
     step_ms, build_ms, vox_ms, sort_ms, e2e_ms = rig.reduce_max([step_ms, build_ms, vox_ms, sort_ms, e2e_ms])
     if rank == 0:
         peak, peak_src = measured_peak()
-        passes = 3   # 24-bit keys when no consumer traverses the hierarchy (scatter path), else 4
+        passes = 2   # 16-bit keys when no consumer traverses the hierarchy (scatter path); 4 with one
         sort_bytes = 16.0 * T * passes
         build_bytes = 228.0 * T
         # as run (no hierarchy: the scatter path does not traverse one): indices 12T and vertices 12V read by k_morton and
