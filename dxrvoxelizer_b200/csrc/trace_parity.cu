@@ -22,10 +22,10 @@
 //                          Tracing: candidate triangles -> row units (triangle x z row, with a
 //                          conservative y interval) -> (row unit, column) pairs, both flattened over the
 //                          32 lanes of a warp; every pair gets the exact crossing test, and a crossing
-//                          XORs a suffix mask into the column's shared-memory bit row plus one bit into
-//                          the column's word mask -- XOR makes the order of crossings irrelevant, so no
-//                          per-column hit list or sort is needed.  Write-out: the word mask tells which
-//                          whole words to flip; coalesced 128-bit stores.
+//                          XORs a suffix mask into the column's shared-memory bit row -- XOR makes the
+//                          order of crossings irrelevant, so no per-column hit list or sort is needed.
+//                          Write-out: bit 31 of every word (the parity of its crossings) tells which of
+//                          the following whole words to flip; coalesced 128-bit stores.
 //                        A super-tile whose candidate list overflowed (huge meshes) walks the tree itself,
 //                        CTA-cooperatively, instead of reading a list.
 #include <algorithm>
@@ -51,7 +51,6 @@ struct ParityParams
     const Tri48* tris;
     uint32_t numTris;
     uint32_t N, P, Ps;       // grid size, words per global row, words per shared row
-    uint32_t Mw;             // words of the per-row word mask: ceil(Ps / 32)
     uint32_t gprShift;       // log2(Ps / 4) when Ps <= 128 (Ps is then a power of two)
     uint32_t z0, z1;
     uint32_t tilesY;         // super-tiles along y
@@ -67,7 +66,7 @@ struct ParityParams
     uint32_t* emptyTiles;    // [numTiles]
     uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}
     uint32_t* heavyArrive;   // [kHeavySlots] parts of a split tile that have merged (self-resetting)
-    uint32_t* heavyScratch;  // [kHeavySlots][128 * (Ps + Mw)] merged toggle rows + word masks of split tiles (self-cleaning)
+    uint32_t* heavyScratch;  // [kHeavySlots][128 * Ps] merged toggle rows of split tiles (self-cleaning)
     uint32_t* candCount;     // [numTiles]  leaves found by k_walk_columns; > candCap = overflow
     uint32_t* candList;      // [numTiles][candCap]
     uint32_t candCap;
@@ -110,8 +109,20 @@ constexpr uint32_t kHeavyTile = 192;    // candidates from which a tile is sched
 constexpr int kLightClasses = 4;        // light tiles are scheduled by halving classes of candidate count:
                                         // [96,192) [48,96) [24,48) [1,24) -- longest work first, so that the
                                         // kernel's tail is made of its smallest work items
-constexpr uint32_t kSplitTile = 512;    // candidates from which a tile is split ...
-constexpr uint32_t kPartSize = 256;     // ... into parts of about this many candidates
+#ifndef DXRV_SPLIT_TILE
+#define DXRV_SPLIT_TILE 512
+#endif
+#ifndef DXRV_PART_SIZE
+#define DXRV_PART_SIZE 256
+#endif
+#ifndef DXRV_CHUNK_NUM
+#define DXRV_CHUNK_NUM 2
+#endif
+#ifndef DXRV_CHUNK_DEN
+#define DXRV_CHUNK_DEN 1
+#endif
+constexpr uint32_t kSplitTile = DXRV_SPLIT_TILE;    // candidates from which a tile is split ...
+constexpr uint32_t kPartSize = DXRV_PART_SIZE;     // ... into parts of about this many candidates
 constexpr uint32_t kMaxParts = 64;
 constexpr uint32_t kHeavySlots = 1024;  // tiles that can be split per launch
 constexpr uint32_t kExtraParts = 2048;  // extra CTAs (beyond one per tile) a launch provides
@@ -490,16 +501,16 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     __shared__ uint32_t sNext;     // listed candidates: next chunk to hand out
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t N = prm.N, P = prm.P, Ps = prm.Ps, Mw = prm.Mw;
+    const uint32_t N = prm.N, P = prm.P, Ps = prm.Ps;
     const float fN = (float)N, invNPow2 = prm.invNPow2;
 
     // A crossing whose first inside voxel is ix flips every voxel >= ix of its column.  Inside the word of
-    // ix that is one XOR with a suffix mask; for the words after it, it is one bit in the column's WORD
-    // MASK, and the write-out flips word w when the mask has an odd number of bits below w.  (A single
-    // toggle bit per crossing + a 128-bit prefix-XOR at write-out costs four times the ALU work.)
+    // ix that is one XOR with a suffix mask.  Every suffix mask holds bit 31, so bit 31 of a word of the row
+    // is the parity of the crossings inside that word, and the write-out flips word w when an odd number of
+    // the row's words before w have bit 31 set -- no second structure to keep.  (A single toggle bit per
+    // crossing + a 128-bit prefix-XOR at write-out costs four times the ALU work.)
     uint32_t* rows = smem;                                     // [kCols][Ps] occupancy bits, column = zl*SY + yl
-    uint32_t* wmask = rows + (uint32_t)kCols * Ps;             // [kCols][Mw] word masks
-    float* tileY = reinterpret_cast<float*>(wmask + (uint32_t)kCols * Mw);  // [SY] scene Y of the columns (decreasing)
+    float* tileY = reinterpret_cast<float*>(rows + (uint32_t)kCols * Ps);   // [SY] scene Y of the columns (decreasing)
     float* tileZ = tileY + SY;                                 // [SZ]
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
@@ -528,7 +539,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
 
     uint32_t myCrossings = 0;
     {
-        for (uint32_t i = tid; i < ((uint32_t)kCols * (Ps + Mw)) >> 2; i += kThreads) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < ((uint32_t)kCols * Ps) >> 2; i += kThreads) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
         if (tid < SY) tileY[tid] = (sy0 + tid < N) ? -centreOf(sy0 + tid, fN, invNPow2) : INFINITY;
         if (tid >= 32 && tid < 32 + SZ) tileZ[tid - 32] = (sz0 + tid - 32 < prm.z1) ? centreOf(sz0 + tid - 32, fN, invNPow2) : INFINITY;
         if (tid == 0) { stack[0] = 0; sTop[0] = 1u; sTop[1] = 0; sCand = 0; sNext = 0; }
@@ -574,7 +585,6 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
                 {
                     const uint32_t col = zl * SY + yl, w = ix >> 5;
                     atomicXor(&rows[col * Ps + w], 0xffffffffu << (ix & 31u));
-                    atomicXor(&wmask[col * Mw + (w >> 5)], 1u << (w & 31u));
                 }
             }
         };
@@ -738,7 +748,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
             const uint32_t mine = (uint32_t)(((uint64_t)listed * (part + 1u)) / parts) - partBegin;   // this CTA's share
             const uint32_t* list = prm.candList + (size_t)tile * prm.candCap + partBegin;
             uint32_t C = 32u;
-            while (C > 4u && mine < C * (uint32_t)W * 2u) C >>= 1;
+            while (C > 4u && mine * DXRV_CHUNK_DEN < C * (uint32_t)W * DXRV_CHUNK_NUM) C >>= 1;
             for (;;)   // the warps take chunks as they become free: pair counts per chunk vary a lot
             {
                 uint32_t first = 0;
@@ -864,8 +874,8 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
         {
             // ---- split tile: merge this part's toggles into the tile's scratch rows; the last part to
             // arrive takes the merged rows back and carries on to the fill, the others are done ----
-            uint32_t* scratch = prm.heavyScratch + (size_t)hslot * kCols * (Ps + Mw);
-            for (uint32_t i = tid; i < (uint32_t)kCols * (Ps + Mw); i += kThreads)
+            uint32_t* scratch = prm.heavyScratch + (size_t)hslot * kCols * Ps;
+            for (uint32_t i = tid; i < (uint32_t)kCols * Ps; i += kThreads)
             {
                 const uint32_t v = rows[i];
                 if (v) atomicXor(scratch + i, v);
@@ -881,7 +891,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
                 return;
             }
             __threadfence();
-            for (uint32_t i = tid; i < ((uint32_t)kCols * (Ps + Mw)) >> 2; i += kThreads)
+            for (uint32_t i = tid; i < ((uint32_t)kCols * Ps) >> 2; i += kThreads)
             {
                 uint4* src = reinterpret_cast<uint4*>(scratch) + i;
                 reinterpret_cast<uint4*>(rows)[i] = __ldcg(src);
@@ -898,20 +908,27 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     const uint32_t groupsPerRow = Ps >> 2;            // 128-bit groups per shared row
     const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
     const uint4* rows4 = reinterpret_cast<const uint4*>(rows) + (size_t)warp * kRowsPerWarp * groupsPerRow;
-    const uint32_t* wmaskW = wmask + warp * (uint32_t)kRowsPerWarp * Mw;
     const uint32_t warpGroups = (uint32_t)kRowsPerWarp * groupsPerRow;   // a multiple of 32 for every (W, Ps) launched
 
-    // occupancy bits of group gi (words 4gi .. 4gi+3) of the warp's row rowInWarp; g = the group's index
-    auto occupancy = [&](uint32_t g, uint32_t rowInWarp, uint32_t gi) -> uint4 {
-        uint4 t = rows4[g];
-        const uint32_t w0 = gi * 4u, mw = w0 >> 5;     // the group's four words share one mask word
-        const uint32_t* m = wmaskW + rowInWarp * Mw;
-        uint32_t below = 0;                              // XOR of the mask words before mw (none up to N = 1024)
-        for (uint32_t k = 0; k < mw; ++k) below ^= m[k];
-        // bit j of e: parity of the mask bits below word 32*mw + j
-        const uint32_t e = (prefixXor32(m[mw]) << 1) ^ (0u - (__popc(below) & 1u));
-        const uint32_t f = e >> (w0 & 31u);
-        t.x ^= 0u - (f & 1u); t.y ^= 0u - ((f >> 1) & 1u); t.z ^= 0u - ((f >> 2) & 1u); t.w ^= 0u - ((f >> 3) & 1u);
+    // occupancy bits of the group this lane holds (t = four consecutive words of a row, as traced).  The groups of a
+    // row sit in consecutive lanes (groupsPerRow <= 32: rows aligned to groupsPerRow lanes) or in consecutive
+    // iterations (longer rows: `carry` = parity of the crossings in the row's earlier iterations, warp-uniform).
+    const uint32_t lt = laneMaskLt();
+    const uint32_t rowBelow = groupsPerRow <= 32u ? lt & ~((1u << (lane & ~(groupsPerRow - 1u))) - 1u) : lt;
+    uint32_t carry = 0;
+    auto occupancy = [&](uint4 t, uint32_t g0) -> uint4 {
+        const uint32_t top = __ballot_sync(0xffffffffu, (int)t.x < 0) ^ __ballot_sync(0xffffffffu, (int)t.y < 0) ^
+                             __ballot_sync(0xffffffffu, (int)t.z < 0) ^ __ballot_sync(0xffffffffu, (int)t.w < 0);
+        uint32_t before = __popc(top & rowBelow);
+        if (groupsPerRow > 32u)
+        {
+            if (g0 % groupsPerRow == 0u) carry = 0;
+            before += carry;
+            carry ^= __popc(top) & 1u;
+        }
+        const uint32_t mx = 0u - (before & 1u);
+        const uint32_t my = mx ^ (uint32_t)((int)t.x >> 31), mz = my ^ (uint32_t)((int)t.y >> 31), mw = mz ^ (uint32_t)((int)t.z >> 31);
+        t.x ^= mx; t.y ^= my; t.z ^= mz; t.w ^= mw;
         return t;
     };
 
@@ -929,7 +946,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
             const uint32_t g = g0 + lane;
             const uint32_t rr = g >> prm.gprShift, gi = g & (groupsPerRow - 1u);
             const uint32_t col = warp * (uint32_t)kRowsPerWarp + rr;
-            uint4 t = occupancy(g, rr, gi);
+            const uint4 t = occupancy(rows4[g], g0);
             if (gi < gprG) base[(col >> 4) * zStride + (col & 15u) * gprG + gi] = t;
         }
     }
@@ -941,7 +958,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
             uint32_t rowInWarp, gi;
             if (groupsPerRow <= 32u) { rowInWarp = g >> prm.gprShift; gi = g & (groupsPerRow - 1u); }
             else { rowInWarp = g0 / groupsPerRow; gi = g - rowInWarp * groupsPerRow; }
-            uint4 t = occupancy(g, rowInWarp, gi);
+            uint4 t = occupancy(rows4[g], g0);
 
             const uint32_t col = warp * (uint32_t)kRowsPerWarp + rowInWarp;
             const uint32_t yl = col % SY, zl = col / SY;
@@ -1021,7 +1038,7 @@ uint32_t sharedRowWords(uint32_t P)
 template <int W, int SY, int SZ>
 void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 {
-    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * (prm.Ps + prm.Mw) + SY + SZ + (size_t)(kStackPerThread + kCandPerThread) * 32 * W);
+    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + (size_t)(kStackPerThread + kCandPerThread) * 32 * W);
     static bool attrSet[64] = {};
     static int smCount[64] = {};
     int dev = 0;
@@ -1086,14 +1103,14 @@ size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
     uint32_t numTiles, candCap;
     parityTileCounts(N, z0, z1, numTiles, candCap);
     const size_t tilesPad = (numTiles + 31u) & ~31u;
-    const size_t Ps = sharedRowWords((N + 31) / 32), Mw = (Ps + 31) / 32;
-    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw) + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
+    const size_t Ps = sharedRowWords((N + 31) / 32);
+    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
 }
 
 size_t parityScratchZeroWords(uint32_t N)
 {
-    const size_t Ps = sharedRowWords((N + 31) / 32), Mw = (Ps + 31) / 32;
-    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * (Ps + Mw);
+    const size_t Ps = sharedRowWords((N + 31) / 32);
+    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * Ps;
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
@@ -1101,7 +1118,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
 {
     ParityParams prm;
     prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
-    prm.N = N; prm.P = (N + 31) / 32; prm.Ps = sharedRowWords(prm.P); prm.Mw = (prm.Ps + 31) / 32;
+    prm.N = N; prm.P = (N + 31) / 32; prm.Ps = sharedRowWords(prm.P);
     prm.gprShift = 0;
     while ((1u << prm.gprShift) < (prm.Ps >> 2)) ++prm.gprShift;
     prm.z0 = z0; prm.z1 = z1;
@@ -1114,7 +1131,7 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     uint32_t* p = walkBuf;
     prm.bucketCount = p;  p += kCounterWords;
     prm.heavyArrive = p;  p += kHeavySlots;
-    prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * (prm.Ps + prm.Mw);      // 16-byte aligned: all sizes are multiples of 4 words
+    prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * prm.Ps;      // 16-byte aligned: all sizes are multiples of 4 words
     prm.lightTiles = p;   p += kLightClasses * tilesPad;
     prm.emptyTiles = p;   p += tilesPad;
     prm.candCount = p;    p += tilesPad;
