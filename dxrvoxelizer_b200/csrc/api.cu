@@ -25,6 +25,14 @@ int checkDeviceError(dxrv_ctx* ctx)
     if (e == kErrNone) return DXRV_OK;
     cudaMemsetAsync(ctx->dErr, 0, sizeof(uint32_t), ctx->stream);
     ctx->walkZeroed = 0;  // a kernel that bailed out may have left the split-tile scratch dirty
+    if (e == kErrBarrierTimeout)
+    {
+        // the fused build's CTAs were not co-resident after all: clean its barrier words, use the multi-kernel build from now on
+        if (ctx->fusedScratch) cudaMemsetAsync(ctx->fusedScratch, 0, 64, ctx->stream);
+        ctx->fusedBuild = false;
+        ctx->haveBvh = false;
+        return fail(ctx, DXRV_ERR_CUDA, "fused build: grid barrier timed out (fused build disabled for this context; build again)");
+    }
     if (e == kErrBadIndex) return fail(ctx, DXRV_ERR_INVALID_ARG, "index buffer references a vertex >= numVerts");
     return fail(ctx, DXRV_ERR_CUDA, "traversal stack overflow / corrupt hierarchy");
 }
@@ -159,6 +167,24 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     }
 
     cudaStream_t s = ctx->stream;
+    // Small meshes: the whole build in one cooperative kernel (lbvh.cu, k_build_fused); DXRV_FUSED_BUILD=0 keeps the
+    // multi-kernel path (tests run both and require identical structures).
+    // Measured inside a build + voxelize step (tools/build_time.py): 100 k triangles 39.5 -> 33 us, 200 k 41 -> 34 us; at
+    // 20 k both take ~27 us (four grid barriers cost what five kernel boundaries do), so small meshes keep the kernels
+    // that can overlap across streams.  DXRV_FUSED_BUILD=1 fuses whatever fits.
+    const char* fusedEnv = std::getenv("DXRV_FUSED_BUILD");
+    const bool fusedOff = fusedEnv && fusedEnv[0] == '0', fusedAll = fusedEnv && fusedEnv[0] == '1';
+    uint32_t fusedCtas = 0, fusedRounds = 0;
+    bool fused = ctx->fusedBuild && !fusedOff && (fusedAll || T >= kFusedBuildMinTris) && fusedBuildPlan(T, ctx->smCount, fusedCtas, fusedRounds);
+    if (fused && !ctx->fusedScratch)
+    {
+        if (!fusedBuildSupported(ctx->device) || cudaMalloc(&ctx->fusedScratch, fusedBuildScratchBytes(ctx->smCount)) != cudaSuccess)
+        {
+            cudaGetLastError();
+            ctx->fusedBuild = fused = false;
+        }
+        else DXRV_CUDA(cudaMemsetAsync(ctx->fusedScratch, 0, fusedBuildScratchBytes(ctx->smCount), s));
+    }
     // small meshes: 8 bits per axis (24-bit keys, three radix passes); large: all 30 bits
     // Key width.  With the hierarchy (a consumer traverses it): 8 bits per axis for small meshes (three radix passes),
     // all 30 bits for large ones -- the tree's quality depends on it.  Without (MODE_PARITY: the sorted order only
@@ -189,12 +215,23 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     std::vector<uint8_t> key;
     keyPush(key, (uint32_t)0xB01Du);
     keyPush(key, m.verts); keyPush(key, m.numVerts); keyPush(key, m.stride); keyPush(key, m.indices); keyPush(key, m.numTris);
-    keyPush(key, (uint32_t)haveBound); keyPush(key, bnd); keyPush(key, (uint32_t)withTree);
+    keyPush(key, (uint32_t)haveBound); keyPush(key, bnd); keyPush(key, (uint32_t)withTree); keyPush(key, (uint32_t)fused);
     keyPush(key, ctx->keysA); keyPush(key, ctx->keysB); keyPush(key, ctx->valsA); keyPush(key, ctx->valsB);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris); keyPush(key, ctx->pyramid); keyPush(key, ctx->sortTemp); keyPush(key, ctx->refitScratch);
     const int rc = runCaptured(ctx, key, [&]() {
         const bool prof = ctx->profiling;   // (runCaptured launches directly, without a graph, while profiling)
         if (prof) cudaEventRecord(ctx->profBuild[0], s);
+        if (fused && launchFusedBuild(s, m, ctx->smCount, haveBound ? bnd : nullptr, ctx->dBound, ctx->dPartials, ctx->fusedScratch, ctx->keysA, ctx->valsA,
+                                      ctx->keysB, ctx->valsB, withTree ? nullptr : ctx->tris, keyShift, numPasses, ctx->dErr))
+        {
+            ctx->launches += 1;
+            if (prof) { cudaEventRecord(ctx->profBuild[1], s); cudaEventRecord(ctx->profBuild[2], s); }   // (no separate sort phase)
+            if (withTree)
+                ctx->launches += (uint64_t)launchLeavesAndHierarchy(s, &ctx->side, m, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
+                                                                    ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr, kBuildLeaves | kBuildTree);
+            if (prof) { cudaEventRecord(ctx->profBuild[3], s); ctx->profBuildValid = true; }
+            return;
+        }
         if (haveBound) { launchSetBound(s, bnd[0], bnd[1], bnd[2], bnd[3], ctx->dBound); }
         else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
         ctx->launches += 1;
@@ -216,6 +253,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     DXRV_CUDA(cudaGetLastError());
     ctx->haveBvh = true;
     ctx->treeBuilt = withTree || T < 2;
+    ctx->pyramidBuilt = withTree || !fused;   // the fused kernel writes the sorted records only; a later hierarchy redoes the leaves
     return DXRV_OK;
 }
 
@@ -225,7 +263,8 @@ void enqueueTree(dxrv_ctx* ctx)
 {
     if (ctx->treeBuilt) return;
     ctx->launches += (uint64_t)launchLeavesAndHierarchy(ctx->stream, &ctx->side, ctx->mesh, ctx->dBound, ctx->keysA, ctx->valsA, ctx->nodes, ctx->tris,
-                                                        ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr, kBuildTree);
+                                                        ctx->pyramid, ctx->refitScratch, ctx->dRootBox, ctx->dErr,
+                                                        ctx->pyramidBuilt ? kBuildTree : (kBuildLeaves | kBuildTree));
 }
 
 int validateMeshArgs(dxrv_ctx* ctx, const void* v, uint32_t numVerts, uint32_t stride, const uint32_t* idx, uint32_t numIndices,
@@ -308,7 +347,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     commRelease(ctx);
     void* ptrs[] = {ctx->gridFull, ctx->dSlabs, ctx->vertsOwned, ctx->idxOwned, ctx->keysA, ctx->keysB, ctx->valsA, ctx->valsB, ctx->nodes, ctx->tris,
                     ctx->pyramid, ctx->refitScratch, ctx->sortTemp, ctx->dSmall, ctx->gridOwned, ctx->texels, ctx->u8Temp, ctx->walkBuf, ctx->mips, ctx->sparseBuf,
-                    ctx->binsBuf};
+                    ctx->binsBuf, ctx->fusedScratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -541,7 +580,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     DXRV_CUDA(cudaGetLastError());
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
-    if (needTree) ctx->treeBuilt = true;
+    if (needTree) ctx->treeBuilt = ctx->pyramidBuilt = true;
     ctx->treeWanted = usesTree;   // the next build includes the hierarchy iff this consumer traversed it
     if (algo == DXRV_MODE_SHADER && useBins) ctx->binsValid = true;
     return DXRV_OK;

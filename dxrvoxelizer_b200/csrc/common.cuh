@@ -46,6 +46,7 @@ enum DeviceError : uint32_t
     kErrNone = 0,
     kErrBadIndex = 1,       // an index >= numVerts
     kErrStackOverflow = 2,  // traversal stack exhausted (never expected)
+    kErrBarrierTimeout = 3, // the fused build's grid barrier gave up (its CTAs were not co-resident)
 };
 
 // ---- arithmetic contract -----------------------------------------------------------------------

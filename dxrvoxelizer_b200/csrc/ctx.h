@@ -35,6 +35,10 @@ struct dxrv_ctx
     // The hierarchy (topology + child boxes) is built with the rest when the previous consumer traversed it, else on
     // demand by the first dxrv_voxelize that does (include/dxrv.h, dxrv_build_bvh).
     bool treeBuilt = false, treeWanted = false;
+    // Small meshes are built by ONE cooperative kernel (k_build_fused); it writes no box pyramid, so a hierarchy asked for
+    // later redoes the leaf pass (pyramidBuilt).  fusedBuild goes off for good if the device cannot run it.
+    bool fusedBuild = true, pyramidBuilt = false;
+    void* fusedScratch = nullptr;
 
     // LBVH
     uint32_t *keysA = nullptr, *keysB = nullptr, *valsA = nullptr, *valsB = nullptr;

@@ -25,6 +25,19 @@ void launchSetBound(cudaStream_t s, float cx, float cy, float cz, float w, float
 // passes into hist (which must be zero).
 void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32_t* keys, uint32_t* vals,
                   uint32_t keyShift, int numPasses, uint32_t* hist, uint32_t* dErr);
+// The whole build of a small mesh (bounds, keys, stable radix sort[, sorted triangle records]) in ONE cooperative kernel
+// with grid barriers; same output as launchBounds/launchSetBound + launchMorton + radixSortPairs (+ the records of
+// k_leaf_setup when tris != null; the box pyramid is NOT written).  fusedBuildPlan: does the mesh fit (<= 2 triangles
+// per thread of one 1024-thread CTA per SM)?  scratch: fusedBuildScratchBytes(), zero before its first use.
+// bnd: null = compute {c, w} from the vertices.  Returns false when nothing was launched (the caller takes the
+// multi-kernel path).
+constexpr int kMaxFusedPasses = 4;
+constexpr uint32_t kFusedBuildMinTris = 49152;   // below: the multi-kernel build is as fast (measured)
+size_t fusedBuildScratchBytes(int smCount);
+bool fusedBuildPlan(uint32_t numTris, int smCount, uint32_t& ctas, uint32_t& rounds);
+bool fusedBuildSupported(int device);
+bool launchFusedBuild(cudaStream_t s, const MeshView& m, int smCount, const float* bnd, float* dBound, float* dPartials, void* scratch,
+                      uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB, Tri48* tris, uint32_t keyShift, int numPasses, uint32_t* dErr);
 constexpr int kMaxBoxLevels = 8;
 // float4 entries needed for the leaf-box pyramid of numTris leaves
 size_t boxPyramidFloat4s(uint32_t numTris);

@@ -351,6 +351,299 @@ k_leaf_setup(MeshView m, const float* __restrict__ boundPtr, const uint32_t* __r
     }
 }
 
+// ---- the whole build of a small mesh in ONE kernel -------------------------------------------------------------------
+// A 100 k-triangle build is six dependent launches (bounds, keys, two or three radix passes, leaves), each at its
+// latency floor of 7-10 us although the data (a few MB) would stream through the machine in about one.  Here every
+// triangle lives in the registers of one thread of a grid that is resident as a whole (cooperative launch, one CTA of
+// 1024 threads per SM, up to kFusedRounds triangles per thread), and the phases are separated by grid barriers (~1.5 us)
+// instead of kernel boundaries:
+//   vertex min/max -> BARRIER -> {c, w}, keys, per-(round, warp) digit counts -> BARRIER -> digit bases from all CTAs'
+//   counts, stable ranks, scatter -> BARRIER -> next radix pass ... -> the last pass writes the sorted (key, triangle)
+//   pairs AND, when no hierarchy follows, the scene-space triangle records straight into their sorted slots.
+// The sort is the same stable LSD radix sort over the same keys as k_morton + onesweep (identical output): CTA c owns
+// the items [c * rounds * 1024, ...) of the current order, item = (round, warp, lane); a (round, warp) counts its
+// digits with match_any, a 256-thread scan turns the counts into exclusive offsets inside the CTA, and the CTAs'
+// totals go through global memory [pass][digit][cta].
+constexpr int kFusedThreads = 1024;
+constexpr int kFusedRounds = 2;
+constexpr int kFusedMaxCtas = 160;                // CTAs of the grid (one per SM; a multiple of 32)
+constexpr uint32_t kFusedSpinLimit = 1u << 21;   // polls of a barrier word (~1 us each) before the kernel gives up
+
+struct FusedBuildParams
+{
+    MeshView m;
+    float* bound;        // out: {c, w}
+    float* partials;     // [gridDim.x][6]
+    uint32_t* hist;      // [numPasses][256][gridDim.x]
+    uint32_t* sync;      // [0] barrier arrivals, [1] CTAs that have finished; both zero between launches
+    uint32_t *keysA, *valsA, *keysB, *valsB;   // the last pass lands in A
+    Tri48* tris;         // null: sorted pairs only (k_leaf_setup follows)
+    uint32_t* err;
+    uint32_t keyShift, numPasses, rounds, haveBound;
+    float bnd[4];
+};
+
+__device__ __forceinline__ uint32_t loadAcquire(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs of the (co-resident) grid; false = gave up waiting (error raised, the caller returns)
+__device__ __forceinline__ bool gridBarrier(uint32_t* sync, uint32_t& target, uint32_t* err, uint32_t* sOk)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(sync, 1u);
+        uint32_t spins = 0, ok = 1u;
+        while (loadAcquire(sync) < target)
+            if (++spins > kFusedSpinLimit) { ok = 0u; atomicMax(err, (uint32_t)kErrBarrierTimeout); break; }
+        *sOk = ok;
+        __threadfence();
+    }
+    __syncthreads();
+    return *sOk != 0u;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_build_fused(const FusedBuildParams p)
+{
+    __shared__ uint16_t sTab[kFusedRounds * 32][256];   // digit counts per (round, warp) -> exclusive offsets inside the CTA
+    __shared__ uint32_t sBase[256];
+    __shared__ uint32_t sSeg[4][256];
+    __shared__ float sRed[32][6];
+    __shared__ float sBound[4];
+    __shared__ uint32_t sWarpTot[8];
+    __shared__ uint32_t sOk;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, G = gridDim.x, cta = blockIdx.x;
+    const uint32_t T = p.m.numTris, R = p.rounds;
+    const uint32_t itemBase = cta * R * (uint32_t)kFusedThreads;
+    const uint32_t lt = laneMaskLt();
+    uint32_t target = 0;
+
+    // ---- this thread's triangles: object-space box centres (issued before anything waits) ----
+    float cx[kFusedRounds], cy[kFusedRounds], cz[kFusedRounds];
+#pragma unroll
+    for (int r = 0; r < kFusedRounds; ++r)
+    {
+        cx[r] = cy[r] = cz[r] = 0.0f;
+        const uint32_t k = itemBase + (uint32_t)r * kFusedThreads + tid;
+        if ((uint32_t)r < R && k < T)
+        {
+            uint32_t i0 = __ldg(p.m.indices + 3 * (size_t)k), i1 = __ldg(p.m.indices + 3 * (size_t)k + 1), i2 = __ldg(p.m.indices + 3 * (size_t)k + 2);
+            if (i0 >= p.m.numVerts || i1 >= p.m.numVerts || i2 >= p.m.numVerts)
+            {
+                atomicMax(p.err, (uint32_t)kErrBadIndex);
+                i0 = i1 = i2 = 0;
+            }
+            const float3 a = loadPos(p.m.verts, p.m.stride, i0), b = loadPos(p.m.verts, p.m.stride, i1), c = loadPos(p.m.verts, p.m.stride, i2);
+            cx[r] = 0.5f * (fminf(fminf(a.x, b.x), c.x) + fmaxf(fmaxf(a.x, b.x), c.x));
+            cy[r] = 0.5f * (fminf(fminf(a.y, b.y), c.y) + fmaxf(fmaxf(a.y, b.y), c.y));
+            cz[r] = 0.5f * (fminf(fminf(a.z, b.z), c.z) + fmaxf(fmaxf(a.z, b.z), c.z));
+        }
+    }
+
+    // ---- {c, w} (Voxelizer.cpp:52-57), over ALL vertices as the reference's computeAABB ----
+    if (!p.haveBound)
+    {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = cta * kFusedThreads + tid; i < p.m.numVerts; i += G * kFusedThreads)
+        {
+            const float3 q = loadPos(p.m.verts, p.m.stride, i);
+            mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
+            mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
+            mn[2] = fminf(mn[2], q.z); mx[2] = fmaxf(mx[2], q.z);
+        }
+        warpMinMax(mn, mx);
+        if (lane == 0)
+            for (int a = 0; a < 3; ++a) { sRed[warp][a] = mn[a]; sRed[warp][3 + a] = mx[a]; }
+        __syncthreads();
+        if (warp == 0)
+        {
+            for (int a = 0; a < 3; ++a) { mn[a] = sRed[lane][a]; mx[a] = sRed[lane][3 + a]; }
+            warpMinMax(mn, mx);
+            if (lane == 0)
+                for (int a = 0; a < 3; ++a) { p.partials[6 * cta + a] = mn[a]; p.partials[6 * cta + 3 + a] = mx[a]; }
+        }
+        if (!gridBarrier(p.sync, target, p.err, &sOk)) return;
+        if (warp == 0)
+        {
+            for (int a = 0; a < 3; ++a) { mn[a] = INFINITY; mx[a] = -INFINITY; }
+            for (uint32_t b = lane; b < G; b += 32u)
+                for (int a = 0; a < 3; ++a)
+                {
+                    mn[a] = fminf(mn[a], __ldcg(p.partials + 6 * b + a));
+                    mx[a] = fmaxf(mx[a], __ldcg(p.partials + 6 * b + 3 + a));
+                }
+            warpMinMax(mn, mx);
+            if (lane == 0)
+            {
+                const float ex = __fsub_rn(mx[0], mn[0]), ey = __fsub_rn(mx[1], mn[1]), ez = __fsub_rn(mx[2], mn[2]);
+                sBound[0] = __fdiv_rn(__fadd_rn(mx[0], mn[0]), 2.0f);
+                sBound[1] = __fdiv_rn(__fadd_rn(mx[1], mn[1]), 2.0f);
+                sBound[2] = __fdiv_rn(__fadd_rn(mx[2], mn[2]), 2.0f);
+                float m = ey > ez ? ey : ez;
+                m = ex > m ? ex : m;
+                sBound[3] = __fdiv_rn(m, 2.0f);
+            }
+        }
+    }
+    else if (tid < 4) sBound[tid] = p.bnd[tid];
+    __syncthreads();
+    const float4 bound = make_float4(sBound[0], sBound[1], sBound[2], sBound[3]);
+    if (cta == 0 && tid < 4) p.bound[tid] = sBound[tid];
+
+    // ---- keys: exactly k_morton's ----
+    uint32_t key[kFusedRounds], val[kFusedRounds], rank[kFusedRounds];
+    {
+        const float invW = 1.0f / bound.w;
+#pragma unroll
+        for (int r = 0; r < kFusedRounds; ++r)
+        {
+            const float x = (cx[r] - bound.x) * invW, y = (cy[r] - bound.y) * invW, z = (cz[r] - bound.z) * invW;
+            key[r] = ((expandBits10(quantize10(x)) << 2) | (expandBits10(quantize10(y)) << 1) | expandBits10(quantize10(z))) >> p.keyShift;
+            val[r] = itemBase + (uint32_t)r * kFusedThreads + tid;
+            rank[r] = 0;
+        }
+    }
+
+    // ---- stable LSD radix passes ----
+    for (uint32_t pass = 0; pass < p.numPasses; ++pass)
+    {
+        const bool last = pass + 1u == p.numPasses;
+        const bool outA = ((p.numPasses - 1u - pass) & 1u) == 0u;
+        const uint32_t* keysIn = outA ? p.keysB : p.keysA;
+        const uint32_t* valsIn = outA ? p.valsB : p.valsA;
+        uint32_t* keysOut = outA ? p.keysA : p.keysB;
+        uint32_t* valsOut = outA ? p.valsA : p.valsB;
+        const uint32_t shift = 8u * pass;
+        for (uint32_t i = tid; i < (uint32_t)(sizeof(sTab) / sizeof(uint4)); i += kFusedThreads) reinterpret_cast<uint4*>(&sTab[0][0])[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kFusedRounds; ++r)
+        {
+            const uint32_t i = itemBase + (uint32_t)r * kFusedThreads + tid;
+            const bool valid = (uint32_t)r < R && i < T;
+            if (pass > 0u && valid) { key[r] = __ldcg(keysIn + i); val[r] = __ldcg(valsIn + i); }
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            if (valid)
+            {
+                const uint32_t d = (key[r] >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(vm, d);
+                rank[r] = (uint32_t)__popc(peers & lt);
+                if (rank[r] == 0u) sTab[r * 32 + (int)warp][d] = (uint16_t)__popc(peers);
+            }
+        }
+        __syncthreads();
+        {
+            // counts -> exclusive offsets inside the CTA, per digit over the (round, warp) rows in order: four threads per
+            // digit scan a quarter of the rows each, then add the quarters before theirs
+            const uint32_t d = tid & 255u, q = tid >> 8, rows = R * 8u;
+            uint32_t run = 0;
+            for (uint32_t vw = q * rows; vw < (q + 1u) * rows; ++vw)
+            {
+                const uint32_t c = sTab[vw][d];
+                sTab[vw][d] = (uint16_t)run;
+                run += c;
+            }
+            sSeg[q][d] = run;
+            __syncthreads();
+            uint32_t add = 0, all = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) { const uint32_t v = sSeg[k][d]; add += k < q ? v : 0u; all += v; }
+            if (q > 0u)
+                for (uint32_t vw = q * rows; vw < (q + 1u) * rows; ++vw) sTab[vw][d] = (uint16_t)(sTab[vw][d] + add);
+            if (q == 0u) p.hist[((size_t)pass * 256u + d) * G + cta] = all;
+        }
+        if (!gridBarrier(p.sync, target, p.err, &sOk)) return;
+        {
+            // digit bases: warp w takes the digits w, w + 32, ...; its lanes read the counts of all CTAs for a digit with
+            // independent coalesced loads ([pass][digit][cta]) and fold them with warp reductions
+            uint32_t v[8][kFusedMaxCtas / 32];
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k)
+#pragma unroll
+                for (uint32_t j = 0; j < (uint32_t)(kFusedMaxCtas / 32); ++j)
+                {
+                    const uint32_t c = j * 32u + lane;
+                    v[k][j] = c < G ? __ldcg(p.hist + ((size_t)pass * 256u + (k * 32u + warp)) * G + c) : 0u;
+                }
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k)
+            {
+                uint32_t total = 0, before = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < (uint32_t)(kFusedMaxCtas / 32); ++j) { total += v[k][j]; before += (j * 32u + lane < cta) ? v[k][j] : 0u; }
+                total = __reduce_add_sync(0xffffffffu, total);
+                before = __reduce_add_sync(0xffffffffu, before);
+                if (lane == 0) { sSeg[0][k * 32u + warp] = total; sSeg[1][k * 32u + warp] = before; }
+            }
+        }
+        __syncthreads();
+        if (tid < 256u)
+        {
+            const uint32_t total = sSeg[0][tid], before = sSeg[1][tid];
+            uint32_t incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31u) sWarpTot[warp] = incl;
+            sBase[tid] = incl - total + before;   // (the earlier warps' totals are added below)
+        }
+        __syncthreads();
+        if (tid < 256u)
+        {
+            uint32_t add = 0;
+            for (uint32_t w = 0; w < warp; ++w) add += sWarpTot[w];
+            sBase[tid] += add;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kFusedRounds; ++r)
+        {
+            const uint32_t i = itemBase + (uint32_t)r * kFusedThreads + tid;
+            if ((uint32_t)r < R && i < T)
+            {
+                const uint32_t d = (key[r] >> shift) & 255u;
+                const uint32_t dst = sBase[d] + sTab[r * 32 + (int)warp][d] + rank[r];
+                keysOut[dst] = key[r];
+                valsOut[dst] = val[r];
+                if (last && p.tris)
+                {
+                    // the sorted leaf record (k_leaf_setup's, without the box pyramid nobody reads in this mode)
+                    const uint32_t k = val[r];
+                    uint32_t i0 = __ldg(p.m.indices + 3 * (size_t)k), i1 = __ldg(p.m.indices + 3 * (size_t)k + 1), i2 = __ldg(p.m.indices + 3 * (size_t)k + 2);
+                    if (i0 >= p.m.numVerts || i1 >= p.m.numVerts || i2 >= p.m.numVerts) i0 = i1 = i2 = 0;   // (error raised above)
+                    const float3 a = scenePos(p.m.verts, p.m.stride, i0, bound);
+                    const float3 b = scenePos(p.m.verts, p.m.stride, i1, bound);
+                    const float3 c = scenePos(p.m.verts, p.m.stride, i2, bound);
+                    Tri48 t;
+                    t.a = make_float4(a.x, a.y, a.z, __uint_as_float(k));
+                    t.b = make_float4(b.x, b.y, b.z, 0.0f);
+                    t.c = make_float4(c.x, c.y, c.z, 0.0f);
+                    p.tris[dst] = t;
+                }
+            }
+        }
+        if (!last && !gridBarrier(p.sync, target, p.err, &sOk)) return;
+    }
+
+    // ---- leave the barrier words zero for the next launch: the last CTA to get here knows everybody is past them ----
+    __syncthreads();
+    if (tid == 0)
+    {
+        __threadfence();
+        if (atomicAdd(p.sync + 1, 1u) == G - 1u) { p.sync[0] = 0u; p.sync[1] = 0u; }
+    }
+}
+
 // level l (>= 3) from level l-1: one thread per entry, 16 children each; also the children's scans
 __global__ void __launch_bounds__(128)
 k_box_level(float4* __restrict__ src, uint32_t srcCount, float4* __restrict__ dst, uint32_t dstCount, uint32_t S)
@@ -745,6 +1038,41 @@ void launchMorton(cudaStream_t s, const MeshView& m, const float* dBound, uint32
     if (!m.numTris) return;
     const uint32_t blocks = std::min<uint32_t>((m.numTris + 255) / 256, 148u * 8u);
     k_morton<<<blocks, 256, 0, s>>>(m, dBound, keys, vals, keyShift, numPasses, hist, dErr);
+}
+
+size_t fusedBuildScratchBytes(int smCount) { return sizeof(uint32_t) * (16 + (size_t)kMaxFusedPasses * (size_t)smCount * 256u); }
+
+bool fusedBuildPlan(uint32_t numTris, int smCount, uint32_t& ctas, uint32_t& rounds)
+{
+    if (numTris < 2 || smCount < 1) return false;
+    ctas = std::min<uint32_t>(std::min<uint32_t>((uint32_t)smCount, kFusedMaxCtas), (numTris + kFusedThreads - 1) / kFusedThreads);
+    rounds = (numTris + ctas * kFusedThreads - 1) / (ctas * kFusedThreads);
+    return rounds <= (uint32_t)kFusedRounds;
+}
+
+bool fusedBuildSupported(int device)
+{
+    int coop = 0, perSm = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) { cudaGetLastError(); return false; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_build_fused, kFusedThreads, 0) != cudaSuccess || perSm < 1) { cudaGetLastError(); return false; }
+    return true;
+}
+
+bool launchFusedBuild(cudaStream_t s, const MeshView& m, int smCount, const float* bnd, float* dBound, float* dPartials, void* scratch,
+                      uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB, Tri48* tris, uint32_t keyShift, int numPasses, uint32_t* dErr)
+{
+    FusedBuildParams p;
+    uint32_t ctas = 0, rounds = 0;
+    if (!fusedBuildPlan(m.numTris, smCount, ctas, rounds) || numPasses < 1 || numPasses > kMaxFusedPasses) return false;
+    p.m = m; p.bound = dBound; p.partials = dPartials;
+    p.sync = static_cast<uint32_t*>(scratch); p.hist = p.sync + 16;
+    p.keysA = keysA; p.valsA = valsA; p.keysB = keysB; p.valsB = valsB; p.tris = tris; p.err = dErr;
+    p.keyShift = keyShift; p.numPasses = (uint32_t)numPasses; p.rounds = rounds; p.haveBound = bnd ? 1u : 0u;
+    for (int i = 0; i < 4; ++i) p.bnd[i] = bnd ? bnd[i] : 0.0f;
+    void* args[] = {&p};
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_build_fused), dim3(ctas), dim3(kFusedThreads), args, 0, s);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
 }
 
 size_t boxPyramidFloat4s(uint32_t numTris)

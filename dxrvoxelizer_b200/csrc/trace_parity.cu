@@ -42,8 +42,16 @@ constexpr int kStackGuard = 64;   // >= LBVH depth bound (62): head-room kept fo
 constexpr int kWalkStack = 512;   // per-warp stack of k_walk_columns
 constexpr int kWalkWarps = 8;     // warps (= super-tiles) per CTA of k_walk_columns (<= 32)
 // in-kernel fallback walk of the fill kernel, per thread of the CTA: stack entries and leaf-ring entries (>= 3)
-constexpr int kStackPerThread = 8;
-constexpr int kCandPerThread = 6;
+#ifndef DXRV_CHUNK_MAX
+#define DXRV_CHUNK_MAX 32
+#endif
+#ifndef DXRV_FILL_CTAS
+#define DXRV_FILL_CTAS 9
+#endif
+constexpr int kChunkMax = DXRV_CHUNK_MAX;                 // candidates a warp stages per chunk (listed-candidates path)
+constexpr int kStagePerWarp = 3 * kChunkMax + 16;         // float4: kChunkMax records of 48 bytes + 32 row units of 8 bytes
+constexpr int kCandPerThread = kChunkMax >= 32 ? 6 : 3;
+constexpr int kStackPerThread = kStagePerWarp / 8 - kCandPerThread;   // the walk's buffers share the staging area
 
 struct ParityParams
 {
@@ -188,6 +196,7 @@ k_walk_columns(const ParityParams prm)
     DXRV_TL_SCOPE();
     __shared__ uint32_t sStack[kWalkWarps][kWalkStack];
     __shared__ uint32_t sCount[32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *prm.crossings = 0ull;   // (accumulated by the fill kernel)
     const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x * kWalkWarps + warp;
     if (threadIdx.x < 32) sCount[threadIdx.x] = 0xffffffffu;
@@ -272,6 +281,7 @@ __global__ void __launch_bounds__(256)
 k_bin_columns(const ParityParams prm)
 {
     extern __shared__ float sRect[];   // exact rectangles of the tiles: yMin/yMax per tile column, zMin/zMax per tile row
+    if (blockIdx.x == 0 && threadIdx.x == 0) *prm.crossings = 0ull;   // (accumulated by the fill kernel)
     const uint32_t tilesY = prm.tilesY, tilesZ = (prm.z1 - prm.z0 + SZ - 1) / SZ;
     float* yMin = sRect; float* yMax = yMin + tilesY; float* zMin = yMax + tilesY; float* zMax = zMin + tilesZ;
     const float fN = (float)prm.N, halfN = 0.5f * fN;
@@ -515,7 +525,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
     float4* stage = reinterpret_cast<float4*>(stack);          // [W][32 x 3]  triangle records of the listed-candidates path
-    static_assert((kStackPerThread + kCandPerThread) * 4 >= 48, "staging area must fit the fallback walk's buffers");
+    static_assert((kStackPerThread + kCandPerThread) * 8 >= kStagePerWarp && kCandPerThread >= 3 && kStackPerThread >= 4, "staging area must fit the fallback walk's buffers");
 
     // work items are numbered heavy parts first, then the light tiles class by class (see fileTiles)
     __shared__ uint32_t sIsLast;
@@ -606,8 +616,8 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
         // 32 items (one warp-wide OR),  owner(p) = #records started before the window + popc(starts up to
         // p's lane) - 1.
         auto processWarpChunkStaged = [&](bool has, uint32_t slot) {
-            float4* tab = stage + warp * 112u;                           // 32 records x 3 float4 ...
-            uint2* units = reinterpret_cast<uint2*>(tab + 96);            // ... and 32 row units
+            float4* tab = stage + warp * (uint32_t)kStagePerWarp;          // kChunkMax records x 3 float4 ...
+            uint2* units = reinterpret_cast<uint2*>(tab + 3 * kChunkMax);            // ... and 32 row units
             const uint32_t lt = laneMaskLt(), le = lt | (1u << lane);
             float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
             uint32_t zA = 0, h = 0;
@@ -747,7 +757,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
             const uint32_t partBegin = (uint32_t)(((uint64_t)listed * part) / parts);
             const uint32_t mine = (uint32_t)(((uint64_t)listed * (part + 1u)) / parts) - partBegin;   // this CTA's share
             const uint32_t* list = prm.candList + (size_t)tile * prm.candCap + partBegin;
-            uint32_t C = 32u;
+            uint32_t C = (uint32_t)kChunkMax;
             while (C > 4u && mine * DXRV_CHUNK_DEN < C * (uint32_t)W * DXRV_CHUNK_NUM) C >>= 1;
             for (;;)   // the warps take chunks as they become free: pair counts per chunk vary a lot
             {
@@ -990,7 +1000,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
 // The first CTAs of the launch write the empty tiles (one writer per SM); the others take the work items
 // in order -- heavy parts first -- and, when there are more items than CTAs, further ones at a stride.
 template <int W, int SY, int SZ>
-__global__ void __launch_bounds__(32 * W, W == 4 ? 9 : W == 8 ? 4 : 2)
+__global__ void __launch_bounds__(32 * W, W == 4 ? DXRV_FILL_CTAS : W == 8 ? 4 : 2)
 k_trace_fill_columns(const ParityParams prm)
 {
     DXRV_TL_SCOPE();
@@ -1073,7 +1083,7 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 #endif
     // enough CTAs for kFillWaves full waves of work items; more items than that are taken at a stride
     const uint32_t waves = kFillWaves;
-    const uint32_t perSm = W == 4 ? 9u : W == 8 ? 4u : 2u;
+    const uint32_t perSm = W == 4 ? (uint32_t)DXRV_FILL_CTAS : W == 8 ? 4u : 2u;
     const uint32_t workCtas = std::min<uint32_t>(prm.numTiles + kExtraParts, std::max(1u, waves * perSm * (prm.numWriters / 2u)));
     k_trace_fill_columns<W, SY, SZ><<<prm.numWriters + workCtas, 32 * W, smemBytes, s>>>(prm);
     if (ev) cudaEventRecord(ev[2], s);
@@ -1096,6 +1106,15 @@ void parityTileCounts(uint32_t N, uint32_t z0, uint32_t z1, uint32_t& numTiles, 
     while (candCap < 32768u && (uint64_t)numTiles * candCap * 2u * sizeof(uint32_t) <= (256ull << 20)) candCap *= 2u;
 }
 
+// The per-tile candidate counters sit right behind the launch counters (ONE memset node clears both) and are sized for
+// the whole grid, so that the zero-on-first-use head of the scratch depends on N only, not on the slab.
+static size_t fullGridTilesPad(uint32_t N)
+{
+    uint32_t numTiles, candCap;
+    parityTileCounts(N, 0, N, numTiles, candCap);
+    return (numTiles + 31u) & ~31u;
+}
+
 // words of device scratch launchTraceFillColumns needs (see the layout below); the region up to
 // parityScratchZeroWords() must be zero when first used (it is self-cleaning afterwards)
 size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
@@ -1104,13 +1123,13 @@ size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1)
     parityTileCounts(N, z0, z1, numTiles, candCap);
     const size_t tilesPad = (numTiles + 31u) & ~31u;
     const size_t Ps = sharedRowWords((N + 31) / 32);
-    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + (2 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
+    return kCounterWords + fullGridTilesPad(N) + kHeavySlots + (size_t)kHeavySlots * 128 * Ps + (1 + kLightClasses) * tilesPad + 2 * (tilesPad + kExtraParts) + (size_t)numTiles * candCap;
 }
 
 size_t parityScratchZeroWords(uint32_t N)
 {
     const size_t Ps = sharedRowWords((N + 31) / 32);
-    return kCounterWords + kHeavySlots + (size_t)kHeavySlots * 128 * Ps;
+    return kCounterWords + fullGridTilesPad(N) + kHeavySlots + (size_t)kHeavySlots * 128 * Ps;
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
@@ -1130,17 +1149,16 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.tilesPad = (uint32_t)tilesPad;
     uint32_t* p = walkBuf;
     prm.bucketCount = p;  p += kCounterWords;
+    prm.candCount = p;    p += fullGridTilesPad(N);
     prm.heavyArrive = p;  p += kHeavySlots;
     prm.heavyScratch = p; p += (size_t)kHeavySlots * 128 * prm.Ps;      // 16-byte aligned: all sizes are multiples of 4 words
     prm.lightTiles = p;   p += kLightClasses * tilesPad;
     prm.emptyTiles = p;   p += tilesPad;
-    prm.candCount = p;    p += tilesPad;
     prm.heavyEntries = reinterpret_cast<uint2*>(p); p += 2 * (tilesPad + kExtraParts);
     prm.candList = p;
     prm.crossings = dCrossings; prm.err = dErr;
-    cudaMemsetAsync(dCrossings, 0, sizeof(unsigned long long), s);
-    cudaMemsetAsync(prm.bucketCount, 0, kCounterWords * sizeof(uint32_t), s);
-    if (!prm.nodes) cudaMemsetAsync(prm.candCount, 0, tilesPad * sizeof(uint32_t), s);   // the binning kernel counts with atomics
+    // one memset node: the launch counters and, behind them, the tile counters the binning kernel counts up with atomics
+    cudaMemsetAsync(prm.bucketCount, 0, (kCounterWords + (prm.nodes ? 0 : tilesPad)) * sizeof(uint32_t), s);
     // warps per CTA by row length (see k_trace_fill_columns); every choice keeps rows-per-warp x groups-per-row
     // a multiple of 32
     if (prm.Ps <= 32) launchVariant<4, 16, 8>(s, prm, ev);

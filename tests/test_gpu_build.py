@@ -152,3 +152,54 @@ def test_bad_index_is_reported(vox, meshes_mod):
         vox.synchronize()
     vox.build_bvh(c)          # the context stays usable
     vox.synchronize()
+
+
+def _build_snapshot(d, mesh, fused, tree, bound=None, N=64):
+    """Sorted keys / triangle order / records of a fresh context; `tree`: the previous consumer traversed the hierarchy."""
+    import os
+    os.environ["DXRV_FUSED_BUILD"] = "1" if fused else "0"
+    try:
+        v = d.Voxelizer(0)
+        v.build_bvh(mesh, bound)
+        v.voxelize(N, d.MODE_SHADER if tree else d.MODE_PARITY)     # sets what the NEXT build includes
+        v.build_bvh(mesh, bound)
+        v.synchronize()
+        T = mesh.num_triangles
+        snap = (v.bound(), v.debug_read(L.DBG_MORTON_SORTED, np.uint32, T), v.debug_read(L.DBG_PRIM_SORTED, np.uint32, T),
+                v.debug_read(L.DBG_TRIS, np.uint32, T * 12))
+        v.voxelize(N, d.MODE_PARITY)
+        grid_p = v.fetch_bits()
+        v.voxelize(N, d.MODE_SHADER)                                # (fused, no tree: redoes the leaves for the pyramid)
+        grid_s = v.fetch_bits()
+        nodes = v.debug_read(L.DBG_NODES, np.uint32, (T - 1) * 16) if T > 1 else np.zeros(0, np.uint32)
+        v.close()
+        return snap + (grid_p, grid_s, nodes)
+    finally:
+        os.environ.pop("DXRV_FUSED_BUILD", None)
+
+
+@pytest.mark.parametrize("shape", ["dragon", "bowl", "cube", "ico20480", "knot200k", "ico327680"])
+@pytest.mark.parametrize("tree", [False, True])
+def test_fused_build_equals_multi_kernel_build(assets, meshes_mod, shape, tree):
+    """k_build_fused (one cooperative kernel: bounds, keys, stable radix passes, sorted records) against the
+    multi-kernel build: same bound, keys, order, records, hierarchy and grids, bit for bit.  ico327680 is beyond
+    the fused kernel's capacity (two triangles per thread of 148 CTAs): both runs take the multi-kernel path."""
+    import dxrvoxelizer_b200 as d
+    m = {"dragon": lambda: assets("dragon.obj"), "bowl": lambda: assets("TuringBowl.obj"), "cube": meshes_mod.cube,
+         "ico20480": lambda: meshes_mod.icosphere(5, seed=3, rotate=True), "knot200k": lambda: meshes_mod.torus_knot(1000, 100, seed=5),
+         "ico327680": lambda: meshes_mod.icosphere(7, seed=1)}[shape]()
+    a = _build_snapshot(d, m, True, tree)
+    b = _build_snapshot(d, m, False, tree)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_fused_build_with_given_bound(assets):
+    import dxrvoxelizer_b200 as d
+    m = assets("bunny.obj")
+    bound = np.array([0.01, 0.1, 0.0, 0.13], np.float32)
+    a = _build_snapshot(d, m, True, False, bound)
+    b = _build_snapshot(d, m, False, False, bound)
+    assert np.array_equal(a[0], bound)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
