@@ -65,12 +65,15 @@ struct ParityParams
     uint32_t numTiles;
     uint32_t tilesPad;       // numTiles rounded up to a multiple of 32
     uint32_t numWriters;     // leading CTAs of the fill kernel that only write the empty super-tiles
+#ifdef DXRV_EXPERIMENT
+    uint32_t noTrace;
+#endif
     uint32_t bulkStores;     // 0: the writers use ordinary stores (DXRV_NO_BULK_STORE=1; compute-sanitizer's
                              // initcheck does not see what cp.async.bulk writes)
     float invNPow2;          // 1/N when N is a power of two, else 0
     uint32_t* grid;
     uint32_t* bucketCount;   // [0] heavy entries, [2] empty tiles, [3] heavy slots, [4] extra parts, [5] cursor of the empty-tile writers, [6] (scatter path) huge-triangle count, [8..11] light tiles per class, [32 + smid] writer claim of an SM
-    uint32_t* lightTiles;    // [kLightClasses][tilesPad]  light tiles, classed by candidate count
+    uint32_t* lightTiles;    // [kLightClasses][tilesPad]  light tiles, classed by candidate count: tile | count << 24
     uint32_t* emptyTiles;    // [numTiles]
     uint2* heavyEntries;     // [numTiles + kExtraParts]  {tile, part | parts << 8 | slot << 16}
     uint32_t* heavyArrive;   // [kHeavySlots] parts of a split tile that have merged (self-resetting)
@@ -113,7 +116,7 @@ __device__ __forceinline__ void testNode(const BvhNode* __restrict__ nodes, uint
 // toggle rows through a scratch buffer with atomicXor (XOR commutes); the last one to arrive fills.
 // Real meshes leave most of the (y,z) plane empty and put hundreds of triangles into a few tiles
 // (surfaces seen edge-on): without the split those few CTAs are the kernel's critical path.
-constexpr uint32_t kHeavyTile = 192;    // candidates from which a tile is scheduled first
+constexpr uint32_t kHeavyTile = 192;    // candidates from which a tile is scheduled first (<= 256: light entries pack the count into 8 bits)
 constexpr int kLightClasses = 4;        // light tiles are scheduled by halving classes of candidate count:
                                         // [96,192) [48,96) [24,48) [1,24) -- longest work first, so that the
                                         // kernel's tail is made of its smallest work items
@@ -165,7 +168,7 @@ __device__ __forceinline__ void fileTiles(const ParityParams& prm, uint32_t firs
     for (int k = 0; k < kLightClasses; ++k)
     {
         const uint32_t b = __shfl_sync(0xffffffffu, baseC[k], 0);
-        if (cls == k) prm.lightTiles[(size_t)k * prm.tilesPad + b + __popc(mC[k] & lt)] = tile;
+        if (cls == k) prm.lightTiles[(size_t)k * prm.tilesPad + b + __popc(mC[k] & lt)] = tile | (count << 24);   // count < kHeavyTile <= 256, tile < 2^24
     }
 
     uint32_t parts = isHeavy ? 1u : 0u, slot = 0xffffu;
@@ -505,6 +508,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     constexpr int kCols = SY * SZ;
     constexpr int kRowsPerWarp = kCols / W;
     constexpr int kStackCap = kStackPerThread * kThreads, kCandCap = kCandPerThread * kThreads;
+    constexpr int kIdStage = 2 * kThreads;   // candidate slots staged in shared memory per item
     static_assert(kCols % W == 0 && SY == 16, "rows are dealt to the warps in equal runs");
     __shared__ uint32_t sTop[2];   // fallback walk: stack height, double-buffered by iteration parity
     __shared__ uint32_t sCand;     // fallback walk: leaves queued so far
@@ -525,27 +529,40 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     uint32_t* stack = reinterpret_cast<uint32_t*>(tileZ + SZ); // [kStackCap]  (fallback walk only)
     uint32_t* cand = stack + kStackCap;                        // [kCandCap]   (fallback walk only)
     float4* stage = reinterpret_cast<float4*>(stack);          // [W][32 x 3]  triangle records of the listed-candidates path
+    uint32_t* ids = cand + kCandCap;                           // [kIdStage]   first candidate slots of the item
     static_assert((kStackPerThread + kCandPerThread) * 8 >= kStagePerWarp && kCandPerThread >= 3 && kStackPerThread >= 4, "staging area must fit the fallback walk's buffers");
 
     // work items are numbered heavy parts first, then the light tiles class by class (see fileTiles)
     __shared__ uint32_t sIsLast;
-    uint32_t tile, part = 0, parts = 1, hslot = 0xffffu;
+    uint32_t tile, listed, part = 0, parts = 1, hslot = 0xffffu;
     if (bIdx < nHeavy)
     {
         const uint2 e = __ldg(prm.heavyEntries + bIdx);
         tile = e.x; part = e.y & 0xffu; parts = (e.y >> 8) & 0xffu; hslot = e.y >> 16;
+        listed = __ldg(prm.candCount + tile);
     }
     else
     {
         bIdx -= nHeavy;
         uint32_t cls = 0;
         if (bIdx >= nLight.x) { bIdx -= nLight.x; cls = 1; if (bIdx >= nLight.y) { bIdx -= nLight.y; cls = 2; if (bIdx >= nLight.z) { bIdx -= nLight.z; cls = 3; } } }
-        tile = __ldg(prm.lightTiles + (size_t)cls * prm.tilesPad + bIdx);
+        const uint32_t e = __ldg(prm.lightTiles + (size_t)cls * prm.tilesPad + bIdx);   // the count rides along: one dependent load less
+        tile = e & 0xffffffu; listed = e >> 24;
     }
     const uint32_t sy0 = (tile % prm.tilesY) * SY;
     const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
-    const uint32_t listed = __ldg(prm.candCount + tile);
     const uint32_t yLast = min(sy0 + SY - 1, N - 1) - sy0, zLast = min(sz0 + SZ - 1, prm.z1 - 1) - sz0;
+    // this CTA's share of the tile's candidate list (a split tile has several parts)
+    const uint32_t partBegin = (uint32_t)(((uint64_t)min(listed, prm.candCap) * part) / parts);
+    const uint32_t mine = listed <= prm.candCap ? (uint32_t)(((uint64_t)listed * (part + 1u)) / parts) - partBegin : 0u;
+    const uint32_t* list = prm.candList + (size_t)tile * prm.candCap + partBegin;
+    // The first kIdStage candidate slots go to shared memory and their records are PREFETCHED into L1 while the rows
+    // are being zeroed: the chunk loop below then neither waits for the list nor (mostly) for the records -- those two
+    // dependent L2 round trips per chunk were the largest single stall of the kernel.
+    uint32_t stagedId[kIdStage / kThreads];
+#pragma unroll
+    for (uint32_t k = 0; k < (uint32_t)(kIdStage / kThreads); ++k)
+        stagedId[k] = (k * kThreads + tid < mine) ? __ldg(list + k * kThreads + tid) : 0xffffffffu;
 
     uint32_t myCrossings = 0;
     {
@@ -553,6 +570,17 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
         if (tid < SY) tileY[tid] = (sy0 + tid < N) ? -centreOf(sy0 + tid, fN, invNPow2) : INFINITY;
         if (tid >= 32 && tid < 32 + SZ) tileZ[tid - 32] = (sz0 + tid - 32 < prm.z1) ? centreOf(sz0 + tid - 32, fN, invNPow2) : INFINITY;
         if (tid == 0) { stack[0] = 0; sTop[0] = 1u; sTop[1] = 0; sCand = 0; sNext = 0; }
+#pragma unroll
+        for (uint32_t k = 0; k < (uint32_t)(kIdStage / kThreads); ++k)
+        {
+            ids[k * kThreads + tid] = stagedId[k];
+            if (stagedId[k] != 0xffffffffu)
+            {
+                const char* rec = reinterpret_cast<const char*>(prm.tris + stagedId[k]);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 32));
+            }
+        }
         __syncthreads();
         const float halfN = 0.5f * fN;
 
@@ -754,9 +782,6 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
         {
             // ---- candidates were listed by k_walk_columns: dealt to the warps in chunks of C (small
             // chunks when there are few candidates, so that all W warps get some) ----
-            const uint32_t partBegin = (uint32_t)(((uint64_t)listed * part) / parts);
-            const uint32_t mine = (uint32_t)(((uint64_t)listed * (part + 1u)) / parts) - partBegin;   // this CTA's share
-            const uint32_t* list = prm.candList + (size_t)tile * prm.candCap + partBegin;
             uint32_t C = (uint32_t)kChunkMax;
             while (C > 4u && mine * DXRV_CHUNK_DEN < C * (uint32_t)W * DXRV_CHUNK_NUM) C >>= 1;
             for (;;)   // the warps take chunks as they become free: pair counts per chunk vary a lot
@@ -766,7 +791,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
                 first = __shfl_sync(0xffffffffu, first, 0);
                 if (first >= mine) break;
                 const bool has = lane < C && first + lane < mine;
-                processWarpChunkStaged(has, has ? __ldg(list + first + lane) : 0u);
+                processWarpChunkStaged(has, has ? (first + lane < (uint32_t)kIdStage ? ids[first + lane] : __ldg(list + first + lane)) : 0u);
             }
         }
         else if (prm.nodes == nullptr)
@@ -1020,12 +1045,18 @@ k_trace_fill_columns(const ParityParams prm)
         __syncthreads();
         if (sDuplicate != 0u) return;
         DXRV_TL_ROLE(1);
+#ifdef DXRV_EXPERIMENT
+        if (prm.bulkStores == 2u) return;   // (timing experiment: trace alone, the empty tiles stay unwritten)
+#endif
         writeEmptyTiles<SY, SZ>(prm, nEmpty, smem);
         return;
     }
     const uint32_t stride = gridDim.x - prm.numWriters;
     uint32_t item = blockIdx.x - prm.numWriters;
     if (item < nWork) DXRV_TL_ROLE(item < nHeavy ? 2 : 3);
+#ifdef DXRV_EXPERIMENT
+    if (prm.noTrace) return;   // (timing experiment: the writers alone)
+#endif
     for (bool first = true; item < nWork; item += stride, first = false)
     {
         if (!first) __syncthreads();   // the previous item's write-out has read the shared rows
@@ -1048,7 +1079,7 @@ uint32_t sharedRowWords(uint32_t P)
 template <int W, int SY, int SZ>
 void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
 {
-    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + (size_t)(kStackPerThread + kCandPerThread) * 32 * W);
+    const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + (size_t)(kStackPerThread + kCandPerThread + 2) * 32 * W);
     static bool attrSet[64] = {};
     static int smCount[64] = {};
     int dev = 0;
@@ -1062,6 +1093,11 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
     prm.numWriters = (dev >= 0 && dev < 64 && smCount[dev] > 0) ? 2u * (uint32_t)smCount[dev] : 296u;
     static const bool noBulk = [] { const char* e = std::getenv("DXRV_NO_BULK_STORE"); return e && e[0] && e[0] != '0'; }();
     prm.bulkStores = noBulk ? 0u : 1u;
+#ifdef DXRV_EXPERIMENT
+    if (const char* e = std::getenv("DXRV_EXP_NO_WRITERS")) if (e[0] == '1') prm.bulkStores = 2u;
+    prm.noTrace = 0;
+    if (const char* e = std::getenv("DXRV_EXP_NO_TRACE")) if (e[0] == '1') prm.noTrace = 1u;
+#endif
     if (ev) cudaEventRecord(ev[0], s);
     if (prm.nodes)
         k_walk_columns<SY, SZ><<<(prm.numTiles + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
