@@ -302,6 +302,10 @@ def run_c3(args):
     rig = Rig(args)
     torch, vox, stream, rank, world = rig.torch, rig.vox, rig.stream, rig.rank, rig.world
     N = GRID
+    # host threads of the library's read-back pool (dxrv_voxelize_to_host, sparse transport): the ranks of one box share its cores
+    host_pool_threads = max(2, min(32, host_threads() // world))
+    os.environ.setdefault("DXRV_HOST_THREADS", str(host_pool_threads))
+    host_pool_threads = int(os.environ["DXRV_HOST_THREADS"])
     mesh = d.load_obj(d.asset_path("dragon.obj")) if rank == 0 else None
     host_mesh, (h_vb, h_ib, d_vb, d_ib, nv, stride, ni) = rig.replicate_mesh(mesh)
     T = ni // 3
@@ -419,19 +423,24 @@ def run_c3(args):
             best = min(best, time.perf_counter() - tcal)
         rates = [None] * world
         rig.dist.all_gather_object(rates, cal_bytes / best * 1e-9)
-        ez0, ez1 = proportional_slabs(N, rates)[rank]
+        dz0, dz1 = proportional_slabs(N, rates)[rank]     # dense copy: cut by the measured link rates
+        ez0, ez1 = c0, c1                                 # default transport (compact blob + host expansion): equal cuts
         cal_rates = [round(float(r), 2) for r in rates]
         del cal_h
         e_ref = oracle.voxelize(host_mesh.vertices, host_mesh.indices, N, oracle.MODE_PARITY, z0=ez0, z1=ez1,
                                 threads=max(1, host_threads() // world))["bits"]
+        d_ref = oracle.voxelize(host_mesh.vertices, host_mesh.indices, N, oracle.MODE_PARITY, z0=dz0, z1=dz1,
+                                threads=max(1, host_threads() // world))["bits"]
     else:
         ez0, ez1, e_ref, cal_rates = z0, z1, gate_ref, None
+        dz0, dz1, d_ref = z0, z1, gate_ref
     e_bytes = (ez1 - ez0) * N * P * 4
+    d_bytes = (dz1 - dz0) * N * P * 4
     with numa_local(rig.local):
-        h_grid = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
+        h_grid = torch.empty(max(e_bytes, d_bytes), dtype=torch.uint8).pin_memory()
         h_grid.zero_()
 
-    def step_e2e():
+    def upload_and_build():
         if world > 1:
             # replicate the host mesh of rank 0: H2D on rank 0, NCCL broadcast, build from device memory
             with torch.cuda.stream(stream):
@@ -443,13 +452,36 @@ def run_c3(args):
             build()
         else:
             vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
-        # voxelize + read-back pipelined in 8 z sub-slabs: D2H of chunk k runs beside the fill of chunk k + 1
+
+    def step_e2e():
+        # the public call with its default transport (DXRV_READ_BACK_AUTO: at this size the slab comes back as a
+        # DXRV_FORMAT_SPARSE_BRICKS blob and is expanded into the dense host grid by the library's host threads)
+        upload_and_build()
         vox.voxelize_to_host(N, d.MODE_PARITY, ez0, ez1, h_grid.data_ptr(), e_bytes, chunks=8)
 
+    def step_e2e_dense():
+        # the same call, grid copied densely: pipelined in 8 z sub-slabs (D2H of chunk k beside the fill of chunk k + 1)
+        upload_and_build()
+        vox.voxelize_to_host(N, d.MODE_PARITY, dz0, dz1, h_grid.data_ptr(), d_bytes, chunks=8)
+
+    from dxrvoxelizer_b200 import _lib as L
+    vox.set_read_back(L.READ_BACK_DENSE)
+    for _ in range(3):
+        step_e2e_dense()
+    dense_mism = popcount(h_grid.numpy()[:d_bytes].view(np.uint32) ^ d_ref.reshape(-1))
+    rig.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_dense()
+    rig.barrier()
+    dense_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    vox.set_read_back(L.READ_BACK_AUTO)
+    h_grid.fill_(0xA5)            # the expansion must produce every byte, zeros included
     for _ in range(3):
         step_e2e()
-    e2e_mism = popcount(h_grid.numpy().view(np.uint32) ^ e_ref.reshape(-1))
-    e2e_mism_total, = rig.reduce_sum([e2e_mism])
+    e2e_d2h = vox.info(L.INFO_LAST_D2H_BYTES)
+    e2e_mism = popcount(h_grid.numpy()[:e_bytes].view(np.uint32) ^ e_ref.reshape(-1)) + dense_mism
+    e2e_mism_total, e2e_d2h_total = rig.reduce_sum([e2e_mism, e2e_d2h])
     if e2e_mism_total != 0:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "error": "end-to-end host grid differs from the CPU oracle", "n_gpus": world,
@@ -458,25 +490,21 @@ def run_c3(args):
         raise SystemExit(3)
     rig.barrier()
     t0 = time.perf_counter()
+    dbg = []
     for _ in range(args.steps):
+        ta = time.perf_counter()
         step_e2e()
+        dbg.append((time.perf_counter() - ta) * 1e3)
     rig.barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if os.environ.get("DXRV_BENCH_DEBUG"):
+        sys.stderr.write("e2e steps ms: %s\n" % " ".join("%.2f" % v for v in dbg))
     # ---- the same end-to-end step with the compact read-back format (DXRV_FORMAT_SPARSE_BRICKS, lossless): side number
     with numa_local(rig.local):
         h_sparse = torch.empty(e_bytes + e_bytes // 64 + (1 << 16), dtype=torch.uint8).pin_memory()
 
     def step_e2e_sparse():
-        if world > 1:
-            with torch.cuda.stream(stream):
-                if rank == 0:
-                    d_vb.copy_(h_vb, non_blocking=True)
-                    d_ib.copy_(h_ib, non_blocking=True)
-                rig.dist.broadcast(d_vb, 0)
-                rig.dist.broadcast(d_ib, 0)
-            build()
-        else:
-            vox.build_bvh_host_ptr(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni)
+        upload_and_build()
         vox.voxelize(N, d.MODE_PARITY, ez0, ez1)
         return vox.fetch_sparse_into(h_sparse.data_ptr(), h_sparse.numel())
 
@@ -526,13 +554,13 @@ def run_c3(args):
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
     fill_ms_rank0 = fill_ms   # the roofline of the kernel is a per-GPU figure: rank 0's launches against rank 0's bytes
-    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms, sparse_ms = rig.reduce_max(
-        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0, sparse_ms])
+    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms, sparse_ms, dense_ms = rig.reduce_max(
+        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0, sparse_ms, dense_ms])
     sparse_bytes_total, sparse_mism_total = rig.reduce_sum([sparse_bytes, sparse_mism])
     per_rank = None
     if world > 1:
         gathered = [None] * world
-        rig.dist.all_gather_object(gathered, {"rank": rank, "slab": [z0, z1], "e2e_slab": [ez0, ez1], "d2h_gbs": round(d2h_gbs, 2), "d2h_ms": round(down_ms, 4),
+        rig.dist.all_gather_object(gathered, {"rank": rank, "slab": [z0, z1], "e2e_slab": [ez0, ez1], "dense_copy_slab": [dz0, dz1], "d2h_gbs": round(d2h_gbs, 2), "d2h_ms": round(down_ms, 4),
                                               "fill_kernel_ms": round(fill_ms_rank0, 5)})
         per_rank = gathered
 
@@ -558,18 +586,26 @@ def run_c3(args):
                        "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), same z-slabs, LBVH + direction bins rebuilt every step"},
             "ms_per_1024_cubed_grid": step_ms,
             "e2e": {"value": total_voxels / (e2e_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(N * N * P * 4),
+                    "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(e2e_d2h_total),
+                    "host_grid_bytes_per_step": int(N * N * P * 4),
                     "timing": "wall clock around synchronising C-ABI calls, max over ranks",
-                    "how": "dxrv_build_bvh (host arrays) + dxrv_voxelize_to_host (8 z sub-slabs: D2H of chunk k beside the fill of chunk k+1); "
-                           "the 128 MiB dense bit grid over PCIe is the floor (d2h_grid below, measured unpipelined); N > 1: slabs cut in "
-                           "proportion to every rank's measured read-back rate (bytes, not compute, bound the step; the GPUs of a box share "
-                           "host links unevenly), every rank's host buffer checked against the oracle",
+                    "transport": "DXRV_READ_BACK_AUTO = sparse bricks + host expansion at this size",
+                    "how": "dxrv_build_bvh (host arrays) + dxrv_voxelize_to_host into a pinned host buffer that ends up holding the DENSE "
+                           "128 MiB bit grid (filled with 0xA5 beforehand, checked against the oracle).  Default transport of the call: "
+                           "the slab is encoded as DXRV_FORMAT_SPARSE_BRICKS on the GPU, `d2h_bytes_per_step` cross PCIe, and the "
+                           "library's host threads (%d per rank) expand the blob into the dense layout -- they zero the buffer with "
+                           "streaming stores while the GPU is still computing; the floor is the host's memory write bandwidth, not "
+                           "the link.  `dense_copy` = the same call with DXRV_READ_BACK_DENSE (8 z sub-slabs, D2H of chunk k beside the "
+                           "fill of chunk k+1: the PCIe floor, `phases_ms.d2h_grid` measured unpipelined; N > 1: its slabs are cut in "
+                           "proportion to every rank's measured read-back rate)" % host_pool_threads,
+                    "dense_copy": {"value": total_voxels / (dense_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": dense_ms,
+                                   "d2h_bytes_per_step": int(N * N * P * 4)},
                     "mismatched_voxels": int(e2e_mism_total), "readback_calibration_gbs": cal_rates,
                     "sparse_bricks": {"value": total_voxels / (sparse_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": sparse_ms,
                                       "d2h_bytes_per_step": int(sparse_bytes_total), "mismatched_voxels_after_decode": int(sparse_mism_total),
                                       "what": "same step, read-back as DXRV_FORMAT_SPARSE_BRICKS (lossless: header + 2-bit brick states + the "
                                               "mixed 32x4x4 bricks; dxrv_fetch_grid_sparse / dxrv_sparse_decode) -- a side number for consumers "
-                                              "that can take the compact form; `e2e.value` above is the dense grid, which is at the PCIe roofline"},
+                                              "that can take the compact form and skip the host expansion"},
                     "phases_ms": {"h2d_mesh_build_voxelize": up_ms, "d2h_grid": down_ms}, "d2h_gbs_rank0": d2h_gbs,
                     "per_rank": per_rank},
             "gpu_launches": int(launches),

@@ -13,8 +13,9 @@ OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_NO_BVH, ERR_NO_GRID, ERR_IO, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
 MODE_SHADER, MODE_PARITY, EMIT_TEXELS = 0, 1, 0x100
 FORMAT_BITS, FORMAT_U8, FORMAT_R10G10B10A2 = 0, 1, 2
+READ_BACK_AUTO, READ_BACK_DENSE, READ_BACK_SPARSE = 0, 1, 2
 INFO_NUM_TRIANGLES, INFO_NUM_NODES, INFO_KERNEL_LAUNCHES, INFO_CROSSINGS, INFO_SM_COUNT = 0, 1, 2, 3, 4
-INFO_LAST_WALK_NS, INFO_LAST_FILL_NS, INFO_LAST_BUILD_NS, INFO_LAST_SORT_NS = 5, 6, 7, 8
+INFO_LAST_WALK_NS, INFO_LAST_FILL_NS, INFO_LAST_BUILD_NS, INFO_LAST_SORT_NS, INFO_LAST_D2H_BYTES = 5, 6, 7, 8, 9
 DBG_MORTON_SORTED, DBG_PRIM_SORTED, DBG_NODES, DBG_TRIS, DBG_ROOT_BOX, DBG_BINS_STATE = 0, 1, 2, 3, 5, 6
 
 _c = ctypes
@@ -35,6 +36,7 @@ SIGNATURES = {
     "dxrv_fetch_grid_sparse": (_int, [_vp, _vp, _sz, _c.POINTER(_sz)]),
     "dxrv_sparse_decode": (_int, [_vp, _sz, _vp, _sz]),
     "dxrv_voxelize_to_host": (_int, [_vp, _u32, _u32, _u32, _u32, _vp, _sz, _u32]),
+    "dxrv_set_read_back": (_int, [_vp, _u32]),
     "dxrv_grid_device": (_int, [_vp, _c.POINTER(_vp), _c.POINTER(_sz)]),
     "dxrv_set_grid_target": (_int, [_vp, _vp, _sz]),
     "dxrv_count_inside": (_int, [_vp, _c.POINTER(_u64)]),

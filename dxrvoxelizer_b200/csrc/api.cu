@@ -14,6 +14,8 @@
 #include <cstdlib>
 
 #include "ctx.h"
+#include "host_pool.h"
+#include "sparse_host.h"
 
 namespace
 {
@@ -278,6 +280,57 @@ int validateMeshArgs(dxrv_ctx* ctx, const void* v, uint32_t numVerts, uint32_t s
     if (bound && !(bound[3] > 0.0f)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_build_bvh: bound[3] (half extent) must be > 0");
     return DXRV_OK;
 }
+// dxrv_voxelize_to_host through the compact transport: voxelize the slab, encode it on the device (sparse.cu), bring the
+// blob back into pinned staging memory and expand it into hostDst -- whose zeroing by the host pool starts before the
+// GPU does.  DXRV_ERR_UNSUPPORTED: the grid did not compress (nothing copied; the slab is resident in ctx->gridOwned).
+int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd, void* hostDst, size_t bytes)
+{
+    NvtxRange range("dxrv voxelize to host (sparse transport + host expansion)");
+    const SparseLayout L = sparseLayout(N, slabEnd - slabBegin);
+    const size_t countsOff = (L.maxBytes + 255) & ~(size_t)255;
+    cudaError_t e = ensure(ctx->sparseBuf, ctx->sparseCap, countsOff + (size_t)L.numBlocks * sizeof(uint32_t));
+    if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(sparse bricks)");
+    auto ensureStaging = [&](size_t need, size_t keep) -> cudaError_t {   // keep: leading bytes that survive a re-allocation
+        if (need <= ctx->hostBlobCap && ctx->hostBlob) return cudaSuccess;
+        uint8_t* fresh = nullptr;
+        const size_t cap = need + need / 2;
+        const cudaError_t err = cudaHostAlloc(reinterpret_cast<void**>(&fresh), cap, cudaHostAllocDefault);
+        if (err != cudaSuccess) return err;
+        if (ctx->hostBlob) { std::memcpy(fresh, ctx->hostBlob, std::min(keep, ctx->hostBlobCap)); cudaFreeHost(ctx->hostBlob); }
+        ctx->hostBlob = fresh; ctx->hostBlobCap = cap;
+        return cudaSuccess;
+    };
+    if ((e = ensureStaging(L.offPayload + (1u << 20), 0)) != cudaSuccess) return cudaFail(ctx, e, "cudaHostAlloc(blob staging)");
+    hostZeroBegin(hostDst, bytes);   // runs beside everything up to hostZeroWait()
+    int rc = dxrv_voxelize(ctx, N, mode, slabBegin, slabEnd);
+    if (rc == DXRV_OK)
+    {
+        ctx->launches += (uint64_t)launchSparseEncode(ctx->stream, ctx->gridOwned, N, slabBegin, slabEnd, ctx->sparseBuf,
+                                                      reinterpret_cast<uint32_t*>(ctx->sparseBuf + countsOff));
+        // the header (number of mixed bricks) and the brick states in one copy; then exactly the payload that exists
+        if (cudaMemcpyAsync(ctx->hostBlob, ctx->sparseBuf, L.offPayload, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = cudaFail(ctx, cudaGetLastError(), "sparse transport: header copy");
+    }
+    size_t total = 0;
+    if (rc == DXRV_OK)
+    {
+        const uint32_t numMixed = reinterpret_cast<const uint32_t*>(ctx->hostBlob)[9];
+        total = L.offPayload + (size_t)numMixed * 64;
+        if (total > bytes / 2) rc = DXRV_ERR_UNSUPPORTED;
+        else if ((e = ensureStaging(total, L.offPayload)) != cudaSuccess) rc = cudaFail(ctx, e, "cudaHostAlloc(blob staging)");
+        else if (numMixed && (cudaMemcpyAsync(ctx->hostBlob + L.offPayload, ctx->sparseBuf + L.offPayload, total - L.offPayload, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                              cudaStreamSynchronize(ctx->stream) != cudaSuccess))
+            rc = cudaFail(ctx, cudaGetLastError(), "sparse transport: payload copy");
+    }
+    hostZeroWait();
+    if (rc != DXRV_OK) return rc;
+    SparseBlobView v;
+    if (!sparseParse(ctx->hostBlob, total, v) || !sparseExpand(v, static_cast<uint32_t*>(hostDst), true))
+        return fail(ctx, DXRV_ERR_CUDA, "sparse transport: inconsistent blob");
+    ctx->lastD2hBytes = total;
+    return checkDeviceError(ctx);
+}
 }  // namespace
 
 namespace dxrv
@@ -350,6 +403,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
                     ctx->binsBuf, ctx->fusedScratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->hostBlob) cudaFreeHost(ctx->hostBlob);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     for (cudaEvent_t e : ctx->chunkDone) if (e) cudaEventDestroy(e);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
@@ -614,6 +668,7 @@ int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format)
     else return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid: unknown format");
     if (bytes != need) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid: bytes does not match the slab size in this format");
     DXRV_CUDA(cudaMemcpyAsync(hostDst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->lastD2hBytes = need;
     return checkDeviceError(ctx);
 }
 
@@ -628,6 +683,24 @@ int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sla
     if (bytes != layerBytes * layers) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bytes does not match the slab size");
     if (ctx->gridTarget) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: not with an external grid target");
     DeviceGuard g(ctx->device);
+    // Transport (dxrv_set_read_back).  The dense grid over one PCIe link is the floor of the copying path (128 MiB: 2.4 ms);
+    // a solid voxelization is mostly empty space and solid interior, so by default a large slab comes back as
+    // DXRV_FORMAT_SPARSE_BRICKS (a few MB) and is expanded into hostDst by the host pool's threads, which zero hostDst
+    // while the GPU is still computing.  The host's memory write bandwidth is then the floor (~1.1 ms for 128 MiB on 16
+    // cores).  A grid that does not compress (more than half of the dense size) is copied densely after all.
+    {
+        uint32_t transport = ctx->readBack;
+        if (const char* e = std::getenv("DXRV_TO_HOST")) transport = !std::strcmp(e, "dense") ? 1u : (!std::strcmp(e, "sparse") ? 2u : transport);
+        if (transport == 0u) transport = (bytes >= (8u << 20) && hostPoolThreads() >= 4u) ? 2u : 1u;
+        if (transport == 2u)
+        {
+            const int rcS = voxelizeToHostSparse(ctx, N, mode, slabBegin, slabEnd, hostDst, bytes);
+            if (rcS != DXRV_ERR_UNSUPPORTED) return rcS;   // UNSUPPORTED: did not compress; the slab is resident, copy it densely
+            DXRV_CUDA(cudaMemcpyAsync(hostDst, ctx->gridOwned, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->lastD2hBytes = bytes + 64;
+            return checkDeviceError(ctx);
+        }
+    }
     if (chunks < 1) chunks = 1;
     if (chunks > layers) chunks = layers;
     if (layerBytes % 16) chunks = 1;   // sub-slab offsets must keep the 128-bit store alignment
@@ -662,7 +735,16 @@ int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sla
     // the context now describes the whole slab, resident in its own grid
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = false; ctx->mipLevels = 0;
+    ctx->lastD2hBytes = bytes;
     return checkDeviceError(ctx);
+}
+
+int dxrv_set_read_back(dxrv_ctx* ctx, uint32_t transport)
+{
+    if (!ctx) return DXRV_ERR_INVALID_ARG;
+    if (transport > DXRV_READ_BACK_SPARSE) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_set_read_back: unknown transport");
+    ctx->readBack = transport;
+    return DXRV_OK;
 }
 
 int dxrv_fetch_grid_sparse(dxrv_ctx* ctx, void* hostDst, size_t capacity, size_t* bytesWritten)
@@ -690,42 +772,17 @@ int dxrv_fetch_grid_sparse(dxrv_ctx* ctx, void* hostDst, size_t capacity, size_t
     *bytesWritten = total;
     if (capacity < total) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_fetch_grid_sparse: capacity too small (needed size returned in *bytesWritten)");
     DXRV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(hostDst) + 64, ctx->sparseBuf + 64, total - 64, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->lastD2hBytes = total;
     return checkDeviceError(ctx);
 }
 
 int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_t denseBytes)
 {
-    // pure host code: the inverse of the encoding in sparse.cu
-    if (!blob || !denseDst || blobBytes < 64) return DXRV_ERR_INVALID_ARG;
-    const uint32_t* h = static_cast<const uint32_t*>(blob);
-    if (h[0] != 0x42525844u || h[1] != 1u || h[12] != 32u || h[13] != 4u || h[14] != 4u) return DXRV_ERR_INVALID_ARG;
-    const uint32_t N = h[2], z0 = h[3], z1 = h[4], P = h[5], BY = h[6], BZ = h[7], numBricks = h[8], numMixed = h[9];
-    if (z1 <= z0 || P != (N + 31) / 32 || BY != (N + 3) / 4 || BZ != (z1 - z0 + 3) / 4 || (uint64_t)numBricks != (uint64_t)P * BY * BZ) return DXRV_ERR_INVALID_ARG;
-    const size_t offStates = h[10], offPayload = h[11];
-    if (blobBytes < offPayload + (size_t)numMixed * 64 || offPayload < offStates + (size_t)((numBricks + 15) / 16) * 4) return DXRV_ERR_INVALID_ARG;
-    const uint32_t layers = z1 - z0;
-    if (denseBytes != (size_t)layers * N * P * 4) return DXRV_ERR_INVALID_ARG;
-    const uint32_t* states = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(blob) + offStates);
-    const uint32_t* payload = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(blob) + offPayload);
-    uint32_t* out = static_cast<uint32_t*>(denseDst);
-    const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
-    size_t rank = 0;
-    for (uint32_t b = 0; b < numBricks; ++b)
-    {
-        const uint32_t st = (states[b >> 4] >> (2u * (b & 15u))) & 3u;
-        const uint32_t bx = b % P, t = b / P, by = t % BY, bz = t / BY;
-        const uint32_t fullWord = (bx == P - 1u) ? tailMask : 0xffffffffu;
-        if (st == 2u && rank >= numMixed) return DXRV_ERR_INVALID_ARG;
-        for (uint32_t k = 0; k < 4u; ++k)
-            for (uint32_t j = 0; j < 4u; ++j)
-            {
-                const uint32_t y = 4u * by + j, z = 4u * bz + k;
-                if (y >= N || z >= layers) continue;
-                out[((size_t)z * N + y) * P + bx] = st == 0u ? 0u : (st == 1u ? fullWord : payload[rank * 16 + 4u * k + j]);
-            }
-        if (st == 2u) ++rank;
-    }
-    return rank == numMixed ? DXRV_OK : DXRV_ERR_INVALID_ARG;
+    // pure host code (sparse_host.cpp): the inverse of the encoding in sparse.cu, on the host pool's threads
+    SparseBlobView v;
+    if (!denseDst || !sparseParse(blob, blobBytes, v)) return DXRV_ERR_INVALID_ARG;
+    if (denseBytes != (size_t)(v.z1 - v.z0) * v.N * v.P * 4) return DXRV_ERR_INVALID_ARG;
+    return sparseExpand(v, static_cast<uint32_t*>(denseDst), false) ? DXRV_OK : DXRV_ERR_INVALID_ARG;
 }
 
 int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes)
@@ -843,6 +900,7 @@ int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value)
     case DXRV_INFO_NUM_NODES: *value = (ctx->haveBvh && ctx->mesh.numTris) ? 2ull * ctx->mesh.numTris - 1 : 0; return DXRV_OK;
     case DXRV_INFO_KERNEL_LAUNCHES: *value = ctx->launches; return DXRV_OK;
     case DXRV_INFO_SM_COUNT: *value = (uint64_t)ctx->smCount; return DXRV_OK;
+    case DXRV_INFO_LAST_D2H_BYTES: *value = ctx->lastD2hBytes; return DXRV_OK;
     case DXRV_INFO_LAST_WALK_NS:
     case DXRV_INFO_LAST_FILL_NS:
     {

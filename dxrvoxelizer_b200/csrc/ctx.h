@@ -66,6 +66,9 @@ struct dxrv_ctx
     uint32_t* texels = nullptr; size_t texCap = 0;
     uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
     uint8_t* sparseBuf = nullptr; size_t sparseCap = 0;   // DXRV_FORMAT_SPARSE_BRICKS blob + block counts
+    uint8_t* hostBlob = nullptr; size_t hostBlobCap = 0;  // pinned staging of the blob (dxrv_voxelize_to_host, sparse transport)
+    uint32_t readBack = 0;                                // DXRV_READ_BACK_* (dxrv_set_read_back)
+    uint64_t lastD2hBytes = 0;                            // DXRV_INFO_LAST_D2H_BYTES
     uint32_t* mips = nullptr; size_t mipCap = 0;      // occupancy pyramid levels 1.. (concatenated)
     uint32_t mipLevels = 0;                            // levels incl. level 0; 0 = not built for the current grid
     uint32_t* walkBuf = nullptr; size_t walkCap = 0, walkZeroed = 0;  // MODE_PARITY candidate lists + split-tile scratch

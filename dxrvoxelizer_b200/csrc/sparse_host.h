@@ -1,0 +1,24 @@
+// sparse_host.h -- host side of DXRV_FORMAT_SPARSE_BRICKS (include/dxrv.h): parse a blob, expand it into the dense
+// DXRV_FORMAT_BITS layout with the host pool's threads.  Internal to libdxrv.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace dxrv
+{
+struct SparseBlobView
+{
+    uint32_t N, z0, z1, P, BY, BZ, numBricks, numMixed;
+    const uint32_t* states;
+    const uint32_t* payload;
+};
+// false: not a blob of this format / truncated / inconsistent sizes
+bool sparseParse(const void* blob, size_t blobBytes, SparseBlobView& v);
+// Expand into dst (layers * N * P words).  dstIsZero: dst holds zeros already (hostZero below, typically issued while
+// the GPU was still computing) and only the non-empty bricks are written; otherwise every word is written.
+// false: the states disagree with the header's count of mixed bricks (nothing reliable was written).
+bool sparseExpand(const SparseBlobView& v, uint32_t* dst, bool dstIsZero);
+// Zero `bytes` at dst with the pool's threads: begin returns at once, wait blocks (host_pool.h: one batch at a time).
+void hostZeroBegin(void* dst, size_t bytes);
+void hostZeroWait();
+}  // namespace dxrv

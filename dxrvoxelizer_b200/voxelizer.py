@@ -146,8 +146,12 @@ class Voxelizer:
         self._shape = (z1 - z0, N, (N + 31) // 32)
         self._N = N
 
+    def set_read_back(self, transport):
+        """dxrv_set_read_back: L.READ_BACK_AUTO / _DENSE (pipelined PCIe copy) / _SPARSE (compact blob + host expansion)."""
+        self._check(self._lib.dxrv_set_read_back(self._h, transport))
+
     def voxelize_to_host(self, N, mode, z0, z1, ptr, nbytes, chunks=8):
-        """dxrv_voxelize_to_host: voxelize + read-back pipelined in z sub-slabs (ptr: host memory, ideally pinned)."""
+        """dxrv_voxelize_to_host: voxelize + read-back of the dense bit grid into host memory at ptr (transport: set_read_back)."""
         self._check(self._lib.dxrv_voxelize_to_host(self._h, N, mode, z0, z1, ptr, nbytes, chunks))
         self._shape = (z1 - z0, N, (N + 31) // 32)
         self._N = N

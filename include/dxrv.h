@@ -130,10 +130,22 @@ DXRV_API int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sl
  * bytes must equal the slab size in `format`.  The reference has no read-back of the grid
  * (only of the back buffer, DXRVoxelizer.cpp:436,476); this is the headless replacement. */
 DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format);
-/* dxrv_voxelize + dxrv_fetch_grid(DXRV_FORMAT_BITS) as one pipelined call: the slab is computed in `chunks` z sub-slabs
- * (0 or 1 = no pipelining), and each is copied to hostDst (pinned memory: dxrv_host_alloc) on a second stream while the
- * next one is computed.  Returns when hostDst holds the whole slab; the context then describes that slab exactly as
- * after dxrv_voxelize.  bytes must equal the slab size.  Not available with an external grid target. */
+/* dxrv_voxelize + dxrv_fetch_grid(DXRV_FORMAT_BITS) as one call that returns when hostDst holds the whole slab (dense BITS
+ * layout, bytes = the slab size); the context then describes that slab exactly as after dxrv_voxelize.  Not available
+ * with an external grid target.  How the grid travels is chosen with dxrv_set_read_back (or DXRV_TO_HOST=dense|sparse):
+ *   DXRV_READ_BACK_DENSE   the slab is computed in `chunks` z sub-slabs (0 or 1 = no pipelining) and each is copied to
+ *                          hostDst (pinned memory: dxrv_host_alloc) on a second stream while the next one is computed.
+ *                          Floor: the dense grid over the PCIe link (128 MiB at 1024^3: 2.4 ms).
+ *   DXRV_READ_BACK_SPARSE  the slab is encoded as DXRV_FORMAT_SPARSE_BRICKS on the device, the blob (a few MB) is copied
+ *                          to pinned staging memory of the context and expanded into hostDst by a pool of host threads
+ *                          (DXRV_HOST_THREADS, default all cores up to 32), which zero hostDst while the GPU is still
+ *                          computing.  Floor: the host's memory write bandwidth.  A grid whose blob exceeds half the
+ *                          dense size is copied densely after all.  hostDst is bit-identical either way.
+ *   DXRV_READ_BACK_AUTO    (default) SPARSE for slabs of 8 MiB and more when at least 4 host threads exist, else DENSE. */
+#define DXRV_READ_BACK_AUTO   0u
+#define DXRV_READ_BACK_DENSE  1u
+#define DXRV_READ_BACK_SPARSE 2u
+DXRV_API int dxrv_set_read_back(dxrv_ctx* ctx, uint32_t transport);
 DXRV_API int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd,
                                    void* hostDst, size_t bytes, uint32_t chunks);
 /* DXRV_FORMAT_SPARSE_BRICKS: a lossless compact form of the slab's BITS grid for consumers that can take it (a solid
@@ -145,7 +157,8 @@ DXRV_API int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uin
  *   payload 16 words per mixed brick {z = 4 bz + k {y = 4 by + j}}, in brick order
  * dxrv_fetch_grid_sparse encodes the slab of the last voxelize on the device and copies exactly the bytes that exist;
  * *bytesWritten receives their number (also when `capacity` is too small: DXRV_ERR_INVALID_ARG, nothing but the header
- * copied).  dxrv_sparse_decode (pure host code) expands a blob into the dense BITS layout. */
+ * copied).  dxrv_sparse_decode (pure host code, on the same pool of host threads) expands a blob into the dense BITS
+ * layout. */
 DXRV_API int dxrv_fetch_grid_sparse(dxrv_ctx* ctx, void* hostDst, size_t capacity, size_t* bytesWritten);
 DXRV_API int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_t denseBytes);
 /* Device pointer / byte size of the slab's DXRV_FORMAT_BITS grid (valid until the next
@@ -190,7 +203,8 @@ enum dxrv_info
     DXRV_INFO_LAST_WALK_NS = 5,    /* device time of the last k_walk_columns (needs dxrv_set_profiling) */
     DXRV_INFO_LAST_FILL_NS = 6,    /* device time of the last k_trace_fill_columns                       */
     DXRV_INFO_LAST_BUILD_NS = 7,   /* device time of the last acceleration-structure build (needs dxrv_set_profiling) */
-    DXRV_INFO_LAST_SORT_NS = 8     /* ... of its onesweep radix-sort passes alone                        */
+    DXRV_INFO_LAST_SORT_NS = 8,    /* ... of its onesweep radix-sort passes alone                        */
+    DXRV_INFO_LAST_D2H_BYTES = 9   /* bytes the last dxrv_voxelize_to_host / dxrv_fetch_grid[_sparse] copied device -> host */
 };
 DXRV_API int dxrv_get_info(dxrv_ctx* ctx, uint32_t what, uint64_t* value);
 /* Record CUDA events around the MODE_PARITY kernels of every dxrv_voxelize and around the phases of every build

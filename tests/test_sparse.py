@@ -85,3 +85,46 @@ def test_empty_and_full_grids(vox, meshes_mod):
     dense = vox.fetch_bits()
     blob = vox.fetch_sparse()
     assert np.array_equal(d.sparse_decode(blob), dense)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,N,z0,z1,mode", [("dragon.obj", 512, 0, 512, 1), ("bunny.obj", 1000, 100, 901, 1), ("TuringBowl.obj", 192, 0, 192, 0),
+                                               ("dragon.obj", 1024, 0, 1024, 1), ("bunny.obj", 33, 0, 33, 1)])
+def test_to_host_transports_agree(vox, assets, name, N, z0, z1, mode):
+    """dxrv_voxelize_to_host: the pipelined dense copy, the sparse transport (device encoder + host expansion into a
+    buffer full of garbage) and the automatic choice all leave the same dense grid as dxrv_voxelize + dxrv_fetch_grid."""
+    from dxrvoxelizer_b200 import _lib as L
+    m = assets(name)
+    vox.build_bvh(m)
+    vox.voxelize(N, mode, z0, z1)
+    want = vox.fetch_bits()
+    try:
+        for transport in (L.READ_BACK_DENSE, L.READ_BACK_SPARSE, L.READ_BACK_AUTO):
+            vox.set_read_back(transport)
+            got = np.full(want.shape, 0xDEADBEEF, np.uint32)
+            vox.voxelize_to_host(N, mode, z0, z1, got.ctypes.data, got.nbytes, chunks=4)
+            assert np.array_equal(got, want), transport
+            assert np.array_equal(vox.fetch_bits(), want)       # the context describes the whole slab afterwards
+    finally:
+        vox.set_read_back(L.READ_BACK_AUTO)
+
+
+@pytest.mark.gpu
+def test_to_host_sparse_transport_falls_back_when_the_grid_does_not_compress(vox):
+    """A soup of random triangles: most bricks are mixed, the blob would exceed half the dense size -> dense copy."""
+    from dxrvoxelizer_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    pos = rng.uniform(-1, 1, size=(3000, 3)).astype(np.float32)
+    m = d.Mesh.from_arrays(pos, rng.integers(0, 3000, size=(4000, 3)).astype(np.uint32))
+    vox.build_bvh(m)
+    N = 128
+    vox.voxelize(N, d.MODE_PARITY)
+    want = vox.fetch_bits()
+    assert vox.fetch_sparse().size > want.nbytes // 2
+    vox.set_read_back(L.READ_BACK_SPARSE)
+    try:
+        got = np.full(want.shape, 0xDEADBEEF, np.uint32)
+        vox.voxelize_to_host(N, d.MODE_PARITY, 0, N, got.ctypes.data, got.nbytes)
+        assert np.array_equal(got, want)
+    finally:
+        vox.set_read_back(L.READ_BACK_AUTO)
