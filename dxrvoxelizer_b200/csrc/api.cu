@@ -27,6 +27,7 @@ int checkDeviceError(dxrv_ctx* ctx)
     if (e == kErrNone) return DXRV_OK;
     cudaMemsetAsync(ctx->dErr, 0, sizeof(uint32_t), ctx->stream);
     ctx->walkZeroed = 0;  // a kernel that bailed out may have left the split-tile scratch dirty
+    ctx->binsReady.valid = false;
     if (e == kErrBarrierTimeout)
     {
         // the fused build's CTAs were not co-resident after all: clean its barrier words, use the multi-kernel build from now on
@@ -142,6 +143,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
     ctx->haveBvh = false;
     ctx->haveGrid = false;
     ctx->binsValid = false;
+    ctx->binsReady.valid = false;
     if (T > ctx->capTris || !ctx->nodes)
     {
         const size_t cap = T + T / 8 + 16;
@@ -234,6 +236,7 @@ int buildOnDevice(dxrv_ctx* ctx, const float bound[4])
             if (prof) { cudaEventRecord(ctx->profBuild[3], s); ctx->profBuildValid = true; }
             return;
         }
+        if (fused) ctx->fusedBuild = false;   // the cooperative launch was refused: multi-kernel builds from now on
         if (haveBound) { launchSetBound(s, bnd[0], bnd[1], bnd[2], bnd[3], ctx->dBound); }
         else { launchBounds(s, m, ctx->dBound, ctx->dPartials, ctx->dCounter); }
         ctx->launches += 1;
@@ -552,6 +555,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
         const bool reallocated = !ctx->walkBuf || walkBytes > ctx->walkCap;
         cudaError_t e = ensure(ctx->walkBuf, ctx->walkCap, walkBytes);
         if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc(walk lists)");
+        if (reallocated) ctx->binsReady.valid = false;
         if (reallocated || zeroBytes != ctx->walkZeroed)
         {
             // the split-tile scratch is self-cleaning; it only needs zeroing when (re)allocated or resized
@@ -599,7 +603,9 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     const bool usesTree = algo == DXRV_MODE_SHADER || (!scatter && walkTree);
     const bool needTree = usesTree && !ctx->treeBuilt;
     if (algo == DXRV_MODE_PARITY && !(walkTree && !scatter)) bvh.nodes = nullptr;
-    keyPush(key, (uint32_t)needTree); keyPush(key, (uint32_t)walkTree);
+    const bool tileBins = algo == DXRV_MODE_PARITY && !scatter && !walkTree;
+    const bool binsReady = tileBins && ctx->binsReady.valid && ctx->binsReady.N == N && ctx->binsReady.z0 == slabBegin && ctx->binsReady.z1 == slabEnd;
+    keyPush(key, (uint32_t)needTree); keyPush(key, (uint32_t)walkTree); keyPush(key, (uint32_t)binsReady);
     keyPush(key, ctx->binsBuf); keyPush(key, (uint32_t)buildBins); keyPush(key, (uint32_t)useBins); keyPush(key, ctx->binsSizes.R);
     keyPush(key, ctx->nodes); keyPush(key, ctx->tris);
     keyPush(key, ctx->mesh.verts); keyPush(key, ctx->mesh.numVerts); keyPush(key, ctx->mesh.stride); keyPush(key, ctx->mesh.indices); keyPush(key, ctx->mesh.numTris);
@@ -612,7 +618,7 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
                                                                     ctx->profiling ? ctx->prof : nullptr);
             else
                 ctx->launches += (uint64_t)launchTraceFillColumns(ctx->stream, bvh, N, slabBegin, slabEnd, grid, ctx->walkBuf,
-                                                                  ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr);
+                                                                  ctx->dCrossings, ctx->dErr, ctx->profiling ? ctx->prof : nullptr, binsReady);
             ctx->profValid = ctx->profiling;
         }
         else
@@ -635,6 +641,11 @@ int dxrv_voxelize(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, 
     ctx->N = N; ctx->z0 = slabBegin; ctx->z1 = slabEnd; ctx->mode = mode;
     ctx->haveGrid = true; ctx->haveTexels = wantTexels; ctx->mipLevels = 0;
     if (needTree) ctx->treeBuilt = ctx->pyramidBuilt = true;
+    if (algo == DXRV_MODE_PARITY)
+    {
+        // the lists this call left (or used) stay valid for the same structure, grid and slab; the other paths overwrite them
+        ctx->binsReady.valid = tileBins; ctx->binsReady.N = N; ctx->binsReady.z0 = slabBegin; ctx->binsReady.z1 = slabEnd;
+    }
     ctx->treeWanted = usesTree;   // the next build includes the hierarchy iff this consumer traversed it
     if (algo == DXRV_MODE_SHADER && useBins) ctx->binsValid = true;
     return DXRV_OK;

@@ -39,6 +39,9 @@ struct dxrv_ctx
     // later redoes the leaf pass (pyramidBuilt).  fusedBuild goes off for good if the device cannot run it.
     bool fusedBuild = true, pyramidBuilt = false;
     void* fusedScratch = nullptr;
+    // MODE_PARITY candidate lists in walkBuf: valid for the current acceleration structure and exactly this grid / slab
+    // (left by a tile-path voxelize; the next voxelize with the same parameters starts at k_file_columns)
+    struct BinState { bool valid = false; uint32_t N = 0, z0 = 0, z1 = 0; } binsReady;
 
     // LBVH
     uint32_t *keysA = nullptr, *keysB = nullptr, *valsA = nullptr, *valsB = nullptr;

@@ -92,7 +92,8 @@ size_t parityScratchWords(uint32_t N, uint32_t z0, uint32_t z1);
 size_t parityScratchZeroWords(uint32_t N);
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1,
                            uint32_t* grid, uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr,
-                           cudaEvent_t* ev /* nullable: {before walk, between, after fill} */);
+                           cudaEvent_t* ev /* nullable: {before walk, between, after fill} */,
+                           bool binsReady = false /* the candidate lists of exactly this grid / slab / structure are in walkBuf already */);
 
 // ---- scatter_parity.cu --------------------------------------------------------------------------
 // MODE_PARITY for meshes that are fine relative to the grid (useScatterParity): triangle-parallel scatter of

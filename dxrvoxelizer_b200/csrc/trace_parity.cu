@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include "kernels.h"
 #include "parity_common.cuh"
+#include "parity_bins.cuh"
 #include "timeline_debug.cuh"
 
 namespace dxrv
@@ -283,113 +284,31 @@ template <int SY, int SZ>
 __global__ void __launch_bounds__(256)
 k_bin_columns(const ParityParams prm)
 {
-    extern __shared__ float sRect[];   // exact rectangles of the tiles: yMin/yMax per tile column, zMin/zMax per tile row
+    extern __shared__ float sRect[];   // exact rectangles of the tiles (parity_bins.cuh)
     if (blockIdx.x == 0 && threadIdx.x == 0) *prm.crossings = 0ull;   // (accumulated by the fill kernel)
-    const uint32_t tilesY = prm.tilesY, tilesZ = (prm.z1 - prm.z0 + SZ - 1) / SZ;
-    float* yMin = sRect; float* yMax = yMin + tilesY; float* zMin = yMax + tilesY; float* zMax = zMin + tilesZ;
-    const float fN = (float)prm.N, halfN = 0.5f * fN;
-    for (uint32_t i = threadIdx.x; i < tilesY; i += blockDim.x)
-    {
-        const uint32_t sy0 = i * SY, yLast = min(sy0 + SY - 1, prm.N - 1);
-        yMax[i] = -centreOf(sy0, fN, prm.invNPow2);   // scene Y decreases with y
-        yMin[i] = -centreOf(yLast, fN, prm.invNPow2);
-    }
-    for (uint32_t i = threadIdx.x; i < tilesZ; i += blockDim.x)
-    {
-        const uint32_t sz0 = prm.z0 + i * SZ, zLast = min(sz0 + SZ - 1, prm.z1 - 1);
-        zMin[i] = centreOf(sz0, fN, prm.invNPow2);
-        zMax[i] = centreOf(zLast, fN, prm.invNPow2);
-    }
+    BinParams bp;
+    bp.N = prm.N; bp.z0 = prm.z0; bp.z1 = prm.z1; bp.tilesY = prm.tilesY; bp.candCap = prm.candCap; bp.invNPow2 = prm.invNPow2;
+    bp.candCount = prm.candCount; bp.candList = prm.candList;
+    binTablesSetup<SY, SZ>(bp, sRect);
     __syncthreads();
-    const uint32_t lane = laneId();
-    const int layers = (int)(prm.z1 - prm.z0);
     const uint32_t rounded = (prm.numTris + 31u) & ~31u;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < rounded; j += gridDim.x * blockDim.x)
     {
-        int ty0 = 0, ty1 = -1, tz0 = 0, tz1 = -1;
-        float ylo = 0, yhi = 0, zlo = 0, zhi = 0;
-        if (j < prm.numTris)
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        const bool has = j < prm.numTris;
+        if (has)
         {
             const float4* t = reinterpret_cast<const float4*>(prm.tris + j);
-            const float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
-            ylo = fminf(fminf(a.y, b.y), c.y); yhi = fmaxf(fmaxf(a.y, b.y), c.y);
-            zlo = fminf(fminf(a.z, b.z), c.z); zhi = fmaxf(fmaxf(a.z, b.z), c.z);
-            // conservative index range (one voxel of slack; the exact compares below decide), then tiles
-            const float yA = (1.0f - yhi) * halfN - 1.5f, yB = (1.0f - ylo) * halfN + 0.5f;
-            const float zA = (zlo + 1.0f) * halfN - 1.5f - (float)prm.z0, zB = (zhi + 1.0f) * halfN + 0.5f - (float)prm.z0;
-            if (yB >= 0.0f && yA <= fN - 1.0f && zB >= 0.0f && zA <= (float)(layers - 1))   // (false for NaN boxes)
-            {
-                ty0 = max((int)floorf(yA), 0) / SY; ty1 = min((int)ceilf(yB), (int)prm.N - 1) / SY;
-                tz0 = max((int)floorf(zA), 0) / SZ; tz1 = min((int)ceilf(zB), layers - 1) / SZ;
-            }
+            a = __ldg(t); b = __ldg(t + 1); c = __ldg(t + 2);
         }
-        const uint32_t nu = (uint32_t)max(ty1 - ty0 + 1, 0), nv = (uint32_t)max(tz1 - tz0 + 1, 0), n = nu * nv;
-        auto emitTile = [&](uint32_t slot, int ty, int tz, float bylo, float byhi, float bzlo, float bzhi) {
-            if (bylo <= yMax[ty] && byhi >= yMin[ty] && bzlo <= zMax[tz] && bzhi >= zMin[tz])
-            {
-                const uint32_t tile = (uint32_t)tz * tilesY + (uint32_t)ty;
-                const uint32_t at = atomicAdd(prm.candCount + tile, 1u);
-                if (at < prm.candCap) prm.candList[(size_t)tile * prm.candCap + at] = slot;
-            }
-        };
-        // Small rectangles, all lanes in step: neighbours in Morton order mostly hit the SAME tile, so the lanes of a warp
-        // that do are served by one atomic (a crowded tile otherwise takes thousands of serialised same-address atomics).
-        const uint32_t nSmall = n <= 16u ? n : 0u;
-        const uint32_t rounds = __reduce_max_sync(0xffffffffu, nSmall);
-        // four rounds per batch: their atomics are all issued before the first result is consumed (one L2 round trip
-        // per batch instead of one per round -- the kernel is a latency chain, not a throughput problem)
-        for (uint32_t q0 = 0; q0 < rounds; q0 += 4u)
-        {
-            uint32_t tileK[4], peersK[4], atK[4];
-#pragma unroll
-            for (uint32_t k = 0; k < 4u; ++k)
-            {
-                const uint32_t q = q0 + k;
-                bool has = false;
-                tileK[k] = 0; peersK[k] = 0; atK[k] = 0;
-                if (q < nSmall)
-                {
-                    const int ty = ty0 + (int)(q % nu), tz = tz0 + (int)(q / nu);
-                    has = ylo <= yMax[ty] && yhi >= yMin[ty] && zlo <= zMax[tz] && zhi >= zMin[tz];
-                    tileK[k] = (uint32_t)tz * tilesY + (uint32_t)ty;
-                }
-                const uint32_t act = __ballot_sync(0xffffffffu, has);
-                if (has)
-                {
-                    peersK[k] = __match_any_sync(act, tileK[k]);
-                    if ((int)lane == __ffs(peersK[k]) - 1) atK[k] = atomicAdd(prm.candCount + tileK[k], (uint32_t)__popc(peersK[k]));
-                }
-            }
-#pragma unroll
-            for (uint32_t k = 0; k < 4u; ++k)
-            {
-                const uint32_t act = __ballot_sync(0xffffffffu, peersK[k] != 0u);
-                if (peersK[k] != 0u)
-                {
-                    (void)act;
-                    const uint32_t at = __shfl_sync(peersK[k], atK[k], __ffs(peersK[k]) - 1) + (uint32_t)__popc(peersK[k] & laneMaskLt());
-                    if (at < prm.candCap) prm.candList[(size_t)tileK[k] * prm.candCap + at] = j;
-                }
-            }
-        }
-        uint32_t big = __ballot_sync(0xffffffffu, n > 16u);
-        while (big)
-        {
-            const int L = __ffs(big) - 1;
-            big &= big - 1u;
-            const uint32_t bn = __shfl_sync(0xffffffffu, n, L), bnu = __shfl_sync(0xffffffffu, nu, L);
-            const int by0 = __shfl_sync(0xffffffffu, ty0, L), bz0 = __shfl_sync(0xffffffffu, tz0, L);
-            const uint32_t bj = __shfl_sync(0xffffffffu, j, L);
-            const float b0 = __shfl_sync(0xffffffffu, ylo, L), b1 = __shfl_sync(0xffffffffu, yhi, L);
-            const float b2 = __shfl_sync(0xffffffffu, zlo, L), b3 = __shfl_sync(0xffffffffu, zhi, L);
-            for (uint32_t q = lane; q < bn; q += 32u) emitTile(bj, by0 + (int)(q % bnu), bz0 + (int)(q / bnu), b0, b1, b2, b3);
-        }
+        binTriangleWarp<SY, SZ>(bp, sRect, has, a, b, c, j);
     }
 }
 
 __global__ void __launch_bounds__(32 * kWalkWarps)
 k_file_columns(const ParityParams prm)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *prm.crossings = 0ull;   // (again: k_bin_columns does not run when the lists were ready)
     const uint32_t firstTile = (blockIdx.x * kWalkWarps + (threadIdx.x >> 5)) * 32u;
     if (firstTile >= prm.numTiles) return;
     const uint32_t tile = firstTile + laneId();
@@ -1077,7 +996,7 @@ uint32_t sharedRowWords(uint32_t P)
 }
 
 template <int W, int SY, int SZ>
-void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
+void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev, bool binsReady)
 {
     const size_t smemBytes = sizeof(uint32_t) * ((size_t)SY * SZ * prm.Ps + SY + SZ + (size_t)(kStackPerThread + kCandPerThread + 2) * 32 * W);
     static bool attrSet[64] = {};
@@ -1106,7 +1025,7 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev)
         // candidates by triangle-parallel binning (the default): no hierarchy needed
         const uint32_t tilesZ = (prm.z1 - prm.z0 + SZ - 1) / SZ;
         const uint32_t binBlocks = std::max(1u, std::min<uint32_t>((prm.numTris + 255u) / 256u, 148u * 8u));
-        k_bin_columns<SY, SZ><<<binBlocks, 256, sizeof(float) * 2 * (prm.tilesY + tilesZ), s>>>(prm);
+        if (!binsReady) k_bin_columns<SY, SZ><<<binBlocks, 256, sizeof(float) * 2 * (prm.tilesY + tilesZ), s>>>(prm);
         const uint32_t groups = (prm.numTiles + 31u) / 32u;
         k_file_columns<<<(groups + kWalkWarps - 1) / kWalkWarps, 32 * kWalkWarps, 0, s>>>(prm);
     }
@@ -1169,7 +1088,7 @@ size_t parityScratchZeroWords(uint32_t N)
 }
 
 int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint32_t z0, uint32_t z1, uint32_t* grid,
-                           uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr, cudaEvent_t* ev)
+                           uint32_t* walkBuf, unsigned long long* dCrossings, uint32_t* dErr, cudaEvent_t* ev, bool binsReady)
 {
     ParityParams prm;
     prm.nodes = bvh.nodes; prm.tris = bvh.tris; prm.numTris = bvh.numTris;
@@ -1194,12 +1113,13 @@ int launchTraceFillColumns(cudaStream_t s, const BvhView& bvh, uint32_t N, uint3
     prm.candList = p;
     prm.crossings = dCrossings; prm.err = dErr;
     // one memset node: the launch counters and, behind them, the tile counters the binning kernel counts up with atomics
-    cudaMemsetAsync(prm.bucketCount, 0, (kCounterWords + (prm.nodes ? 0 : tilesPad)) * sizeof(uint32_t), s);
+    if (prm.nodes) binsReady = false;
+    cudaMemsetAsync(prm.bucketCount, 0, (kCounterWords + ((prm.nodes || binsReady) ? 0 : tilesPad)) * sizeof(uint32_t), s);
     // warps per CTA by row length (see k_trace_fill_columns); every choice keeps rows-per-warp x groups-per-row
     // a multiple of 32
-    if (prm.Ps <= 32) launchVariant<4, 16, 8>(s, prm, ev);
-    else if (prm.Ps <= 64) launchVariant<8, 16, 8>(s, prm, ev);
-    else launchVariant<16, 16, 8>(s, prm, ev);
-    return prm.nodes ? 2 : 3;
+    if (prm.Ps <= 32) launchVariant<4, 16, 8>(s, prm, ev, binsReady);
+    else if (prm.Ps <= 64) launchVariant<8, 16, 8>(s, prm, ev, binsReady);
+    else launchVariant<16, 16, 8>(s, prm, ev, binsReady);
+    return (prm.nodes || binsReady) ? 2 : 3;
 }
 }  // namespace dxrv

@@ -443,3 +443,30 @@ def test_binned_candidates_overflow_scans_all_triangles(vox, meshes_mod, oracle_
         ref = oracle_mod.voxelize(m.vertices, m.indices, 64, 1)
         assert popcount(got ^ ref["bits"]) == 0, how
         assert vox.info(L.INFO_CROSSINGS) == ref["crossings"], how
+
+
+def test_candidate_lists_are_reused_for_the_same_structure_grid_and_slab(assets):
+    """MODE_PARITY tile path: a second voxelize of the same acceleration structure with the same grid and slab starts at
+    k_file_columns (the candidate lists are still in the scratch buffer); a rebuild, another grid / slab or another
+    mesh bins again.  Same grids every time."""
+    import dxrvoxelizer_b200 as d
+    from dxrvoxelizer_b200 import _lib as L
+    v = d.Voxelizer(0)
+    launches = lambda: v.info(L.INFO_KERNEL_LAUNCHES)
+    for mesh in (assets("dragon.obj"), assets("bunny.obj")):
+        v.build_bvh(mesh)
+        for N, z0, z1 in ((640, 0, 640), (704, 13, 150)):        # (4 T < N^2: the tile path, not the scatter path)
+            n0 = launches(); v.voxelize(N, d.MODE_PARITY, z0, z1); first = v.fetch_bits(); n1 = launches()
+            v.voxelize(N, d.MODE_PARITY, z0, z1); second = v.fetch_bits(); n2 = launches()
+            assert n1 - n0 == 3 and n2 - n1 == 2                   # k_bin_columns skipped the second time
+            assert np.array_equal(first, second)
+            v.voxelize(N, d.MODE_PARITY, z0, z1 - 1)               # another slab: bins again
+            assert launches() - n2 == 3
+            assert np.array_equal(v.fetch_bits(), first[:-1])
+            v.voxelize(N, d.MODE_SHADER, z0, z0 + 2)               # (does not touch the lists)
+            v.voxelize(N, d.MODE_PARITY, z0, z1 - 1)
+            assert np.array_equal(v.fetch_bits(), first[:-1])
+            v.build_bvh(mesh)                                      # a new structure: bins again
+            n3 = launches(); v.voxelize(N, d.MODE_PARITY, z0, z1 - 1); n4 = launches()
+            assert n4 - n3 == 3 and np.array_equal(v.fetch_bits(), first[:-1])
+    v.close()
