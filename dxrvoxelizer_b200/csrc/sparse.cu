@@ -84,8 +84,10 @@ k_brick_classify(const BrickGeom g, uint32_t* __restrict__ states, uint32_t* __r
 }
 
 __global__ void __launch_bounds__(1024)
-k_brick_scan(uint32_t* __restrict__ blockCounts, uint32_t numBlocks, uint32_t* __restrict__ header)
+k_brick_scan(uint32_t* __restrict__ blockCounts, uint32_t numBlocks, uint32_t* __restrict__ header, uint32_t padBegin, uint32_t padEnd)
 {
+    // the alignment gap between the states and the payload is part of the blob: it must not carry stale device memory
+    for (uint32_t i = padBegin + threadIdx.x; i < padEnd; i += blockDim.x) header[i] = 0u;
     __shared__ uint32_t warpSums[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -162,7 +164,7 @@ int launchSparseEncode(cudaStream_t s, const uint32_t* grid, uint32_t N, uint32_
     cudaMemcpyAsync(header, h, sizeof(h), cudaMemcpyHostToDevice, s);
     uint32_t* states = reinterpret_cast<uint32_t*>(blob + L.offStates);
     k_brick_classify<<<L.numBlocks, kBrickThreads, 0, s>>>(g, states, blockCounts);
-    k_brick_scan<<<1, 1024, 0, s>>>(blockCounts, L.numBlocks, header);
+    k_brick_scan<<<1, 1024, 0, s>>>(blockCounts, L.numBlocks, header, (uint32_t)(L.offStates / 4) + L.stateWords, (uint32_t)(L.offPayload / 4));
     k_brick_pack<<<L.numBlocks, kBrickThreads, 0, s>>>(g, states, blockCounts, reinterpret_cast<uint4*>(blob + L.offPayload));
     return 3;
 }
