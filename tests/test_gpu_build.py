@@ -203,3 +203,34 @@ def test_fused_build_with_given_bound(assets):
     assert np.array_equal(a[0], bound)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_fused_builds_of_two_contexts_run_concurrently(assets):
+    """Two contexts on one GPU, two host threads, each rebuilding and voxelizing a 100 k-triangle mesh back to back: the
+    cooperative one-kernel builds of different streams must not starve each other's grid barriers (a barrier that gives
+    up raises a device error, so a failure shows up here as an exception, not as a hang)."""
+    import threading
+    import dxrvoxelizer_b200 as d
+    meshes = [assets("dragon.obj"), assets("bunny.obj")]
+    want = []
+    for m in meshes:
+        v = d.Voxelizer(0)
+        v.build_bvh(m); v.voxelize(640, d.MODE_PARITY); want.append(v.fetch_bits()); v.close()
+    errors = []
+
+    def work(k):
+        try:
+            v = d.Voxelizer(0)
+            for _ in range(40):
+                v.build_bvh(meshes[k])
+                v.voxelize(640, d.MODE_PARITY)
+            if not np.array_equal(v.fetch_bits(), want[k]):
+                errors.append("grid of thread %d differs" % k)
+            v.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errors, errors
