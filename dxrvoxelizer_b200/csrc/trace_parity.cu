@@ -325,7 +325,10 @@ k_file_columns(const ParityParams prm)
 // left -- everything, for a mostly empty grid -- is written one tile per CTA by the launch's surplus
 // CTAs (there is one CTA per tile, and empty tiles need none), i.e. by the whole machine.
 constexpr uint32_t kCounterWords = 32 + 1024;   // bucketCount[32] + one writer claim per SM (%smid < 1024)
-constexpr uint32_t kFillWaves = 4;               // CTAs of the fill kernel per resident CTA slot of the machine
+#ifndef DXRV_FILL_WAVES
+#define DXRV_FILL_WAVES 4
+#endif
+constexpr uint32_t kFillWaves = DXRV_FILL_WAVES;   // (1 and 2 measured: 43.5 / 37.2 us for the dragon, 54.5 / 48.7 us for the bowl against 37.4 / 42.7; 8: no change)               // CTAs of the fill kernel per resident CTA slot of the machine
 constexpr uint32_t kWriterBatch = 4;             // empty tiles a writer warp takes per grab
 
 // zero layers zFirst, zFirst + zStep, ... of an empty tile (one warp)
@@ -471,6 +474,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     const uint32_t sy0 = (tile % prm.tilesY) * SY;
     const uint32_t sz0 = prm.z0 + (tile / prm.tilesY) * SZ;
     const uint32_t yLast = min(sy0 + SY - 1, N - 1) - sy0, zLast = min(sz0 + SZ - 1, prm.z1 - 1) - sz0;
+    DXRV_TL_STAMP(0);
     // this CTA's share of the tile's candidate list (a split tile has several parts)
     const uint32_t partBegin = (uint32_t)(((uint64_t)min(listed, prm.candCap) * part) / parts);
     const uint32_t mine = listed <= prm.candCap ? (uint32_t)(((uint64_t)listed * (part + 1u)) / parts) - partBegin : 0u;
@@ -501,6 +505,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
             }
         }
         __syncthreads();
+        DXRV_TL_STAMP(1);
         const float halfN = 0.5f * fN;
 
         // Up to 32 candidate triangles per call (one per lane; `has` marks real ones), processed by the
@@ -823,6 +828,7 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
             }
         }
         __syncthreads();
+        DXRV_TL_STAMP(2);
 
         if (parts > 1u)
         {
