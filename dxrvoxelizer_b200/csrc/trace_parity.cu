@@ -128,8 +128,8 @@ constexpr int kLightClasses = 4;        // light tiles are scheduled by halving 
 #define DXRV_PART_SIZE 256
 #endif
 #ifndef DXRV_CHUNK_NUM
-#define DXRV_CHUNK_NUM 2
-#endif
+#define DXRV_CHUNK_NUM 1   // a warp's chunk: candidates / (NUM/DEN * warps), as a power of two in [4, 32].  1: at least one chunk per warp
+#endif                   // (2 = two chunks per warp: 10 % more warp instructions, equal or up to 4 % slower on five mesh / grid pairs; 1/2: mixed)
 #ifndef DXRV_CHUNK_DEN
 #define DXRV_CHUNK_DEN 1
 #endif
