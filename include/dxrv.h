@@ -141,7 +141,7 @@ DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_
  *                          (DXRV_HOST_THREADS, default all cores up to 32), which zero hostDst while the GPU is still
  *                          computing.  Floor: the host's memory write bandwidth.  A grid whose blob exceeds half the
  *                          dense size is copied densely after all.  hostDst is bit-identical either way.
- *   DXRV_READ_BACK_AUTO    (default) SPARSE for slabs of 8 MiB and more when at least 4 host threads exist, else DENSE. */
+ *   DXRV_READ_BACK_AUTO    (default) SPARSE for slabs of 8 MiB and more when the pool has at least 8 host threads, else DENSE. */
 #define DXRV_READ_BACK_AUTO   0u
 #define DXRV_READ_BACK_DENSE  1u
 #define DXRV_READ_BACK_SPARSE 2u
