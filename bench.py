@@ -8,7 +8,12 @@ Dragon.bat) at ONE 1024^3 bit-packed grid, MODE_PARITY, the LBVH rebuilt every s
   N=2,4,8  STRONG scaling: the same 1024^3 grid split into N cost-balanced z-slabs, one per rank; the mesh is
            replicated (NCCL broadcast), every rank builds the identical LBVH, no collective in the timed region.
            (`weak_scaling` in the JSON is a side number: the grid grown to 1280^3/1664^3/2048^3.)
-A step = LBVH build (bounds, Morton, onesweep sort, Karras hierarchy, boxes) + trace/fill of the rank's slab.
+A step = acceleration-structure build + trace/fill of the rank's slab.  What the build holds: bounds, Morton keys,
+onesweep radix sort, Morton-sorted scene-space triangle records -- and the Karras hierarchy + node boxes WHEN the
+consumer traverses them (include/dxrv.h states the rule).  MODE_SHADER and the LBVH-walk candidate path do;
+MODE_PARITY's default path finds its candidates by triangle-parallel 2-D binning and does not, so the headline step
+builds no hierarchy.  `phases_ms.step_full_lbvh_walk` is the same step WITH the full LBVH (hierarchy + boxes rebuilt
+every step, candidates by the warp-cooperative walk; DXRV_PARITY_CANDIDATES=walk), gated against the oracle too.
 
 `mismatched_voxels`  correctness GATE, run before anything is timed: every rank fetches its slab and XORs it against
              the CPU oracle's grid of the same layers; the sum over ranks must be 0 or the bench exits non-zero.
@@ -188,7 +193,10 @@ def run_reference(args):
 
 
 def workload_config(N, world, tris, verts):
-    return {"workload": "dragon.obj %d^3 MODE_PARITY, LBVH rebuilt every step, one grid split into %d z-slab(s)" % (N, world),
+    return {"workload": "dragon.obj %d^3 MODE_PARITY, acceleration structure rebuilt every step, one grid split into %d z-slab(s)" % (N, world),
+            "acceleration_structure": "bounds + Morton keys + radix sort + sorted triangle records + per-tile candidate bins, all inside the timed "
+                                      "step; the Karras hierarchy is built on demand and this mode's default path does not traverse it "
+                                      "(phases_ms.step_full_lbvh_walk = the step with hierarchy + LBVH walk)",
             "grid": N, "voxels_total": N * N * N, "slabs": "one z-slab per GPU, cut points balance stores + triangles per layer",
             "triangles": int(tris), "vertices": int(verts), "mode": "parity", "parallelism": "zslab%d" % world,
             "l2": "flushed between timed steps (256 MiB device write, untimed)"}
@@ -382,6 +390,30 @@ def run_c3(args):
     vox.set_profiling(False)
     walk_ms, fill_ms = walk_ns / prof_steps * 1e-6, fill_ns / prof_steps * 1e-6
 
+    # ---- the same step with the FULL LBVH: hierarchy + node boxes rebuilt every step, candidates by the LBVH walk ---
+    # (a side number: what the step costs when the consumer traverses the tree; gated like the headline)
+    os.environ["DXRV_PARITY_CANDIDATES"] = "walk"
+    for _ in range(3):
+        step_resident()                                # (the first voxelize builds the tree on demand, later builds include it)
+    full_bits = vox.fetch_bits()
+    full_mism = popcount(full_bits ^ gate_ref)
+    del full_bits
+    full_steps = min(args.steps, 50)
+    fev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(full_steps)]
+    rig.barrier()
+    for i in range(full_steps):
+        rig.flush_l2(i)
+        fev[i][0].record(stream)
+        step_resident()
+        fev[i][1].record(stream)
+    rig.barrier()
+    vox.synchronize()
+    full_ms = sum(e[0].elapsed_time(e[1]) for e in fev) / full_steps
+    del os.environ["DXRV_PARITY_CANDIDATES"]
+    for _ in range(2):
+        step_resident()                                # back to the default path (no hierarchy wanted)
+    vox.synchronize()
+
     # ---- MODE_SHADER on the same slab (the reference's own function), bins rebuilt every step ------------------
     shader_steps = max(2, min(args.steps, 5))
     for _ in range(2):
@@ -554,9 +586,9 @@ def run_c3(args):
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
     fill_ms_rank0 = fill_ms   # the roofline of the kernel is a per-GPU figure: rank 0's launches against rank 0's bytes
-    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms, sparse_ms, dense_ms = rig.reduce_max(
-        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0, sparse_ms, dense_ms])
-    sparse_bytes_total, sparse_mism_total = rig.reduce_sum([sparse_bytes, sparse_mism])
+    step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak_ms, sparse_ms, dense_ms, full_ms = rig.reduce_max(
+        [step_ms, build_ms, trace_ms, e2e_ms, walk_ms, fill_ms, shader_ms, weak[1] if weak else 0.0, sparse_ms, dense_ms, full_ms])
+    sparse_bytes_total, sparse_mism_total, full_mism_total = rig.reduce_sum([sparse_bytes, sparse_mism, full_mism])
     per_rank = None
     if world > 1:
         gathered = [None] * world
@@ -581,7 +613,10 @@ def run_c3(args):
                                                             "shader_mismatched_voxels": int(smism_total),
                                                             "how": "XOR-popcount of every rank's fetched slab against the CPU oracle before timing"},
             "phases_ms": {"bvh_build": build_ms, "voxelize": trace_ms, "k_walk_columns": walk_ms, "k_trace_fill_columns": fill_ms,
-                          "shader_1024": shader_ms},
+                          "shader_1024": shader_ms, "step_full_lbvh_walk": full_ms},
+            "full_lbvh": {"ms_per_step": full_ms, "gvoxels_per_s": total_voxels / (full_ms * 1e-3) * 1e-9, "mismatched_voxels": int(full_mism_total),
+                          "what": "the same step with the whole LBVH rebuilt every step (bounds, Morton, three radix passes, leaves, Karras "
+                                  "hierarchy, node boxes) and the candidates found by the warp-cooperative LBVH walk instead of the binning"},
             "shader": {"ms_per_1024_cubed_grid_incl_build_and_bins": shader_ms, "grays_per_s": total_voxels / (shader_ms * 1e-3) * 1e-9,
                        "what": "MODE_SHADER (DXRVoxelizer.hlsl radial closest hit), same z-slabs, LBVH + direction bins rebuilt every step"},
             "ms_per_1024_cubed_grid": step_ms,

@@ -947,6 +947,44 @@ __device__ __forceinline__ void traceFillItem(const ParityParams& prm, uint32_t 
     if (lane == 0 && myCrossings) atomicAdd(prm.crossings, (unsigned long long)myCrossings);
 }
 
+// Order in which the launch's CTAs take the work items (numbered heavy parts first, then the light tiles by
+// decreasing class, see fileTiles).  CTAs start in the order of their numbers, so this is the order in time.
+#ifndef DXRV_ITEM_ORDER
+#define DXRV_ITEM_ORDER 0
+#endif
+#ifndef DXRV_DYNAMIC_ITEMS
+#define DXRV_DYNAMIC_ITEMS 0
+#endif
+struct ItemOrder
+{
+    uint32_t nWork, nHeavy, K, n;
+    // smallest stride >= 0.618 n that is coprime to n: i -> i * K mod n visits the items evenly spread over the classes
+    static __device__ __forceinline__ uint32_t goldenStride(uint32_t n)
+    {
+        if (n < 3u || n > 65535u) return 1u;                     // (i * K stays below 2^32; larger launches keep their order)
+        uint32_t k = (n * 40503u) >> 16;                          // 0.618 n
+        for (;; ++k)
+        {
+            uint32_t a = n, b = k % n;
+            while (b) { const uint32_t t = a % b; a = b; b = t; }
+            if (a == 1u) return k % n;
+        }
+    }
+    __device__ __forceinline__ ItemOrder(uint32_t nWork_, uint32_t nHeavy_) : nWork(nWork_), nHeavy(nHeavy_), K(1u), n(nWork_)
+    {
+        if (DXRV_ITEM_ORDER == 2) K = goldenStride(n);
+        if (DXRV_ITEM_ORDER == 4) { n = nWork - nHeavy; K = goldenStride(n); }
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const
+    {
+        if (DXRV_ITEM_ORDER == 1) return nWork - 1u - i;                                   // smallest first
+        if (DXRV_ITEM_ORDER == 2) return (i * K) % n;                                // evenly mixed
+        if (DXRV_ITEM_ORDER == 3) return i < nHeavy ? i : nWork - 1u - (i - nHeavy);       // heavy parts, then smallest first
+        if (DXRV_ITEM_ORDER == 4) return i < nHeavy ? i : nHeavy + ((i - nHeavy) * K) % n;   // heavy parts, then mixed
+        return i;                                                                          // largest first
+    }
+};
+
 // The first CTAs of the launch write the empty tiles (one writer per SM); the others take the work items
 // in order -- heavy parts first -- and, when there are more items than CTAs, further ones at a stride.
 template <int W, int SY, int SZ>
@@ -982,11 +1020,26 @@ k_trace_fill_columns(const ParityParams prm)
 #ifdef DXRV_EXPERIMENT
     if (prm.noTrace) return;   // (timing experiment: the writers alone)
 #endif
+    const ItemOrder order(nWork, nHeavy);
+#if DXRV_DYNAMIC_ITEMS
+    // one CTA per resident slot; the first item is the CTA's own number, further ones come from a counter that is
+    // read one item ahead (the atomic's round trip hides behind the item being traced)
+    __shared__ uint32_t sItem;
+    for (bool first = true; item < nWork; first = false)
+    {
+        if (!first) __syncthreads();   // the previous item's write-out has read the shared rows (and every thread sItem)
+        if (threadIdx.x == 0) sItem = stride + atomicAdd(prm.bucketCount + 16, 1u);
+        traceFillItem<W, SY, SZ>(prm, order(item), nHeavy, nLight, smem);
+        __syncthreads();
+        item = sItem;
+    }
+#else
     for (bool first = true; item < nWork; item += stride, first = false)
     {
         if (!first) __syncthreads();   // the previous item's write-out has read the shared rows
-        traceFillItem<W, SY, SZ>(prm, item, nHeavy, nLight, smem);
+        traceFillItem<W, SY, SZ>(prm, order(item), nHeavy, nLight, smem);
     }
+#endif
 }
 
 uint32_t sharedRowWords(uint32_t P)
@@ -1043,7 +1096,7 @@ void launchVariant(cudaStream_t s, ParityParams prm, cudaEvent_t* ev, bool binsR
     }
 #endif
     // enough CTAs for kFillWaves full waves of work items; more items than that are taken at a stride
-    const uint32_t waves = kFillWaves;
+    const uint32_t waves = DXRV_DYNAMIC_ITEMS ? 1u : kFillWaves;
     const uint32_t perSm = W == 4 ? (uint32_t)DXRV_FILL_CTAS : W == 8 ? 4u : 2u;
     const uint32_t workCtas = std::min<uint32_t>(prm.numTiles + kExtraParts, std::max(1u, waves * perSm * (prm.numWriters / 2u)));
     k_trace_fill_columns<W, SY, SZ><<<prm.numWriters + workCtas, 32 * W, smemBytes, s>>>(prm);
