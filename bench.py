@@ -509,8 +509,8 @@ def run_c3(args):
     dense_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     vox.set_read_back(L.READ_BACK_AUTO)
     h_grid.fill_(0xA5)            # the expansion must produce every byte, zeros included
-    for _ in range(3):
-        step_e2e()
+    for _ in range(warm):         # (the host threads of the pool were asleep during the dense-copy arm: the first steps after
+        step_e2e()                #  that run at 1.2 ms while the cores wake up and clock up, the steady state is 0.77 ms)
     e2e_d2h = vox.info(L.INFO_LAST_D2H_BYTES)
     e2e_mism = popcount(h_grid.numpy()[:e_bytes].view(np.uint32) ^ e_ref.reshape(-1)) + dense_mism
     e2e_mism_total, e2e_d2h_total = rig.reduce_sum([e2e_mism, e2e_d2h])
@@ -630,9 +630,11 @@ def run_c3(args):
                     "how": "dxrv_build_bvh (host arrays) + dxrv_voxelize_to_host into a pinned host buffer that ends up holding the DENSE "
                            "128 MiB bit grid (filled with 0xA5 beforehand, checked against the oracle).  Default transport of the call: "
                            "the slab is encoded as DXRV_FORMAT_SPARSE_BRICKS on the GPU, `d2h_bytes_per_step` cross PCIe, and the "
-                           "library's host threads (%d per rank) expand the blob into the dense layout -- they zero the buffer with "
-                           "streaming stores while the GPU is still computing; the floor is the host's memory write bandwidth, not "
-                           "the link.  `dense_copy` = the same call with DXRV_READ_BACK_DENSE (8 z sub-slabs, D2H of chunk k beside the "
+                           "library's host threads (%d per rank) write the dense layout in ONE pass of streaming stores: they start "
+                           "zeroing the buffer from the outside of the slab inwards while the GPU is still computing and, once the blob "
+                           "is on the host, write the remaining brick layers with their final contents; the floor is the host's "
+                           "memory write bandwidth (128 MiB / 0.69 ms on these 16 cores), not the link.  "
+                           "`dense_copy` = the same call with DXRV_READ_BACK_DENSE (8 z sub-slabs, D2H of chunk k beside the "
                            "fill of chunk k+1: the PCIe floor, `phases_ms.d2h_grid` measured unpipelined; N > 1: its slabs are cut in "
                            "proportion to every rank's measured read-back rate)" % host_pool_threads,
                     "dense_copy": {"value": total_voxels / (dense_ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": dense_ms,

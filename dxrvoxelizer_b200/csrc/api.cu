@@ -5,9 +5,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 #include <algorithm>
@@ -304,7 +306,16 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
         return cudaSuccess;
     };
     if ((e = ensureStaging(L.offPayload + (1u << 20), 0)) != cudaSuccess) return cudaFail(ctx, e, "cudaHostAlloc(blob staging)");
-    hostZeroBegin(hostDst, bytes);   // runs beside everything up to hostZeroWait()
+    // DXRV_DBG_E2E=1: the phases of this call on stderr (development aid)
+    static const bool dbgPhases = [] { const char* e = std::getenv("DXRV_DBG_E2E"); return e && e[0] == '1'; }();
+    auto nowUs = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tBegin = dbgPhases ? nowUs() : 0.0;
+    // The host pool starts on the caller's grid at once (zeroing it from the outside of the slab inwards) and is handed
+    // the blob as soon as it is here: the brick layers still to do are then written with their final contents in the
+    // same pass (sparse_host.cpp).  DXRV_HOST_FILL=twopass: zero everything, then expand (the earlier scheme).
+    static const bool twoPass = [] { const char* e = std::getenv("DXRV_HOST_FILL"); return e && !std::strcmp(e, "twopass"); }();
+    if (twoPass) hostZeroBegin(hostDst, bytes);   // runs beside everything up to hostZeroWait()
+    else hostFillBegin(hostDst, N, slabEnd - slabBegin);
     int rc = dxrv_voxelize(ctx, N, mode, slabBegin, slabEnd);
     if (rc == DXRV_OK)
     {
@@ -326,11 +337,29 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
                               cudaStreamSynchronize(ctx->stream) != cudaSuccess))
             rc = cudaFail(ctx, cudaGetLastError(), "sparse transport: payload copy");
     }
-    hostZeroWait();
-    if (rc != DXRV_OK) return rc;
+    const double tGpu = dbgPhases ? nowUs() : 0.0;
     SparseBlobView v;
-    if (!sparseParse(ctx->hostBlob, total, v) || !sparseExpand(v, static_cast<uint32_t*>(hostDst), true))
-        return fail(ctx, DXRV_ERR_CUDA, "sparse transport: inconsistent blob");
+    bool good = rc == DXRV_OK && sparseParse(ctx->hostBlob, total, v);
+    double tZero = 0.0;
+    if (twoPass)
+    {
+        hostZeroWait();
+        tZero = dbgPhases ? nowUs() : 0.0;
+        if (rc != DXRV_OK) return rc;
+        good = good && sparseExpand(v, static_cast<uint32_t*>(hostDst), true);
+    }
+    else
+    {
+        good = good && hostFillPublish(v);
+        tZero = dbgPhases ? nowUs() : 0.0;
+        const bool filled = hostFillWait();      // (always: the pool must be done with hostDst before this call returns)
+        if (rc != DXRV_OK) return rc;
+        good = good && filled;
+    }
+    if (!good) return fail(ctx, DXRV_ERR_CUDA, "sparse transport: inconsistent blob");
+    if (dbgPhases)
+        std::fprintf(stderr, "dxrv e2e phases (us): voxelize + encode + blob copy %.0f | %s %.0f | %s %.0f | call %.0f\n", tGpu - tBegin,
+                     twoPass ? "rest of the zeroing" : "publish", tZero - tGpu, twoPass ? "expansion" : "rest of the pass", nowUs() - tZero, nowUs() - tBegin);
     ctx->lastD2hBytes = total;
     return checkDeviceError(ctx);
 }
@@ -696,9 +725,10 @@ int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sla
     DeviceGuard g(ctx->device);
     // Transport (dxrv_set_read_back).  The dense grid over one PCIe link is the floor of the copying path (128 MiB: 2.4 ms);
     // a solid voxelization is mostly empty space and solid interior, so by default a large slab comes back as
-    // DXRV_FORMAT_SPARSE_BRICKS (a few MB) and is expanded into hostDst by the host pool's threads, which zero hostDst
-    // while the GPU is still computing.  The host's memory write bandwidth is then the floor (~1.1 ms for 128 MiB on 16
-    // cores).  A grid that does not compress (more than half of the dense size) is copied densely after all.
+    // DXRV_FORMAT_SPARSE_BRICKS (a few MB) and is written into hostDst by the host pool's threads in one pass (zeros from
+    // the outside of the slab inwards while the GPU is still computing, final contents once the blob is here).  The host's
+    // memory write bandwidth is then the floor (0.69 ms for 128 MiB on 16 cores; the call takes 0.63-0.75 ms).  A grid
+    // that does not compress (more than half of the dense size) is copied densely after all.
     {
         uint32_t transport = ctx->readBack;
         if (const char* e = std::getenv("DXRV_TO_HOST")) transport = !std::strcmp(e, "dense") ? 1u : (!std::strcmp(e, "sparse") ? 2u : transport);
@@ -795,7 +825,17 @@ int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_
     SparseBlobView v;
     if (!denseDst || !sparseParse(blob, blobBytes, v)) return DXRV_ERR_INVALID_ARG;
     if (denseBytes != (size_t)(v.z1 - v.z0) * v.N * v.P * 4) return DXRV_ERR_INVALID_ARG;
-    return sparseExpand(v, static_cast<uint32_t*>(denseDst), false) ? DXRV_OK : DXRV_ERR_INVALID_ARG;
+    // one pass of the host pool over the dense grid (sparse_host.cpp); DXRV_HOST_FILL_DELAY_US (tests) publishes the blob
+    // late, so that the pool has zeroed brick layers before it knows their contents and must expand them afterwards
+    hostFillBegin(denseDst, v.N, v.z1 - v.z0);
+    if (const char* e = std::getenv("DXRV_HOST_FILL_DELAY_US"))
+    {
+        const long us = std::atol(e);
+        if (us > 0 && us <= 1000000) std::this_thread::sleep_for(std::chrono::microseconds(us));
+    }
+    const bool published = hostFillPublish(v);
+    const bool filled = hostFillWait();
+    return published && filled ? DXRV_OK : DXRV_ERR_INVALID_ARG;
 }
 
 int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes)

@@ -2,6 +2,7 @@
 #include "host_pool.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <mutex>
@@ -22,10 +23,14 @@ struct Pool
     std::atomic<unsigned long long> state{0};
     unsigned long generation = 0, current = 0;
     bool busy = false, stop = false;
+    std::atomic<unsigned long> published{0};   // == generation once a batch is fully described (read without the mutex)
+    std::atomic<bool> stopping{false};
+    long spinUs = 2000;                 // a worker polls this long for the next batch before it blocks (DXRV_HOST_SPIN_US)
     std::mutex callers;                 // one batch at a time
 
     explicit Pool(unsigned n)
     {
+        if (const char* e = std::getenv("DXRV_HOST_SPIN_US")) { const long v = std::atol(e); if (v >= 0 && v <= 1000000) spinUs = v; }
         for (unsigned i = 0; i + 1 < n; ++i) workers.emplace_back([this] { loop(); });
     }
     ~Pool()
@@ -33,6 +38,7 @@ struct Pool
         {
             std::lock_guard<std::mutex> g(m);
             stop = true;
+            stopping.store(true, std::memory_order_release);
         }
         wake.notify_all();
         for (auto& t : workers) t.join();
@@ -65,9 +71,29 @@ struct Pool
     }
     void loop()
     {
+        // A caller that voxelizes every frame starts a batch every millisecond or so: a worker that went to sleep on
+        // the condition variable after every batch would spend the first ~0.1 ms of the next one waking up (futex,
+        // the convoy on the mutex, a core that has dropped into an idle state).  So a worker first POLLS for the next
+        // batch for spinUs microseconds and only then blocks; an idle process costs nothing after that.
         unsigned long seen = 0;
         for (;;)
         {
+            bool found = false;
+            if (seen != 0 && spinUs > 0)
+            {
+                const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spinUs);
+                for (unsigned polls = 0;; ++polls)
+                {
+                    if (stopping.load(std::memory_order_acquire)) return;
+                    const unsigned long g = published.load(std::memory_order_acquire);
+                    if (g != seen) { seen = g; found = true; break; }
+#if defined(__x86_64__)
+                    __builtin_ia32_pause();
+#endif
+                    if ((polls & 63u) == 63u && std::chrono::steady_clock::now() >= until) break;
+                }
+            }
+            if (!found)
             {
                 std::unique_lock<std::mutex> g(m);
                 wake.wait(g, [&] { return stop || generation != seen; });
@@ -89,6 +115,7 @@ struct Pool
             busy = n != 0;
             current = generation;
             state.store((unsigned long long)(generation & 0xfffffffful) << 32);
+            published.store(generation, std::memory_order_release);
         }
         wake.notify_all();
     }

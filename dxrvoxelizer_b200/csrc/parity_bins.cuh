@@ -22,6 +22,9 @@ struct BinParams
 };
 
 constexpr int kBinSY = 16, kBinSZ = 8;   // the super-tile of the fill kernel
+#ifndef DXRV_BIN_EXACT_RECT
+#define DXRV_BIN_EXACT_RECT 1
+#endif
 
 template <int SY, int SZ>
 __device__ __forceinline__ uint32_t binTableFloats(const BinParams& bp) { return 2u * (bp.tilesY + (bp.z1 - bp.z0 + SZ - 1) / SZ); }
@@ -72,6 +75,16 @@ __device__ __forceinline__ void binTriangleWarp(const BinParams& bp, const float
             tz0 = max((int)floorf(zA), 0) / SZ; tz1 = min((int)ceilf(zB), layers - 1) / SZ;
         }
     }
+#if DXRV_BIN_EXACT_RECT
+    // The tiles that pass the exact compares form a sub-rectangle of the conservative one (the tabulated limits are
+    // monotonic along each axis, and the y and z compares are independent): shrink the range here, once, instead of
+    // testing every tile of the conservative range in the rounds below -- a triangle near a tile border no longer costs
+    // its whole warp extra rounds (each batch of rounds is a round trip of atomics), and the rounds need no division.
+    while (ty0 <= ty1 && !(ylo <= yMax[ty0] && yhi >= yMin[ty0])) ++ty0;
+    while (ty1 >= ty0 && !(ylo <= yMax[ty1] && yhi >= yMin[ty1])) --ty1;
+    while (tz0 <= tz1 && !(zlo <= zMax[tz0] && zhi >= zMin[tz0])) ++tz0;
+    while (tz1 >= tz0 && !(zlo <= zMax[tz1] && zhi >= zMin[tz1])) --tz1;
+#endif
     const uint32_t nu = (uint32_t)max(ty1 - ty0 + 1, 0), nv = (uint32_t)max(tz1 - tz0 + 1, 0), n = nu * nv;
     auto emitTile = [&](uint32_t slot, int ty, int tz, float bylo, float byhi, float bzlo, float bzhi) {
         if (bylo <= yMax[ty] && byhi >= yMin[ty] && bzlo <= zMax[tz] && bzhi >= zMin[tz])
@@ -87,6 +100,9 @@ __device__ __forceinline__ void binTriangleWarp(const BinParams& bp, const float
     const uint32_t rounds = __reduce_max_sync(0xffffffffu, nSmall);
     // four rounds per batch: their atomics are all issued before the first result is consumed (one L2 round trip
     // per batch instead of one per round -- the kernel is a latency chain, not a throughput problem)
+#if DXRV_BIN_EXACT_RECT
+    uint32_t cy = 0, rowTile = (uint32_t)tz0 * tilesY + (uint32_t)ty0;   // round q = tile (ty0 + cy, row of rowTile)
+#endif
     for (uint32_t q0 = 0; q0 < rounds; q0 += 4u)
     {
         uint32_t tileK[4], peersK[4], atK[4];
@@ -96,12 +112,21 @@ __device__ __forceinline__ void binTriangleWarp(const BinParams& bp, const float
             const uint32_t q = q0 + k;
             bool hit = false;
             tileK[k] = 0; peersK[k] = 0; atK[k] = 0;
+#if DXRV_BIN_EXACT_RECT
+            if (q < nSmall)
+            {
+                hit = true;
+                tileK[k] = rowTile + cy;
+                if (++cy == nu) { cy = 0; rowTile += tilesY; }
+            }
+#else
             if (q < nSmall)
             {
                 const int ty = ty0 + (int)(q % nu), tz = tz0 + (int)(q / nu);
                 hit = ylo <= yMax[ty] && yhi >= yMin[ty] && zlo <= zMax[tz] && zhi >= zMin[tz];
                 tileK[k] = (uint32_t)tz * tilesY + (uint32_t)ty;
             }
+#endif
             const uint32_t act = __ballot_sync(0xffffffffu, hit);
             if (hit)
             {

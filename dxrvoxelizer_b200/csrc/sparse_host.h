@@ -21,4 +21,12 @@ bool sparseExpand(const SparseBlobView& v, uint32_t* dst, bool dstIsZero);
 // Zero `bytes` at dst with the pool's threads: begin returns at once, wait blocks (host_pool.h: one batch at a time).
 void hostZeroBegin(void* dst, size_t bytes);
 void hostZeroWait();
+// The dense grid of a slab (layers * N * P words at dst) in ONE pass of the pool: begin returns at once and the threads
+// start zeroing from the outside of the slab inwards; publish hands them the blob (as soon as it is on the host: the
+// brick layers still to do are then written with their final contents); wait blocks until the grid is complete (brick
+// layers zeroed before the publish are expanded last).  publish: false = the blob does not fit the grid / is
+// inconsistent (nothing changes); wait: false = nothing was published (the grid holds zeros).
+void hostFillBegin(void* dst, uint32_t N, uint32_t layers);
+bool hostFillPublish(const SparseBlobView& v);
+bool hostFillWait();
 }  // namespace dxrv

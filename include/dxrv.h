@@ -138,8 +138,11 @@ DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_
  *                          Floor: the dense grid over the PCIe link (128 MiB at 1024^3: 2.4 ms).
  *   DXRV_READ_BACK_SPARSE  the slab is encoded as DXRV_FORMAT_SPARSE_BRICKS on the device, the blob (a few MB) is copied
  *                          to pinned staging memory of the context and expanded into hostDst by a pool of host threads
- *                          (DXRV_HOST_THREADS, default all cores up to 32), which zero hostDst while the GPU is still
- *                          computing.  Floor: the host's memory write bandwidth.  A grid whose blob exceeds half the
+ *                          (DXRV_HOST_THREADS, default all cores up to 32) in ONE pass of streaming stores: they start
+ *                          zeroing hostDst from the outside of the slab inwards while the GPU is still computing and,
+ *                          once the blob has arrived, write the remaining brick layers with their final contents (the
+ *                          workers poll for the next call for DXRV_HOST_SPIN_US microseconds, default 2000, before they
+ *                          sleep).  Floor: the host's memory write bandwidth.  A grid whose blob exceeds half the
  *                          dense size is copied densely after all.  hostDst is bit-identical either way.
  *   DXRV_READ_BACK_AUTO    (default) SPARSE for slabs of 8 MiB and more when the pool has at least 8 host threads, else DENSE. */
 #define DXRV_READ_BACK_AUTO   0u

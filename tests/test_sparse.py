@@ -37,8 +37,14 @@ def numpy_encode(bits, N, z0):
     return blob
 
 
-@pytest.mark.parametrize("N,layers,seed", [(64, 64, 1), (100, 37, 2), (33, 5, 3), (128, 2, 4), (31, 31, 5)])
-def test_decoder_against_a_numpy_encoder(N, layers, seed):
+@pytest.mark.parametrize("delay_us", [0, 3000])
+@pytest.mark.parametrize("N,layers,seed", [(64, 64, 1), (100, 37, 2), (33, 5, 3), (128, 2, 4), (31, 31, 5), (256, 256, 6), (512, 42, 7)])
+def test_decoder_against_a_numpy_encoder(N, layers, seed, delay_us, monkeypatch):
+    # The decoder is ONE pass of the host pool over the dense grid (csrc/sparse_host.cpp, the same pass dxrv_voxelize_to_host
+    # runs): brick layers reached before the blob is published are zeroed and expanded afterwards, the others are written
+    # with their final contents at once.  delay_us = 3000 publishes the blob after the pool has zeroed everything.
+    # (N = 512: rows of whole 16-word groups, the AVX-512 line composer where the host has it.)
+    monkeypatch.setenv("DXRV_HOST_FILL_DELAY_US", str(delay_us))
     rng = np.random.default_rng(seed)
     P = (N + 31) // 32
     occ = np.zeros((layers, N, N), bool)
@@ -53,6 +59,9 @@ def test_decoder_against_a_numpy_encoder(N, layers, seed):
         d.sparse_decode(bad)
     with pytest.raises(d.DxrvError):
         d.sparse_decode(blob[:-8] if blob.size > 72 and blob[:64].view(np.uint32)[9] else blob[:60])
+    bad = blob.copy(); bad[64] |= 3                                                               # brick 0 in the undefined state 3
+    with pytest.raises(d.DxrvError):
+        d.sparse_decode(bad)
 
 
 @pytest.mark.gpu

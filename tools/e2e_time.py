@@ -11,7 +11,10 @@ vox = d.Voxelizer(0)
 nbytes = N * N * ((N + 31) // 32) * 4
 h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 vb = torch.from_numpy(m.vertex_bytes.copy()).pin_memory(); ib = torch.from_numpy(m.indices.view(np.int32).copy()).pin_memory()
+only = sys.argv[3] if len(sys.argv) > 3 else None
 for name, tr in (("dense", L.READ_BACK_DENSE), ("sparse", L.READ_BACK_SPARSE)):
+    if only and name != only:
+        continue
     vox.set_read_back(tr)
     def step():
         vox.build_bvh_host_ptr(vb.data_ptr(), m.num_vertices, m.stride, ib.data_ptr(), m.indices.size)
@@ -20,4 +23,5 @@ for name, tr in (("dense", L.READ_BACK_DENSE), ("sparse", L.READ_BACK_SPARSE)):
     t = []
     for _ in range(30):
         t0 = time.perf_counter(); step(); t.append((time.perf_counter() - t0) * 1e3)
+    print(" ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("DXRV_")) or "(defaults)", end=" ")
     print("%s: e2e mean %.3f ms, min %.3f ms -> %.0f Gvoxel/s" % (name, np.mean(t), min(t), N ** 3 / np.mean(t) * 1e-6))
