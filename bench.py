@@ -488,6 +488,11 @@ def run_c3(args):
     def step_e2e():
         # the public call with its default transport (DXRV_READ_BACK_AUTO: at this size the slab comes back as a
         # DXRV_FORMAT_SPARSE_BRICKS blob and is expanded into the dense host grid by the library's host threads)
+        if world == 1:
+            # upload + build + voxelize + read-back as the library's ONE call for a frame (dxrv_voxelize_mesh_to_host): the host
+            # threads start on the grid buffer before the upload and the build instead of after them
+            vox.voxelize_mesh_to_host(h_vb.data_ptr(), nv, stride, h_ib.data_ptr(), ni, N, d.MODE_PARITY, ez0, ez1, h_grid.data_ptr(), e_bytes, chunks=8)
+            return
         upload_and_build()
         vox.voxelize_to_host(N, d.MODE_PARITY, ez0, ez1, h_grid.data_ptr(), e_bytes, chunks=8)
 
@@ -627,7 +632,8 @@ def run_c3(args):
                     "transport": "DXRV_READ_BACK_AUTO = %s" % ("sparse bricks + host expansion (slab >= 8 MiB, pool of >= 8 host threads)"
                                                                if host_pool_threads >= 8 and e_bytes >= (8 << 20) else
                                                                "dense copy (fewer than 8 host threads per rank, or a slab below 8 MiB)"),
-                    "how": "dxrv_build_bvh (host arrays) + dxrv_voxelize_to_host into a pinned host buffer that ends up holding the DENSE "
+                    "how": "dxrv_voxelize_mesh_to_host (N = 1; = dxrv_build_bvh from host arrays + dxrv_voxelize_to_host, which N > 1 calls "
+                           "separately after the NCCL broadcast of the mesh) into a pinned host buffer that ends up holding the DENSE "
                            "128 MiB bit grid (filled with 0xA5 beforehand, checked against the oracle).  Default transport of the call: "
                            "the slab is encoded as DXRV_FORMAT_SPARSE_BRICKS on the GPU, `d2h_bytes_per_step` cross PCIe, and the "
                            "library's host threads (%d per rank) write the dense layout in ONE pass of streaming stores: they start "

@@ -288,6 +288,34 @@ int validateMeshArgs(dxrv_ctx* ctx, const void* v, uint32_t numVerts, uint32_t s
 // dxrv_voxelize_to_host through the compact transport: voxelize the slab, encode it on the device (sparse.cu), bring the
 // blob back into pinned staging memory and expand it into hostDst -- whose zeroing by the host pool starts before the
 // GPU does.  DXRV_ERR_UNSUPPORTED: the grid did not compress (nothing copied; the slab is resident in ctx->gridOwned).
+bool hostFillTwoPass()
+{
+    static const bool twoPass = [] { const char* e = std::getenv("DXRV_HOST_FILL"); return e && !std::strcmp(e, "twopass"); }();
+    return twoPass;
+}
+
+// transport of dxrv_voxelize_to_host for a slab of `bytes`: 1 dense copy, 2 compact blob + host pass
+uint32_t toHostTransport(const dxrv_ctx* ctx, size_t bytes)
+{
+    uint32_t transport = ctx->readBack;
+    if (const char* e = std::getenv("DXRV_TO_HOST")) transport = !std::strcmp(e, "dense") ? 1u : (!std::strcmp(e, "sparse") ? 2u : transport);
+    // (a host thread zeroes ~12 GB/s with streaming stores, the link copies ~55 GB/s: from eight threads on the host pass
+    // wins -- measured with the ranks of an 8-GPU box sharing 32 cores: 4 threads each 1.41 ms, dense copy 1.24 ms)
+    if (transport == 0u) transport = (bytes >= (8u << 20) && hostPoolThreads() >= 8u) ? 2u : 1u;
+    return transport;
+}
+
+int toHostArgsCheck(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd, const void* hostDst, size_t bytes)
+{
+    if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
+    if (slabBegin >= slabEnd || slabEnd > N || N == 0 || N > 8192) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: need 0 <= slabBegin < slabEnd <= N <= 8192");
+    if (mode & DXRV_EMIT_TEXELS) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bit grid only");
+    const size_t layerBytes = (size_t)N * ((N + 31) / 32) * sizeof(uint32_t);
+    if (bytes != layerBytes * (slabEnd - slabBegin)) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bytes does not match the slab size");
+    if (ctx->gridTarget) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: not with an external grid target");
+    return DXRV_OK;
+}
+
 int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd, void* hostDst, size_t bytes)
 {
     NvtxRange range("dxrv voxelize to host (sparse transport + host expansion)");
@@ -313,8 +341,9 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
     // The host pool starts on the caller's grid at once (zeroing it from the outside of the slab inwards) and is handed
     // the blob as soon as it is here: the brick layers still to do are then written with their final contents in the
     // same pass (sparse_host.cpp).  DXRV_HOST_FILL=twopass: zero everything, then expand (the earlier scheme).
-    static const bool twoPass = [] { const char* e = std::getenv("DXRV_HOST_FILL"); return e && !std::strcmp(e, "twopass"); }();
+    const bool twoPass = hostFillTwoPass();
     if (twoPass) hostZeroBegin(hostDst, bytes);   // runs beside everything up to hostZeroWait()
+    else if (ctx->hostFillBegun) ctx->hostFillBegun = false;   // (dxrv_voxelize_mesh_to_host started the pass before the upload)
     else hostFillBegin(hostDst, N, slabEnd - slabBegin);
     int rc = dxrv_voxelize(ctx, N, mode, slabBegin, slabEnd);
     if (rc == DXRV_OK)
@@ -715,13 +744,9 @@ int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_t format)
 int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd, void* hostDst, size_t bytes,
                           uint32_t chunks)
 {
-    if (!ctx || !hostDst) return DXRV_ERR_INVALID_ARG;
-    if (slabBegin >= slabEnd || slabEnd > N || N == 0 || N > 8192) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: need 0 <= slabBegin < slabEnd <= N <= 8192");
-    if (mode & DXRV_EMIT_TEXELS) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bit grid only");
+    if (const int bad = toHostArgsCheck(ctx, N, mode, slabBegin, slabEnd, hostDst, bytes)) return bad;
     const size_t layerBytes = (size_t)N * ((N + 31) / 32) * sizeof(uint32_t);
     const uint32_t layers = slabEnd - slabBegin;
-    if (bytes != layerBytes * layers) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: bytes does not match the slab size");
-    if (ctx->gridTarget) return fail(ctx, DXRV_ERR_INVALID_ARG, "dxrv_voxelize_to_host: not with an external grid target");
     DeviceGuard g(ctx->device);
     // Transport (dxrv_set_read_back).  The dense grid over one PCIe link is the floor of the copying path (128 MiB: 2.4 ms);
     // a solid voxelization is mostly empty space and solid interior, so by default a large slab comes back as
@@ -730,12 +755,7 @@ int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sla
     // memory write bandwidth is then the floor (0.69 ms for 128 MiB on 16 cores; the call takes 0.63-0.75 ms).  A grid
     // that does not compress (more than half of the dense size) is copied densely after all.
     {
-        uint32_t transport = ctx->readBack;
-        if (const char* e = std::getenv("DXRV_TO_HOST")) transport = !std::strcmp(e, "dense") ? 1u : (!std::strcmp(e, "sparse") ? 2u : transport);
-        // (a host thread zeroes ~8 GB/s with streaming stores, the link copies ~55 GB/s: from eight threads on the expansion
-        // wins -- measured with the ranks of an 8-GPU box sharing 32 cores: 4 threads each 1.41 ms, dense copy 1.24 ms)
-        if (transport == 0u) transport = (bytes >= (8u << 20) && hostPoolThreads() >= 8u) ? 2u : 1u;
-        if (transport == 2u)
+        if (toHostTransport(ctx, bytes) == 2u)
         {
             const int rcS = voxelizeToHostSparse(ctx, N, mode, slabBegin, slabEnd, hostDst, bytes);
             if (rcS != DXRV_ERR_UNSUPPORTED) return rcS;   // UNSUPPORTED: did not compress; the slab is resident, copy it densely
@@ -780,6 +800,31 @@ int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t sla
     ctx->haveGrid = true; ctx->haveTexels = false; ctx->mipLevels = 0;
     ctx->lastD2hBytes = bytes;
     return checkDeviceError(ctx);
+}
+
+int dxrv_voxelize_mesh_to_host(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts, uint32_t strideBytes, const uint32_t* indices,
+                               uint32_t numIndices, const float bound[4], uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd,
+                               void* hostDst, size_t bytes, uint32_t chunks)
+{
+    // dxrv_build_bvh + dxrv_voxelize_to_host as ONE call: a frame of a deforming mesh (upload, rebuild, voxelize, read back).
+    // What the single call buys: with the compact transport the host pool starts on hostDst BEFORE the upload and the build,
+    // i.e. ~0.1 ms earlier, and the pass over the host grid is what bounds the call.
+    int rc = validateMeshArgs(ctx, vertices, numVerts, strideBytes, indices, numIndices, bound);
+    if (rc) return rc;
+    if ((rc = toHostArgsCheck(ctx, N, mode, slabBegin, slabEnd, hostDst, bytes)) != DXRV_OK) return rc;
+    if (toHostTransport(ctx, bytes) == 2u && !hostFillTwoPass())
+    {
+        hostFillBegin(hostDst, N, slabEnd - slabBegin);
+        ctx->hostFillBegun = true;
+    }
+    rc = dxrv_build_bvh(ctx, vertices, numVerts, strideBytes, indices, numIndices, bound);
+    if (rc == DXRV_OK) rc = dxrv_voxelize_to_host(ctx, N, mode, slabBegin, slabEnd, hostDst, bytes, chunks);
+    if (ctx->hostFillBegun)   // the build failed, or the voxelize left before it took the pass over: release the pool
+    {
+        hostFillWait();
+        ctx->hostFillBegun = false;
+    }
+    return rc;
 }
 
 int dxrv_set_read_back(dxrv_ctx* ctx, uint32_t transport)

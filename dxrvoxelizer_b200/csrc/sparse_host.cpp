@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -277,6 +278,7 @@ struct FillState
     std::vector<uint32_t> base;          // rank of the first mixed brick of every brick layer
     std::vector<uint8_t> zeroedOnly;     // per task: its brick layers were zeroed before the blob arrived
     bool active = false;
+    std::mutex owner;                    // held from hostFillBegin to hostFillWait: one pass at a time per process
 } gFill;
 
 #if defined(__x86_64__)
@@ -433,6 +435,7 @@ void fillLayer(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32_t fir
 void hostFillBegin(void* dst, uint32_t N, uint32_t layers)
 {
     FillState& f = gFill;
+    f.owner.lock();                      // (a second context's call waits here until the first one's pass is complete)
     f.dst = static_cast<uint32_t*>(dst);
     f.N = N; f.P = (N + 31u) / 32u; f.BY = (N + 3u) / 4u; f.BZ = (layers + 3u) / 4u; f.layers = layers;
     // a task = a group of brick layers of about 512 KiB
@@ -480,7 +483,7 @@ bool hostFillWait()
     hostParallelWait();
     f.active = false;
     const SparseBlobView* v = f.blob.load(std::memory_order_acquire);
-    if (!v) return false;                // nothing was published: the grid holds zeros only
+    if (!v) { f.owner.unlock(); return false; }   // nothing was published: the grid holds zeros only
     // the brick layers that were zeroed before the blob arrived: expand the ones that hold something
     std::vector<uint32_t> todo;
     const uint32_t perLayer = v->BY * v->P;
@@ -491,6 +494,7 @@ bool hostFillWait()
     if (!todo.empty())
         hostParallelFor((unsigned)todo.size(), [&](unsigned i) { expandLayer(*v, f.dst, todo[i], f.base[todo[i]], true); });
     f.blob.store(nullptr, std::memory_order_relaxed);
+    f.owner.unlock();
     return true;
 }
 }  // namespace dxrv

@@ -156,6 +156,14 @@ class Voxelizer:
         self._shape = (z1 - z0, N, (N + 31) // 32)
         self._N = N
 
+    def voxelize_mesh_to_host(self, vptr, num_verts, stride, iptr, num_indices, N, mode, z0, z1, ptr, nbytes, bound=None, chunks=8):
+        """dxrv_voxelize_mesh_to_host: dxrv_build_bvh (host arrays at vptr / iptr) + dxrv_voxelize_to_host as one call."""
+        b = None if bound is None else np.ascontiguousarray(bound, dtype=np.float32)
+        self._check(self._lib.dxrv_voxelize_mesh_to_host(self._h, vptr, num_verts, stride, iptr, num_indices, None if b is None else b.ctypes.data,
+                                                         N, mode, z0, z1, ptr, nbytes, chunks))
+        self._shape = (z1 - z0, N, (N + 31) // 32)
+        self._N = N
+
     def fetch_bits(self, out=None):
         """uint32[(z1-z0), N, P] in the DXRV_FORMAT_BITS layout."""
         if out is None:

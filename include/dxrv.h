@@ -151,6 +151,15 @@ DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_
 DXRV_API int dxrv_set_read_back(dxrv_ctx* ctx, uint32_t transport);
 DXRV_API int dxrv_voxelize_to_host(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slabBegin, uint32_t slabEnd,
                                    void* hostDst, size_t bytes, uint32_t chunks);
+/* dxrv_build_bvh + dxrv_voxelize_to_host as ONE call -- a frame of a deforming mesh: upload, rebuild, voxelize, read
+ * back (the reference rebuilds nothing per frame, Voxelizer.cpp:264-326 runs once; this is the call the "incl. BVH build"
+ * metric times end to end).  Same arguments, results and errors as the two calls in sequence; the host arrays are
+ * borrowed for the duration of the call.  With the compact transport the host threads start on hostDst before the
+ * upload and the build instead of after them. */
+DXRV_API int dxrv_voxelize_mesh_to_host(dxrv_ctx* ctx, const void* vertices, uint32_t numVerts, uint32_t strideBytes,
+                                        const uint32_t* indices, uint32_t numIndices, const float bound[4], uint32_t N,
+                                        uint32_t mode, uint32_t slabBegin, uint32_t slabEnd, void* hostDst, size_t bytes,
+                                        uint32_t chunks);
 /* DXRV_FORMAT_SPARSE_BRICKS: a lossless compact form of the slab's BITS grid for consumers that can take it (a solid
  * voxelization is almost all empty space and solid interior; the dense grid is already at the PCIe roofline).  Bricks
  * of 32 (x) x 4 (y) x 4 (z) voxels = 16 words of the dense grid; brick b = (bz * BY + by) * P + bx.  Blob:

@@ -119,6 +119,41 @@ def test_to_host_transports_agree(vox, assets, name, N, z0, z1, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,N,z0,z1,mode", [("dragon.obj", 1024, 0, 1024, 1), ("bunny.obj", 512, 37, 500, 1), ("TuringBowl.obj", 192, 0, 192, 0),
+                                               ("bunny.obj", 100, 10, 47, 1)])
+def test_mesh_to_host_is_build_plus_to_host(vox, assets, name, N, z0, z1, mode):
+    """dxrv_voxelize_mesh_to_host (upload + build + voxelize + read-back as one call; the host pool starts on the buffer
+    before the upload) leaves the same host grid as dxrv_build_bvh + dxrv_voxelize + dxrv_fetch_grid, with every transport;
+    a call that fails (bad arguments, bad mesh) leaves the pool usable."""
+    from dxrvoxelizer_b200 import _lib as L
+    m = assets(name)
+    other = assets("bunny.obj" if name != "bunny.obj" else "dragon.obj")
+    vox.build_bvh(m)
+    vox.voxelize(N, mode, z0, z1)
+    want = vox.fetch_bits()
+    vb, ib = np.ascontiguousarray(m.vertex_bytes), np.ascontiguousarray(m.indices)
+    try:
+        for transport in (L.READ_BACK_SPARSE, L.READ_BACK_DENSE, L.READ_BACK_AUTO):
+            vox.set_read_back(transport)
+            vox.build_bvh(other)                                  # (the call must rebuild: another mesh is resident)
+            got = np.full(want.shape, 0xDEADBEEF, np.uint32)
+            vox.voxelize_mesh_to_host(vb.ctypes.data, m.num_vertices, m.stride, ib.ctypes.data, ib.size, N, mode, z0, z1, got.ctypes.data, got.nbytes, chunks=4)
+            assert np.array_equal(got, want), transport
+            assert np.array_equal(vox.fetch_bits(), want)
+        vox.set_read_back(L.READ_BACK_SPARSE)
+        got = np.full(want.shape, 0xDEADBEEF, np.uint32)
+        with pytest.raises(d.DxrvError):                          # wrong byte count: refused before the pool starts
+            vox.voxelize_mesh_to_host(vb.ctypes.data, m.num_vertices, m.stride, ib.ctypes.data, ib.size, N, mode, z0, z1, got.ctypes.data, got.nbytes - 4)
+        bad = ib.copy(); bad[5] = m.num_vertices + 7                 # an index out of range: the build reports it after the pool has started
+        with pytest.raises(d.DxrvError):
+            vox.voxelize_mesh_to_host(vb.ctypes.data, m.num_vertices, m.stride, bad.ctypes.data, bad.size, N, mode, z0, z1, got.ctypes.data, got.nbytes)
+        vox.voxelize_mesh_to_host(vb.ctypes.data, m.num_vertices, m.stride, ib.ctypes.data, ib.size, N, mode, z0, z1, got.ctypes.data, got.nbytes)
+        assert np.array_equal(got, want)
+    finally:
+        vox.set_read_back(L.READ_BACK_AUTO)
+
+
+@pytest.mark.gpu
 def test_to_host_sparse_transport_falls_back_when_the_grid_does_not_compress(vox):
     """A soup of random triangles: most bricks are mixed, the blob would exceed half the dense size -> dense copy."""
     from dxrvoxelizer_b200 import _lib as L

@@ -17,11 +17,14 @@ for name, tr in (("dense", L.READ_BACK_DENSE), ("sparse", L.READ_BACK_SPARSE)):
         continue
     vox.set_read_back(tr)
     def step():
+        if os.environ.get("E2E_ONE_CALL", "1") == "1":
+            vox.voxelize_mesh_to_host(vb.data_ptr(), m.num_vertices, m.stride, ib.data_ptr(), m.indices.size, N, d.MODE_PARITY, 0, N, h.data_ptr(), nbytes, chunks=8)
+            return
         vox.build_bvh_host_ptr(vb.data_ptr(), m.num_vertices, m.stride, ib.data_ptr(), m.indices.size)
         vox.voxelize_to_host(N, d.MODE_PARITY, 0, N, h.data_ptr(), nbytes, chunks=8)
-    for _ in range(5): step()
+    for _ in range(15): step()
     t = []
     for _ in range(30):
         t0 = time.perf_counter(); step(); t.append((time.perf_counter() - t0) * 1e3)
-    print(" ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("DXRV_")) or "(defaults)", end=" ")
+    print(" ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("DXRV_") or k.startswith("E2E_")) or "(defaults)", end=" ")
     print("%s: e2e mean %.3f ms, min %.3f ms -> %.0f Gvoxel/s" % (name, np.mean(t), min(t), N ** 3 / np.mean(t) * 1e-6))
