@@ -334,6 +334,14 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
         return cudaSuccess;
     };
     if ((e = ensureStaging(L.offPayload + (1u << 20), 0)) != cudaSuccess) return cudaFail(ctx, e, "cudaHostAlloc(blob staging)");
+    if (ctx->hostRanksCap < L.numBlocks)
+    {
+        if (ctx->hostRanks) cudaFreeHost(ctx->hostRanks);
+        ctx->hostRanks = nullptr; ctx->hostRanksCap = 0;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->hostRanks), (size_t)L.numBlocks * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess) ctx->hostRanksCap = L.numBlocks;
+        else { ctx->hostRanks = nullptr; cudaGetLastError(); }   // (not fatal: the host pass counts the states itself)
+    }
+    bool haveRanks = false;
     // DXRV_DBG_E2E=1: the phases of this call on stderr (development aid)
     static const bool dbgPhases = [] { const char* e = std::getenv("DXRV_DBG_E2E"); return e && e[0] == '1'; }();
     auto nowUs = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -350,7 +358,10 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
     {
         ctx->launches += (uint64_t)launchSparseEncode(ctx->stream, ctx->gridOwned, N, slabBegin, slabEnd, ctx->sparseBuf,
                                                       reinterpret_cast<uint32_t*>(ctx->sparseBuf + countsOff));
-        // the header (number of mixed bricks) and the brick states in one copy; then exactly the payload that exists
+        // the encoder's per-block ranks (32 KB for 1024^3: the host pass then has nothing to count), the header (number of
+        // mixed bricks) and the brick states in one go; then exactly the payload that exists
+        haveRanks = ctx->hostRanks != nullptr &&
+                    cudaMemcpyAsync(ctx->hostRanks, ctx->sparseBuf + countsOff, (size_t)L.numBlocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
         if (cudaMemcpyAsync(ctx->hostBlob, ctx->sparseBuf, L.offPayload, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             rc = cudaFail(ctx, cudaGetLastError(), "sparse transport: header copy");
@@ -379,7 +390,7 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
     }
     else
     {
-        good = good && hostFillPublish(v);
+        good = good && hostFillPublish(v, haveRanks ? ctx->hostRanks : nullptr, kSparseBlockBricks);
         tZero = dbgPhases ? nowUs() : 0.0;
         const bool filled = hostFillWait();      // (always: the pool must be done with hostDst before this call returns)
         if (rc != DXRV_OK) return rc;
@@ -465,6 +476,7 @@ void dxrv_destroy(dxrv_ctx* ctx)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->hostBlob) cudaFreeHost(ctx->hostBlob);
+    if (ctx->hostRanks) cudaFreeHost(ctx->hostRanks);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     for (cudaEvent_t e : ctx->chunkDone) if (e) cudaEventDestroy(e);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);

@@ -70,6 +70,7 @@ struct dxrv_ctx
     uint8_t* u8Temp = nullptr; size_t u8Cap = 0;
     uint8_t* sparseBuf = nullptr; size_t sparseCap = 0;   // DXRV_FORMAT_SPARSE_BRICKS blob + block counts
     uint8_t* hostBlob = nullptr; size_t hostBlobCap = 0;  // pinned staging of the blob (dxrv_voxelize_to_host, sparse transport)
+    uint32_t* hostRanks = nullptr; size_t hostRanksCap = 0;  // pinned: the encoder's per-block ranks (handed to the host pass)
     bool hostFillBegun = false;                           // dxrv_voxelize_mesh_to_host has started the host pool's pass already
     uint32_t readBack = 0;                                // DXRV_READ_BACK_* (dxrv_set_read_back)
     uint64_t lastD2hBytes = 0;                            // DXRV_INFO_LAST_D2H_BYTES

@@ -144,6 +144,7 @@ struct SparseLayout
     uint32_t P, BY, BZ, numBricks, stateWords, numBlocks;
     size_t offStates, offPayload, maxBytes;
 };
+constexpr uint32_t kSparseBlockBricks = 256;   // bricks per block of the encoder; after the encode blockCounts[i] = rank of block i's first mixed brick
 SparseLayout sparseLayout(uint32_t N, uint32_t layers);
 // blob: device memory of sparseLayout().maxBytes; blockCounts: numBlocks words of scratch.  Returns kernels launched.
 int launchSparseEncode(cudaStream_t s, const uint32_t* grid, uint32_t N, uint32_t z0, uint32_t z1, uint8_t* blob, uint32_t* blockCounts);

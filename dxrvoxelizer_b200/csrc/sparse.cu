@@ -23,7 +23,7 @@ namespace dxrv
 {
 namespace
 {
-constexpr int kBrickThreads = 256;
+constexpr int kBrickThreads = (int)kSparseBlockBricks;
 
 struct BrickGeom
 {

@@ -153,13 +153,14 @@ bool sparseExpand(const SparseBlobView& v, uint32_t* dst, bool dstIsZero)
     return true;
 }
 
-// Zeroing WITHOUT read-for-ownership: an ordinary memset of a 1 MiB piece reads every line before it overwrites it
-// (glibc only switches to streaming stores for much larger blocks).  Measured on a B200 box's 16 cores
-// (tools/host_zero_bw.c, 128 MiB): streaming stores of 16 / 32 / 64 bytes 184 / 188 / 187 GB/s, `rep stosb` 172 GB/s,
-// memset 161 GB/s; inside the end-to-end call the 16-byte stores were the best by a few per cent (1.23 ms against 1.26 for
-// AVX-512 and 1.37 for `rep stosb`, two-pass scheme), so they stay the default.  (On the 8-core build container
-// `rep stosb` was 2.2x faster than the 16-byte stores: do not tune this anywhere but on the target.)
-// DXRV_HOST_ZERO = sse2 | avx2 | avx512 | stosb | memset overrides the choice.
+// Zeroing without read-for-ownership.  Measured on a B200 box's 16 cores, bare loops over 128 MiB (tools/host_zero_bw.c):
+// streaming stores of 16 / 32 / 64 bytes 184 / 188 / 187 GB/s, `rep stosb` 172 GB/s, glibc memset 161 GB/s -- but
+// INSIDE the end-to-end call, methods alternated within one process (tools/e2e_ab.py; separate processes differ by more
+// than the methods do): `rep stosb` 0.708 ms and memset 0.699 ms (glibc takes `rep stosb` at these sizes) against
+// 0.784 / 0.779 / 0.817 ms for the 16 / 32 / 64-byte streaming stores; the same order for the bunny.  Fast strings
+// write whole lines without ownership reads and leave the memory system more room for the other threads than a
+// stream of non-temporal stores does.  `rep stosb` is the default; DXRV_HOST_ZERO = stosb | sse2 | avx2 | avx512 |
+// memset overrides it (looked at again at the start of every pass).
 enum class ZeroMethod { Memset, Sse2, Avx2, Avx512, Stosb };
 
 #if defined(__x86_64__)
@@ -196,7 +197,7 @@ static void zeroStosb(uint8_t* p, size_t n) { __asm__ volatile("rep stosb" : "+D
 static ZeroMethod pickZeroMethod()
 {
     __builtin_cpu_init();
-    ZeroMethod m = ZeroMethod::Sse2;
+    ZeroMethod m = ZeroMethod::Stosb;
     if (const char* e = std::getenv("DXRV_HOST_ZERO"))
     {
         if (!std::strcmp(e, "stosb")) m = ZeroMethod::Stosb;
@@ -209,10 +210,24 @@ static ZeroMethod pickZeroMethod()
 }
 #endif
 
+static std::atomic<int> gZeroMethod{-1};
+static std::atomic<int> gLinePlain{0};   // DXRV_HOST_LINE=plain: the line composer uses ordinary 64-byte stores (A/B switch)
+// (the environment is looked at again at the start of every pass: tools A/B the methods inside one process, on one box)
+static void refreshZeroMethod()
+{
+#if defined(__x86_64__)
+    gZeroMethod.store((int)pickZeroMethod(), std::memory_order_relaxed);
+    const char* e = std::getenv("DXRV_HOST_LINE");
+    gLinePlain.store(e && !std::strcmp(e, "plain") ? 1 : 0, std::memory_order_relaxed);
+#endif
+}
+
 static void zeroStreaming(uint8_t* p, size_t n)
 {
 #if defined(__x86_64__)
-    static const ZeroMethod method = pickZeroMethod();
+    int mi = gZeroMethod.load(std::memory_order_relaxed);
+    if (mi < 0) { refreshZeroMethod(); mi = gZeroMethod.load(std::memory_order_relaxed); }
+    const ZeroMethod method = (ZeroMethod)mi;
     if (method == ZeroMethod::Memset) { std::memset(p, 0, n); return; }
     if (method == ZeroMethod::Stosb) { zeroStosb(p, n); return; }
     while (n && (reinterpret_cast<uintptr_t>(p) & 63u)) { *p++ = 0; --n; }
@@ -228,6 +243,7 @@ static void zeroStreaming(uint8_t* p, size_t n)
 
 void hostZeroBegin(void* dst, size_t bytes)
 {
+    refreshZeroMethod();
     const size_t chunk = 1u << 20;
     const unsigned tasks = (unsigned)((bytes + chunk - 1) / chunk);
     uint8_t* p = static_cast<uint8_t*>(dst);
@@ -295,6 +311,11 @@ void fillLayerAvx512(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32
     const __m512i iota = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
     const __m512i zero = _mm512_setzero_si512();
     const int* payload = reinterpret_cast<const int*>(v.payload);
+    const bool plain = gLinePlain.load(std::memory_order_relaxed) != 0;
+    auto put = [plain](uint32_t* p, __m512i v) __attribute__((target("avx512f"))) {
+        if (plain) _mm512_store_si512(reinterpret_cast<__m512i*>(p), v);
+        else _mm512_stream_si512(reinterpret_cast<__m512i*>(p), v);
+    };
     for (uint32_t k = 0; k < 4u; ++k)
     {
         const uint32_t z = 4u * bz + k;
@@ -302,17 +323,24 @@ void fillLayerAvx512(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32
         uint32_t rank = firstRank;
         uint32_t* out = dst + (size_t)z * N * P;                             // row y of this layer: out + y * P
         const uint32_t* sw = states;
-        for (uint32_t by = 0; by < BY; ++by, out += 4u * P)
-            for (uint32_t g = 0; g < groups; ++g, ++sw)
+        uint8_t* zeroFrom = nullptr;                                         // pending run of empty row runs (contiguous in the grid)
+        for (uint32_t by = 0; by < BY; ++by, out += 4u * P, sw += groups)
+        {
+            uint32_t any = 0;
+            for (uint32_t g = 0; g < groups; ++g) any |= sw[g];
+            if (any == 0u)
+            {
+                if (!zeroFrom) zeroFrom = reinterpret_cast<uint8_t*>(out);
+                continue;
+            }
+            if (zeroFrom) { zeroStreaming(zeroFrom, (size_t)(reinterpret_cast<uint8_t*>(out) - zeroFrom)); zeroFrom = nullptr; }
+            for (uint32_t g = 0; g < groups; ++g)
             {
                 uint32_t* line = out + 16u * g;
-                const uint32_t w = *sw;
+                const uint32_t w = sw[g];
                 if (w == 0u)
                 {
-                    _mm512_stream_si512(reinterpret_cast<__m512i*>(line), zero);
-                    _mm512_stream_si512(reinterpret_cast<__m512i*>(line + P), zero);
-                    _mm512_stream_si512(reinterpret_cast<__m512i*>(line + 2u * P), zero);
-                    _mm512_stream_si512(reinterpret_cast<__m512i*>(line + 3u * P), zero);
+                    put(line, zero); put(line + P, zero); put(line + 2u * P, zero); put(line + 3u * P, zero);
                     continue;
                 }
                 const uint32_t lo = _pext_u32(w, 0x55555555u), hi = _pext_u32(w, 0xaaaaaaaau);
@@ -324,10 +352,12 @@ void fillLayerAvx512(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32
                 for (uint32_t j = 0; j < 4u; ++j)
                 {
                     const __m512i val = mixed ? _mm512_mask_i32gather_epi32(fullv, mixed, _mm512_add_epi32(idx, _mm512_set1_epi32((int)j)), payload, 4) : fullv;
-                    _mm512_stream_si512(reinterpret_cast<__m512i*>(line + j * P), val);
+                    put(line + j * P, val);
                 }
                 rank += (uint32_t)__builtin_popcount(hi);
             }
+        }
+        if (zeroFrom) zeroStreaming(zeroFrom, (size_t)(reinterpret_cast<uint8_t*>(out) - zeroFrom));
     }
     _mm_sfence();
 }
@@ -436,6 +466,7 @@ void hostFillBegin(void* dst, uint32_t N, uint32_t layers)
 {
     FillState& f = gFill;
     f.owner.lock();                      // (a second context's call waits here until the first one's pass is complete)
+    refreshZeroMethod();
     f.dst = static_cast<uint32_t*>(dst);
     f.N = N; f.P = (N + 31u) / 32u; f.BY = (N + 3u) / 4u; f.BZ = (layers + 3u) / 4u; f.layers = layers;
     // a task = a group of brick layers of about 512 KiB
@@ -463,15 +494,28 @@ void hostFillBegin(void* dst, uint32_t N, uint32_t layers)
     });
 }
 
-bool hostFillPublish(const SparseBlobView& v)
+bool hostFillPublish(const SparseBlobView& v, const uint32_t* blockRanks, uint32_t bricksPerBlock)
 {
     FillState& f = gFill;
     if (!f.active || v.N != f.N || v.z1 - v.z0 != f.layers || v.BZ != f.BZ || v.BY != f.BY || v.P != f.P) return false;
     const uint32_t perLayer = v.BY * v.P;
     f.base.assign(f.BZ + 1u, 0u);
-    uint32_t undefinedState = 0;   // (state 3 does not exist: such a blob would read payload it does not have)
-    for (uint32_t bz = 0; bz < f.BZ; ++bz) f.base[bz + 1u] = f.base[bz] + countMixed(v.states, bz * perLayer, (bz + 1u) * perLayer, &undefinedState);
-    if (f.base[f.BZ] != v.numMixed || undefinedState) return false;
+    if (blockRanks && bricksPerBlock && perLayer % bricksPerBlock == 0u)
+    {
+        // the encoder's own exclusive ranks per block of bricks (sparse.cu: k_brick_scan), brick layers being whole blocks:
+        // nothing to count here (reading the 0.5 MB of states of a 1024^3 grid on this thread took 0.06 - 0.4 ms while the
+        // pool's streaming stores saturate the memory system)
+        const uint32_t blocksPerLayer = perLayer / bricksPerBlock;
+        for (uint32_t bz = 0; bz < f.BZ; ++bz) f.base[bz] = blockRanks[(size_t)bz * blocksPerLayer];
+        f.base[f.BZ] = v.numMixed;
+        for (uint32_t bz = 0; bz < f.BZ; ++bz) if (f.base[bz] > f.base[bz + 1u]) return false;
+    }
+    else
+    {
+        uint32_t undefinedState = 0;   // (state 3 does not exist: such a blob would read payload it does not have)
+        for (uint32_t bz = 0; bz < f.BZ; ++bz) f.base[bz + 1u] = f.base[bz] + countMixed(v.states, bz * perLayer, (bz + 1u) * perLayer, &undefinedState);
+        if (f.base[f.BZ] != v.numMixed || undefinedState) return false;
+    }
     f.view = v;
     f.blob.store(&f.view, std::memory_order_release);
     return true;

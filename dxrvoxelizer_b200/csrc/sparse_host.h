@@ -27,6 +27,8 @@ void hostZeroWait();
 // layers zeroed before the publish are expanded last).  publish: false = the blob does not fit the grid / is
 // inconsistent (nothing changes); wait: false = nothing was published (the grid holds zeros).
 void hostFillBegin(void* dst, uint32_t N, uint32_t layers);
-bool hostFillPublish(const SparseBlobView& v);
+// blockRanks (optional): rank of the first mixed brick of every block of bricksPerBlock bricks, as the device encoder
+// computed them -- used instead of counting the states when brick layers are whole blocks.
+bool hostFillPublish(const SparseBlobView& v, const uint32_t* blockRanks = nullptr, uint32_t bricksPerBlock = 0);
 bool hostFillWait();
 }  // namespace dxrv
