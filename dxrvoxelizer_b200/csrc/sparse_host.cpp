@@ -211,14 +211,11 @@ static ZeroMethod pickZeroMethod()
 #endif
 
 static std::atomic<int> gZeroMethod{-1};
-static std::atomic<int> gLinePlain{0};   // DXRV_HOST_LINE=plain: the line composer uses ordinary 64-byte stores (A/B switch)
 // (the environment is looked at again at the start of every pass: tools A/B the methods inside one process, on one box)
 static void refreshZeroMethod()
 {
 #if defined(__x86_64__)
     gZeroMethod.store((int)pickZeroMethod(), std::memory_order_relaxed);
-    const char* e = std::getenv("DXRV_HOST_LINE");
-    gLinePlain.store(e && !std::strcmp(e, "plain") ? 1 : 0, std::memory_order_relaxed);
 #endif
 }
 
@@ -311,11 +308,8 @@ void fillLayerAvx512(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32
     const __m512i iota = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
     const __m512i zero = _mm512_setzero_si512();
     const int* payload = reinterpret_cast<const int*>(v.payload);
-    const bool plain = gLinePlain.load(std::memory_order_relaxed) != 0;
-    auto put = [plain](uint32_t* p, __m512i v) __attribute__((target("avx512f"))) {
-        if (plain) _mm512_store_si512(reinterpret_cast<__m512i*>(p), v);
-        else _mm512_stream_si512(reinterpret_cast<__m512i*>(p), v);
-    };
+    // (streaming stores: ordinary 64-byte stores measured 0.20 ms slower per 1024^3 grid -- they pull the lines through the caches)
+    auto put = [](uint32_t* p, __m512i v) __attribute__((target("avx512f"))) { _mm512_stream_si512(reinterpret_cast<__m512i*>(p), v); };
     for (uint32_t k = 0; k < 4u; ++k)
     {
         const uint32_t z = 4u * bz + k;
