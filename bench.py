@@ -629,9 +629,9 @@ def run_c3(args):
                     "h2d_bytes_per_step": int(nv * stride + ni * 4), "d2h_bytes_per_step": int(e2e_d2h_total),
                     "host_grid_bytes_per_step": int(N * N * P * 4),
                     "timing": "wall clock around synchronising C-ABI calls, max over ranks",
-                    "transport": "DXRV_READ_BACK_AUTO = %s" % ("sparse bricks + host expansion (slab >= 8 MiB, pool of >= 8 host threads)"
-                                                               if host_pool_threads >= 8 and e_bytes >= (8 << 20) else
-                                                               "dense copy (fewer than 8 host threads per rank, or a slab below 8 MiB)"),
+                    "transport": "DXRV_READ_BACK_AUTO = %s" % ("sparse bricks + one-pass host grid (slab >= 8 MiB, pool of >= 4 host threads)"
+                                                               if host_pool_threads >= 4 and e_bytes >= (8 << 20) else
+                                                               "dense copy (fewer than 4 host threads per rank, or a slab below 8 MiB)"),
                     "how": "dxrv_voxelize_mesh_to_host (N = 1; = dxrv_build_bvh from host arrays + dxrv_voxelize_to_host, which N > 1 calls "
                            "separately after the NCCL broadcast of the mesh) into a pinned host buffer that ends up holding the DENSE "
                            "128 MiB bit grid (filled with 0xA5 beforehand, checked against the oracle).  Default transport of the call: "

@@ -299,9 +299,11 @@ uint32_t toHostTransport(const dxrv_ctx* ctx, size_t bytes)
 {
     uint32_t transport = ctx->readBack;
     if (const char* e = std::getenv("DXRV_TO_HOST")) transport = !std::strcmp(e, "dense") ? 1u : (!std::strcmp(e, "sparse") ? 2u : transport);
-    // (a host thread zeroes ~12 GB/s with streaming stores, the link copies ~55 GB/s: from eight threads on the host pass
-    // wins -- measured with the ranks of an 8-GPU box sharing 32 cores: 4 threads each 1.41 ms, dense copy 1.24 ms)
-    if (transport == 0u) transport = (bytes >= (8u << 20) && hostPoolThreads() >= 8u) ? 2u : 1u;
+    // (a host thread writes ~12 GB/s, the link copies ~55 GB/s when one GPU has it to itself and 16-28 GB/s when the
+    // eight GPUs of a box read back together.  Measured with the ranks of an 8-GPU box sharing 32 cores, 4 threads each:
+    // one-pass host grid 0.94 ms against 1.32-1.48 ms for the dense copy -- the old two-pass expansion was 1.41 ms, hence
+    // the threshold of eight threads it had; below four threads nothing has been measured and the copy stays)
+    if (transport == 0u) transport = (bytes >= (8u << 20) && hostPoolThreads() >= 4u) ? 2u : 1u;
     return transport;
 }
 

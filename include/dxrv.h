@@ -144,7 +144,7 @@ DXRV_API int dxrv_fetch_grid(dxrv_ctx* ctx, void* hostDst, size_t bytes, uint32_
  *                          workers poll for the next call for DXRV_HOST_SPIN_US microseconds, default 2000, before they
  *                          sleep).  Floor: the host's memory write bandwidth.  A grid whose blob exceeds half the
  *                          dense size is copied densely after all.  hostDst is bit-identical either way.
- *   DXRV_READ_BACK_AUTO    (default) SPARSE for slabs of 8 MiB and more when the pool has at least 8 host threads, else DENSE. */
+ *   DXRV_READ_BACK_AUTO    (default) SPARSE for slabs of 8 MiB and more when the pool has at least 4 host threads, else DENSE. */
 #define DXRV_READ_BACK_AUTO   0u
 #define DXRV_READ_BACK_DENSE  1u
 #define DXRV_READ_BACK_SPARSE 2u
