@@ -354,7 +354,7 @@ int voxelizeToHostSparse(dxrv_ctx* ctx, uint32_t N, uint32_t mode, uint32_t slab
     const bool twoPass = hostFillTwoPass();
     if (twoPass) hostZeroBegin(hostDst, bytes);   // runs beside everything up to hostZeroWait()
     else if (ctx->hostFillBegun) ctx->hostFillBegun = false;   // (dxrv_voxelize_mesh_to_host started the pass before the upload)
-    else hostFillBegin(hostDst, N, slabEnd - slabBegin);
+    else hostFillBegin(hostDst, N, slabBegin, slabEnd - slabBegin);
     int rc = dxrv_voxelize(ctx, N, mode, slabBegin, slabEnd);
     if (rc == DXRV_OK)
     {
@@ -828,7 +828,7 @@ int dxrv_voxelize_mesh_to_host(dxrv_ctx* ctx, const void* vertices, uint32_t num
     if ((rc = toHostArgsCheck(ctx, N, mode, slabBegin, slabEnd, hostDst, bytes)) != DXRV_OK) return rc;
     if (toHostTransport(ctx, bytes) == 2u && !hostFillTwoPass())
     {
-        hostFillBegin(hostDst, N, slabEnd - slabBegin);
+        hostFillBegin(hostDst, N, slabBegin, slabEnd - slabBegin);
         ctx->hostFillBegun = true;
     }
     rc = dxrv_build_bvh(ctx, vertices, numVerts, strideBytes, indices, numIndices, bound);
@@ -886,7 +886,7 @@ int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_
     if (denseBytes != (size_t)(v.z1 - v.z0) * v.N * v.P * 4) return DXRV_ERR_INVALID_ARG;
     // one pass of the host pool over the dense grid (sparse_host.cpp); DXRV_HOST_FILL_DELAY_US (tests) publishes the blob
     // late, so that the pool has zeroed brick layers before it knows their contents and must expand them afterwards
-    hostFillBegin(denseDst, v.N, v.z1 - v.z0);
+    hostFillBegin(denseDst, v.N, v.z0, v.z1 - v.z0);
     if (const char* e = std::getenv("DXRV_HOST_FILL_DELAY_US"))
     {
         const long us = std::atol(e);

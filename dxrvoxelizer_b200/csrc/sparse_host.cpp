@@ -289,7 +289,8 @@ struct FillState
     std::atomic<const SparseBlobView*> blob{nullptr};
     SparseBlobView view{};
     std::vector<uint32_t> base;          // rank of the first mixed brick of every brick layer
-    std::vector<uint8_t> zeroedOnly;     // per task: its brick layers were zeroed before the blob arrived
+    std::vector<uint8_t> zeroedOnly;     // per group: its brick layers were zeroed before the blob arrived
+    std::vector<uint32_t> order;         // task -> group of brick layers, farthest from the grid's centre first
     bool active = false;
     std::mutex owner;                    // held from hostFillBegin to hostFillWait: one pass at a time per process
 } gFill;
@@ -456,7 +457,7 @@ void fillLayer(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32_t fir
 }
 }  // namespace
 
-void hostFillBegin(void* dst, uint32_t N, uint32_t layers)
+void hostFillBegin(void* dst, uint32_t N, uint32_t z0, uint32_t layers)
 {
     FillState& f = gFill;
     f.owner.lock();                      // (a second context's call waits here until the first one's pass is complete)
@@ -469,11 +470,23 @@ void hostFillBegin(void* dst, uint32_t N, uint32_t layers)
     f.numTasks = (f.BZ + f.group - 1u) / f.group;
     f.blob.store(nullptr, std::memory_order_relaxed);
     f.zeroedOnly.assign(f.numTasks, 0);
+    // From the outside of the GRID inwards (a z-slab of a multi-GPU run has the mesh at one of its ends, not in its
+    // middle): groups ordered by the distance of their middle layer from the grid's centre plane, farthest first.
+    f.order.resize(f.numTasks);
+    for (uint32_t g = 0; g < f.numTasks; ++g) f.order[g] = g;
+    {
+        const uint32_t group = f.group, BZ = f.BZ;
+        const double centre = 0.5 * (double)N;
+        auto dist = [=](uint32_t g) {
+            const double mid = (double)z0 + 2.0 * ((double)g * group + (double)std::min((g + 1u) * group, BZ));   // 4 * (bz0 + bz1) / 2
+            return mid > centre ? mid - centre : centre - mid;
+        };
+        std::stable_sort(f.order.begin(), f.order.end(), [&](uint32_t a, uint32_t b) { return dist(a) > dist(b); });
+    }
     f.active = true;
     hostParallelBegin(f.numTasks, [](unsigned t) {
         FillState& s = gFill;
-        // outside-in: even tasks from the first brick layer up, odd ones from the last one down
-        const uint32_t g = (t & 1u) ? s.numTasks - 1u - (t >> 1) : (t >> 1);
+        const uint32_t g = s.order[t];
         const uint32_t bz0 = g * s.group, bz1 = std::min(bz0 + s.group, s.BZ);
         const SparseBlobView* v = s.blob.load(std::memory_order_acquire);
         if (!v)

@@ -22,11 +22,11 @@ bool sparseExpand(const SparseBlobView& v, uint32_t* dst, bool dstIsZero);
 void hostZeroBegin(void* dst, size_t bytes);
 void hostZeroWait();
 // The dense grid of a slab (layers * N * P words at dst) in ONE pass of the pool: begin returns at once and the threads
-// start zeroing from the outside of the slab inwards; publish hands them the blob (as soon as it is on the host: the
+// start zeroing from the outside of the grid inwards (the layers of the slab farthest from the grid's centre first); publish hands them the blob (as soon as it is on the host: the
 // brick layers still to do are then written with their final contents); wait blocks until the grid is complete (brick
 // layers zeroed before the publish are expanded last).  publish: false = the blob does not fit the grid / is
 // inconsistent (nothing changes); wait: false = nothing was published (the grid holds zeros).
-void hostFillBegin(void* dst, uint32_t N, uint32_t layers);
+void hostFillBegin(void* dst, uint32_t N, uint32_t z0, uint32_t layers);   // the slab [z0, z0 + layers) of an N^3 grid
 // blockRanks (optional): rank of the first mixed brick of every block of bricksPerBlock bricks, as the device encoder
 // computed them -- used instead of counting the states when brick layers are whole blocks.
 bool hostFillPublish(const SparseBlobView& v, const uint32_t* blockRanks = nullptr, uint32_t bricksPerBlock = 0);
