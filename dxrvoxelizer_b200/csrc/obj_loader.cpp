@@ -378,7 +378,59 @@ inline bool fastInt(const char*& p, const char* end, long long& out)
     return true;
 }
 
-// One pass over a chunk.  kStore = false: count records and detect anything unusual.
+// Pass A of the fast path: COUNT the records of a chunk -- positions, normals, texture coordinates, triangles (a face of
+// c corners = c - 2 triangles) -- without converting a single number.  Everything else (number syntax, corner syntax,
+// trailing junk) is checked by pass B, which parses every token anyway and sends the file to the reference-grammar
+// parser when something is unusual; the counts only have to be right for files pass B accepts, where a face's corners
+// are exactly its blank-separated tokens.  (Pass A used to parse every number just to validate it: the same
+// std::from_chars work twice.  C5 file, one thread, build container: 156 -> 274 MB/s; dragon.obj 181 -> 233 MB/s.)
+void countChunk(Chunk& ch)
+{
+    const char* p = ch.begin;
+    Counts k;
+    while (p < ch.end)
+    {
+        const char* eol = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(ch.end - p)));
+        if (!eol) eol = ch.end;
+        if (eol - p > 255) { ch.odd = true; return; }
+        const char* q = p;
+        while (q < eol && isBlank(*q)) ++q;
+        const char* tok = q;
+        while (q < eol && !isBlank(*q)) ++q;
+        const size_t len = static_cast<size_t>(q - tok);
+        if (len == 0) { p = eol + 1; continue; }
+        const char c0 = tok[0];
+        if (c0 == 'v')
+        {
+            if (len == 1) ++k.positions;
+            else if (len == 2 && tok[1] == 'n') ++k.normals;
+            else if (len == 2 && tok[1] == 't') ++k.texcoords;
+            else { ch.odd = true; return; }
+        }
+        else if (c0 == 'f')
+        {
+            if (len != 1) { ch.odd = true; return; }
+            uint32_t corners = 0;
+            while (true)
+            {
+                while (q < eol && isBlank(*q)) ++q;
+                if (q >= eol) break;
+                ++corners;
+                while (q < eol && !isBlank(*q)) ++q;
+            }
+            if (corners < 3) { ch.odd = true; return; }
+            k.triangles += corners - 2;
+        }
+        else if ((c0 >= '0' && c0 <= '9') || c0 == '-' || c0 == '+')
+        {
+            ch.odd = true; return;   // could be the continuation of a face on the previous line
+        }
+        p = eol + 1;
+    }
+    ch.counts = k;
+}
+
+// Pass B: parse and store a chunk (kStore = false: the same checks without storing; kept for the template's callers).
 template <bool kStore>
 void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8_t* vb, uint32_t stride, float* normals,
                uint32_t* indices, uint32_t* nrmIdx, Counts base)
@@ -518,33 +570,10 @@ bool parseObjFast(const char* text, size_t size, ObjMesh& m, std::string& err, u
         for (auto& t : pool) t.join();
     };
 
-    // pass A: counts + well-formedness (corner syntax is checked with "has everything" semantics off: it needs
-    // the file-level flags, so it is checked in pass B)
-    Counts dummy;
-    parallelFor([&](size_t i) { scanChunk<false>(chunks[i], false, false, dummy, nullptr, 0, nullptr, nullptr, nullptr, Counts()); });
-    // pass A parsed corners as bare integers; files with '/' need the flags first: recount with them
+    // pass A: counts only (countChunk); pass B validates while it parses
     Counts total;
-    bool sawOdd = false;
-    for (auto& ch : chunks) sawOdd |= ch.odd;
-    if (sawOdd)
-    {
-        // maybe only because corners carry '/' parts: count v/vt/vn cheaply, then redo pass A with the flags
-        Counts recs;
-        for (const char* p = text; p < text + size;)
-        {
-            const char* eol = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(text + size - p)));
-            if (!eol) eol = text + size;
-            const char* q = p;
-            while (q < eol && isBlank(*q)) ++q;
-            if (q + 1 < eol && q[0] == 'v' && q[1] == 't' && (q + 2 == eol || isBlank(q[2]))) ++recs.texcoords;
-            else if (q + 1 < eol && q[0] == 'v' && q[1] == 'n' && (q + 2 == eol || isBlank(q[2]))) ++recs.normals;
-            p = eol + 1;
-        }
-        if (!recs.texcoords && !recs.normals) return false;
-        for (auto& ch : chunks) { ch.odd = false; ch.counts = Counts(); }
-        parallelFor([&](size_t i) { scanChunk<false>(chunks[i], recs.texcoords != 0, recs.normals != 0, dummy, nullptr, 0, nullptr, nullptr, nullptr, Counts()); });
-        for (auto& ch : chunks) if (ch.odd) return false;
-    }
+    parallelFor([&](size_t i) { countChunk(chunks[i]); });
+    for (auto& ch : chunks) if (ch.odd) return false;
     std::vector<Counts> base(numChunks);
     for (size_t i = 0; i < numChunks; ++i)
     {
