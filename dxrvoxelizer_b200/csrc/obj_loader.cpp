@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace dxrv
 {
@@ -348,7 +351,57 @@ struct Chunk
     bool odd = false;
 };
 
-inline bool isBlank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+inline bool isBlank(char c) { return c == ' ' || (static_cast<unsigned char>(c - '\t') <= 4u && c != '\n'); }   // ' ', \t, \v, \f, \r
+
+// first '\n' in [p, end), or end.  OBJ lines are ~30 bytes: a library memchr call per line cost as much as the line's
+// numbers (10-15 ns of call and set-up); 16 bytes at a time inline is a few cycles.
+inline const char* findNewline(const char* p, const char* end)
+{
+#if defined(__SSE2__)
+    const __m128i nl = _mm_set1_epi8('\n');
+    while (end - p >= 16)
+    {
+        const int mask = _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(p)), nl));
+        if (mask) return p + __builtin_ctz(static_cast<unsigned>(mask));
+        p += 16;
+    }
+#endif
+    while (p < end && *p != '\n') ++p;
+    return p;
+}
+
+// Plain decimals without an exponent -- what OBJ writers emit -- are converted here: the digits as one integer w
+// (exact in a double below 2^53), one correctly rounded double division by a power of ten (exact up to 10^22), one
+// rounding to float.  Rounding twice differs from rounding once only when the double lands EXACTLY on the midpoint of
+// two floats (its low 29 bits are 0x10000000): rounding to double is monotonic and the midpoint is a double, so any other
+// double lies on the same side of it as the exact value.  Those, and everything else (exponents, more than 18 digits,
+// inf / nan), go to std::from_chars below; both are correctly rounded like the reference's fscanf("%f").
+inline bool decimalToFloat(const char* s, const char* end, const char*& stop, float& out)
+{
+    static const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20,
+                                      1e21, 1e22};
+    bool neg = false;
+    if (s < end && *s == '-') { neg = true; ++s; }
+    uint64_t w = 0;
+    int digits = 0, frac = 0;
+    while (s < end && *s >= '0' && *s <= '9') { w = w * 10u + (uint64_t)(*s++ - '0'); ++digits; }
+    if (s < end && *s == '.')
+    {
+        ++s;
+        while (s < end && *s >= '0' && *s <= '9') { w = w * 10u + (uint64_t)(*s++ - '0'); ++digits; ++frac; }
+    }
+    if (digits == 0 || digits > 18 || frac > 22 || w >= (1ull << 53)) return false;
+    if (s < end && !isBlank(*s)) return false;                                  // an exponent, a suffix: not here
+    const double d = (double)w / kPow10[frac];
+    uint64_t bits;
+    std::memcpy(&bits, &d, sizeof bits);
+    const uint32_t low = (uint32_t)(bits & 0x1fffffffu);
+    if (low >= 0x0fffffffu && low <= 0x10000001u) return false;                 // (on or next to) a float midpoint
+    const float f = (float)d;
+    out = neg ? -f : f;
+    stop = s;
+    return true;
+}
 
 inline bool fastReal(const char*& p, const char* end, float& out)
 {
@@ -358,6 +411,10 @@ inline bool fastReal(const char*& p, const char* end, float& out)
     const char* d = q;
     if (d < end && *d == '-') ++d;
     if (d >= end || !((*d >= '0' && *d <= '9') || *d == '.')) return false;   // inf / nan / hex: not here
+    {
+        const char* stop = nullptr;
+        if (decimalToFloat(q, end, stop, out)) { p = stop; return true; }
+    }
     auto r = std::from_chars(q, end, out);
     if (r.ec != std::errc() || r.ptr == q) return false;
     if (r.ptr < end && !isBlank(*r.ptr)) return false;                          // e.g. 0x10, 1.5f
@@ -390,8 +447,7 @@ void countChunk(Chunk& ch)
     Counts k;
     while (p < ch.end)
     {
-        const char* eol = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(ch.end - p)));
-        if (!eol) eol = ch.end;
+        const char* eol = findNewline(p, ch.end);
         if (eol - p > 255) { ch.odd = true; return; }
         const char* q = p;
         while (q < eol && isBlank(*q)) ++q;
@@ -439,8 +495,7 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
     Counts k;
     while (p < ch.end)
     {
-        const char* eol = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(ch.end - p)));
-        if (!eol) eol = ch.end;
+        const char* eol = findNewline(p, ch.end);
         if (eol - p > 255) { ch.odd = true; return; }
         const char* q = p;
         while (q < eol && isBlank(*q)) ++q;
