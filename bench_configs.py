@@ -177,7 +177,7 @@ def run_c5(args, Rig, ClockSampler, measured_peak, host_threads, popcount):
     import oracle
     rig = Rig(args)
     torch, rank, world = rig.torch, rig.rank, rig.world
-    N, n_mesh, n_streams = 256, int(os.environ.get("DXRV_C5_MESHES", "256")), 4
+    N, n_mesh, n_streams = 256, int(os.environ.get("DXRV_C5_MESHES", "256")), int(os.environ.get("DXRV_C5_STREAMS", "4"))
     tmp = os.path.join(tempfile.gettempdir(), "dxrv_c5_%d" % os.getuid())
     os.makedirs(tmp, exist_ok=True)
     mine = list(range(rank, n_mesh, world))
@@ -197,25 +197,34 @@ def run_c5(args, Rig, ClockSampler, measured_peak, host_threads, popcount):
     os.environ["DXRV_OBJ_THREADS"] = "1"          # one thread per file, the pool parallelises over the files
     loaders = ThreadPoolExecutor(max_workers=max(2, host_threads() // world))
 
+    drivers = ThreadPoolExecutor(max_workers=n_streams)
+
     def run_share(fetch):
-        """parse (thread pool) -> build + voxelize on stream k -> optional D2H; returns the loaded meshes"""
+        """parse (thread pool) -> build + voxelize on stream k % n_streams -> optional D2H; returns the loaded meshes.
+        Every stream (= context) is driven by its own host thread: a context's calls -- upload (waits for the copy), build,
+        voxelize, read-back of its previous grid -- take ~0.25 ms of host time per mesh, and issued from ONE thread for all
+        four streams they were what bounded the step (63 ms for 256 meshes, with 16 parser threads idle most of the time).
+        Distinct contexts are independent (include/dxrv.h); ctypes releases the GIL during the calls."""
         futures = [loaders.submit(d.load_obj, paths[i]) for i in mine]
-        loaded = []
-        in_flight = [None] * n_streams                     # mesh whose grid is still on stream s
-        for k, fut in enumerate(futures):
-            m = fut.result()
-            s = k % n_streams
+        loaded = [None] * len(futures)
+
+        def drive(s):
             c = ctxs[s]
-            if fetch and in_flight[s] is not None:         # read back the previous grid of THIS stream only: the other
-                c.fetch_into(h_grids[in_flight[s]].data_ptr(), grid_bytes)   # streams keep the GPU busy meanwhile
-            c.build_bvh(m)
-            c.voxelize(N, d.MODE_PARITY)
-            in_flight[s] = k
-            loaded.append(m)
-        for s, c in enumerate(ctxs):
-            if fetch and in_flight[s] is not None:
-                c.fetch_into(h_grids[in_flight[s]].data_ptr(), grid_bytes)
+            prev = None                                    # mesh whose grid is still on this stream
+            for k in range(s, len(futures), n_streams):
+                m = futures[k].result()
+                if fetch and prev is not None:             # read back the previous grid of THIS stream only: the other
+                    c.fetch_into(h_grids[prev].data_ptr(), grid_bytes)   # streams keep the GPU busy meanwhile
+                c.build_bvh(m)
+                c.voxelize(N, d.MODE_PARITY)
+                prev = k
+                loaded[k] = m
+            if fetch and prev is not None:
+                c.fetch_into(h_grids[prev].data_ptr(), grid_bytes)
             c.synchronize()
+
+        for f in [drivers.submit(drive, s) for s in range(n_streams)]:
+            f.result()
         return loaded
 
     # ---- gate: EVERY grid of this rank against the oracle ----------------------------------------------------------
