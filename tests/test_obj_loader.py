@@ -161,6 +161,19 @@ def test_decimal_conversion_matches_reference_loader(seed, tmp_path, oracle_mod)
     # this file are exactly where that differs from fscanf / the product -- e.g. seed 1, vertex 1: ...437 against ...438.)
 
 
+def test_random_obj_files_match_reference_loader(tmp_path, oracle_mod):
+    """A slice of the differential fuzzer (tools/fuzz_obj.py: random records, all four corner syntaxes, polygons,
+    negative indices, comments, odd blanks, CRLF, no final newline; 1 650 files compared when it was written)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_obj", os.path.join(os.path.dirname(__file__), "..", "tools", "fuzz_obj.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    for seed in range(40):
+        p = tmp_path / ("fuzz_%d.obj" % seed)
+        p.write_bytes(fz.make_obj(seed).encode())
+        _same_as_reference(str(p), oracle_mod)
+
+
 def test_loader_semantics_without_reference(tmp_path):
     """Same conventions checked directly (runs even when oracle/_ref is absent)."""
     p = tmp_path / "t.obj"
