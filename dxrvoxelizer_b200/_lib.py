@@ -58,6 +58,7 @@ SIGNATURES = {
     "dxrv_obj_indices": (_vp, [_vp]),
     "dxrv_obj_aabb": (None, [_vp, _vp]),
     "dxrv_obj_bound": (None, [_vp, _vp]),
+    "dxrv_voxelize_obj_batch": (_int, [_c.POINTER(_vp), _u32, _c.POINTER(_c.c_char_p), _u32, _u32, _u32, _vp, _sz, _u32, _vp]),
     "dxrv_host_alloc": (_vp, [_sz]),
     "dxrv_host_free": (None, [_vp]),
     "dxrv_ipc_export_grid": (_int, [_vp, _sz, _vp, _c.POINTER(_vp)]),

@@ -708,7 +708,7 @@ bool parseObjFast(const char* text, size_t size, ObjMesh& m, std::string& err, u
     return finishMesh(m, normals, nrmIdx, hasNorm, err);
 }
 
-bool loadObj(const char* path, ObjMesh& mesh, std::string& err)
+bool loadObj(const char* path, ObjMesh& mesh, std::string& err, unsigned threads)
 {
     FILE* f = std::fopen(path, "rb");
     if (!f) { err = std::string("cannot open ") + path; return false; }
@@ -739,7 +739,7 @@ bool loadObj(const char* path, ObjMesh& mesh, std::string& err)
     std::fclose(f);
     // well-formed files take the multi-threaded parser; anything unusual is parsed exactly like the reference does
     std::string fastErr;
-    if (parseObjFast(text, size, mesh, fastErr, 0)) return true;
+    if (parseObjFast(text, size, mesh, fastErr, threads)) return true;
     if (!fastErr.empty()) { err = fastErr; return false; }
     return parseObj(text, size, mesh, err);
 }

@@ -38,7 +38,9 @@ struct ObjMesh
 
 // Returns false (and fills err) when the file cannot be read -- the reference returns false
 // from Import when fopen fails (XUSGObjLoader.cpp:21-23).
-bool loadObj(const char* path, ObjMesh& mesh, std::string& err);
+// threads: parser threads for this file (0: DXRV_OBJ_THREADS, else one per core up to 16; a batch loader that parses many
+// files at once passes 1).
+bool loadObj(const char* path, ObjMesh& mesh, std::string& err, unsigned threads = 0);
 // Same, from a memory buffer holding the OBJ text (follows the reference's fscanf grammar token by token).
 bool parseObj(const char* text, size_t size, ObjMesh& mesh, std::string& err);
 // Multi-threaded parser for well-formed files; returns false with an empty `err` when the text needs the

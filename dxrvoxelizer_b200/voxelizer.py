@@ -325,6 +325,33 @@ class Voxelizer:
         self._check(self._lib.dxrv_ipc_close(self._h, d_ptr))
 
 
+def voxelize_obj_batch(voxelizers, paths, N, mode=L.MODE_SHADER, out=None, out_ptr=None, loader_threads=0, fetch=True):
+    """dxrv_voxelize_obj_batch: OBJ files -> one N^3 bit grid each, as a pipeline inside the library (loader threads parse,
+    every Voxelizer of `voxelizers` -- distinct contexts, typically 4 per GPU -- takes meshes s, s + len(voxelizers), ...).
+    The grids land in `out` (uint32[len(paths), N, N, ceil(N/32)], allocated here when None) or at the raw address
+    `out_ptr` (e.g. pinned memory); fetch=False voxelizes only.  Returns (out or None, triangles per mesh)."""
+    lib = L.lib()
+    n = len(paths)
+    P = (N + 31) // 32
+    grid_bytes = N * N * P * 4
+    if fetch and out_ptr is None:
+        if out is None:
+            out = np.empty((n, N, N, P), np.uint32)
+        if out.nbytes != n * grid_bytes or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous array of len(paths) * N * N * ceil(N/32) * 4 bytes")
+        out_ptr = out.ctypes.data
+    handles = (ctypes.c_void_p * len(voxelizers))(*[v._h for v in voxelizers])
+    cpaths = (ctypes.c_char_p * max(1, n))(*[str(p).encode() for p in paths])
+    tris = np.zeros(max(1, n), np.uint32)
+    rc = lib.dxrv_voxelize_obj_batch(handles, len(voxelizers), cpaths, n, N, mode, out_ptr if fetch else None,
+                                     grid_bytes if fetch else 0, loader_threads, tris.ctypes.data)
+    if rc != L.OK:
+        raise L.DxrvError(rc, lib.dxrv_last_error(None).decode())
+    for v in voxelizers:                       # every context holds the last grid it voxelized
+        v._shape, v._N = (N, N, P), N
+    return (out if fetch else None), tris[:n]
+
+
 def sparse_decode(blob):
     """DXRV_FORMAT_SPARSE_BRICKS blob -> dense uint32[(z1-z0), N, P] (dxrv_sparse_decode, host code)."""
     b = np.ascontiguousarray(blob, dtype=np.uint8)
