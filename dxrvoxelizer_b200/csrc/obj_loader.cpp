@@ -404,6 +404,41 @@ inline bool decimalToFloat(const char* s, const char* end, const char*& stop, fl
     return true;
 }
 
+// The same conversion for the vertex fast path of pass B: leading spaces, an optional '-', digits [. digits], then a
+// blank or the line's '\n' -- which the caller guarantees lies ahead, so no loop checks a bound.  Same acceptance rule as
+// decimalToFloat (false = let the general code look at the line), same arithmetic.
+inline bool plainDecimal(const char*& p, float& out)
+{
+    static const double kPow10[19] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18};
+    const char* s = p;
+    while (*s == ' ') ++s;
+    const bool neg = *s == '-';
+    s += neg;
+    uint64_t w = 0;
+    uint32_t d;
+    const char* i0 = s;
+    while ((d = static_cast<uint32_t>(static_cast<unsigned char>(*s)) - '0') <= 9u) { w = w * 10u + d; ++s; }
+    int digits = static_cast<int>(s - i0), frac = 0;
+    if (*s == '.')
+    {
+        const char* f0 = ++s;
+        while ((d = static_cast<uint32_t>(static_cast<unsigned char>(*s)) - '0') <= 9u) { w = w * 10u + d; ++s; }
+        frac = static_cast<int>(s - f0);
+        digits += frac;
+    }
+    if (digits == 0 || digits > 18 || w >= (1ull << 53)) return false;
+    if (!(*s == ' ' || *s == '\n' || *s == '\r')) return false;
+    const double x = static_cast<double>(w) / kPow10[frac];
+    uint64_t bits;
+    std::memcpy(&bits, &x, sizeof bits);
+    const uint32_t low = static_cast<uint32_t>(bits & 0x1fffffffu);
+    if (low >= 0x0fffffffu && low <= 0x10000001u) return false;                 // (on or next to) a float midpoint
+    const float f = static_cast<float>(x);
+    out = neg ? -f : f;
+    p = s;
+    return true;
+}
+
 inline bool fastReal(const char*& p, const char* end, float& out)
 {
     while (p < end && isBlank(*p)) ++p;
@@ -551,6 +586,63 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
     {
         const char* eol = findNewline(p, ch.end);
         if (eol - p > 255) { ch.odd = true; return; }
+        // The two records a mesh file is made of, in the form exporters write them -- "v x y z" with plain decimals and
+        // "f a b c" with positive indices, from column 0 -- are read here without a bounds check per character: the
+        // line's own '\n' (eol < ch.end) ends every loop.  Anything else about the line (other blanks, signs on indices,
+        // slashes, polygons, exponents, trailing fields) leaves it to the general code below, which parses it again.
+        if (eol < ch.end && eol - p >= 6 && p[1] == ' ')
+        {
+            if (p[0] == 'f' && !hasTexc && !hasNorm)
+            {
+                const char* q = p + 2;
+                uint32_t idx[3];
+                bool plain = true;
+                for (int c = 0; c < 3; ++c)
+                {
+                    while (*q == ' ') ++q;
+                    const char* d0 = q;
+                    uint32_t v = 0, d;
+                    while ((d = static_cast<uint32_t>(static_cast<unsigned char>(*q)) - '0') <= 9u) { v = v * 10u + d; ++q; }
+                    if (q == d0 || q - d0 > 9 || v == 0) { plain = false; break; }
+                    idx[c] = v - 1u;
+                }
+                if (plain)
+                {
+                    while (*q == ' ' || *q == '\r') ++q;
+                    if (q == eol)
+                    {
+                        if (kStore)
+                        {
+                            const size_t t = 3 * static_cast<size_t>(base.triangles + k.triangles);
+                            indices[t] = idx[0]; indices[t + 1] = idx[1]; indices[t + 2] = idx[2];
+                        }
+                        ++k.triangles;
+                        p = eol + 1;
+                        continue;
+                    }
+                }
+            }
+            else if (p[0] == 'v')
+            {
+                const char* q = p + 2;
+                float v[3];
+                if (plainDecimal(q, v[0]) && plainDecimal(q, v[1]) && plainDecimal(q, v[2]))
+                {
+                    while (*q == ' ' || *q == '\r') ++q;
+                    if (q == eol)
+                    {
+                        if (kStore)
+                        {
+                            float* dst = reinterpret_cast<float*>(vb + static_cast<size_t>(stride) * (base.positions + k.positions));
+                            dst[0] = v[0]; dst[1] = v[1]; dst[2] = -v[2];
+                        }
+                        ++k.positions;
+                        p = eol + 1;
+                        continue;
+                    }
+                }
+            }
+        }
         const char* q = p;
         while (q < eol && isBlank(*q)) ++q;
         const char* tok = q;
