@@ -6,7 +6,8 @@
 // ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity (default shader = the
 // reference's function; parity = the column-parity fast path), -device k,
 // -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words),
-// -view file.ppm (the reference's viewer pass, 1280 x 720).
+// -view file.ppm (the reference's viewer pass, 1280 x 720), -batch list.txt [-streams k] (one grid per OBJ path
+// of the list through dxrv_voxelize_obj_batch: k contexts per GPU, -gpus GPUs; -out prefix writes prefix00000.bin ...).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/dxrv.h"
 #include "voxelizer_host.h"
 
 namespace
@@ -38,7 +40,7 @@ struct Args
     // would swallow absolute paths, so '/' only introduces an option when a known name follows.
     static bool knownOption(const char* name)
     {
-        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus", "view"};
+        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus", "view", "batch", "streams"};
         for (const char* n : names) if (lower(name) == n) return true;
         return false;
     }
@@ -50,11 +52,83 @@ struct Args
         return a[0] != '-' || (a[1] >= '0' && a[1] <= '9') || a[1] == '.';
     }
 };
+// -batch: the streaming case.  Every path of the list file (one per line; blank lines and lines starting with '#'
+// are skipped) becomes one grid; `streams` contexts on each of `gpus` GPUs share the work (mesh-parallel), the host
+// grids of a round live in pinned memory (rounds of at most 2 GiB of grids).
+int runBatch(const std::string& listPath, uint32_t grid, uint32_t mode, int device, int gpus, int streams, const std::string& outPrefix)
+{
+    FILE* lf = std::fopen(listPath.c_str(), "r");
+    if (!lf) { std::fprintf(stderr, "cannot open %s\n", listPath.c_str()); return 1; }
+    std::vector<std::string> files;
+    char line[4096];
+    while (std::fgets(line, sizeof line, lf))
+    {
+        std::string t = line;
+        while (!t.empty() && (t.back() == '\n' || t.back() == '\r' || t.back() == ' ' || t.back() == '\t')) t.pop_back();
+        size_t b = 0;
+        while (b < t.size() && (t[b] == ' ' || t[b] == '\t')) ++b;
+        if (b < t.size() && t[b] != '#') files.push_back(t.substr(b));
+    }
+    std::fclose(lf);
+    if (files.empty()) { std::fprintf(stderr, "%s lists no meshes\n", listPath.c_str()); return 1; }
+    if (grid == 0 || grid > 8192) { std::fprintf(stderr, "-grid must be in [1, 8192]\n"); return 2; }
+    gpus = std::max(1, gpus); streams = std::max(1, std::min(streams, 64));
+
+    std::vector<dxrv_ctx*> ctxs;
+    auto cleanup = [&](void* pinned) { for (dxrv_ctx* c : ctxs) dxrv_destroy(c); if (pinned) dxrv_host_free(pinned); };
+    for (int i = 0; i < gpus * streams; ++i)
+    {
+        dxrv_ctx* c = nullptr;
+        if (dxrv_create(&c, device + i % gpus) != DXRV_OK) { std::fprintf(stderr, "Init failed: %s\n", dxrv_last_error(nullptr)); cleanup(nullptr); return 1; }
+        ctxs.push_back(c);
+    }
+    const size_t words = (size_t)grid * grid * ((grid + 31) / 32), gridBytes = words * 4;
+    const size_t perRound = std::max<size_t>(ctxs.size(), std::min<size_t>(files.size(), ((size_t)2 << 30) / gridBytes));
+    void* pinned = dxrv_host_alloc(perRound * gridBytes);
+    if (!pinned) { std::fprintf(stderr, "cannot allocate %zu bytes of pinned host memory\n", perRound * gridBytes); cleanup(nullptr); return 1; }
+
+    using clock = std::chrono::steady_clock;
+    unsigned long long inside = 0, triangles = 0;
+    double seconds = 0.0;
+    std::vector<uint32_t> tris(perRound);
+    for (size_t first = 0; first < files.size(); first += perRound)
+    {
+        const size_t n = std::min(perRound, files.size() - first);
+        std::vector<const char*> paths(n);
+        for (size_t k = 0; k < n; ++k) paths[k] = files[first + k].c_str();
+        const auto t0 = clock::now();
+        const int rc = dxrv_voxelize_obj_batch(ctxs.data(), (uint32_t)ctxs.size(), paths.data(), (uint32_t)n, grid, mode, pinned, gridBytes, 0, tris.data());
+        seconds += std::chrono::duration<double>(clock::now() - t0).count();
+        if (rc != DXRV_OK) { std::fprintf(stderr, "Voxelize failed: %s\n", dxrv_last_error(nullptr)); cleanup(pinned); return 1; }
+        for (size_t k = 0; k < n; ++k)
+        {
+            const uint32_t* g = static_cast<const uint32_t*>(pinned) + k * words;
+            triangles += tris[k];
+            for (size_t w = 0; w < words; ++w) inside += (unsigned long long)__builtin_popcount(g[w]);
+            if (!outPrefix.empty())
+            {
+                char name[32];
+                std::snprintf(name, sizeof name, "%05zu.bin", first + k);
+                FILE* f = std::fopen((outPrefix + name).c_str(), "wb");
+                if (!f) { std::fprintf(stderr, "cannot write %s%s\n", outPrefix.c_str(), name); cleanup(pinned); return 1; }
+                std::fwrite(g, sizeof(uint32_t), words, f);
+                std::fclose(f);
+            }
+        }
+    }
+    std::printf("{\"batch\": %zu, \"grid\": %u, \"mode\": \"%s\", \"gpus\": %d, \"contexts\": %zu, \"triangles\": %llu, \"inside\": %llu, "
+                "\"seconds\": %.4f, \"meshes_per_s\": %.1f}\n",
+                files.size(), grid, mode == DXRV_MODE_SHADER ? "shader" : "parity", gpus, ctxs.size(), triangles, inside, seconds,
+                (double)files.size() / seconds);
+    cleanup(pinned);
+    return 0;
+}
 }  // namespace
 
 int main(int argc, char** argv)
 {
-    std::string mesh = "Assets/bunny.obj", out, view;
+    std::string mesh = "Assets/bunny.obj", out, view, batch;
+    int streams = 4;
     float posScale[4] = {0.0f, 0.0f, 0.0f, 1.0f};
     uint32_t grid = 64, slab0 = 0, slab1 = 0;
     int device = 0, frames = 1, gpus = 1;
@@ -76,6 +150,8 @@ int main(int argc, char** argv)
         else if (a.matches(i, "gpus") && a.hasValue(i)) gpus = std::atoi(argv[++i]);
         else if (a.matches(i, "out") && a.hasValue(i)) out = argv[++i];
         else if (a.matches(i, "view") && a.hasValue(i)) view = argv[++i];
+        else if (a.matches(i, "batch") && a.hasValue(i)) batch = argv[++i];
+        else if (a.matches(i, "streams") && a.hasValue(i)) streams = std::atoi(argv[++i]);
         else if (a.matches(i, "slab") && a.hasValue(i))
         {
             slab0 = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
@@ -89,6 +165,9 @@ int main(int argc, char** argv)
             else { std::fprintf(stderr, "unknown -mode %s (shader|parity)\n", m.c_str()); return 2; }
         }
     }
+
+    if (!batch.empty())
+        return runBatch(batch, grid, mode == DXRVoxelizer::MODE_SHADER ? DXRV_MODE_SHADER : DXRV_MODE_PARITY, device, gpus, streams, out);
 
     DXRVoxelizer vox;
     vox.SetDevice(device);

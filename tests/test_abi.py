@@ -69,3 +69,19 @@ def test_cli_reports_failure_like_reference_init(tmp_path):
     assert os.path.exists(exe)
     r = subprocess.run([exe, "-mesh", str(tmp_path / "missing.obj"), "0.0", "2.8", "0.0", "0.03"], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr   # Init returns false when Import fails
+
+
+def test_cli_batch_mode_reports_failures(tmp_path):
+    """-batch list.txt (dxrv_voxelize_obj_batch): a missing list, an empty list and -- without a GPU -- the loud failure."""
+    exe = os.path.join(ROOT, "dxrvoxelizer_b200", "dxrvoxelizer")
+    r = subprocess.run([exe, "-batch", str(tmp_path / "nolist.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+    empty = tmp_path / "empty.txt"
+    empty.write_text("# nothing\n\n")
+    r = subprocess.run([exe, "-batch", str(empty)], capture_output=True, text=True)
+    assert r.returncode == 1 and "lists no meshes" in r.stderr
+    lst = tmp_path / "list.txt"
+    lst.write_text("# one mesh\n%s\n" % os.path.join(ROOT, "assets", "missing.obj"))
+    r = subprocess.run([exe, "-batch", str(lst), "-grid", "64", "-mode", "parity", "-streams", "2"], capture_output=True, text=True,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
