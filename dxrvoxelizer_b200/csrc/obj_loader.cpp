@@ -590,21 +590,30 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
         // "f a b c" with positive indices, from column 0 -- are read here without a bounds check per character: the
         // line's own '\n' (eol < ch.end) ends every loop.  Anything else about the line (other blanks, signs on indices,
         // slashes, polygons, exponents, trailing fields) leaves it to the general code below, which parses it again.
-        if (eol < ch.end && eol - p >= 6 && p[1] == ' ')
+        if (eol < ch.end && eol - p >= 6)
         {
-            if (p[0] == 'f' && !hasTexc && !hasNorm)
+            const char r0 = p[0], r1 = p[1];
+            if (r0 == 'f' && r1 == ' ')
             {
+                // three corners "v", "v/vt", "v//vn" or "v/vt/vn" -- the form the FILE's records call for -- of positive indices
                 const char* q = p + 2;
-                uint32_t idx[3];
+                uint32_t vIdx[3], nIdx[3] = {0, 0, 0};
                 bool plain = true;
-                for (int c = 0; c < 3; ++c)
-                {
-                    while (*q == ' ') ++q;
+                auto index = [&q](uint32_t& out) {
                     const char* d0 = q;
                     uint32_t v = 0, d;
                     while ((d = static_cast<uint32_t>(static_cast<unsigned char>(*q)) - '0') <= 9u) { v = v * 10u + d; ++q; }
-                    if (q == d0 || q - d0 > 9 || v == 0) { plain = false; break; }
-                    idx[c] = v - 1u;
+                    out = v - 1u;
+                    return q != d0 && q - d0 <= 9 && v != 0;
+                };
+                for (int c = 0; c < 3 && plain; ++c)
+                {
+                    while (*q == ' ') ++q;
+                    uint32_t t;
+                    plain = index(vIdx[c]);
+                    if (plain && hasTexc) plain = *q++ == '/' && index(t);
+                    if (plain && hasNorm) plain = *q++ == '/' && (hasTexc || *q++ == '/') && index(nIdx[c]);
+                    if (plain) plain = *q == ' ' || *q == '\r' || *q == '\n';
                 }
                 if (plain)
                 {
@@ -614,7 +623,8 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
                         if (kStore)
                         {
                             const size_t t = 3 * static_cast<size_t>(base.triangles + k.triangles);
-                            indices[t] = idx[0]; indices[t + 1] = idx[1]; indices[t + 2] = idx[2];
+                            indices[t] = vIdx[0]; indices[t + 1] = vIdx[1]; indices[t + 2] = vIdx[2];
+                            if (hasNorm) { nrmIdx[t] = nIdx[0]; nrmIdx[t + 1] = nIdx[1]; nrmIdx[t + 2] = nIdx[2]; }
                         }
                         ++k.triangles;
                         p = eol + 1;
@@ -622,9 +632,10 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
                     }
                 }
             }
-            else if (p[0] == 'v')
+            else if (r0 == 'v' && (r1 == ' ' || (r1 == 'n' && p[2] == ' ')))
             {
-                const char* q = p + 2;
+                const bool isNormal = r1 == 'n';
+                const char* q = p + (isNormal ? 3 : 2);
                 float v[3];
                 if (plainDecimal(q, v[0]) && plainDecimal(q, v[1]) && plainDecimal(q, v[2]))
                 {
@@ -633,10 +644,11 @@ void scanChunk(Chunk& ch, bool hasTexc, bool hasNorm, const Counts& total, uint8
                     {
                         if (kStore)
                         {
-                            float* dst = reinterpret_cast<float*>(vb + static_cast<size_t>(stride) * (base.positions + k.positions));
+                            float* dst = isNormal ? normals + 3 * static_cast<size_t>(base.normals + k.normals)
+                                                  : reinterpret_cast<float*>(vb + static_cast<size_t>(stride) * (base.positions + k.positions));
                             dst[0] = v[0]; dst[1] = v[1]; dst[2] = -v[2];
                         }
-                        ++k.positions;
+                        if (isNormal) ++k.normals; else ++k.positions;
                         p = eol + 1;
                         continue;
                     }
