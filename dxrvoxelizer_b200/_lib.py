@@ -43,6 +43,7 @@ SIGNATURES = {
     "dxrv_count_inside": (_int, [_vp, _c.POINTER(_u64)]),
     "dxrv_default_view": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "dxrv_render_view": (_int, [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _sz]),
+    "dxrv_save_image": (_int, [_c.c_char_p, _vp, _u32, _u32, _u32, _u32]),
     "dxrv_build_mips": (_int, [_vp, _c.POINTER(_u32)]),
     "dxrv_fetch_mip": (_int, [_vp, _u32, _vp, _sz]),
     "dxrv_get_info": (_int, [_vp, _u32, _c.POINTER(_u64)]),

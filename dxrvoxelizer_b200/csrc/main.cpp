@@ -6,7 +6,7 @@
 // ignored.  New flags: -grid N (replaces #define GRID_SIZE 64), -mode shader|parity (default shader = the
 // reference's function; parity = the column-parity fast path), -device k,
 // -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words),
-// -view file.ppm (the reference's viewer pass, 1280 x 720), -batch list.txt [-streams k] (one grid per OBJ path
+// -view file.ppm|file.png (the reference's viewer pass, 1280 x 720; .png = its screenshot format), -batch list.txt [-streams k] (one grid per OBJ path
 // of the list through dxrv_voxelize_obj_batch: k contexts per GPU, -gpus GPUs; -out prefix writes prefix00000.bin ...).
 #include <algorithm>
 #include <chrono>
@@ -210,11 +210,19 @@ int main(int argc, char** argv)
         // what the reference's window shows (1280 x 720, Main.cpp:17), as a binary PPM
         std::vector<uint8_t> rgba;
         if (!vox.RenderView(1280, 720, rgba)) { std::fprintf(stderr, "view failed: %s\n", vox.LastError()); return 1; }
-        FILE* f = std::fopen(view.c_str(), "wb");
-        if (!f) { std::fprintf(stderr, "cannot write %s\n", view.c_str()); return 1; }
-        std::fprintf(f, "P6\n1280 720\n255\n");
-        for (size_t i = 0; i < rgba.size(); i += 4) std::fwrite(&rgba[i], 1, 3, f);
-        std::fclose(f);
+        const bool png = view.size() >= 4 && lower(view.substr(view.size() - 4)) == ".png";
+        if (png)   // the reference's screenshot format (SaveImage, DXRVoxelizer.cpp:531-551: RGB PNG)
+        {
+            if (dxrv_save_image(view.c_str(), rgba.data(), 1280, 720, 1280 * 4, 3) != DXRV_OK) { std::fprintf(stderr, "cannot write %s\n", view.c_str()); return 1; }
+        }
+        else
+        {
+            FILE* f = std::fopen(view.c_str(), "wb");
+            if (!f) { std::fprintf(stderr, "cannot write %s\n", view.c_str()); return 1; }
+            std::fprintf(f, "P6\n1280 720\n255\n");
+            for (size_t i = 0; i < rgba.size(); i += 4) std::fwrite(&rgba[i], 1, 3, f);
+            std::fclose(f);
+        }
     }
     return 0;
 }

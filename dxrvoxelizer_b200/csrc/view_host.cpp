@@ -6,7 +6,11 @@
 // row-vector convention DirectXMath uses (p' = p * M).
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <new>
+#include <vector>
 
 #include "../../include/dxrv.h"
 
@@ -106,4 +110,90 @@ extern "C" int dxrv_default_view(const float bound[4], const float posScale[4], 
     transformCoord(lightPt, worldI, light);
     transformCoord(e, worldI, eye);
     return DXRV_OK;
+}
+
+// ---- dxrv_save_image: DXRVoxelizer::SaveImage (DXRVoxelizer.cpp:531-551) -- the screenshot the reference writes with
+// stbi_write_png.  A PNG of 8-bit RGB (comp = 3, the reference's default) or RGBA (comp = 4) from an R8G8B8A8 buffer
+// with a row pitch; the image data go into stored (uncompressed) deflate blocks: every decoder reads them, and the
+// encoder is forty lines instead of a compressor.
+namespace
+{
+uint32_t crc32Of(const uint8_t* p, size_t n, uint32_t crc)
+{
+    static uint32_t table[256];
+    static const bool ready = [] {
+        for (uint32_t i = 0; i < 256; ++i)
+        {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        return true;
+    }();
+    (void)ready;
+    crc = ~crc;
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return ~crc;
+}
+void putBE32(std::vector<uint8_t>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back(static_cast<uint8_t>(x >> s)); }
+bool writeChunk(FILE* f, const char type[4], const std::vector<uint8_t>& data)
+{
+    std::vector<uint8_t> head;
+    putBE32(head, static_cast<uint32_t>(data.size()));
+    head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32Of(reinterpret_cast<const uint8_t*>(type), 4, 0);
+    if (!data.empty()) crc = crc32Of(data.data(), data.size(), crc);
+    std::vector<uint8_t> tail;
+    putBE32(tail, crc);
+    return std::fwrite(head.data(), 1, head.size(), f) == head.size() && (data.empty() || std::fwrite(data.data(), 1, data.size(), f) == data.size()) &&
+           std::fwrite(tail.data(), 1, tail.size(), f) == tail.size();
+}
+}  // namespace
+
+extern "C" int dxrv_save_image(const char* fileName, const void* rgba, uint32_t width, uint32_t height, uint32_t rowPitchBytes, uint32_t comp)
+{
+    if (!fileName || !rgba || width == 0 || height == 0 || width > 32768 || height > 32768 || (comp != 3 && comp != 4) ||
+        rowPitchBytes < width * 4u)
+        return DXRV_ERR_INVALID_ARG;
+    try
+    {
+        // scanlines: filter type 0 + comp bytes per pixel
+        const size_t rowBytes = 1 + static_cast<size_t>(width) * comp;
+        std::vector<uint8_t> raw(rowBytes * height);
+        const uint8_t* src = static_cast<const uint8_t*>(rgba);
+        for (uint32_t y = 0; y < height; ++y)
+        {
+            uint8_t* dst = &raw[rowBytes * y];
+            *dst++ = 0;
+            const uint8_t* s = src + static_cast<size_t>(rowPitchBytes) * y;
+            for (uint32_t x = 0; x < width; ++x, s += 4)
+                for (uint32_t k = 0; k < comp; ++k) *dst++ = s[k];
+        }
+        // zlib stream: header, stored blocks of at most 65535 bytes, Adler-32 of the raw data
+        std::vector<uint8_t> z;
+        z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+        z.push_back(0x78); z.push_back(0x01);
+        uint32_t a = 1, b = 0;
+        for (size_t off = 0; off < raw.size();)
+        {
+            const size_t len = std::min<size_t>(65535, raw.size() - off);
+            z.push_back(off + len == raw.size() ? 1 : 0);
+            z.push_back(static_cast<uint8_t>(len & 0xff)); z.push_back(static_cast<uint8_t>(len >> 8));
+            z.push_back(static_cast<uint8_t>(~len & 0xff)); z.push_back(static_cast<uint8_t>((~len >> 8) & 0xff));
+            z.insert(z.end(), raw.begin() + off, raw.begin() + off + len);
+            for (size_t i = off; i < off + len; ++i) { a += raw[i]; if (a >= 65521u) a -= 65521u; b += a; if (b >= 65521u) b -= 65521u; }
+            off += len;
+        }
+        putBE32(z, (b << 16) | a);
+        std::vector<uint8_t> ihdr;
+        putBE32(ihdr, width); putBE32(ihdr, height);
+        ihdr.push_back(8); ihdr.push_back(comp == 3 ? 2 : 6); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+        FILE* f = std::fopen(fileName, "wb");
+        if (!f) return DXRV_ERR_IO;
+        static const uint8_t signature[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+        bool ok = std::fwrite(signature, 1, 8, f) == 8 && writeChunk(f, "IHDR", ihdr) && writeChunk(f, "IDAT", z) && writeChunk(f, "IEND", {});
+        ok = (std::fclose(f) == 0) && ok;
+        return ok ? DXRV_OK : DXRV_ERR_IO;
+    }
+    catch (const std::bad_alloc&) { return DXRV_ERR_OOM; }
 }

@@ -78,6 +78,16 @@ def default_view(bound, width=1280, height=720, pos_scale=None):
     return m.reshape(4, 4), eye, light
 
 
+def save_image(path, rgba, comp=3):
+    """dxrv_save_image: the reference's SaveImage (PNG screenshot) for an (H, W, 4) uint8 image, e.g. Voxelizer.render_view's."""
+    img = np.ascontiguousarray(rgba, dtype=np.uint8)
+    if img.ndim != 3 or img.shape[2] != 4:
+        raise ValueError("rgba must be (height, width, 4) uint8")
+    rc = L.lib().dxrv_save_image(str(path).encode(), img.ctypes.data, img.shape[1], img.shape[0], img.shape[1] * 4, comp)
+    if rc != L.OK:
+        raise L.DxrvError(rc, "dxrv_save_image: cannot write %s" % path)
+
+
 class Voxelizer:
     """One context = one GPU + one stream.  Not thread-safe (same as the C ABI)."""
 

@@ -201,6 +201,11 @@ DXRV_API int dxrv_default_view(const float bound[4], const float posScale[4], ui
  * (row-major, y down, bytes = width * height * 4).  Synchronises. */
 DXRV_API int dxrv_render_view(dxrv_ctx* ctx, uint32_t width, uint32_t height, const float screenToLocal[16],
                               const float eye[3], const float light[3], void* hostRGBA, size_t bytes);
+/* DXRVoxelizer::SaveImage (DXRVoxelizer.cpp:531-551; the F11 screenshot, stbi_write_png there): an 8-bit PNG of
+ * comp = 3 (RGB, the reference's default) or 4 (RGBA) channels from an R8G8B8A8 image with rowPitchBytes >= width * 4
+ * -- e.g. the output of dxrv_render_view.  Pure host code. */
+DXRV_API int dxrv_save_image(const char* fileName, const void* rgba, uint32_t width, uint32_t height, uint32_t rowPitchBytes,
+                             uint32_t comp);
 /* Number of set voxels in the slab of the last voxelize (device popcount; synchronises). */
 DXRV_API int dxrv_count_inside(dxrv_ctx* ctx, uint64_t* count);
 

@@ -195,3 +195,29 @@ def test_gpu_shader_artefact_against_the_hires_screenshot(vox, assets):
             return vox.render_view(1920, 1080, s, e, l)
         return f
     _hires_pin(render(d.MODE_SHADER), render(d.MODE_PARITY), vox.bound())
+
+
+def test_save_image_writes_the_reference_screenshot_format(tmp_path):
+    """dxrv_save_image = DXRVoxelizer::SaveImage (DXRVoxelizer.cpp:531-551): an RGB (default) or RGBA PNG from an
+    R8G8B8A8 buffer with a row pitch; decoded here by an independent reader (PIL)."""
+    Image = pytest.importorskip("PIL.Image")
+    from dxrvoxelizer_b200 import _lib as L
+    rng = np.random.default_rng(7)
+    for h, w in [(720, 1280), (1, 1), (37, 513), (3, 30000)]:          # (the last two: rows that straddle stored-block limits)
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        for comp in (3, 4):
+            p = tmp_path / ("img_%d_%d_%d.png" % (h, w, comp))
+            d.save_image(p, img, comp)
+            got = np.asarray(Image.open(p))
+            assert got.shape == (h, w, comp) and np.array_equal(got, img[:, :, :comp])
+    # a row pitch wider than the image (the reference's read-back buffer is pitched: rowPitch / 4 pixels per row)
+    wide = rng.integers(0, 256, (20, 48, 4), dtype=np.uint8)
+    p = tmp_path / "pitched.png"
+    assert L.lib().dxrv_save_image(str(p).encode(), wide.ctypes.data, 40, 20, 48 * 4, 3) == L.OK
+    assert np.array_equal(np.asarray(Image.open(p)), wide[:, :40, :3])
+    # argument checks
+    lib = L.lib()
+    assert lib.dxrv_save_image(str(p).encode(), wide.ctypes.data, 40, 20, 40 * 4 - 1, 3) == L.ERR_INVALID_ARG
+    assert lib.dxrv_save_image(str(p).encode(), wide.ctypes.data, 40, 20, 48 * 4, 2) == L.ERR_INVALID_ARG
+    assert lib.dxrv_save_image(None, wide.ctypes.data, 40, 20, 48 * 4, 3) == L.ERR_INVALID_ARG
+    assert lib.dxrv_save_image(str(tmp_path / "no_such_dir" / "x.png").encode(), wide.ctypes.data, 40, 20, 48 * 4, 3) == L.ERR_IO
