@@ -174,6 +174,29 @@ def test_random_obj_files_match_reference_loader(tmp_path, oracle_mod):
         _same_as_reference(str(p), oracle_mod)
 
 
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_multi_chunk_file_and_non_finite_coordinates_match_reference_loader(tmp_path, oracle_mod, meshes_mod, monkeypatch, threads):
+    """A 3 MB file (icosphere(6): 81 920 triangles, parsed in several chunks) as written, and with nan / inf / signed
+    zeros sprinkled into the coordinates -- vertex 0 included: fscanf reads them, the face normals and the AABB
+    (first strict minimum wins, a NaN in vertex 0 poisons its axis) must come out bit for bit."""
+    from bench_configs import write_obj
+    monkeypatch.setenv("DXRV_OBJ_THREADS", threads)
+    p = tmp_path / "ico6.obj"
+    write_obj(str(p), meshes_mod.icosphere(6, seed=3, rotate=True, normals=False))
+    _same_as_reference(str(p), oracle_mod)
+    txt = p.read_text().splitlines()
+    rng = np.random.default_rng(5)
+    for i in rng.integers(1, 40000, 300):
+        if txt[i].startswith("v "):
+            parts = txt[i].split()
+            parts[int(rng.integers(1, 4))] = ["nan", "inf", "-inf", "-0.0", "0.0", "-0"][int(rng.integers(0, 6))]
+            txt[i] = " ".join(parts)
+    txt[1] = "v nan 0.5 -0.0"
+    q = tmp_path / "ico6_nonfinite.obj"
+    q.write_text("\n".join(txt) + "\n")
+    _same_as_reference(str(q), oracle_mod)
+
+
 def test_loader_semantics_without_reference(tmp_path):
     """Same conventions checked directly (runs even when oracle/_ref is absent)."""
     p = tmp_path / "t.obj"
