@@ -37,15 +37,25 @@ def test_loader_matches_reference_crc_pins(name):
     np.testing.assert_allclose(m.bound, BOUNDS[name], rtol=2e-5, atol=1e-6)
 
 
-def _same_as_reference(path, oracle_mod):
+def _same_as_reference(path, oracle_mod, nan_bits=True):
     if not oracle_mod.ref_loader_available():
         pytest.skip("oracle/_ref not built (reference tree absent)")
     vb, ib, st, aabb = oracle_mod.ref_load_obj(path)
     m = d.load_obj(path)
     assert m.stride == st
     assert np.array_equal(m.indices, ib)
-    assert m.vertex_bytes.tobytes() == vb.tobytes()   # bit-exact, NaNs included
-    assert m.aabb.tobytes() == aabb.tobytes()
+    if nan_bits:
+        assert m.vertex_bytes.tobytes() == vb.tobytes()   # bit-exact, NaNs included
+        assert m.aabb.tobytes() == aabb.tobytes()
+    else:
+        # every value bit for bit (signed zeros and infinities included), a NaN where the reference has a NaN -- but not the
+        # NaN's sign and payload: x86 hands on the FIRST operand's NaN, so they follow the compiler's operand order (they
+        # differ between two builds of the reference itself), not the loader's semantics
+        for ours, ref in ((m.vertex_bytes, vb), (m.aabb.view(np.uint8), aabb.view(np.uint8))):
+            a, b = ours.view(np.uint32), ref.view(np.uint32)
+            nan_a, nan_b = np.isnan(ours.view(np.float32)), np.isnan(ref.view(np.float32))
+            assert np.array_equal(nan_a, nan_b)
+            assert np.array_equal(a[~nan_a], b[~nan_b])
 
 
 @pytest.mark.parametrize("name", sorted(PINS))
@@ -178,7 +188,7 @@ def test_random_obj_files_match_reference_loader(tmp_path, oracle_mod):
 def test_multi_chunk_file_and_non_finite_coordinates_match_reference_loader(tmp_path, oracle_mod, meshes_mod, monkeypatch, threads):
     """A 3 MB file (icosphere(6): 81 920 triangles, parsed in several chunks) as written, and with nan / inf / signed
     zeros sprinkled into the coordinates -- vertex 0 included: fscanf reads them, the face normals and the AABB
-    (first strict minimum wins, a NaN in vertex 0 poisons its axis) must come out bit for bit."""
+    (first strict minimum wins, a NaN in vertex 0 poisons its axis) must come out bit for bit, NaNs as NaNs."""
     from bench_configs import write_obj
     monkeypatch.setenv("DXRV_OBJ_THREADS", threads)
     p = tmp_path / "ico6.obj"
@@ -194,7 +204,7 @@ def test_multi_chunk_file_and_non_finite_coordinates_match_reference_loader(tmp_
     txt[1] = "v nan 0.5 -0.0"
     q = tmp_path / "ico6_nonfinite.obj"
     q.write_text("\n".join(txt) + "\n")
-    _same_as_reference(str(q), oracle_mod)
+    _same_as_reference(str(q), oracle_mod, nan_bits=False)
 
 
 def test_loader_semantics_without_reference(tmp_path):
