@@ -1,6 +1,6 @@
 """Differential fuzzing of the product OBJ loader against the reference's own XUSGObjLoader.cpp (oracle/_ref).
 
-  python tools/fuzz_obj.py [--seeds A:B] [--scale S] [--dir /tmp/fuzz_obj]        (DXRV_OBJ_THREADS=k: chunks per file)
+  python tools/fuzz_obj.py [--seeds A:B] [--scale S] [--exotic] [--dir /tmp/fuzz_obj]        (DXRV_OBJ_THREADS=k: chunks per file)
 
 Every seed writes one OBJ text of random records -- positions, normals, texture coordinates, faces in one corner syntax
 per file, polygons, negative indices, comments, blank lines, leading blanks, tabs, CRLF, no
@@ -113,6 +113,59 @@ def make_obj(seed):
     return text
 
 
+def make_exotic(seed):
+    """Files the reference's TOKEN grammar accepts but no exporter writes: faces continued on the next line, several
+    records on one line, unknown records (`vp`, `l`, `p`), comment / group lines longer than the reference's 255-byte
+    fgets buffer (what is left of such a line is then read as records), vt records of one to three numbers.  These take
+    the product's second parser (parseObj, the token-by-token restatement of the reference's grammar)."""
+    rng = np.random.default_rng(seed)
+    nv = int(rng.integers(4, 40))
+    nf = int(rng.integers(2, 30))
+    lines = []
+    pending = []
+
+    def flush():
+        if pending:
+            lines.append(" ".join(pending))
+            pending.clear()
+
+    def emit(rec):
+        pending.append(rec)
+        if rng.random() < 0.8:
+            flush()
+
+    def noise():
+        r = rng.random()
+        if r < 0.25:
+            flush(); lines.append("# " + "x" * int(rng.integers(230, 300)) + " v 1 2 3")      # around the 255-byte limit
+        elif r < 0.4:
+            flush(); lines.append("g " + "name" * int(rng.integers(60, 80)))
+        elif r < 0.55:
+            flush(); lines.append(["vp 0.5 0.5", "l 1 2 3", "p 1", "curv 0 1 1 2", "s 2"][int(rng.integers(0, 5))])
+        elif r < 0.7:
+            flush(); lines.append("#" + "y" * 254)
+        elif r < 0.8:
+            flush(); lines.append("#" + "z" * 253 + " ")
+
+    for _ in range(nv):
+        if rng.random() < 0.15:
+            noise()
+        flush(); lines.append("v " + " ".join(number(rng) for _ in range(3)))   # (a second `v` on the line would be dropped by the reference: one per line)
+    for _ in range(nf):
+        if rng.random() < 0.2:
+            noise()
+        corners = [str(int(rng.integers(1, nv + 1))) for _ in range(int(rng.integers(3, 7)))]
+        if rng.random() < 0.3:                                   # continued on the next line(s)
+            flush()
+            cut = int(rng.integers(1, len(corners)))
+            lines.append("f " + " ".join(corners[:cut]))
+            lines.append(" ".join(corners[cut:]))
+        else:
+            emit("f " + " ".join(corners))
+    flush()
+    return "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
+
+
 def child(paths):
     sys.path.insert(0, ROOT)
     import oracle
@@ -144,6 +197,7 @@ def main():
     ap.add_argument("--seeds", default="0:500")
     ap.add_argument("--dir", default="/tmp/fuzz_obj")
     ap.add_argument("--scale", type=int, default=1)
+    ap.add_argument("--exotic", action="store_true", help="token-grammar files (make_exotic) instead of exporter-style ones")
     ap.add_argument("--child", nargs="*")
     a = ap.parse_args()
     global SCALE
@@ -160,7 +214,7 @@ def main():
         for s in range(b, min(hi, b + batch)):
             p = os.path.join(a.dir, "fuzz_%d.obj" % s)
             with open(p, "wb") as f:
-                f.write(make_obj(s).encode())
+                f.write((make_exotic(s) if a.exotic else make_obj(s)).encode())
             paths.append(p)
         while paths:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"] + paths, capture_output=True, text=True)
