@@ -68,6 +68,11 @@ extern "C" int dxrv_voxelize_obj_batch(dxrv_ctx* const* ctxs, uint32_t numCtx, c
     for (uint32_t k = 0; k < numMeshes; ++k)
         if (!paths[k]) { dxrv::globalError() = "dxrv_voxelize_obj_batch: null path"; return DXRV_ERR_INVALID_ARG; }
     const size_t P = (static_cast<size_t>(N) + 31) / 32;
+    if (mode != DXRV_MODE_SHADER && mode != DXRV_MODE_PARITY)
+    {
+        dxrv::globalError() = "dxrv_voxelize_obj_batch: mode must be DXRV_MODE_SHADER or DXRV_MODE_PARITY (bit grids only)";
+        return DXRV_ERR_INVALID_ARG;
+    }
     if (N == 0 || N > 8192) { dxrv::globalError() = "dxrv_voxelize_obj_batch: N must be in [1, 8192]"; return DXRV_ERR_INVALID_ARG; }
     if (hostGrids && gridBytes != static_cast<size_t>(N) * N * P * 4)
     {

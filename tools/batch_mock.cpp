@@ -179,6 +179,8 @@ int main(int argc, char** argv)
         CHECK(dxrv_voxelize_obj_batch(one, 1, paths.data(), 1, N, 1, grids.data(), gridBytes - 4, 0, nullptr) == DXRV_ERR_INVALID_ARG);
         CHECK(dxrv_voxelize_obj_batch(one, 1, paths.data(), 1, 0, 1, nullptr, 0, 0, nullptr) == DXRV_ERR_INVALID_ARG);
         CHECK(dxrv_voxelize_obj_batch(one, 1, nullptr, 1, N, 1, nullptr, 0, 0, nullptr) == DXRV_ERR_INVALID_ARG);
+        CHECK(dxrv_voxelize_obj_batch(one, 1, paths.data(), 1, N, DXRV_MODE_SHADER | DXRV_EMIT_TEXELS, nullptr, 0, 0, nullptr) == DXRV_ERR_INVALID_ARG);
+        CHECK(dxrv_voxelize_obj_batch(one, 1, paths.data(), 1, N, 7, nullptr, 0, 0, nullptr) == DXRV_ERR_INVALID_ARG);
     }
     CHECK(g_overlap.load() == 0);
     std::printf("batch pipeline: all checks passed\n");
