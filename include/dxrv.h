@@ -262,14 +262,16 @@ DXRV_API void dxrv_obj_aabb(const dxrv_mesh* mesh, float out[6]);
 DXRV_API void dxrv_obj_bound(const dxrv_mesh* mesh, float out[4]);
 
 /* ---- a stream of distinct meshes (BASELINE config 5) -----------------------------------------
- * LoadAssets + voxelize per mesh (DXRVoxelizer.cpp:190-199, Voxelizer.cpp:351-369) as a pipeline inside the library:
- * `loaderThreads` host threads parse the OBJ files (0: one per core, <= 32; one thread per file), context s -- driven by
- * its own host thread -- takes meshes s, s + numCtx, ... in order: dxrv_build_bvh (bound = NULL), dxrv_voxelize(N, mode, 0, N), and, when hostGrids is not NULL, dxrv_fetch_grid of mesh k
- * into hostGrids + k * gridBytes (DXRV_FORMAT_BITS; gridBytes = N * N * ceil(N/32) * 4; pinned memory copies fastest).
- * mode is DXRV_MODE_SHADER or DXRV_MODE_PARITY (bit grids; no flags).  The contexts must be distinct (typically 4 per GPU; they may sit on different GPUs) and are left holding their last
- * mesh.  numTriangles (optional): triangles of every mesh.  Parsed meshes waiting for a stream are bounded, whatever the
- * batch size.  Returns the first failure (the message names the file; dxrv_last_error(NULL)); grids of meshes processed
- * before it are valid. */
+ * LoadAssets + voxelize per mesh (DXRVoxelizer.cpp:190-199, Voxelizer.cpp:351-369) as a pipeline inside
+ * the library: `loaderThreads` host threads parse the OBJ files (0: one per core, <= 32; one thread per
+ * file); context s -- driven by its own host thread -- takes meshes s, s + numCtx, ... in order:
+ * dxrv_build_bvh (bound = NULL), dxrv_voxelize(N, mode, 0, N) and, when hostGrids is not NULL,
+ * dxrv_fetch_grid of mesh k into hostGrids + k * gridBytes (DXRV_FORMAT_BITS; gridBytes =
+ * N * N * ceil(N/32) * 4; pinned memory copies fastest).  mode is DXRV_MODE_SHADER or DXRV_MODE_PARITY
+ * (bit grids; no flags).  The contexts must be distinct (typically 4 per GPU; they may sit on different
+ * GPUs) and are left holding their last mesh.  numTriangles (optional): triangles of every mesh.  Parsed
+ * meshes waiting for a stream are bounded, whatever the batch size.  Returns the first failure (the
+ * message names the file; dxrv_last_error(NULL)); grids of meshes processed before it are valid. */
 DXRV_API int dxrv_voxelize_obj_batch(dxrv_ctx* const* ctxs, uint32_t numCtx, const char* const* paths, uint32_t numMeshes,
                                      uint32_t N, uint32_t mode, void* hostGrids, size_t gridBytes, uint32_t loaderThreads,
                                      uint32_t* numTriangles);
