@@ -7,7 +7,8 @@
 // reference's function; parity = the column-parity fast path), -device k,
 // -slab z0 z1, -frames n, -gpus k (z-slabs over k GPUs), -out file.bin (raw DXRV_FORMAT_BITS words),
 // -view file.ppm|file.png (the reference's viewer pass, 1280 x 720; .png = its screenshot format), -batch list.txt [-streams k] (one grid per OBJ path
-// of the list through dxrv_voxelize_obj_batch: k contexts per GPU, -gpus GPUs; -out prefix writes prefix00000.bin ...).
+// of the list through dxrv_voxelize_obj_batch: k contexts per GPU, -gpus GPUs; -out prefix writes prefix00000.bin ...),
+// -dryrun (print the parsed arguments and exit).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -40,7 +41,7 @@ struct Args
     // would swallow absolute paths, so '/' only introduces an option when a known name follows.
     static bool knownOption(const char* name)
     {
-        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus", "view", "batch", "streams"};
+        static const char* const names[] = {"warp", "uma", "mesh", "grid", "device", "frames", "out", "slab", "mode", "gpus", "view", "batch", "streams", "dryrun"};
         for (const char* n : names) if (lower(name) == n) return true;
         return false;
     }
@@ -134,10 +135,12 @@ int main(int argc, char** argv)
     int device = 0, frames = 1, gpus = 1;
     DXRVoxelizer::Mode mode = DXRVoxelizer::MODE_SHADER;   // Dragon.sh / TuringBowl.sh reproduce the reference's grid
 
+    bool dryRun = false;
     Args a{argc, argv};
     for (int i = 1; i < argc; ++i)
     {
         if (a.matches(i, "warp") || a.matches(i, "uma")) continue;
+        else if (a.matches(i, "dryrun")) dryRun = true;
         else if (a.matches(i, "mesh"))
         {
             if (a.hasValue(i)) mesh = argv[++i];
@@ -166,6 +169,14 @@ int main(int argc, char** argv)
         }
     }
 
+    if (dryRun)   // the parsed command line, nothing else (the argument grammar is part of the drop-in surface: tests/test_abi.py)
+    {
+        std::printf("{\"mesh\": \"%s\", \"posScale\": [%g, %g, %g, %g], \"grid\": %u, \"mode\": \"%s\", \"device\": %d, \"frames\": %d, "
+                    "\"gpus\": %d, \"slab\": [%u, %u], \"out\": \"%s\", \"view\": \"%s\", \"batch\": \"%s\", \"streams\": %d}\n",
+                    mesh.c_str(), posScale[0], posScale[1], posScale[2], posScale[3], grid, mode == DXRVoxelizer::MODE_SHADER ? "shader" : "parity",
+                    device, frames, gpus, slab0, slab1, out.c_str(), view.c_str(), batch.c_str(), streams);
+        return 0;
+    }
     if (!batch.empty())
         return runBatch(batch, grid, mode == DXRVoxelizer::MODE_SHADER ? DXRV_MODE_SHADER : DXRV_MODE_PARITY, device, gpus, streams, out);
 

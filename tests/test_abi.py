@@ -85,3 +85,30 @@ def test_cli_batch_mode_reports_failures(tmp_path):
     r = subprocess.run([exe, "-batch", str(lst), "-grid", "64", "-mode", "parity", "-streams", "2"], capture_output=True, text=True,
                        env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def _dry(*args):
+    import json
+    exe = os.path.join(ROOT, "dxrvoxelizer_b200", "dxrvoxelizer")
+    r = subprocess.run([exe, "-dryrun"] + list(args), capture_output=True, text=True, check=True)
+    return json.loads(r.stdout)
+
+
+def test_cli_argument_grammar_follows_the_reference():
+    """DXRVoxelizer::ParseCommandLineArgs (DXRVoxelizer.cpp:363-408): '-' or '/' prefix, case-insensitive names, a value may
+    start with '-' only when a digit or '.' follows, `-mesh path [x y z scale]`, defaults Assets/bunny.obj and (0,0,0,1)
+    (DXRVoxelizer.cpp:36-37); -warp / -uma accepted.  The .bat files: Dragon.bat = `-mesh Assets/dragon.obj`,
+    TuringBowl.bat = `-mesh Assets/TuringBowl.obj 0.0 2.8 0.0 0.03`."""
+    d0 = _dry()
+    assert d0["mesh"] == "Assets/bunny.obj" and d0["posScale"] == [0, 0, 0, 1] and d0["grid"] == 64 and d0["mode"] == "shader"
+    t = _dry("-mesh", "Assets/TuringBowl.obj", "0.0", "2.8", "0.0", "0.03")
+    assert t["mesh"] == "Assets/TuringBowl.obj" and t["posScale"] == pytest.approx([0.0, 2.8, 0.0, 0.03])
+    assert _dry("/MESH", "a.obj", "-WARP", "-uma")["mesh"] == "a.obj"                       # '/' prefix, any case
+    n = _dry("-mesh", "a.obj", "-0.5", ".5", "-1", "2", "-grid", "256")
+    assert n["posScale"] == pytest.approx([-0.5, 0.5, -1.0, 2.0]) and n["grid"] == 256      # negative numbers are values
+    p = _dry("-mesh", "a.obj", "1.5", "-mode", "parity")                                     # fewer than four numbers: the rest keep their defaults
+    assert p["posScale"] == pytest.approx([1.5, 0, 0, 1]) and p["mode"] == "parity"
+    assert _dry("-mesh", "-grid", "128")["mesh"] == "Assets/bunny.obj"                       # an option is not a value
+    assert _dry("-mesh", "/abs/path/mesh.obj")["mesh"] == "/abs/path/mesh.obj"              # (Linux deviation: absolute paths)
+    b = _dry("-batch", "list.txt", "-streams", "8", "-gpus", "2", "-slab", "3", "9", "-out", "g.bin", "-view", "v.png")
+    assert (b["batch"], b["streams"], b["gpus"], b["slab"], b["out"], b["view"]) == ("list.txt", 8, 2, [3, 9], "g.bin", "v.png")
