@@ -35,6 +35,7 @@ SIGNATURES = {
     "dxrv_fetch_grid": (_int, [_vp, _vp, _sz, _u32]),
     "dxrv_fetch_grid_sparse": (_int, [_vp, _vp, _sz, _c.POINTER(_sz)]),
     "dxrv_sparse_decode": (_int, [_vp, _sz, _vp, _sz]),
+    "dxrv_sparse_encode": (_int, [_vp, _sz, _u32, _u32, _u32, _vp, _sz, _c.POINTER(_sz)]),
     "dxrv_voxelize_to_host": (_int, [_vp, _u32, _u32, _u32, _u32, _vp, _sz, _u32]),
     "dxrv_voxelize_mesh_to_host": (_int, [_vp, _vp, _u32, _u32, _vp, _u32, _vp, _u32, _u32, _u32, _u32, _vp, _sz, _u32]),
     "dxrv_set_read_back": (_int, [_vp, _u32]),

@@ -897,6 +897,23 @@ int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_
     return published && filled ? DXRV_OK : DXRV_ERR_INVALID_ARG;
 }
 
+int dxrv_sparse_encode(const void* dense, size_t denseBytes, uint32_t N, uint32_t slabBegin, uint32_t slabEnd, void* blob, size_t capacity,
+                       size_t* bytesWritten)
+{
+    // pure host code (sparse_host.cpp): the device encoder's bytes from a dense host grid
+    if (!dense || !bytesWritten || N == 0 || N > 8192 || slabBegin >= slabEnd || slabEnd > N) return DXRV_ERR_INVALID_ARG;
+    *bytesWritten = 0;
+    if (denseBytes != (size_t)(slabEnd - slabBegin) * N * ((N + 31) / 32) * 4) return DXRV_ERR_INVALID_ARG;
+    size_t bytes = 0;
+    try
+    {
+        const bool ok = sparseEncode(static_cast<const uint32_t*>(dense), N, slabBegin, slabEnd, blob, capacity, bytes);
+        *bytesWritten = bytes;
+        return ok ? DXRV_OK : DXRV_ERR_INVALID_ARG;
+    }
+    catch (const std::bad_alloc&) { return DXRV_ERR_OOM; }
+}
+
 int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes)
 {
     if (!ctx || !d_ptr || !bytes) return DXRV_ERR_INVALID_ARG;

@@ -96,6 +96,74 @@ bool sparseParse(const void* blob, size_t blobBytes, SparseBlobView& v)
     return true;
 }
 
+// Host encoder: classify the bricks of every brick layer on the pool's threads (0 empty, 1 full, 2 mixed; rows and
+// layers beyond the slab do not count against "full" and are stored as zeros), rank the mixed bricks, write header,
+// packed states and payload.  Same bytes as the device encoder (tests/test_sparse.py: both against a numpy encoder).
+bool sparseEncode(const uint32_t* dense, uint32_t N, uint32_t z0, uint32_t z1, void* blob, size_t capacity, size_t& bytes)
+{
+    const uint32_t P = (N + 31u) / 32u, layers = z1 - z0, BY = (N + 3u) / 4u, BZ = (layers + 3u) / 4u;
+    const size_t numBricks = (size_t)P * BY * BZ, perLayer = (size_t)P * BY;
+    const size_t stateWords = (numBricks + 15) / 16, offStates = 64, offPayload = (offStates + stateWords * 4 + 63) & ~(size_t)63;
+    const uint32_t tailMask = (N & 31u) ? ((1u << (N & 31u)) - 1u) : 0xffffffffu;
+    std::vector<uint8_t> state(numBricks);
+    std::vector<size_t> mixedInLayer(BZ, 0);
+    auto brickWords = [&](uint32_t bz, uint32_t by, uint32_t bx, uint32_t out[16], uint32_t& exists) {
+        exists = 0;
+        for (uint32_t k = 0; k < 4u; ++k)
+            for (uint32_t j = 0; j < 4u; ++j)
+            {
+                const uint32_t z = 4u * bz + k, y = 4u * by + j;
+                const bool ex = z < layers && y < N;
+                out[4u * k + j] = ex ? dense[((size_t)z * N + y) * P + bx] : 0u;
+                exists |= (ex ? 1u : 0u) << (4u * k + j);
+            }
+    };
+    hostParallelFor(BZ, [&](unsigned bz) {
+        size_t mixed = 0;
+        for (uint32_t by = 0; by < BY; ++by)
+            for (uint32_t bx = 0; bx < P; ++bx)
+            {
+                uint32_t w[16], exists;
+                brickWords(bz, by, bx, w, exists);
+                const uint32_t fullWord = bx == P - 1u ? tailMask : 0xffffffffu;
+                bool any = false, full = true;
+                for (uint32_t i = 0; i < 16u; ++i)
+                {
+                    any = any || w[i] != 0u;
+                    if ((exists >> i) & 1u) full = full && w[i] == fullWord;
+                }
+                const uint8_t st = !any ? 0 : (full ? 1 : 2);
+                state[(size_t)bz * perLayer + (size_t)by * P + bx] = st;
+                mixed += st == 2;
+            }
+        mixedInLayer[bz] = mixed;
+    });
+    std::vector<size_t> firstRank(BZ + 1, 0);
+    for (uint32_t bz = 0; bz < BZ; ++bz) firstRank[bz + 1] = firstRank[bz] + mixedInLayer[bz];
+    const size_t numMixed = firstRank[BZ];
+    bytes = offPayload + numMixed * 64;
+    if (!blob || capacity < bytes) return false;
+    uint8_t* out = static_cast<uint8_t*>(blob);
+    std::memset(out, 0, offPayload);
+    const uint32_t header[16] = {0x42525844u, 1u, N, z0, z1, P, BY, BZ, (uint32_t)numBricks, (uint32_t)numMixed, (uint32_t)offStates, (uint32_t)offPayload, 32u, 4u, 4u, 0u};
+    std::memcpy(out, header, sizeof header);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(out + offStates);
+    for (size_t b = 0; b < numBricks; ++b) sw[b >> 4] |= (uint32_t)state[b] << (2u * (b & 15u));
+    uint32_t* payload = reinterpret_cast<uint32_t*>(out + offPayload);
+    hostParallelFor(BZ, [&](unsigned bz) {
+        size_t rank = firstRank[bz];
+        for (uint32_t by = 0; by < BY; ++by)
+            for (uint32_t bx = 0; bx < P; ++bx)
+                if (state[(size_t)bz * perLayer + (size_t)by * P + bx] == 2)
+                {
+                    uint32_t exists;
+                    brickWords(bz, by, bx, payload + 16 * rank, exists);
+                    ++rank;
+                }
+    });
+    return true;
+}
+
 // brick layer bz of the blob into dst, word by word (dstIsZero: only the non-empty bricks are written)
 static void expandLayer(const SparseBlobView& v, uint32_t* dst, uint32_t bz, uint32_t firstRank, bool dstIsZero)
 {

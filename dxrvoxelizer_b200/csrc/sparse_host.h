@@ -18,6 +18,9 @@ bool sparseParse(const void* blob, size_t blobBytes, SparseBlobView& v);
 // the GPU was still computing) and only the non-empty bricks are written; otherwise every word is written.
 // false: the states disagree with the header's count of mixed bricks (nothing reliable was written).
 bool sparseExpand(const SparseBlobView& v, uint32_t* dst, bool dstIsZero);
+// The inverse on the host: dense BITS slab (layers * N * P words) -> blob, byte for byte what the device encoder
+// (sparse.cu) writes.  bytes receives the blob's size; false when `capacity` is too small (nothing written but bytes).
+bool sparseEncode(const uint32_t* dense, uint32_t N, uint32_t z0, uint32_t z1, void* blob, size_t capacity, size_t& bytes);
 // Zero `bytes` at dst with the pool's threads: begin returns at once, wait blocks (host_pool.h: one batch at a time).
 void hostZeroBegin(void* dst, size_t bytes);
 void hostZeroWait();

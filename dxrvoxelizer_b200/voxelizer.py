@@ -374,6 +374,23 @@ def sparse_decode(blob):
     return out
 
 
+def sparse_encode(bits, N, z0=0):
+    """dense uint32[layers, N, P] slab starting at layer z0 -> DXRV_FORMAT_SPARSE_BRICKS blob (dxrv_sparse_encode, host code;
+    the same bytes the device encoder writes)."""
+    g = np.ascontiguousarray(bits, dtype=np.uint32)
+    layers = g.shape[0]
+    n = ctypes.c_size_t()
+    lib = L.lib()
+    rc = lib.dxrv_sparse_encode(g.ctypes.data, g.nbytes, N, z0, z0 + layers, None, 0, ctypes.byref(n))   # size query
+    if n.value == 0:
+        raise L.DxrvError(rc, "dxrv_sparse_encode: invalid arguments")
+    blob = np.empty(n.value, np.uint8)
+    rc = lib.dxrv_sparse_encode(g.ctypes.data, g.nbytes, N, z0, z0 + layers, blob.ctypes.data, blob.size, ctypes.byref(n))
+    if rc != L.OK:
+        raise L.DxrvError(rc, "dxrv_sparse_encode failed")
+    return blob
+
+
 def unpack_bits(bits, N):
     """uint32[..., P] -> uint8[..., N] occupancy (bit x&31 of word x>>5)."""
     b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=-1, bitorder="little")

@@ -173,6 +173,11 @@ DXRV_API int dxrv_voxelize_mesh_to_host(dxrv_ctx* ctx, const void* vertices, uin
  * layout. */
 DXRV_API int dxrv_fetch_grid_sparse(dxrv_ctx* ctx, void* hostDst, size_t capacity, size_t* bytesWritten);
 DXRV_API int dxrv_sparse_decode(const void* blob, size_t blobBytes, void* denseDst, size_t denseBytes);
+/* The encoder on the host (pure host code, same pool): the slab [slabBegin, slabEnd) of an N^3 BITS grid at `dense`
+ * (denseBytes = layers * N * ceil(N/32) * 4) -> the same bytes the device encoder writes.  *bytesWritten receives the
+ * blob's size -- also when `capacity` is too small (DXRV_ERR_INVALID_ARG, nothing written; blob may then be NULL). */
+DXRV_API int dxrv_sparse_encode(const void* dense, size_t denseBytes, uint32_t N, uint32_t slabBegin, uint32_t slabEnd,
+                                void* blob, size_t capacity, size_t* bytesWritten);
 /* Device pointer / byte size of the slab's DXRV_FORMAT_BITS grid (valid until the next
  * voxelize with a different size, or destroy). */
 DXRV_API int dxrv_grid_device(dxrv_ctx* ctx, void** d_ptr, size_t* bytes);

@@ -64,6 +64,32 @@ def test_decoder_against_a_numpy_encoder(N, layers, seed, delay_us, monkeypatch)
         d.sparse_decode(bad)
 
 
+@pytest.mark.parametrize("N,layers,z0,seed", [(64, 64, 0, 1), (100, 37, 7, 2), (33, 5, 20, 3), (128, 2, 126, 4), (31, 31, 0, 5), (256, 256, 0, 6),
+                                              (512, 42, 300, 7), (1, 1, 0, 8), (5, 3, 2, 9)])
+def test_host_encoder_against_the_numpy_encoder(N, layers, z0, seed):
+    """dxrv_sparse_encode (host code): the blob of a dense slab, byte for byte what the format description gives (and so what
+    the device encoder writes: test_gpu_encoder_round_trip); the decoder inverts it; an empty and a full grid; capacity."""
+    import ctypes
+    from dxrvoxelizer_b200 import _lib as L
+    rng = np.random.default_rng(seed)
+    P = (N + 31) // 32
+    zz, yy, xx = np.meshgrid(np.arange(layers), np.arange(N), np.arange(N), indexing="ij")
+    occ = (xx - N / 2) ** 2 + (yy - N / 2) ** 2 + (zz - layers / 2) ** 2 < (0.4 * N) ** 2
+    occ ^= rng.random(occ.shape) < 0.001
+    for grid in (occ, np.zeros_like(occ), np.ones_like(occ)):
+        bits = np.packbits(np.pad(grid, ((0, 0), (0, 0), (0, P * 32 - N))), axis=-1, bitorder="little").view(np.uint32).reshape(layers, N, P)
+        blob = d.sparse_encode(bits, N, z0)
+        assert np.array_equal(blob, numpy_encode(bits, N, z0))
+        assert np.array_equal(d.sparse_decode(blob), bits)
+    n = ctypes.c_size_t()
+    small = np.empty(blob.size - 1, np.uint8)
+    lib = L.lib()
+    assert lib.dxrv_sparse_encode(bits.ctypes.data, bits.nbytes, N, z0, z0 + layers, small.ctypes.data, small.size, ctypes.byref(n)) == L.ERR_INVALID_ARG
+    assert n.value == blob.size                                                # the size it needs
+    assert lib.dxrv_sparse_encode(bits.ctypes.data, bits.nbytes - 4, N, z0, z0 + layers, blob.ctypes.data, blob.size, ctypes.byref(n)) == L.ERR_INVALID_ARG
+    assert lib.dxrv_sparse_encode(bits.ctypes.data, bits.nbytes, N, z0, N + 1, blob.ctypes.data, blob.size, ctypes.byref(n)) == L.ERR_INVALID_ARG
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,N,z0,z1,mode", [("dragon.obj", 256, 0, 256, 1), ("bunny.obj", 100, 10, 47, 1), ("TuringBowl.obj", 192, 0, 192, 0),
                                                ("dragon.obj", 1024, 300, 560, 1), ("bunny.obj", 33, 0, 33, 1)])
@@ -75,6 +101,7 @@ def test_gpu_encoder_round_trip(vox, assets, name, N, z0, z1, mode):
     blob = vox.fetch_sparse()
     assert np.array_equal(d.sparse_decode(blob), dense)
     assert np.array_equal(blob, numpy_encode(dense, N, z0))                 # byte-identical to the format description
+    assert np.array_equal(blob, d.sparse_encode(dense, N, z0))              # ... and to the host encoder
     h = blob[:64].view(np.uint32)
     assert h[9] > 0 and blob.size < dense.nbytes                            # a solid object: far smaller than the dense grid
     small = np.empty(128, np.uint8)

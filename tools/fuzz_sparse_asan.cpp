@@ -65,6 +65,24 @@ int main(int argc, char** argv)
             if (decode(blob.data(), blob.size(), &out, delay) != 0 || out.size() * 4 != bits.size() || memcmp(out.data(), bits.data(), bits.size()) != 0)
             { printf("VALID BLOB NOT DECODED: %s (delay %u)\n", argv[a], delay); ++bad; }
         }
+        {   // the host encoder: exact-size buffers, the same bytes as the blob on file
+            dxrv::SparseBlobView v;
+            void* copy = aligned_alloc(64, (blob.size() + 63) / 64 * 64);
+            memcpy(copy, blob.data(), blob.size());
+            if (dxrv::sparseParse(copy, blob.size(), v))
+            {
+                uint32_t* dense = (uint32_t*)malloc(bits.size() ? bits.size() : 4);
+                memcpy(dense, bits.data(), bits.size());
+                unsigned char* out = (unsigned char*)malloc(blob.size());
+                size_t n = 0;
+                const bool ok = dxrv::sparseEncode(dense, v.N, v.z0, v.z1, out, blob.size(), n);
+                if (!ok || n != blob.size() || memcmp(out, blob.data(), n) != 0) { printf("ENCODER DIFFERS: %s\n", argv[a]); ++bad; }
+                size_t need = 0;
+                if (dxrv::sparseEncode(dense, v.N, v.z0, v.z1, out, blob.size() - 1, need) || need != blob.size()) { printf("ENCODER CAPACITY CHECK: %s\n", argv[a]); ++bad; }
+                free(out); free(dense);
+            }
+            free(copy);
+        }
         std::mt19937_64 rng(a * 104729u);
         for (int it = 0; it < 400; ++it)
         {
