@@ -52,6 +52,7 @@ SIGNATURES = {
     "dxrv_debug_read": (_int, [_vp, _u32, _vp, _sz]),
     "dxrv_debug_sort_pairs": (_int, [_vp, _vp, _vp, _u32]),
     "dxrv_obj_load": (_int, [_c.c_char_p, _c.POINTER(_vp)]),
+    "dxrv_obj_parse": (_int, [_c.c_char_p, _sz, _c.POINTER(_vp)]),
     "dxrv_obj_free": (None, [_vp]),
     "dxrv_obj_num_vertices": (_u32, [_vp]),
     "dxrv_obj_num_indices": (_u32, [_vp]),

@@ -38,6 +38,27 @@ int dxrv_obj_load(const char* path, dxrv_mesh** out)
     return DXRV_OK;
 }
 
+int dxrv_obj_parse(const char* text, size_t size, dxrv_mesh** out)
+{
+    if (!text || !out) { dxrv::globalError() = "dxrv_obj_parse: null argument"; return DXRV_ERR_INVALID_ARG; }
+    *out = nullptr;
+    dxrv_mesh* m = new (std::nothrow) dxrv_mesh();
+    if (!m) { dxrv::globalError() = "dxrv_obj_parse: out of memory"; return DXRV_ERR_OOM; }
+    std::string err;
+    bool ok = false;
+    try
+    {
+        // as loadObj: the multi-threaded parser for well-formed text, the reference's token grammar for everything else
+        ok = dxrv::parseObjFast(text, size, m->mesh, err, 0);
+        if (!ok && err.empty()) ok = dxrv::parseObj(text, size, m->mesh, err);
+    }
+    catch (const std::bad_alloc&) { delete m; dxrv::globalError() = "dxrv_obj_parse: out of memory"; return DXRV_ERR_OOM; }
+    catch (...) { ok = false; err = "unexpected exception"; }
+    if (!ok) { delete m; dxrv::globalError() = "dxrv_obj_parse: " + err; return DXRV_ERR_IO; }
+    *out = m;
+    return DXRV_OK;
+}
+
 void dxrv_obj_free(dxrv_mesh* mesh) { delete mesh; }
 uint32_t dxrv_obj_num_vertices(const dxrv_mesh* mesh) { return mesh ? mesh->mesh.numVertices() : 0; }
 uint32_t dxrv_obj_num_indices(const dxrv_mesh* mesh) { return mesh ? mesh->mesh.numIndices() : 0; }

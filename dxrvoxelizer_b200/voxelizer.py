@@ -44,10 +44,15 @@ class Mesh:
         return Mesh(vb, triangles, vb.shape[1] * 4)
 
 
-def load_obj(path):
+def load_obj(path=None, text=None):
+    """dxrv_obj_load(path), or dxrv_obj_parse of OBJ text (bytes) already in memory."""
     lib = L.lib()
     h = ctypes.c_void_p()
-    rc = lib.dxrv_obj_load(str(path).encode(), ctypes.byref(h))
+    if text is not None:
+        data = bytes(text)
+        rc = lib.dxrv_obj_parse(data, len(data), ctypes.byref(h))
+    else:
+        rc = lib.dxrv_obj_load(str(path).encode(), ctypes.byref(h))
     if rc != L.OK:
         raise L.DxrvError(rc, lib.dxrv_last_error(None).decode())
     try:

@@ -255,6 +255,9 @@ DXRV_API int dxrv_debug_sort_pairs(dxrv_ctx* ctx, uint32_t* keys, uint32_t* valu
  * interleaved {float3 pos; float3 nrm} vertices, uint32 indices (z flipped, index array
  * reversed), AABB.  Pure host code. */
 DXRV_API int dxrv_obj_load(const char* path, dxrv_mesh** out);
+/* The same from OBJ text in memory (`size` bytes, no terminator needed): a mesh that arrives over a socket or from an
+ * archive.  Identical output to dxrv_obj_load of a file with these bytes. */
+DXRV_API int dxrv_obj_parse(const char* text, size_t size, dxrv_mesh** out);
 DXRV_API void dxrv_obj_free(dxrv_mesh* mesh);
 DXRV_API uint32_t dxrv_obj_num_vertices(const dxrv_mesh* mesh);
 DXRV_API uint32_t dxrv_obj_num_indices(const dxrv_mesh* mesh);

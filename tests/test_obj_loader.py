@@ -226,6 +226,23 @@ def test_loader_semantics_without_reference(tmp_path):
     np.testing.assert_allclose(n, 1.0, rtol=1e-6)
 
 
+def test_parse_from_memory_equals_load_from_file(tmp_path):
+    """dxrv_obj_parse: OBJ text in memory (no terminator, embedded NUL tolerated as an ordinary byte) = dxrv_obj_load."""
+    for name in ("bunny.obj", "TuringBowl.obj"):
+        path = d.asset_path(name)
+        a = d.load_obj(path)
+        b = d.load_obj(text=open(path, "rb").read())
+        assert a.stride == b.stride and np.array_equal(a.indices, b.indices)
+        assert a.vertex_bytes.tobytes() == b.vertex_bytes.tobytes() and a.aabb.tobytes() == b.aabb.tobytes()
+    for case, text in EDGE_CASES.items():
+        p = tmp_path / (case + ".obj")
+        p.write_bytes(text.encode())
+        a, b = d.load_obj(str(p)), d.load_obj(text=text.encode())
+        assert np.array_equal(a.indices, b.indices) and a.vertex_bytes.tobytes() == b.vertex_bytes.tobytes()
+    with pytest.raises(d.DxrvError):
+        d.load_obj(text=b"v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")
+
+
 def test_loader_missing_file_fails_like_reference():
     with pytest.raises(d.DxrvError) as e:
         d.load_obj("/nonexistent/mesh.obj")
