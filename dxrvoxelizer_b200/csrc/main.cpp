@@ -84,7 +84,7 @@ int runBatch(const std::string& listPath, uint32_t grid, uint32_t mode, int devi
         ctxs.push_back(c);
     }
     const size_t words = (size_t)grid * grid * ((grid + 31) / 32), gridBytes = words * 4;
-    const size_t perRound = std::max<size_t>(ctxs.size(), std::min<size_t>(files.size(), ((size_t)2 << 30) / gridBytes));
+    const size_t perRound = std::min<size_t>(files.size(), std::max<size_t>(1, ((size_t)2 << 30) / gridBytes));
     void* pinned = dxrv_host_alloc(perRound * gridBytes);
     if (!pinned) { std::fprintf(stderr, "cannot allocate %zu bytes of pinned host memory\n", perRound * gridBytes); cleanup(nullptr); return 1; }
 
