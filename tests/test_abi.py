@@ -112,3 +112,13 @@ def test_cli_argument_grammar_follows_the_reference():
     assert _dry("-mesh", "/abs/path/mesh.obj")["mesh"] == "/abs/path/mesh.obj"              # (Linux deviation: absolute paths)
     b = _dry("-batch", "list.txt", "-streams", "8", "-gpus", "2", "-slab", "3", "9", "-out", "g.bin", "-view", "v.png")
     assert (b["batch"], b["streams"], b["gpus"], b["slab"], b["out"], b["view"]) == ("list.txt", 8, 2, [3, 9], "g.bin", "v.png")
+
+
+def test_bat_file_equivalents_pass_the_reference_arguments():
+    """Dragon.sh / TuringBowl.sh = Bin/Dragon.bat / Bin/TuringBowl.bat: the mesh and, for the bowl, `0.0 2.8 0.0 0.03`."""
+    import json
+    for script, mesh, pos_scale in (("Dragon.sh", "dragon.obj", [0, 0, 0, 1]), ("TuringBowl.sh", "TuringBowl.obj", [0.0, 2.8, 0.0, 0.03])):
+        r = subprocess.run([os.path.join(ROOT, script), "-dryrun", "-grid", "256"], capture_output=True, text=True, check=True)
+        j = json.loads(r.stdout)
+        assert j["mesh"].endswith(mesh) and os.path.exists(j["mesh"]) and j["grid"] == 256 and j["mode"] == "shader"
+        assert j["posScale"] == pytest.approx(pos_scale)
