@@ -122,3 +122,16 @@ def test_bat_file_equivalents_pass_the_reference_arguments():
         j = json.loads(r.stdout)
         assert j["mesh"].endswith(mesh) and os.path.exists(j["mesh"]) and j["grid"] == 256 and j["mode"] == "shader"
         assert j["posScale"] == pytest.approx(pos_scale)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/dxrv.h must compile as C99 (what a cgo / JNI / ctypes-free FFI would include) and C++11."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    c = tmp_path / "hdr.c"
+    c.write_text('#include "dxrv.h"\nint main(void) { return DXRV_OK; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(c)], check=True)
+    cpp = tmp_path / "hdr.cpp"
+    cpp.write_text('#include "dxrv.h"\nint main() { return DXRV_OK; }\n')
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(cpp)], check=True)
