@@ -135,3 +135,19 @@ def test_header_is_plain_c(tmp_path):
     cpp = tmp_path / "hdr.cpp"
     cpp.write_text('#include "dxrv.h"\nint main() { return DXRV_OK; }\n')
     subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(cpp)], check=True)
+
+
+def test_plain_c_example_links_against_the_library(tmp_path):
+    """examples/voxelize.c: the ABI bound from C99 -- compiles, links against libdxrv.so, loads a mesh (host code) and, without
+    a GPU, stops at dxrv_create with the library's message."""
+    import shutil
+    import dxrvoxelizer_b200 as d
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    exe = tmp_path / "voxelize"
+    libdir = os.path.join(ROOT, "dxrvoxelizer_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "voxelize.c"), "-L", libdir, "-ldxrv", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), d.asset_path("bunny.obj"), "64"], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert "34835 vertices, 69666 triangles" in r.stdout
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
